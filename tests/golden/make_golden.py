@@ -1,0 +1,216 @@
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference (/root/reference) through the
+stub harness (oracle/refharness).  Run in the build container only:
+
+    NUMBA_CACHE_DIR=/tmp/numba_cache python tests/golden/make_golden.py [case ...]
+
+The reference has no tests or golden vectors of its own, so every pin is an output of
+the reference itself on a deterministic synthetic mesh.  Each fixture stores the mesh in the
+reference's own numbering (nodes/tets/edges/tris; all other tables are derived from these and
+asserted equal to the reference's), the inputs (er, ur, BC description) and reference outputs.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, REPO)
+from oracle.refharness import harness as H  # noqa: E402
+
+H.setup_paths()
+from emerge_b200.synthmesh import box_mesh, mesh_tables  # noqa: E402
+
+WR90 = (22.86e-3, 10.16e-3)
+
+
+def _tables_check(mesh, basis):
+    t = mesh_tables(np.ascontiguousarray(mesh.nodes.T), np.ascontiguousarray(mesh.tets.T), mesh.edges, mesh.tris)
+    for name in ("tet_to_edge", "tet_to_tri", "tri_to_edge", "tri_to_tet"):
+        assert np.array_equal(getattr(t, name), getattr(mesh, name)), name
+    assert np.allclose(t.edge_lengths, mesh.edge_lengths, rtol=0, atol=0)
+    assert np.array_equal(t.tet_to_field, basis.tet_to_field)
+    assert np.array_equal(t.tri_to_field, basis.tri_to_field)
+    assert np.array_equal(t.edge_to_field, basis.edge_to_field)
+    return t
+
+
+def _mesh_dict(mesh):
+    return dict(nodes=mesh.nodes.copy(), tets=mesh.tets.astype(np.int32), edges=mesh.edges.astype(np.int32),
+                tris=mesh.tris.astype(np.int32))
+
+
+def _csr_dict(prefix, M):
+    M = M.tocsr()
+    M.sort_indices()
+    return {prefix + "_indptr": M.indptr.astype(np.int64), prefix + "_indices": M.indices.astype(np.int32),
+            prefix + "_data": M.data.copy()}
+
+
+def _sweep(fem, phys, mesh, freqs, full, out):
+    """Run frequency_domain() and collect outputs; `full` stores matrices/fields, else only checks."""
+    from fem.elements.nedelec2 import Nedelec2
+    phys.frequencies = list(freqs)
+    data = phys.frequency_domain()
+    basis = phys.basis
+    _tables_check(mesh, basis)
+    E, B = phys.assembler.cached_matrices
+    er = mesh.retreive(lambda mat, x, y, z: mat.fer3d_mat(x, y, z), phys.mesher.volumes)
+    ur = mesh.retreive(lambda mat, x, y, z: mat.fur3d_mat(x, y, z), phys.mesher.volumes)
+    out.update(_mesh_dict(mesh))
+    out["er"], out["ur"] = er, ur
+    out["freqs"] = np.asarray(freqs, dtype=np.float64)
+    rng = np.random.default_rng(1234)
+    v = rng.standard_normal(E.shape[0]) + 1j * rng.standard_normal(E.shape[0])
+    out["probe_v"] = v
+    out["E_dot_v"], out["B_dot_v"] = E @ v, B @ v
+    out["E_nnz"] = np.int64(E.nnz)
+    out["E_absmax"], out["B_absmax"] = np.abs(E.data).max(), np.abs(B.data).max()
+    if full:
+        out.update(_csr_dict("E", E))
+        out["B_data"] = B.tocsr().data.copy()
+        assert np.array_equal(E.indptr, B.indptr) and np.array_equal(E.indices, B.indices)
+    ports = [bc for bc in phys.boundary_conditions if isinstance(bc, fem.bc.PortBC)]
+    out["port_numbers"] = np.array([p.port_number for p in ports], dtype=np.int64)
+    S = np.zeros((len(freqs), len(ports), len(ports)), dtype=np.complex128)
+    for i, f in enumerate(freqs):
+        ds = data.item(i)
+        S[i] = ds.Sp.arry
+        K, b, solve_ids, pv = phys.assembler.assemble_freq_matrix(basis, er, ur, phys.boundary_conditions, f,
+                                                                   cache_matrices=True)
+        if i == 0:
+            out["solve_ids"] = np.asarray(solve_ids, dtype=np.int64)
+        out[f"K_dot_v_{i}"] = K @ v
+        for p in ports:
+            out[f"bvec_{i}_p{p.port_number}"] = pv[p.port_number]
+            x = ds._fields[p.port_number]
+            r = K[np.ix_(solve_ids, solve_ids)] @ x[solve_ids] - pv[p.port_number][solve_ids]
+            out[f"xres_{i}_p{p.port_number}"] = np.linalg.norm(r) / np.linalg.norm(pv[p.port_number][solve_ids])
+            if full:
+                out[f"x_{i}_p{p.port_number}"] = x
+        if full and i == 0:
+            K.eliminate_zeros()
+            out.update(_csr_dict("K0", K))
+    out["S"] = S
+    return data
+
+
+def case_wg_tiny():
+    """3x2x4 cells (144 tets), jittered, vacuum, two RectangularWaveguide ports + PEC walls; everything stored."""
+    box = box_mesh(3, 2, 4, *WR90, 20e-3, jitter=0.1, seed=0)
+    fem, phys, mesh = H.build_physics(box)
+    H.rect_waveguide_ports(fem, phys, box)
+    out = dict(kind="rectwg", dims=np.array(box.dims), face_tris=box.face_tris.astype(np.int32), face_tag=box.face_tag)
+    _sweep(fem, phys, mesh, [9e9, 10e9], True, out)
+    # element-level pins: the reference's element matrices for the first 6 tets
+    from fem.mth.tet import ned2_tet_stiff_mass
+    from fem.mth.optimized import matinv
+    from fem.physics.edm.optimized_assembly import local_tet_to_triid, local_tet_to_edgeid
+    basis = phys.basis
+    Es, Bs = [], []
+    for it in range(6):
+        ltm = local_tet_to_triid(basis.tet_to_field, mesh.tets, mesh.tris, it, mesh.n_edges)
+        lem = local_tet_to_edgeid(mesh.tets, mesh.edges, basis.tet_to_field, it)
+        Esub, Bsub = ned2_tet_stiff_mass(mesh.nodes[:, mesh.tets[:, it]], mesh.edge_lengths[mesh.tet_to_edge[:, it]],
+                                         lem, ltm, matinv(out["ur"][:, :, it]), out["er"][:, :, it])
+        Es.append(Esub), Bs.append(Bsub)
+    out["elemE"], out["elemB"] = np.array(Es), np.array(Bs)
+    # full (non-diagonal, non-symmetric) tensors on the same tets: pins matinv's adj*det quirk (App. A.2)
+    rng = np.random.default_rng(7)
+    Es, Bs, ers, urs = [], [], [], []
+    for it in range(4):
+        ert = rng.standard_normal((3, 3)) + 1j * rng.standard_normal((3, 3)) + 3 * np.eye(3)
+        urt = rng.standard_normal((3, 3)) + 1j * rng.standard_normal((3, 3)) + 3 * np.eye(3)
+        ltm = local_tet_to_triid(basis.tet_to_field, mesh.tets, mesh.tris, it, mesh.n_edges)
+        lem = local_tet_to_edgeid(mesh.tets, mesh.edges, basis.tet_to_field, it)
+        Esub, Bsub = ned2_tet_stiff_mass(mesh.nodes[:, mesh.tets[:, it]], mesh.edge_lengths[mesh.tet_to_edge[:, it]],
+                                         lem, ltm, matinv(urt), ert)
+        Es.append(Esub), Bs.append(Bsub), ers.append(ert), urs.append(urt)
+    out["full_er"], out["full_ur"] = np.array(ers), np.array(urs)
+    out["full_elemE"], out["full_elemB"] = np.array(Es), np.array(Bs)
+    return out
+
+
+def _mat_fn(diag):
+    d = np.asarray(diag, dtype=np.complex128)
+
+    def fn(x, y, z):
+        return np.repeat(np.diag(d)[:, :, None], x.shape[0], axis=2)
+    return fn
+
+
+def case_wg_materials():
+    """3x3x4 cells, two volumes: lossy isotropic dielectric and a diagonal-anisotropic, magnetic medium."""
+    a, b = WR90
+    L = 18e-3
+    box = box_mesh(3, 3, 4, a, b, L, jitter=0.12, seed=3, vol_fn=lambda x, y, z: np.where(z < L / 2, 1, 2))
+    H.setup_paths()
+    import fem
+    m1 = fem.Material(er=2.2, tand=0.01)
+    m2 = fem.Material(_fer=_mat_fn([3.0 - 0.2j, 1.5, 2.0 - 0.05j]), _fur=_mat_fn([1.2, 0.9 - 0.1j, 1.0]))
+    fem, phys, mesh = H.build_physics(box, {1: m1, 2: m2})
+    H.rect_waveguide_ports(fem, phys, box)
+    out = dict(kind="rectwg", dims=np.array(box.dims), face_tris=box.face_tris.astype(np.int32), face_tag=box.face_tag)
+    _sweep(fem, phys, mesh, [8.5e9, 11e9], True, out)
+    return out
+
+
+def case_wg_medium():
+    """8x4x16 cells (3072 tets, N~20k), vacuum waveguide: S-parameters + matrix checksums only."""
+    box = box_mesh(8, 4, 16, *WR90, 40e-3, jitter=0.08, seed=1)
+    fem, phys, mesh = H.build_physics(box)
+    H.rect_waveguide_ports(fem, phys, box)
+    out = dict(kind="rectwg", dims=np.array(box.dims), face_tris=box.face_tris.astype(np.int32), face_tag=box.face_tag)
+    _sweep(fem, phys, mesh, [8e9, 9e9, 10e9, 11e9, 12e9], False, out)
+    for k in [k for k in out if k.startswith(("K_dot_v_", "bvec_")) and not k.startswith(("K_dot_v_0", "bvec_0"))]:
+        del out[k]
+    return out
+
+
+def case_abc_lumped():
+    """Patch-like box: dielectric slab, internal PEC patch, vertical LumpedPort plate, AbsorbingBoundary on
+    5 outer faces, PEC ground (look-alike of demo3_patch_antenna.py, SURVEY App. C.7 iii)."""
+    a, b, L = 24e-3, 24e-3, 12e-3           # x,y footprint; z height
+    nx, ny, nz = 6, 6, 4
+    hz = L / nz
+    hx = a / nx
+
+    def vol(x, y, z):
+        return np.where(z < hz, 1, 2)        # slab of one cell height
+
+    def patch(x, y, z):                       # PEC patch on the slab top, central 2x2 cells
+        return (np.abs(z - hz) < 1e-9) & (np.abs(x) < hx) & (np.abs(y) < hx)
+
+    def plate(x, y, z):                       # vertical plate in plane y=0... use plane x = -hx, z<hz, |y|<hx
+        return (np.abs(x + hx) < 1e-9) & (z < hz) & (np.abs(y) < hx)
+
+    box = box_mesh(nx, ny, nz, a, b, L, jitter=0.0, seed=0, vol_fn=vol,
+                   internal_faces=[(7, (0, 0, 1), patch), (8, (1, 0, 0), plate)])
+    H.setup_paths()
+    import fem
+    fem, phys, mesh = H.build_physics(box, {1: fem.Material(er=3.38, tand=0.002), 2: fem.AIR}, pec_extra_tags=(7,))
+    port = fem.bc.LumpedPort(fem.FaceSelection([8]), 1, width=2 * hx, height=hz, direction=fem.ZAX, active=True, Z0=50)
+    abc = fem.bc.AbsorbingBoundary(fem.FaceSelection([1, 2, 3, 4, 6]))
+    phys.assign(port, abc)
+    out = dict(kind="abc_lumped", dims=np.array(box.dims), face_tris=box.face_tris.astype(np.int32),
+               face_tag=box.face_tag, lumped=np.array([2 * hx, hz, 50.0]),
+               vint_start=np.zeros(3), vint_end=np.zeros(3))
+    _sweep(fem, phys, mesh, [2.0e9, 2.4e9], True, out)
+    out["vint_start"], out["vint_end"] = [np.asarray(v, dtype=float) for v in port.voltage_integration_points]
+    out["port_cs_basis"] = port.cs._basis.copy()
+    out["port_cs_origin"] = np.asarray(port.cs.origin, dtype=float)
+    return out
+
+
+CASES = dict(wg_tiny=case_wg_tiny, wg_materials=case_wg_materials, wg_medium=case_wg_medium,
+             abc_lumped=case_abc_lumped)
+
+if __name__ == "__main__":
+    names = sys.argv[1:] or list(CASES)
+    for n in names:
+        out = CASES[n]()
+        path = os.path.join(HERE, n + ".npz")
+        np.savez_compressed(path, **out)
+        print(n, "->", path, f"{os.path.getsize(path) / 1e6:.2f} MB", "S[0]=", out["S"][0].ravel()[:4])
