@@ -1,0 +1,91 @@
+// Context lifetime and CSR export of the C ABI (include/emerge_b200.h).
+#include "context.cuh"
+
+extern "C" const char* emb_version(void) { return "emerge_b200 0.1 (sm_100a)"; }
+
+extern "C" int emb_create(int device, emb_ctx** out) {
+    if (!out) return EMB_ERR_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) return EMB_ERR_CUDA;
+    if (cudaSetDevice(device) != cudaSuccess) return EMB_ERR_CUDA;
+    emb_ctx* c = new emb_ctx();
+    c->device = device;
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess) {
+        delete c;
+        return EMB_ERR_CUDA;
+    }
+    *out = c;
+    return EMB_OK;
+}
+
+static void release_surface(Surface& s) {
+    s.tri.release(); s.xy.release(); s.S.release(); s.slot.release(); s.segptr.release(); s.ent.release();
+    s.Sval.release(); s.slot_s.release(); s.dof.release(); s.dsegptr.release(); s.dent.release();
+    s.bloc.release(); s.bval.release();
+    s = Surface();
+}
+
+extern "C" void emb_destroy(emb_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    c->nodes.release(); c->tris.release(); c->tri2f.release(); c->tetc.release(); c->tetord.release(); c->gid.release();
+    c->er.release(); c->ur.release(); c->adjptr.release(); c->adj.release(); c->rowptr.release(); c->col.release();
+    c->K.release(); c->M.release(); c->newid.release(); c->solve_ids.release(); c->rowptr_s.release();
+    c->col_s.release(); c->src.release(); c->A.release(); c->xs.release(); c->xfull.release();
+    for (auto& w : c->work) w.release();
+    c->dinv.release(); c->pairmate.release(); c->red.release();
+    for (auto& s : c->surf) release_surface(s);
+    cudaEventDestroy(c->ev0);
+    cudaEventDestroy(c->ev1);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+extern "C" const char* emb_last_error(const emb_ctx* c) { return c ? c->err.c_str() : "null context"; }
+extern "C" int64_t emb_launch_count(const emb_ctx* c) { return c ? c->launches : 0; }
+extern "C" double emb_last_ms(const emb_ctx* c, const char* phase) {
+    if (!c || !phase) return -1.0;
+    auto it = c->ms.find(phase);
+    return it == c->ms.end() ? -1.0 : it->second;
+}
+extern "C" int64_t emb_n_field(const emb_ctx* c) { return c ? c->N : 0; }
+extern "C" int64_t emb_nnz(const emb_ctx* c) { return c ? c->nnz : 0; }
+extern "C" int64_t emb_n_solve(const emb_ctx* c) { return c ? c->Ns : 0; }
+
+extern "C" int64_t emb_csr_rows(const emb_ctx* c, int which) {
+    if (!c) return 0;
+    return which == 2 ? c->Ns : c->N;
+}
+extern "C" int64_t emb_csr_nnz(const emb_ctx* c, int which) {
+    if (!c) return 0;
+    return which == 2 ? c->nnz_s : c->nnz;
+}
+
+extern "C" int emb_get_csr(emb_ctx* c, int which, int64_t* indptr, int32_t* indices, emb_c128* data) {
+    if (!c) return EMB_ERR_ARG;
+    const bool solve = which == 2;
+    if ((!solve && !c->have_pattern) || (solve && !c->have_dirichlet)) {
+        c->err = "emb_get_csr: pattern not built";
+        return EMB_ERR_STATE;
+    }
+    const int64_t rows = solve ? c->Ns : c->N, nnz = solve ? c->nnz_s : c->nnz;
+    if (indptr)
+        EMB_CUDA(c, cudaMemcpyAsync(indptr, solve ? c->rowptr_s.p : c->rowptr.p, (rows + 1) * sizeof(int64_t),
+                                    cudaMemcpyDeviceToHost, c->stream));
+    if (indices)
+        EMB_CUDA(c, cudaMemcpyAsync(indices, solve ? c->col_s.p : c->col.p, nnz * sizeof(int), cudaMemcpyDeviceToHost,
+                                    c->stream));
+    if (data) {
+        const cx* src = which == 0 ? c->K.p : which == 1 ? c->M.p : c->A.p;
+        if ((which < 2 && !c->have_KM) || (which == 2 && !c->have_A)) {
+            c->err = "emb_get_csr: values not assembled";
+            return EMB_ERR_STATE;
+        }
+        EMB_CUDA(c, cudaMemcpyAsync(data, src, nnz * sizeof(cx), cudaMemcpyDeviceToHost, c->stream));
+    }
+    EMB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return EMB_OK;
+}

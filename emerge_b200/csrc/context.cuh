@@ -1,0 +1,141 @@
+// Device-side state of one emerge_b200 context (one GPU, one stream, one owner thread).
+#pragma once
+#include "emb_common.cuh"
+#include "emerge_b200.h"
+#include <map>
+#include <vector>
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+};
+
+struct Surface {
+    bool defined = false;
+    int frame = 0;
+    int64_t ntri = 0;
+    DevBuf<int> tri;          // global triangle ids
+    DevBuf<double> xy;        // local 2-D vertex coordinates [ntri][6] (x0,x1,x2,y0,y1,y2)
+    DevBuf<double> S;         // gamma-free blocks [ntri][64]
+    // matrix scatter lists on the FULL pattern (deterministic: entries of one slot summed in list order)
+    int64_t nslot = 0;
+    DevBuf<int64_t> slot;     // unique full-pattern slots, ascending
+    DevBuf<int> segptr;       // [nslot+1] into ent
+    DevBuf<int> ent;          // entry ids (tri*64 + i*8 + j)
+    DevBuf<double> Sval;      // summed value per unique slot
+    DevBuf<int64_t> slot_s;   // same slots mapped to the solve-space pattern (-1 if eliminated)
+    // forcing vector
+    int64_t ndof = 0;
+    DevBuf<int> dof;          // unique dofs, ascending
+    DevBuf<int> dsegptr;      // [ndof+1]
+    DevBuf<int> dent;         // entry ids (tri*8 + i)
+    DevBuf<cx> bloc;          // per-triangle forcing [ntri][8]
+    DevBuf<cx> bval;          // summed forcing per unique dof
+    bool has_rhs = false;
+};
+
+struct emb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int64_t launches = 0;
+    std::map<std::string, double> ms;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+    // mesh
+    int64_t nN = 0, nT = 0, nE = 0, nTri = 0, N = 0;
+    DevBuf<double> nodes;     // [nN][3]
+    DevBuf<int> tris;         // [nTri][3]
+    DevBuf<int> tri2f;        // [8][nTri]
+    DevBuf<int> tetc;         // [nT][4] vertex ids in ascending order
+    DevBuf<int> tetord;       // [nT] packed original local index of k-th smallest vertex (2 bits each)
+    DevBuf<int> gid;          // [nT][20] global dof ids in canonical function order
+    DevBuf<cx> er, ur;        // [9][nT]
+    bool have_mesh = false, have_mat = false;
+
+    // adjacency dof -> (tet*20 + canonical local index), ascending
+    DevBuf<int64_t> adjptr;   // [N+1]
+    DevBuf<int> adj;          // [20 nT]
+    // full pattern
+    DevBuf<int64_t> rowptr;   // [N+1]
+    DevBuf<int> col;          // [nnz]
+    int64_t nnz = 0;
+    bool have_pattern = false;
+    DevBuf<cx> K, M;          // [nnz]
+    bool have_KM = false;
+
+    // solve space
+    int64_t Ns = 0, nnz_s = 0;
+    DevBuf<int> newid;        // [N] full dof -> solve index or -1
+    DevBuf<int> solve_ids;    // [Ns]
+    DevBuf<int64_t> rowptr_s; // [Ns+1]
+    DevBuf<int> col_s;        // [nnz_s]
+    DevBuf<int64_t> src;      // [nnz_s] full-pattern slot of each solve-space entry
+    DevBuf<cx> A;             // [nnz_s]
+    bool have_dirichlet = false, have_A = false;
+    double k0 = 0;
+
+    Surface surf[16];
+
+    // solver workspace
+    DevBuf<cx> xs;            // last solution (solve space)
+    DevBuf<cx> xfull;         // last solution (full space)
+    std::vector<DevBuf<cx>> work;
+    DevBuf<cx> dinv;          // Jacobi / block-Jacobi inverse blocks
+    DevBuf<int> pairmate;     // solve-space index of the paired dof (block-Jacobi) or -1
+    DevBuf<double> red;       // reduction scratch
+};
+
+template <typename T>
+static int dev_alloc(emb_ctx* c, DevBuf<T>& b, size_t n) {
+    if (b.n == n && b.p) return EMB_OK;
+    b.release();
+    if (n == 0) return EMB_OK;
+    cudaError_t e = cudaMalloc((void**)&b.p, n * sizeof(T));
+    if (e != cudaSuccess) {
+        c->err = std::string("cudaMalloc(") + std::to_string(n * sizeof(T)) + " B): " + cudaGetErrorString(e);
+        b.p = nullptr;
+        return EMB_ERR_CUDA;
+    }
+    b.n = n;
+    return EMB_OK;
+}
+
+template <typename T>
+static int h2d(emb_ctx* c, DevBuf<T>& b, const T* h, size_t n) {
+    EMB_TRY(dev_alloc(c, b, n));
+    if (n) EMB_CUDA(c, cudaMemcpyAsync(b.p, h, n * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+    return EMB_OK;
+}
+
+struct PhaseTimer {
+    emb_ctx* c;
+    const char* name;
+    PhaseTimer(emb_ctx* c_, const char* n) : c(c_), name(n) { cudaEventRecord(c->ev0, c->stream); }
+    ~PhaseTimer() {
+        cudaEventRecord(c->ev1, c->stream);
+        cudaEventSynchronize(c->ev1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+        c->ms[name] = ms;
+    }
+};
+
+#define EMB_LAUNCH_CHECK(ctx)                                                        \
+    do {                                                                             \
+        (ctx)->launches++;                                                           \
+        cudaError_t e__ = cudaGetLastError();                                        \
+        if (e__ != cudaSuccess) {                                                    \
+            (ctx)->err = std::string("kernel launch: ") + cudaGetErrorString(e__) +  \
+                         " at " + __FILE__ + ":" + std::to_string(__LINE__);         \
+            return EMB_ERR_CUDA;                                                     \
+        }                                                                            \
+    } while (0)
+
+static inline unsigned blocks_for(int64_t n, int per) { return (unsigned)((n + per - 1) / per); }

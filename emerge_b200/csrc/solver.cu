@@ -1,0 +1,779 @@
+// Complex CSR SpMV and Krylov solvers on the solve space.
+//
+// Reference path replaced: fem/solver.py:405-469 (SolveRoutine.solve) with its direct solvers (:243-309).
+// The reference eliminates prescribed dofs per solve, optionally reorders, factorises (SuperLU/PARDISO).
+// Here the eliminated pattern is built once (operators.cu) and A(f) x = b is solved iteratively:
+//   method 2 (default): COCR (conjugate-orthogonal conjugate-residual, one SpMV per iteration) on the
+//       complex-symmetric part As = (A + A^T)/2, wrapped in defect correction on the true A
+//       (x += As^-1 (b - A x)).  A(f) is not exactly symmetric because the reference's mass matrix is not
+//       (fem/mth/tet.py:1036; relative asymmetry ~5e-5), so each correction gains ~3 digits.
+//   method 0: restarted GMRES(m) on A (classical Gram-Schmidt with re-orthogonalisation).
+//   method 1: BiCGStab on A.
+// Preconditioners: Jacobi, or 2x2 block-Jacobi over the two functions of each edge / face.
+// Kernels are HBM-bound: SpMV moves 20 B per nonzero + 36 B per row; vector updates are fused so an
+// iteration of COCR is 4 launches and no host synchronisation (scalars live on the device, block partial
+// sums are reduced in a fixed order by the consumer kernel => bitwise reproducible).
+#include "context.cuh"
+#include <vector>
+
+constexpr int NPART = 1024;          // block partials per reduction (fixed => deterministic)
+constexpr int VBLOCK = 256;
+
+// ------------------------------------------------------------------------------------------------
+// SpMV: LPR lanes per row
+// ------------------------------------------------------------------------------------------------
+template <int LPR>
+__global__ void __launch_bounds__(256) k_spmv(int64_t n, const int64_t* __restrict__ rowptr, const int* __restrict__ col,
+                                              const cx* __restrict__ val, const cx* __restrict__ x, cx* __restrict__ y) {
+    const int64_t gt = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t r = gt / LPR;
+    const int sub = (int)(gt % LPR);
+    double ar = 0, ai = 0;
+    if (r < n) {
+        const int64_t p0 = rowptr[r], p1 = rowptr[r + 1];
+        for (int64_t k = p0 + sub; k < p1; k += LPR) {
+            const double2 a = __ldg(reinterpret_cast<const double2*>(val + k));
+            const double2 v = __ldg(reinterpret_cast<const double2*>(x + __ldg(col + k)));
+            ar += a.x * v.x - a.y * v.y;
+            ai += a.x * v.y + a.y * v.x;
+        }
+    }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) {
+        ar += __shfl_down_sync(0xffffffffu, ar, o, LPR);
+        ai += __shfl_down_sync(0xffffffffu, ai, o, LPR);
+    }
+    if (r < n && sub == 0) *reinterpret_cast<double2*>(y + r) = make_double2(ar, ai);
+}
+
+static int spmv(emb_ctx* c, const cx* val, const cx* x, cx* y) {
+    constexpr int LPR = 8;
+    k_spmv<LPR><<<blocks_for(c->Ns * LPR, 256), 256, 0, c->stream>>>(c->Ns, c->rowptr_s.p, c->col_s.p, val, x, y);
+    EMB_LAUNCH_CHECK(c);
+    return EMB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// deterministic reductions: each block writes one partial; consumers sum the NPART partials in order
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ cx block_sum(cx v) {
+    __shared__ double s_re[VBLOCK / 32], s_im[VBLOCK / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        v.re += __shfl_down_sync(0xffffffffu, v.re, o);
+        v.im += __shfl_down_sync(0xffffffffu, v.im, o);
+    }
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) { s_re[w] = v.re; s_im[w] = v.im; }
+    __syncthreads();
+    cx out = mk(0.0);
+    if (threadIdx.x == 0)
+        for (int i = 0; i < VBLOCK / 32; ++i) { out.re += s_re[i]; out.im += s_im[i]; }
+    return out;   // valid in thread 0
+}
+
+// sum NPART partials (all threads of the block get the result); fixed order
+__device__ __forceinline__ cx sum_partials(const cx* __restrict__ part) {
+    __shared__ cx s_tot;
+    cx v = mk(0.0);
+    for (int i = threadIdx.x; i < NPART; i += blockDim.x) v += part[i];
+    cx t = block_sum(v);
+    if (threadIdx.x == 0) s_tot = t;
+    __syncthreads();
+    return s_tot;
+}
+
+// partial[blockIdx] = sum over this block's grid-stride range of a_i * b_i (unconjugated) or conj(a_i)*b_i
+template <bool CONJ>
+__global__ void __launch_bounds__(VBLOCK) k_dot(int64_t n, const cx* __restrict__ a, const cx* __restrict__ b,
+                                                cx* __restrict__ part) {
+    cx acc = mk(0.0);
+    const int64_t per = (n + NPART - 1) / NPART;
+    const int64_t i0 = blockIdx.x * per, i1 = (i0 + per < n) ? i0 + per : n;
+    for (int64_t i = i0 + threadIdx.x; i < i1; i += VBLOCK) {
+        const cx u = a[i], v = b[i];
+        if (CONJ) { acc.re += u.re * v.re + u.im * v.im; acc.im += u.re * v.im - u.im * v.re; }
+        else fma_c(acc, u, v);
+    }
+    cx t = block_sum(acc);
+    if (threadIdx.x == 0) part[blockIdx.x] = t;
+}
+__global__ void __launch_bounds__(VBLOCK) k_finish(const cx* __restrict__ part, cx* __restrict__ out) {
+    cx t = sum_partials(part);
+    if (threadIdx.x == 0) *out = t;
+}
+
+// ------------------------------------------------------------------------------------------------
+// small vector kernels
+// ------------------------------------------------------------------------------------------------
+__global__ void k_copy(int64_t n, const cx* __restrict__ a, cx* __restrict__ b) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) b[i] = a[i];
+}
+__global__ void k_zero(int64_t n, cx* __restrict__ a) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) a[i] = cx{0, 0};
+}
+// y = a*x + b*y with device scalars sa[0]*fa, sb[0]*fb (null => 1)
+__global__ void k_axpby(int64_t n, const cx* __restrict__ sa, double fa, const cx* __restrict__ x, const cx* __restrict__ sb,
+                        double fb, cx* __restrict__ y) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const cx a = sa ? fa * (*sa) : mk(fa), b = sb ? fb * (*sb) : mk(fb);
+    y[i] = a * x[i] + b * y[i];
+}
+__global__ void k_gather(int64_t ns, const int* __restrict__ ids, const cx* __restrict__ full, cx* __restrict__ sub) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < ns) sub[i] = full[ids[i]];
+}
+__global__ void k_scatter(int64_t ns, const int* __restrict__ ids, const cx* __restrict__ sub, cx* __restrict__ full) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < ns) full[ids[i]] = sub[i];
+}
+__global__ void k_scatter_rhs(int64_t nd, const int* __restrict__ dof, const cx* __restrict__ bval, const int* __restrict__ newid,
+                              cx* __restrict__ bs) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= nd) return;
+    const int s = newid[dof[i]];
+    if (s >= 0) bs[s] = bval[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// symmetric part and preconditioner setup
+// ------------------------------------------------------------------------------------------------
+// one warp per row: As[k] = (A[k] + A[k^T])/2; the pattern is structurally symmetric
+__global__ void k_sym_part(int64_t n, const int64_t* __restrict__ rowptr, const int* __restrict__ col, const cx* __restrict__ A,
+                           cx* __restrict__ As) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (r >= n) return;
+    for (int64_t k = rowptr[r] + lane; k < rowptr[r + 1]; k += 32) {
+        const int j = col[k];
+        int64_t lo = rowptr[j], hi = rowptr[j + 1] - 1;
+        while (lo < hi) {
+            int64_t mid = (lo + hi) >> 1;
+            if (col[mid] < (int)r) lo = mid + 1; else hi = mid;
+        }
+        cx a = A[k];
+        if (col[lo] == (int)r) { const cx b = A[lo]; a = cx{0.5 * (a.re + b.re), 0.5 * (a.im + b.im)}; }
+        As[k] = a;
+    }
+}
+
+// mate[s] = solve-space index of the other function of the same edge/face (or -1)
+__global__ void k_pairmate(int64_t ns, const int* __restrict__ solve_ids, const int* __restrict__ newid, int64_t nE, int64_t nTri,
+                           int* __restrict__ mate) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= ns) return;
+    const int64_t d = solve_ids[i];
+    int64_t m;
+    if (d < nE) m = d + nE + nTri;                    // edge-a -> edge-b   (fem/elements/nedelec2.py:46-50)
+    else if (d < nE + nTri) m = d + nE + nTri;        // face-a -> face-b
+    else m = d - nE - nTri;                           // b -> a
+    mate[i] = newid[m];
+}
+
+__device__ __forceinline__ cx csr_get(const int64_t* rowptr, const int* col, const cx* val, int r, int cidx) {
+    int64_t lo = rowptr[r], hi = rowptr[r + 1] - 1;
+    while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if (col[mid] < cidx) lo = mid + 1; else hi = mid;
+    }
+    return (lo <= hi && col[lo] == cidx) ? val[lo] : cx{0, 0};
+}
+
+// dinv[2i], dinv[2i+1]: row i of the inverse 2x2 block (acting on (x_i, x_mate));  Jacobi: (1/a_ii, 0)
+__global__ void k_precond_setup(int64_t ns, int mode, const int64_t* __restrict__ rowptr, const int* __restrict__ col,
+                                const cx* __restrict__ val, const int* __restrict__ mate, cx* __restrict__ dinv) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= ns) return;
+    const cx aii = csr_get(rowptr, col, val, (int)i, (int)i);
+    const int m = (mode == 2) ? mate[i] : -1;
+    if (mode == 0) { dinv[2 * i] = mk(1.0); dinv[2 * i + 1] = mk(0.0); return; }
+    if (m < 0) { dinv[2 * i] = cdiv(mk(1.0), aii); dinv[2 * i + 1] = mk(0.0); return; }
+    const cx aim = csr_get(rowptr, col, val, (int)i, m), ami = csr_get(rowptr, col, val, m, (int)i);
+    const cx amm = csr_get(rowptr, col, val, m, m);
+    const cx det = aii * amm - aim * ami;
+    dinv[2 * i] = cdiv(amm, det);
+    dinv[2 * i + 1] = cdiv(-aim, det);
+}
+__global__ void k_precond_apply(int64_t ns, const cx* __restrict__ dinv, const int* __restrict__ mate, const cx* __restrict__ r,
+                                cx* __restrict__ z) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= ns) return;
+    cx v = dinv[2 * i] * r[i];
+    const int m = mate ? mate[i] : -1;
+    if (m >= 0) fma_c(v, dinv[2 * i + 1], r[m]);
+    z[i] = v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused COCR kernels (device scalars: sc[0]=zAz, sc[1]=alpha, sc[2]=beta, sc[3]=|r|^2, sc[4]=zAz_new)
+// ------------------------------------------------------------------------------------------------
+// alpha = zAz / sum(partA);  x += alpha p; r -= alpha Ap; z -= alpha MAp;  partial |r|^2
+__global__ void __launch_bounds__(VBLOCK) k_cocr_update(int64_t n, const cx* __restrict__ partA, cx* __restrict__ sc,
+                                                        const cx* __restrict__ p, const cx* __restrict__ Ap,
+                                                        const cx* __restrict__ MAp, cx* __restrict__ x, cx* __restrict__ r,
+                                                        cx* __restrict__ z, cx* __restrict__ partR) {
+    const cx den = sum_partials(partA);
+    const cx alpha = cdiv(sc[0], den);
+    if (blockIdx.x == 0 && threadIdx.x == 0) sc[1] = alpha;
+    cx acc = mk(0.0);
+    const int64_t per = (n + NPART - 1) / NPART;
+    const int64_t i0 = blockIdx.x * per, i1 = (i0 + per < n) ? i0 + per : n;
+    for (int64_t i = i0 + threadIdx.x; i < i1; i += VBLOCK) {
+        cx xi = x[i], ri = r[i], zi = z[i];
+        fma_c(xi, alpha, p[i]);
+        const cx na = -alpha;
+        fma_c(ri, na, Ap[i]);
+        fma_c(zi, na, MAp[i]);
+        x[i] = xi; r[i] = ri; z[i] = zi;
+        acc.re += ri.re * ri.re + ri.im * ri.im;
+    }
+    cx t = block_sum(acc);
+    if (threadIdx.x == 0) partR[blockIdx.x] = t;
+}
+// beta = sum(partZ)/zAz; zAz = sum(partZ); p = z + beta p; Ap = Az + beta Ap; also finishes |r|^2
+__global__ void __launch_bounds__(VBLOCK) k_cocr_dir(int64_t n, const cx* __restrict__ partZ, const cx* __restrict__ partR,
+                                                     cx* __restrict__ sc, const cx* __restrict__ z, const cx* __restrict__ Az,
+                                                     cx* __restrict__ p, cx* __restrict__ Ap) {
+    const cx znew = sum_partials(partZ);
+    const cx beta = cdiv(znew, sc[0]);
+    const cx rr = sum_partials(partR);
+    const int64_t per = (n + NPART - 1) / NPART;
+    const int64_t i0 = blockIdx.x * per, i1 = (i0 + per < n) ? i0 + per : n;
+    for (int64_t i = i0 + threadIdx.x; i < i1; i += VBLOCK) {
+        cx pi = z[i], api = Az[i];
+        fma_c(pi, beta, p[i]);
+        fma_c(api, beta, Ap[i]);
+        p[i] = pi; Ap[i] = api;
+    }
+    __syncthreads();
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) { sc[2] = beta; sc[3] = rr; sc[4] = znew; }
+}
+// all blocks must have read sc[0] before it is overwritten -> separate tiny kernel
+__global__ void k_cocr_commit(cx* sc) { sc[0] = sc[4]; }
+
+// ------------------------------------------------------------------------------------------------
+// host drivers
+// ------------------------------------------------------------------------------------------------
+struct Work {
+    emb_ctx* c;
+    int64_t n;
+    std::vector<cx*> v;
+};
+
+static int ensure_work(emb_ctx* c, size_t count) {
+    if (c->work.size() < count) c->work.resize(count);
+    for (size_t i = 0; i < count; ++i) EMB_TRY(dev_alloc(c, c->work[i], (size_t)c->Ns));
+    EMB_TRY(dev_alloc(c, c->red, (size_t)(4 * NPART + 16) * 2));
+    return EMB_OK;
+}
+
+static int dot_host(emb_ctx* c, bool conj, const cx* a, const cx* b, cx* out) {
+    cx* part = reinterpret_cast<cx*>(c->red.p);
+    cx* sc = part + 4 * NPART;
+    if (conj) k_dot<true><<<NPART, VBLOCK, 0, c->stream>>>(c->Ns, a, b, part);
+    else k_dot<false><<<NPART, VBLOCK, 0, c->stream>>>(c->Ns, a, b, part);
+    EMB_LAUNCH_CHECK(c);
+    k_finish<<<1, VBLOCK, 0, c->stream>>>(part, sc + 8);
+    EMB_LAUNCH_CHECK(c);
+    EMB_CUDA(c, cudaMemcpyAsync(out, sc + 8, sizeof(cx), cudaMemcpyDeviceToHost, c->stream));
+    EMB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return EMB_OK;
+}
+
+static int precond_setup(emb_ctx* c, int mode, const cx* val) {
+    EMB_TRY(dev_alloc(c, c->dinv, (size_t)c->Ns * 2));
+    if (mode == 2 && !c->pairmate.p) {
+        EMB_TRY(dev_alloc(c, c->pairmate, (size_t)c->Ns));
+        k_pairmate<<<blocks_for(c->Ns, 256), 256, 0, c->stream>>>(c->Ns, c->solve_ids.p, c->newid.p, c->nE, c->nTri, c->pairmate.p);
+        EMB_LAUNCH_CHECK(c);
+    }
+    k_precond_setup<<<blocks_for(c->Ns, 256), 256, 0, c->stream>>>(c->Ns, mode, c->rowptr_s.p, c->col_s.p, val,
+                                                                  mode == 2 ? c->pairmate.p : nullptr, c->dinv.p);
+    EMB_LAUNCH_CHECK(c);
+    return EMB_OK;
+}
+static int precond_apply(emb_ctx* c, int mode, const cx* r, cx* z) {
+    k_precond_apply<<<blocks_for(c->Ns, 256), 256, 0, c->stream>>>(c->Ns, c->dinv.p, mode == 2 ? c->pairmate.p : nullptr, r, z);
+    EMB_LAUNCH_CHECK(c);
+    return EMB_OK;
+}
+
+// COCR on As d = rhs, d starts at 0.  Stops when |r| <= stop_abs or maxit.  Returns iterations in *its.
+static int cocr(emb_ctx* c, int pmode, const cx* As, const cx* rhs, cx* d, double stop_abs, int maxit, int* its,
+                int* spmvs, double* rnorm_out) {
+    const int64_t n = c->Ns;
+    cx *r = c->work[0].p, *z = c->work[1].p, *p = c->work[2].p, *Az = c->work[3].p, *Ap = c->work[4].p, *MAp = c->work[5].p;
+    cx* part = reinterpret_cast<cx*>(c->red.p);
+    cx *partA = part, *partR = part + NPART, *partZ = part + 2 * NPART, *sc = part + 4 * NPART;
+    const unsigned vb = blocks_for(n, 256);
+    k_zero<<<vb, 256, 0, c->stream>>>(n, d); EMB_LAUNCH_CHECK(c);
+    k_copy<<<vb, 256, 0, c->stream>>>(n, rhs, r); EMB_LAUNCH_CHECK(c);
+    EMB_TRY(precond_apply(c, pmode, r, z));
+    k_copy<<<vb, 256, 0, c->stream>>>(n, z, p); EMB_LAUNCH_CHECK(c);
+    EMB_TRY(spmv(c, As, z, Az)); ++*spmvs;
+    k_copy<<<vb, 256, 0, c->stream>>>(n, Az, Ap); EMB_LAUNCH_CHECK(c);
+    k_dot<false><<<NPART, VBLOCK, 0, c->stream>>>(n, z, Az, partZ); EMB_LAUNCH_CHECK(c);
+    k_finish<<<1, VBLOCK, 0, c->stream>>>(partZ, sc); EMB_LAUNCH_CHECK(c);
+    int it = 0;
+    double rn = 1e300;
+    const int check = 10;
+    while (it < maxit) {
+        EMB_TRY(precond_apply(c, pmode, Ap, MAp));
+        k_dot<false><<<NPART, VBLOCK, 0, c->stream>>>(n, Ap, MAp, partA); EMB_LAUNCH_CHECK(c);
+        k_cocr_update<<<NPART, VBLOCK, 0, c->stream>>>(n, partA, sc, p, Ap, MAp, d, r, z, partR); EMB_LAUNCH_CHECK(c);
+        EMB_TRY(spmv(c, As, z, Az)); ++*spmvs;
+        k_dot<false><<<NPART, VBLOCK, 0, c->stream>>>(n, z, Az, partZ); EMB_LAUNCH_CHECK(c);
+        k_cocr_dir<<<NPART, VBLOCK, 0, c->stream>>>(n, partZ, partR, sc, z, Az, p, Ap); EMB_LAUNCH_CHECK(c);
+        k_cocr_commit<<<1, 1, 0, c->stream>>>(sc); EMB_LAUNCH_CHECK(c);
+        ++it;
+        if (it % check == 0 || it == maxit) {
+            cx h[5];
+            EMB_CUDA(c, cudaMemcpyAsync(h, sc, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+            EMB_CUDA(c, cudaStreamSynchronize(c->stream));
+            rn = sqrt(fabs(h[3].re));
+            if (!(rn == rn)) { c->err = "COCR breakdown (NaN)"; *its = it; *rnorm_out = rn; return EMB_NOT_CONVERGED; }
+            if (rn <= stop_abs) break;
+        }
+    }
+    *its = it;
+    *rnorm_out = rn;
+    return EMB_OK;
+}
+
+// restarted GMRES on A with left... right preconditioning: A M^-1 u = b, x = M^-1 u
+static int gmres(emb_ctx* c, int pmode, const cx* A, const cx* b, cx* x, double bnorm, const emb_solve_opts* o, int* its,
+                 int* spmvs, double* relres) {
+    const int64_t n = c->Ns;
+    const int m = o->restart > 0 ? o->restart : 50;
+    EMB_TRY(ensure_work(c, (size_t)m + 8));
+    cx *r = c->work[0].p, *w = c->work[1].p, *t = c->work[2].p;
+    auto V = [&](int j) { return c->work[6 + j].p; };
+    const unsigned vb = blocks_for(n, 256);
+    std::vector<cx> H((size_t)(m + 1) * m), cs(m), sn(m), g(m + 1), y(m);
+    cx* dsc = reinterpret_cast<cx*>(c->red.p) + 4 * NPART + 10;
+    int it = 0;
+    double res = 1.0;
+    auto set_scalar = [&](cx v) { return cudaMemcpyAsync(dsc, &v, sizeof(cx), cudaMemcpyHostToDevice, c->stream); };
+    while (it < o->maxit) {
+        // r = b - A x
+        EMB_TRY(spmv(c, A, x, r)); ++*spmvs;
+        k_axpby<<<vb, 256, 0, c->stream>>>(n, nullptr, 1.0, b, nullptr, -1.0, r); EMB_LAUNCH_CHECK(c);
+        cx rr;
+        EMB_TRY(dot_host(c, true, r, r, &rr));
+        double beta = sqrt(rr.re);
+        res = beta / bnorm;
+        if (res <= o->rtol) break;
+        EMB_CUDA(c, set_scalar(mk(1.0 / beta)));
+        k_axpby<<<vb, 256, 0, c->stream>>>(n, dsc, 1.0, r, nullptr, 0.0, V(0)); EMB_LAUNCH_CHECK(c);
+        std::fill(g.begin(), g.end(), mk(0.0));
+        g[0] = mk(beta);
+        int j = 0;
+        for (; j < m && it < o->maxit; ++j, ++it) {
+            EMB_TRY(precond_apply(c, pmode, V(j), t));
+            EMB_TRY(spmv(c, A, t, w)); ++*spmvs;
+            // classical Gram-Schmidt, two passes
+            for (int i = 0; i <= j; ++i) H[(size_t)i * m + j] = mk(0.0);
+            for (int pass = 0; pass < 2; ++pass) {
+                std::vector<cx> h(j + 1);
+                for (int i = 0; i <= j; ++i) EMB_TRY(dot_host(c, true, V(i), w, &h[i]));
+                for (int i = 0; i <= j; ++i) {
+                    EMB_CUDA(c, set_scalar(-h[i]));
+                    k_axpby<<<vb, 256, 0, c->stream>>>(n, dsc, 1.0, V(i), nullptr, 1.0, w); EMB_LAUNCH_CHECK(c);
+                    EMB_CUDA(c, cudaStreamSynchronize(c->stream));
+                    H[(size_t)i * m + j] += h[i];
+                }
+            }
+            cx ww;
+            EMB_TRY(dot_host(c, true, w, w, &ww));
+            const double hn = sqrt(ww.re);
+            H[(size_t)(j + 1) * m + j] = mk(hn);
+            if (j + 1 < m || true) {
+                EMB_CUDA(c, set_scalar(mk(hn > 0 ? 1.0 / hn : 0.0)));
+                k_axpby<<<vb, 256, 0, c->stream>>>(n, dsc, 1.0, w, nullptr, 0.0, V(j + 1)); EMB_LAUNCH_CHECK(c);
+                EMB_CUDA(c, cudaStreamSynchronize(c->stream));
+            }
+            // Givens
+            for (int i = 0; i < j; ++i) {
+                cx a = H[(size_t)i * m + j], bq = H[(size_t)(i + 1) * m + j];
+                H[(size_t)i * m + j] = conj(cs[i]) * a + conj(sn[i]) * bq;
+                H[(size_t)(i + 1) * m + j] = -sn[i] * a + cs[i] * bq;
+            }
+            {
+                cx a = H[(size_t)j * m + j], bq = H[(size_t)(j + 1) * m + j];
+                double den = sqrt(norm2(a) + norm2(bq));
+                if (den == 0) den = 1e-300;
+                cs[j] = (1.0 / den) * a;
+                sn[j] = (1.0 / den) * bq;
+                H[(size_t)j * m + j] = conj(cs[j]) * a + conj(sn[j]) * bq;
+                H[(size_t)(j + 1) * m + j] = mk(0.0);
+                cx g0 = g[j];
+                g[j] = conj(cs[j]) * g0;
+                g[j + 1] = -sn[j] * g0;
+            }
+            res = sqrt(norm2(g[j + 1])) / bnorm;
+            if (res <= o->rtol) { ++j; ++it; break; }
+        }
+        // solve upper triangular, x += M^-1 V y
+        for (int i = j - 1; i >= 0; --i) {
+            cx s = g[i];
+            for (int k = i + 1; k < j; ++k) s -= H[(size_t)i * m + k] * y[k];
+            y[i] = cdiv(s, H[(size_t)i * m + i]);
+        }
+        k_zero<<<vb, 256, 0, c->stream>>>(n, w); EMB_LAUNCH_CHECK(c);
+        for (int i = 0; i < j; ++i) {
+            EMB_CUDA(c, set_scalar(y[i]));
+            k_axpby<<<vb, 256, 0, c->stream>>>(n, dsc, 1.0, V(i), nullptr, 1.0, w); EMB_LAUNCH_CHECK(c);
+            EMB_CUDA(c, cudaStreamSynchronize(c->stream));
+        }
+        EMB_TRY(precond_apply(c, pmode, w, t));
+        k_axpby<<<vb, 256, 0, c->stream>>>(n, nullptr, 1.0, t, nullptr, 1.0, x); EMB_LAUNCH_CHECK(c);
+    }
+    *its = it;
+    *relres = res;
+    return EMB_OK;
+}
+
+static int bicgstab(emb_ctx* c, int pmode, const cx* A, const cx* b, cx* x, double bnorm, const emb_solve_opts* o, int* its,
+                    int* spmvs, double* relres) {
+    const int64_t n = c->Ns;
+    cx *r = c->work[0].p, *r0 = c->work[1].p, *p = c->work[2].p, *v = c->work[3].p, *s = c->work[4].p, *t = c->work[5].p,
+       *ph = c->work[6].p, *sh = c->work[7].p;
+    const unsigned vb = blocks_for(n, 256);
+    cx* dsc = reinterpret_cast<cx*>(c->red.p) + 4 * NPART + 10;
+    auto set_scalar = [&](cx val) { return cudaMemcpyAsync(dsc, &val, sizeof(cx), cudaMemcpyHostToDevice, c->stream); };
+    auto axpy = [&](cx a, const cx* xx, double bfac, cx* yy) -> int {
+        EMB_CUDA(c, set_scalar(a));
+        k_axpby<<<vb, 256, 0, c->stream>>>(n, dsc, 1.0, xx, nullptr, bfac, yy);
+        EMB_LAUNCH_CHECK(c);
+        EMB_CUDA(c, cudaStreamSynchronize(c->stream));
+        return EMB_OK;
+    };
+    EMB_TRY(spmv(c, A, x, r)); ++*spmvs;
+    k_axpby<<<vb, 256, 0, c->stream>>>(n, nullptr, 1.0, b, nullptr, -1.0, r); EMB_LAUNCH_CHECK(c);
+    k_copy<<<vb, 256, 0, c->stream>>>(n, r, r0); EMB_LAUNCH_CHECK(c);
+    k_zero<<<vb, 256, 0, c->stream>>>(n, p); EMB_LAUNCH_CHECK(c);
+    k_zero<<<vb, 256, 0, c->stream>>>(n, v); EMB_LAUNCH_CHECK(c);
+    cx rho = mk(1.0), alpha = mk(1.0), omega = mk(1.0);
+    int it = 0;
+    double res = 1.0;
+    cx rr;
+    EMB_TRY(dot_host(c, true, r, r, &rr));
+    res = sqrt(rr.re) / bnorm;
+    while (it < o->maxit && res > o->rtol) {
+        cx rho1;
+        EMB_TRY(dot_host(c, true, r0, r, &rho1));
+        if (norm2(rho1) == 0) break;
+        const cx beta = cdiv(rho1, rho) * cdiv(alpha, omega);
+        // p = r + beta (p - omega v)
+        EMB_TRY(axpy(-omega, v, 1.0, p));
+        EMB_TRY(axpy(mk(1.0), r, 0.0, t));       // t = r (temp)
+        EMB_TRY(axpy(beta, p, 1.0, t));          // t = r + beta p
+        k_copy<<<vb, 256, 0, c->stream>>>(n, t, p); EMB_LAUNCH_CHECK(c);
+        EMB_TRY(precond_apply(c, pmode, p, ph));
+        EMB_TRY(spmv(c, A, ph, v)); ++*spmvs;
+        cx r0v;
+        EMB_TRY(dot_host(c, true, r0, v, &r0v));
+        alpha = cdiv(rho1, r0v);
+        k_copy<<<vb, 256, 0, c->stream>>>(n, r, s); EMB_LAUNCH_CHECK(c);
+        EMB_TRY(axpy(-alpha, v, 1.0, s));
+        EMB_TRY(precond_apply(c, pmode, s, sh));
+        EMB_TRY(spmv(c, A, sh, t)); ++*spmvs;
+        cx ts, tt;
+        EMB_TRY(dot_host(c, true, t, s, &ts));
+        EMB_TRY(dot_host(c, true, t, t, &tt));
+        omega = (tt.re > 0) ? (1.0 / tt.re) * ts : mk(0.0);
+        EMB_TRY(axpy(alpha, ph, 1.0, x));
+        EMB_TRY(axpy(omega, sh, 1.0, x));
+        k_copy<<<vb, 256, 0, c->stream>>>(n, s, r); EMB_LAUNCH_CHECK(c);
+        EMB_TRY(axpy(-omega, t, 1.0, r));
+        rho = rho1;
+        EMB_TRY(dot_host(c, true, r, r, &rr));
+        res = sqrt(rr.re) / bnorm;
+        ++it;
+        if (!(res == res)) break;
+    }
+    *its = it;
+    *relres = res;
+    return EMB_OK;
+}
+
+// solves A xs = bs (device, solve space); xs is in/out (initial guess when use_x0)
+static int solve_device(emb_ctx* c, const emb_solve_opts* o, const cx* bs, cx* xs, emb_solve_info* info) {
+    const int64_t n = c->Ns;
+    const unsigned vb = blocks_for(n, 256);
+    EMB_TRY(ensure_work(c, 10));
+    cudaEventRecord(c->ev0, c->stream);
+    int its = 0, spmvs = 0;
+    double relres = 1.0;
+    cx bb;
+    EMB_TRY(dot_host(c, true, bs, bs, &bb));
+    const double bnorm = sqrt(bb.re);
+    int rc = EMB_OK;
+    if (bnorm == 0) {
+        k_zero<<<vb, 256, 0, c->stream>>>(n, xs); EMB_LAUNCH_CHECK(c);
+        relres = 0;
+    } else if (o->method == 0) {
+        if (!o->use_x0) { k_zero<<<vb, 256, 0, c->stream>>>(n, xs); EMB_LAUNCH_CHECK(c); }
+        EMB_TRY(precond_setup(c, o->precond, c->A.p));
+        EMB_TRY(gmres(c, o->precond, c->A.p, bs, xs, bnorm, o, &its, &spmvs, &relres));
+    } else if (o->method == 1) {
+        if (!o->use_x0) { k_zero<<<vb, 256, 0, c->stream>>>(n, xs); EMB_LAUNCH_CHECK(c); }
+        EMB_TRY(precond_setup(c, o->precond, c->A.p));
+        EMB_TRY(bicgstab(c, o->precond, c->A.p, bs, xs, bnorm, o, &its, &spmvs, &relres));
+    } else {
+        // defect correction on A with COCR on the symmetric part
+        DevBuf<cx> As, rr, dd;
+        EMB_TRY(dev_alloc(c, As, (size_t)c->nnz_s));
+        EMB_TRY(dev_alloc(c, rr, (size_t)n));
+        EMB_TRY(dev_alloc(c, dd, (size_t)n));
+        k_sym_part<<<blocks_for(n * 32, 256), 256, 0, c->stream>>>(n, c->rowptr_s.p, c->col_s.p, c->A.p, As.p);
+        EMB_LAUNCH_CHECK(c);
+        EMB_TRY(precond_setup(c, o->precond, As.p));
+        if (!o->use_x0) { k_zero<<<vb, 256, 0, c->stream>>>(n, xs); EMB_LAUNCH_CHECK(c); }
+        double prev = 1e300;
+        for (int outer = 0; outer < 30 && its < o->maxit; ++outer) {
+            EMB_TRY(spmv(c, c->A.p, xs, rr.p)); ++spmvs;
+            k_axpby<<<vb, 256, 0, c->stream>>>(n, nullptr, 1.0, bs, nullptr, -1.0, rr.p); EMB_LAUNCH_CHECK(c);
+            cx r2;
+            EMB_TRY(dot_host(c, true, rr.p, rr.p, &r2));
+            const double rn = sqrt(r2.re);
+            relres = rn / bnorm;
+            if (relres <= o->rtol) break;
+            if (outer > 2 && rn > 0.5 * prev) { /* stagnation of the correction: keep going, but it is visible in info */ }
+            prev = rn;
+            // inner target: two digits below the current residual, never below what the outer loop needs
+            double stop = 1e-2 * rn;
+            const double need = 0.3 * o->rtol * bnorm;
+            if (stop < need) stop = need;
+            int iit = 0;
+            double irn = 0;
+            rc = cocr(c, o->precond, As.p, rr.p, dd.p, stop, o->maxit - its, &iit, &spmvs, &irn);
+            its += iit;
+            if (rc < 0) break;
+            k_axpby<<<vb, 256, 0, c->stream>>>(n, nullptr, 1.0, dd.p, nullptr, 1.0, xs); EMB_LAUNCH_CHECK(c);
+            if (rc == EMB_NOT_CONVERGED) break;
+        }
+        if (rc >= 0) {
+            EMB_TRY(spmv(c, c->A.p, xs, rr.p)); ++spmvs;
+            k_axpby<<<vb, 256, 0, c->stream>>>(n, nullptr, 1.0, bs, nullptr, -1.0, rr.p); EMB_LAUNCH_CHECK(c);
+            cx r2;
+            EMB_TRY(dot_host(c, true, rr.p, rr.p, &r2));
+            relres = sqrt(r2.re) / bnorm;
+        }
+        As.release(); rr.release(); dd.release();
+        if (rc < 0) return rc;
+    }
+    if (o->method != 2 && bnorm > 0) {   // true residual at exit
+        cx* t = c->work[0].p;
+        EMB_TRY(spmv(c, c->A.p, xs, t)); ++spmvs;
+        k_axpby<<<vb, 256, 0, c->stream>>>(n, nullptr, 1.0, bs, nullptr, -1.0, t); EMB_LAUNCH_CHECK(c);
+        cx r2;
+        EMB_TRY(dot_host(c, true, t, t, &r2));
+        relres = sqrt(r2.re) / bnorm;
+    }
+    cudaEventRecord(c->ev1, c->stream);
+    cudaEventSynchronize(c->ev1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+    c->ms["solve"] = ms;
+    if (info) { info->iters = its; info->relres = relres; info->ms = ms; info->spmvs = spmvs; }
+    if (!(relres <= o->rtol)) {
+        c->err = "solver did not reach rtol: relres=" + std::to_string(relres) + " after " + std::to_string(its) + " iterations";
+        return EMB_NOT_CONVERGED;
+    }
+    return EMB_OK;
+}
+
+static int finish_solution(emb_ctx* c, emb_c128* x_full) {
+    EMB_TRY(dev_alloc(c, c->xfull, (size_t)c->N));
+    EMB_CUDA(c, cudaMemsetAsync(c->xfull.p, 0, (size_t)c->N * sizeof(cx), c->stream));
+    k_scatter<<<blocks_for(c->Ns, 256), 256, 0, c->stream>>>(c->Ns, c->solve_ids.p, c->xs.p, c->xfull.p);
+    EMB_LAUNCH_CHECK(c);
+    if (x_full) EMB_CUDA(c, cudaMemcpyAsync(x_full, c->xfull.p, (size_t)c->N * sizeof(cx), cudaMemcpyDeviceToHost, c->stream));
+    EMB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return EMB_OK;
+}
+
+static const emb_solve_opts kDefaultOpts = {2, 2, 50, 100000, 1e-8, 0};
+
+extern "C" int emb_solve(emb_ctx* c, int sid, const emb_solve_opts* opts, emb_c128* x_full, emb_solve_info* info) {
+    if (!c || sid < 0 || sid >= 16) return EMB_ERR_ARG;
+    if (!c->have_A || !c->surf[sid].defined || !c->surf[sid].has_rhs) {
+        c->err = "emb_solve: needs emb_form_A and emb_surface_set_U(sid) first";
+        return EMB_ERR_STATE;
+    }
+    const emb_solve_opts* o = opts ? opts : &kDefaultOpts;
+    Surface& s = c->surf[sid];
+    DevBuf<cx> bs;
+    EMB_TRY(dev_alloc(c, bs, (size_t)c->Ns));
+    EMB_TRY(dev_alloc(c, c->xs, (size_t)c->Ns));
+    k_zero<<<blocks_for(c->Ns, 256), 256, 0, c->stream>>>(c->Ns, bs.p); EMB_LAUNCH_CHECK(c);
+    k_scatter_rhs<<<blocks_for(s.ndof, 128), 128, 0, c->stream>>>(s.ndof, s.dof.p, s.bval.p, c->newid.p, bs.p);
+    EMB_LAUNCH_CHECK(c);
+    if (o->use_x0 && x_full) {
+        EMB_TRY(dev_alloc(c, c->xfull, (size_t)c->N));
+        EMB_CUDA(c, cudaMemcpyAsync(c->xfull.p, x_full, (size_t)c->N * sizeof(cx), cudaMemcpyHostToDevice, c->stream));
+        k_gather<<<blocks_for(c->Ns, 256), 256, 0, c->stream>>>(c->Ns, c->solve_ids.p, c->xfull.p, c->xs.p);
+        EMB_LAUNCH_CHECK(c);
+    }
+    int rc = solve_device(c, o, bs.p, c->xs.p, info);
+    bs.release();
+    if (rc < 0) return rc;
+    EMB_TRY(finish_solution(c, x_full));
+    return rc;
+}
+
+extern "C" int emb_solve_rhs(emb_ctx* c, const emb_c128* b_full, const emb_solve_opts* opts, emb_c128* x_full,
+                             emb_solve_info* info) {
+    if (!c || !b_full) return EMB_ERR_ARG;
+    if (!c->have_A) { c->err = "emb_solve_rhs: needs emb_form_A first"; return EMB_ERR_STATE; }
+    const emb_solve_opts* o = opts ? opts : &kDefaultOpts;
+    DevBuf<cx> bf, bs;
+    EMB_TRY(h2d(c, bf, reinterpret_cast<const cx*>(b_full), (size_t)c->N));
+    EMB_TRY(dev_alloc(c, bs, (size_t)c->Ns));
+    EMB_TRY(dev_alloc(c, c->xs, (size_t)c->Ns));
+    k_gather<<<blocks_for(c->Ns, 256), 256, 0, c->stream>>>(c->Ns, c->solve_ids.p, bf.p, bs.p);
+    EMB_LAUNCH_CHECK(c);
+    if (o->use_x0 && x_full) {
+        EMB_TRY(dev_alloc(c, c->xfull, (size_t)c->N));
+        EMB_CUDA(c, cudaMemcpyAsync(c->xfull.p, x_full, (size_t)c->N * sizeof(cx), cudaMemcpyHostToDevice, c->stream));
+        k_gather<<<blocks_for(c->Ns, 256), 256, 0, c->stream>>>(c->Ns, c->solve_ids.p, c->xfull.p, c->xs.p);
+        EMB_LAUNCH_CHECK(c);
+    }
+    int rc = solve_device(c, o, bs.p, c->xs.p, info);
+    bf.release(); bs.release();
+    if (rc < 0) return rc;
+    EMB_TRY(finish_solution(c, x_full));
+    return rc;
+}
+
+extern "C" int emb_spmv_host(emb_ctx* c, const emb_c128* x, emb_c128* y) {
+    if (!c || !x || !y) return EMB_ERR_ARG;
+    if (!c->have_A) { c->err = "emb_spmv_host: needs emb_form_A first"; return EMB_ERR_STATE; }
+    DevBuf<cx> dx, dy;
+    EMB_TRY(h2d(c, dx, reinterpret_cast<const cx*>(x), (size_t)c->Ns));
+    EMB_TRY(dev_alloc(c, dy, (size_t)c->Ns));
+    {
+        PhaseTimer pt(c, "spmv");
+        EMB_TRY(spmv(c, c->A.p, dx.p, dy.p));
+    }
+    EMB_CUDA(c, cudaMemcpyAsync(y, dy.p, (size_t)c->Ns * sizeof(cx), cudaMemcpyDeviceToHost, c->stream));
+    EMB_CUDA(c, cudaStreamSynchronize(c->stream));
+    dx.release(); dy.release();
+    return EMB_OK;
+}
+
+extern "C" int emb_spmv_bench(emb_ctx* c, int reps, double* ms_per_spmv) {
+    if (!c || reps <= 0 || !ms_per_spmv) return EMB_ERR_ARG;
+    if (!c->have_A) { c->err = "emb_spmv_bench: needs emb_form_A first"; return EMB_ERR_STATE; }
+    DevBuf<cx> dx, dy;
+    EMB_TRY(dev_alloc(c, dx, (size_t)c->Ns));
+    EMB_TRY(dev_alloc(c, dy, (size_t)c->Ns));
+    EMB_CUDA(c, cudaMemsetAsync(dx.p, 0, (size_t)c->Ns * sizeof(cx), c->stream));
+    for (int i = 0; i < 3; ++i) EMB_TRY(spmv(c, c->A.p, dx.p, dy.p));
+    {
+        PhaseTimer pt(c, "spmv");
+        for (int i = 0; i < reps; ++i) EMB_TRY(spmv(c, c->A.p, (i & 1) ? dy.p : dx.p, (i & 1) ? dx.p : dy.p));
+    }
+    *ms_per_spmv = c->ms["spmv"] / reps;
+    c->ms["spmv"] = *ms_per_spmv;
+    dx.release(); dy.release();
+    return EMB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// field evaluation at points with known host tets: per-point part of ned2_tet_interp (fem/mth/tet.py:371-497)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_interp(int64_t npts, const int* __restrict__ tet, const double* __restrict__ xyz, const int* __restrict__ tetc,
+                         const int* __restrict__ gid, const double* __restrict__ nodes, const cx* __restrict__ xfull,
+                         cx* __restrict__ E) {
+    int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k >= npts) return;
+    const int t = tet[k];
+    double p[4][3];
+    for (int v = 0; v < 4; ++v) {
+        const double* q = nodes + (int64_t)tetc[(int64_t)t * 4 + v] * 3;
+        p[v][0] = q[0]; p[v][1] = q[1]; p[v][2] = q[2];
+    }
+    double e1[3], e2[3], e3[3], G[4][3];
+    for (int a = 0; a < 3; ++a) { e1[a] = p[1][a] - p[0][a]; e2[a] = p[2][a] - p[0][a]; e3[a] = p[3][a] - p[0][a]; }
+    G[1][0] = e2[1] * e3[2] - e2[2] * e3[1]; G[1][1] = e2[2] * e3[0] - e2[0] * e3[2]; G[1][2] = e2[0] * e3[1] - e2[1] * e3[0];
+    G[2][0] = e3[1] * e1[2] - e3[2] * e1[1]; G[2][1] = e3[2] * e1[0] - e3[0] * e1[2]; G[2][2] = e3[0] * e1[1] - e3[1] * e1[0];
+    G[3][0] = e1[1] * e2[2] - e1[2] * e2[1]; G[3][1] = e1[2] * e2[0] - e1[0] * e2[2]; G[3][2] = e1[0] * e2[1] - e1[1] * e2[0];
+    for (int a = 0; a < 3; ++a) G[0][a] = -(G[1][a] + G[2][a] + G[3][a]);
+    const double det = e1[0] * G[1][0] + e1[1] * G[1][1] + e1[2] * G[1][2];
+    const double idet = 1.0 / det;
+    double lam[4], grad[4][3];
+    const double dx = xyz[k] - p[0][0], dy = xyz[npts + k] - p[0][1], dz = xyz[2 * npts + k] - p[0][2];
+    for (int v = 1; v < 4; ++v) lam[v] = (G[v][0] * dx + G[v][1] * dy + G[v][2] * dz) * idet;
+    lam[0] = 1.0 - lam[1] - lam[2] - lam[3];
+    for (int v = 0; v < 4; ++v)
+        for (int a = 0; a < 3; ++a) grad[v][a] = G[v][a] * idet;
+    cx Ex = mk(0.0), Ey = mk(0.0), Ez = mk(0.0);
+    // canonical functions: N = s l lam_X (lam_Q grad_P - lam_P grad_Q)
+    const int eA[6] = {0, 0, 0, 1, 1, 2}, eB[6] = {1, 2, 3, 2, 3, 3};
+    const int fA[4] = {0, 0, 0, 1}, fB[4] = {1, 1, 2, 2}, fE[4] = {2, 3, 3, 3};
+    auto dist = [&](int a, int b) {
+        const double x = p[a][0] - p[b][0], y = p[a][1] - p[b][1], z = p[a][2] - p[b][2];
+        return sqrt(x * x + y * y + z * z);
+    };
+    auto add = [&](int cidx, double s, double l, int X, int P, int Q) {
+        const cx c = xfull[gid[(int64_t)t * 20 + cidx]];
+        const double f = s * l * lam[X];
+        const double wx = lam[Q] * grad[P][0] - lam[P] * grad[Q][0];
+        const double wy = lam[Q] * grad[P][1] - lam[P] * grad[Q][1];
+        const double wz = lam[Q] * grad[P][2] - lam[P] * grad[Q][2];
+        fma_r(Ex, f * wx, c); fma_r(Ey, f * wy, c); fma_r(Ez, f * wz, c);
+    };
+    for (int e = 0; e < 6; ++e) {
+        const double l = dist(eA[e], eB[e]);
+        add(e, 1.0, l, eA[e], eA[e], eB[e]);
+        add(10 + e, 1.0, l, eB[e], eA[e], eB[e]);
+    }
+    for (int f = 0; f < 4; ++f) {
+        add(6 + f, -1.0, dist(fA[f], fE[f]), fB[f], fA[f], fE[f]);
+        add(16 + f, 1.0, dist(fA[f], fB[f]), fE[f], fA[f], fB[f]);
+    }
+    E[k] = Ex; E[npts + k] = Ey; E[2 * npts + k] = Ez;
+}
+
+static int interp_impl(emb_ctx* c, const cx* dxfull, int64_t npts, const int64_t* tet_ids, const double* xyz, emb_c128* E) {
+    std::vector<int> ht((size_t)npts);
+    for (int64_t i = 0; i < npts; ++i) {
+        if (tet_ids[i] < 0 || tet_ids[i] >= c->nT) { c->err = "emb_interp: tet id out of range"; return EMB_ERR_ARG; }
+        ht[i] = (int)tet_ids[i];
+    }
+    DevBuf<int> dt;
+    DevBuf<double> dp;
+    DevBuf<cx> dE;
+    EMB_TRY(h2d(c, dt, ht.data(), (size_t)npts));
+    EMB_TRY(h2d(c, dp, xyz, (size_t)npts * 3));
+    EMB_TRY(dev_alloc(c, dE, (size_t)npts * 3));
+    k_interp<<<blocks_for(npts, 128), 128, 0, c->stream>>>(npts, dt.p, dp.p, c->tetc.p, c->gid.p, c->nodes.p, dxfull, dE.p);
+    EMB_LAUNCH_CHECK(c);
+    EMB_CUDA(c, cudaMemcpyAsync(E, dE.p, (size_t)npts * 3 * sizeof(cx), cudaMemcpyDeviceToHost, c->stream));
+    EMB_CUDA(c, cudaStreamSynchronize(c->stream));
+    dt.release(); dp.release(); dE.release();
+    return EMB_OK;
+}
+
+extern "C" int emb_interp(emb_ctx* c, const emb_c128* x_full, int64_t npts, const int64_t* tet_ids, const double* xyz,
+                          emb_c128* E) {
+    if (!c || !x_full || npts <= 0 || !tet_ids || !xyz || !E) return EMB_ERR_ARG;
+    if (!c->have_mesh) { c->err = "emb_interp: mesh not uploaded"; return EMB_ERR_STATE; }
+    DevBuf<cx> dx;
+    EMB_TRY(h2d(c, dx, reinterpret_cast<const cx*>(x_full), (size_t)c->N));
+    int rc = interp_impl(c, dx.p, npts, tet_ids, xyz, E);
+    dx.release();
+    return rc;
+}
+
+extern "C" int emb_interp_last(emb_ctx* c, int64_t npts, const int64_t* tet_ids, const double* xyz, emb_c128* E) {
+    if (!c || npts <= 0 || !tet_ids || !xyz || !E) return EMB_ERR_ARG;
+    if (!c->xfull.p) { c->err = "emb_interp_last: no solution on the device"; return EMB_ERR_STATE; }
+    return interp_impl(c, c->xfull.p, npts, tet_ids, xyz, E);
+}

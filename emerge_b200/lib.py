@@ -1,0 +1,276 @@
+"""ctypes binding of the C ABI in include/emerge_b200.h (libemerge_b200.so, CUDA sm_100a).
+
+There is no CPU fallback: if the shared library is missing or no GPU is visible, constructing a
+`Context` raises.  Loading the library itself (symbol checks) works without a GPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libemerge_b200.so")
+
+c128_p = C.c_void_p
+
+
+class SolveOpts(C.Structure):
+    _fields_ = [("method", C.c_int), ("precond", C.c_int), ("restart", C.c_int), ("maxit", C.c_int),
+                ("rtol", C.c_double), ("use_x0", C.c_int)]
+
+
+class SolveInfo(C.Structure):
+    _fields_ = [("iters", C.c_int), ("relres", C.c_double), ("ms", C.c_double), ("spmvs", C.c_int)]
+
+
+METHODS = {"gmres": 0, "bicgstab": 1, "cocr": 2}
+PRECONDS = {"none": 0, "jacobi": 1, "block": 2}
+
+_SIGS = {
+    "emb_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
+    "emb_destroy": (None, [C.c_void_p]),
+    "emb_last_error": (C.c_char_p, [C.c_void_p]),
+    "emb_version": (C.c_char_p, []),
+    "emb_launch_count": (C.c_int64, [C.c_void_p]),
+    "emb_last_ms": (C.c_double, [C.c_void_p, C.c_char_p]),
+    "emb_upload_mesh": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64] + [C.c_void_p] * 5),
+    "emb_upload_materials": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "emb_symbolic": (C.c_int, [C.c_void_p]),
+    "emb_assemble_KM": (C.c_int, [C.c_void_p]),
+    "emb_n_field": (C.c_int64, [C.c_void_p]),
+    "emb_nnz": (C.c_int64, [C.c_void_p]),
+    "emb_get_csr": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "emb_csr_rows": (C.c_int64, [C.c_void_p, C.c_int]),
+    "emb_csr_nnz": (C.c_int64, [C.c_void_p, C.c_int]),
+    "emb_element_matrices": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
+    "emb_surface_define": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "emb_surface_points": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "emb_surface_set_U": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "emb_surface_blocks": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "emb_set_dirichlet": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p]),
+    "emb_n_solve": (C.c_int64, [C.c_void_p]),
+    "emb_get_solve_ids": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "emb_form_A": (C.c_int, [C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_void_p]),
+    "emb_spmv_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "emb_spmv_bench": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double)]),
+    "emb_solve": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(SolveOpts), C.c_void_p, C.POINTER(SolveInfo)]),
+    "emb_solve_rhs": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(SolveOpts), C.c_void_p, C.POINTER(SolveInfo)]),
+    "emb_interp": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "emb_interp_last": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+}
+
+_lib = None
+
+
+class EmergeB200Error(RuntimeError):
+    """Raised on a negative status of the C ABI (the wrapper's analogue of fem SimulationError)."""
+
+
+class NotConverged(EmergeB200Error):
+    pass
+
+
+def exported_symbols():
+    return sorted(_SIGS)
+
+
+def load_library():
+    """dlopen the CUDA library and bind every symbol of the header; raises if it was not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise EmergeB200Error(f"{LIB_PATH} not found: run `python -m emerge_b200.build` (nvcc, sm_100a). "
+                              "There is no CPU fallback for this path.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGS.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _c(a, dtype):
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+class Context:
+    """One GPU context (opaque handle of the C ABI)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        h = C.c_void_p()
+        rc = self.lib.emb_create(device, C.byref(h))
+        if rc != 0 or not h:
+            raise EmergeB200Error(f"emb_create(device={device}) failed (rc={rc}): no usable CUDA device; "
+                                  "this path has no CPU fallback")
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.emb_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc, allow_positive=False):
+        if rc < 0:
+            raise EmergeB200Error(self.lib.emb_last_error(self.h).decode())
+        if rc > 0 and not allow_positive:
+            raise NotConverged(self.lib.emb_last_error(self.h).decode())
+        return rc
+
+    # ---- info
+    @property
+    def launches(self) -> int:
+        return int(self.lib.emb_launch_count(self.h))
+
+    def last_ms(self, phase: str) -> float:
+        return float(self.lib.emb_last_ms(self.h, phase.encode()))
+
+    @property
+    def n_field(self) -> int:
+        return int(self.lib.emb_n_field(self.h))
+
+    @property
+    def nnz(self) -> int:
+        return int(self.lib.emb_nnz(self.h))
+
+    @property
+    def n_solve(self) -> int:
+        return int(self.lib.emb_n_solve(self.h))
+
+    # ---- mesh / assembly
+    def upload_mesh(self, nodes, tets, tris, tet_to_field, tri_to_field, n_edges):
+        """nodes (3,nN); tets (4,nT); tris (3,nTri); tet_to_field (20,nT); tri_to_field (8,nTri) as the reference
+        holds them (F-order views are passed without a copy when possible)."""
+        nodes_n3 = _c(np.asarray(nodes).T, np.float64)
+        tets_n4 = _c(np.asarray(tets).T, np.int64)
+        tris_n3 = _c(np.asarray(tris).T, np.int64)
+        ttf = _c(tet_to_field, np.int64)
+        t2f = _c(tri_to_field, np.int64)
+        self._check(self.lib.emb_upload_mesh(self.h, nodes_n3.shape[0], tets_n4.shape[0], int(n_edges), tris_n3.shape[0],
+                                             _p(nodes_n3), _p(tets_n4), _p(tris_n3), _p(ttf), _p(t2f)))
+        self.n_tets = tets_n4.shape[0]
+
+    def upload_materials(self, er, ur):
+        er = _c(er, np.complex128)
+        ur = _c(ur, np.complex128)
+        assert er.shape == (3, 3, self.n_tets) and ur.shape == er.shape
+        self._check(self.lib.emb_upload_materials(self.h, _p(er), _p(ur)))
+
+    def symbolic(self):
+        self._check(self.lib.emb_symbolic(self.h))
+
+    def assemble_KM(self):
+        self._check(self.lib.emb_assemble_KM(self.h))
+
+    def get_csr(self, which: int, values: bool = True, pattern: bool = True):
+        rows = int(self.lib.emb_csr_rows(self.h, which))
+        nnz = int(self.lib.emb_csr_nnz(self.h, which))
+        indptr = np.empty(rows + 1, dtype=np.int64) if pattern else None
+        indices = np.empty(nnz, dtype=np.int32) if pattern else None
+        data = np.empty(nnz, dtype=np.complex128) if values else None
+        self._check(self.lib.emb_get_csr(self.h, which, _p(indptr), _p(indices), _p(data)))
+        return indptr, indices, data
+
+    def element_matrices(self, t0, t1):
+        E = np.empty((t1 - t0, 20, 20), dtype=np.complex128)
+        B = np.empty_like(E)
+        self._check(self.lib.emb_element_matrices(self.h, t0, t1, _p(E), _p(B)))
+        return E, B
+
+    # ---- surfaces
+    def surface_define(self, sid, tri_ids, frame=0, basis_inv=None, origin=None):
+        tri_ids = _c(tri_ids, np.int64)
+        bi = _c(basis_inv if basis_inv is not None else np.eye(3), np.float64)
+        og = _c(origin if origin is not None else np.zeros(3), np.float64)
+        self._check(self.lib.emb_surface_define(self.h, sid, len(tri_ids), _p(tri_ids), frame, _p(bi), _p(og)))
+        return len(tri_ids)
+
+    def surface_points(self, sid, ntri):
+        xy = np.empty((2, 6, ntri), dtype=np.float64)
+        self._check(self.lib.emb_surface_points(self.h, sid, _p(xy)))
+        return xy
+
+    def surface_set_U(self, sid, U, want_full=False):
+        U = _c(U, np.complex128)
+        b = np.empty(self.n_field, dtype=np.complex128) if want_full else None
+        self._check(self.lib.emb_surface_set_U(self.h, sid, _p(U), _p(b)))
+        return b
+
+    def surface_blocks(self, sid, ntri):
+        S = np.empty((ntri, 8, 8), dtype=np.float64)
+        self._check(self.lib.emb_surface_blocks(self.h, sid, _p(S)))
+        return S
+
+    # ---- elimination / operator
+    def set_dirichlet(self, pec_ids):
+        ids = _c(pec_ids, np.int64)
+        self._check(self.lib.emb_set_dirichlet(self.h, len(ids), _p(ids)))
+
+    def solve_ids(self):
+        out = np.empty(self.n_solve, dtype=np.int64)
+        self._check(self.lib.emb_get_solve_ids(self.h, _p(out)))
+        return out
+
+    def form_A(self, k0, sids=(), gammas=()):
+        s = _c(list(sids), np.int32)
+        g = _c(list(gammas), np.complex128)
+        self._check(self.lib.emb_form_A(self.h, float(k0), len(s), _p(s), _p(g)))
+
+    def spmv(self, x):
+        x = _c(x, np.complex128)
+        y = np.empty_like(x)
+        self._check(self.lib.emb_spmv_host(self.h, _p(x), _p(y)))
+        return y
+
+    def spmv_bench(self, reps=20):
+        ms = C.c_double()
+        self._check(self.lib.emb_spmv_bench(self.h, reps, C.byref(ms)))
+        return ms.value
+
+    @staticmethod
+    def _opts(method="cocr", precond="block", restart=50, maxit=100000, rtol=1e-8, use_x0=False):
+        return SolveOpts(METHODS[method], PRECONDS[precond], restart, maxit, rtol, int(use_x0))
+
+    def solve(self, sid, want_x=True, raise_on_fail=True, **kw):
+        o = self._opts(**kw)
+        info = SolveInfo()
+        x = np.zeros(self.n_field, dtype=np.complex128) if want_x else None
+        rc = self._check(self.lib.emb_solve(self.h, sid, C.byref(o), _p(x), C.byref(info)), allow_positive=not raise_on_fail)
+        return x, dict(iters=info.iters, relres=info.relres, ms=info.ms, spmvs=info.spmvs, converged=rc == 0)
+
+    def solve_rhs(self, b_full, x0=None, raise_on_fail=True, **kw):
+        b = _c(b_full, np.complex128)
+        o = self._opts(use_x0=x0 is not None, **kw)
+        info = SolveInfo()
+        x = np.zeros(self.n_field, dtype=np.complex128) if x0 is None else _c(x0, np.complex128).copy()
+        rc = self._check(self.lib.emb_solve_rhs(self.h, _p(b), C.byref(o), _p(x), C.byref(info)), allow_positive=not raise_on_fail)
+        return x, dict(iters=info.iters, relres=info.relres, ms=info.ms, spmvs=info.spmvs, converged=rc == 0)
+
+    def interp(self, x_full, tet_ids, xyz):
+        """E (3,npts) at points xyz (3,npts), point k inside tet tet_ids[k]; x_full=None uses the device solution."""
+        tet_ids = _c(tet_ids, np.int64)
+        xyz = _c(xyz, np.float64)
+        E = np.empty((3, len(tet_ids)), dtype=np.complex128)
+        if x_full is None:
+            self._check(self.lib.emb_interp_last(self.h, len(tet_ids), _p(tet_ids), _p(xyz), _p(E)))
+        else:
+            x = _c(x_full, np.complex128)
+            self._check(self.lib.emb_interp(self.h, _p(x), len(tet_ids), _p(tet_ids), _p(xyz), _p(E)))
+        return E

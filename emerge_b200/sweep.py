@@ -1,0 +1,230 @@
+"""Frequency sweep driver: host mirror of Electrodynamics3D.frequency_domain (fem/physics/edm/emfreq3d.py:607-732)
+over the CUDA library.  Everything frequency-independent (K, M, the surface matrices S_p, the eliminated
+pattern, the S-parameter sample points) is set up once; per frequency only gamma_p(f), the incident-field
+samples U_p(f) and the solves cross the boundary.
+
+S-parameter extraction mirrors emfreq3d.py:734-779, fem/mth/sparam.py:72-139 and fem/mth/integrals.py:24-70:
+the field is evaluated on the GPU at the port's Dunavant-4 points (emb_interp) in the tetrahedron the reference's
+interpolation would pick (fem/mth/tet.py:393-497: the LAST tetrahedron of the candidate list containing the
+point wins), the small surface sums are done on the host exactly as the reference does them.
+"""
+from __future__ import annotations
+
+import time
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from .lib import Context, NotConverged
+from . import bc as _bc
+
+C0 = 299792458.0
+
+# gaus_quad_tri(4): rows W, L1, L2, L3 (fem/mth/optimized.py:28-29,77-108)
+_W = (0.223381589678011, 0.109951743655322)
+_L = ((0.108103018168070, 0.445948490915965, 0.445948490915965),
+      (0.816847572980459, 0.091576213509771, 0.091576213509771))
+
+
+def dunavant4() -> np.ndarray:
+    rows = []
+    for w, (l1, l2, l3) in zip(_W, _L):
+        for _ in range(3):
+            rows.append([w, l1, l2, l3])
+            l1, l2, l3 = l2, l3, l1
+    return np.array(rows).T
+
+
+def _is(bc, name):
+    """isinstance by class name through the MRO so reference objects (fem.bc.*) are accepted too."""
+    return any(k.__name__ == name for k in type(bc).__mro__)
+
+
+def _tri_ids(bc, get_triangles):
+    if hasattr(bc, "tri_ids"):
+        return np.asarray(bc.tri_ids, dtype=np.int64)
+    return np.asarray(get_triangles(bc.tags), dtype=np.int64)
+
+
+@dataclass
+class SweepResult:
+    freqs: np.ndarray
+    port_numbers: list
+    S: np.ndarray                                   # (nf, P, P): S[f, i, j] = port i response, port j excited
+    stats: list = field(default_factory=list)       # per (freq, port) solver info dicts
+    fields: dict = field(default_factory=dict)      # optional {(ifreq, port_number): x (n_field)}
+    timings: dict = field(default_factory=dict)
+
+
+class FrequencySweep:
+    """tables: emerge_b200.synthmesh.MeshTables-like object (or any object exposing the reference's arrays:
+    nodes, tets, tris, edges, tri_to_tet, tet_to_field, tri_to_field).  bcs: PEC / RobinBC objects (ours or fem's)."""
+
+    def __init__(self, tables, er, ur, bcs, device: int = 0, get_triangles=None, ctx: Context | None = None):
+        self.t = tables
+        self.er = np.ascontiguousarray(er, dtype=np.complex128)
+        self.ur = np.ascontiguousarray(ur, dtype=np.complex128)
+        self.bcs = list(bcs)
+        self.get_triangles = get_triangles
+        self.ctx = ctx if ctx is not None else Context(device)
+        self.timings = {}
+        self._setup_done = False
+        self.solver_opts = dict(method="cocr", precond="block", rtol=1e-8, maxit=200000, restart=50)
+
+    # ------------------------------------------------------------------ setup (once)
+    def setup(self):
+        t, ctx = self.t, self.ctx
+        n_edges = t.edges.shape[1]
+        t0 = time.perf_counter()
+        ctx.upload_mesh(t.nodes, t.tets, t.tris, t.tet_to_field, t.tri_to_field, n_edges)
+        ctx.upload_materials(self.er, self.ur)
+        self.timings["upload_s"] = time.perf_counter() - t0
+        ctx.symbolic()
+        self.timings["symbolic_ms"] = ctx.last_ms("symbolic")
+        ctx.assemble_KM()
+        self.timings["tet_kernel_ms"] = ctx.last_ms("tet_kernel")
+        self.timings["reduce_ms"] = ctx.last_ms("reduce")
+        # PEC dofs: all 8 functions of every PEC triangle (its 3 edges x2 + face x2), assembler.py:348-359
+        pec = [np.asarray(t.tri_to_field)[:, _tri_ids(b, self.get_triangles)].ravel() for b in self.bcs if _is(b, "PEC")]
+        pec = np.unique(np.concatenate(pec)) if pec else np.zeros(0, dtype=np.int64)
+        self.robin = [b for b in self.bcs if _is(b, "RobinBC")]
+        self.ports = [b for b in self.bcs if _is(b, "PortBC")]
+        self.sid = {}
+        self.ntri = {}
+        self.points = {}
+        for sid, b in enumerate(self.robin):
+            ids = _tri_ids(b, self.get_triangles)
+            if b._include_force:
+                n = ctx.surface_define(sid, ids, 0, np.asarray(b.get_inv_basis(), dtype=float), np.asarray(b.cs.origin, dtype=float))
+                self.points[id(b)] = ctx.surface_points(sid, n)
+            else:
+                n = ctx.surface_define(sid, ids, 1)
+            self.sid[id(b)] = sid
+            self.ntri[id(b)] = n
+        ctx.set_dirichlet(pec)
+        self.pec_ids = pec
+        # S-parameter sample points per port
+        DP = dunavant4()
+        nodes = np.asarray(t.nodes)
+        tris = np.asarray(t.tris)
+        self._sp = {}
+        for b in self.ports:
+            ids = _tri_ids(b, self.get_triangles)
+            tv = tris[:, ids]                                           # (3, ntri)
+            P = nodes[:, tv]                                            # (3 xyz, 3 vert, ntri)
+            pts = np.einsum("kq,xkt->xqt", DP[1:4], P)                 # (3, 6, ntri)  generate_int_points_tri
+            e1, e2 = P[:, 1] - P[:, 0], P[:, 2] - P[:, 0]
+            area = 0.5 * np.linalg.norm(np.cross(e1.T, e2.T), axis=1)   # calc_area
+            tets = np.asarray(t.tri_to_tet)[:, ids].max(axis=0)        # last containing tet wins
+            tet0 = np.asarray(t.tri_to_tet)[0, ids]                     # ertri/urtri use tri_to_tet[0] (emfreq3d.py:621-624)
+            self._sp[id(b)] = dict(pts=pts.reshape(3, -1), tet=np.repeat(tets[None, :], 6, axis=0).ravel(), area=area,
+                                   tet0=tet0, ntri=len(ids))
+            if getattr(b, "v_integration", False):
+                self._setup_vline(b, ids)
+        self._setup_done = True
+
+    def _setup_vline(self, b, ids):
+        """define_lumped_port_integration_points (emfreq3d.py:366-389) + point location for the 10 midpoints."""
+        t = self.t
+        nodes = np.asarray(t.nodes)
+        direction = np.asarray(b.direction.np if hasattr(b.direction, "np") else b.direction, dtype=float)
+        pts = np.unique(np.asarray(t.tris)[:, ids])
+        dotp = nodes[0, pts] * direction[0] + nodes[1, pts] * direction[1] + nodes[2, pts] * direction[2]
+        start = nodes[:, pts[dotp == dotp.min()]].mean(axis=1)
+        end = start + direction * b.height
+        lin = np.linspace(start, end, 11)                               # Line.from_points(start, end, 11)
+        mid = 0.5 * (lin[:-1] + lin[1:])
+        d = lin[1:] - lin[:-1]
+        # candidate tets = those touching a port vertex (emfreq3d.py:648-653); last containing tet wins
+        tets = np.asarray(t.tets)
+        allv = np.zeros(nodes.shape[1], dtype=bool)
+        for p in self.ports:
+            allv[np.unique(np.asarray(t.tris)[:, _tri_ids(p, self.get_triangles)])] = True
+        cand = np.nonzero(allv[tets].any(axis=0))[0]
+        v0 = nodes[:, tets[0, cand]].T
+        Bm = np.stack([nodes[:, tets[k, cand]].T - v0 for k in (1, 2, 3)], axis=2)     # (nc,3,3) columns
+        inv = np.linalg.inv(Bm)
+        loc = np.einsum("cij,pcj->pci", inv, mid[:, None, :] - v0[None, :, :])          # (10, nc, 3)
+        inside = (loc.sum(axis=2) <= 1.00000001) & (loc >= -1e-6).all(axis=2)          # tet.py:425
+        tet_of = np.array([cand[np.nonzero(inside[k])[0][-1]] if inside[k].any() else -1 for k in range(mid.shape[0])])
+        self._sp[id(b)]["vline"] = dict(mid=mid.T.copy(), d=d, tet=tet_of)
+
+    # ------------------------------------------------------------------ per frequency
+    def _port_constants(self, b, sp):
+        tet0 = sp["tet0"]
+        er, ur = self.er, self.ur
+        tr_u = ur[0, 0, tet0] + ur[1, 1, tet0] + ur[2, 2, tet0]
+        tr_e = er[0, 0, tet0] + er[1, 1, tet0] + er[2, 2, tet0]
+        mt = b.modetype
+        if mt == "TEM":
+            return 1 / np.sqrt(tr_u / tr_e)
+        if mt == "TE":
+            return 1 / (tr_u / 3)
+        return 1 / (tr_e / 3)
+
+    def _s_data(self, b, k0, x_full):
+        """(pfield, pmode) of _compute_s_data (emfreq3d.py:734-779)."""
+        sp = self._sp[id(b)]
+        ctx = self.ctx
+        if getattr(b, "v_integration", False):
+            vl = sp["vline"]
+            ok = vl["tet"] >= 0
+            E = np.zeros((3, len(ok)), dtype=np.complex128)
+            if ok.any():
+                E[:, ok] = ctx.interp(x_full, vl["tet"][ok], vl["mid"][:, ok])
+            V = np.sum(E[0] * vl["d"][:, 0] + E[1] * vl["d"][:, 1] + E[2] * vl["d"][:, 2])
+            a, bb = (b.voltage, V - b.voltage) if b.active else (0, V)
+            return np.sqrt(bb ** 2 / (2 * b.Z0)), np.sqrt(a ** 2 / (2 * b.Z0))
+        const = np.squeeze(self._port_constants(b, sp)).astype(np.complex128)
+        E = ctx.interp(x_full, sp["tet"], sp["pts"])
+        mode = np.asarray(b.port_mode_3d_global(sp["pts"][0], sp["pts"][1], sp["pts"][2], k0))
+        Q = 1 if b.active else 0
+        Z = b.Zmode(k0)
+        DP = dunavant4()
+        f1 = (((E - Q * mode) * np.conj(mode)).sum(axis=0) / (2 * Z)).reshape(6, sp["ntri"])
+        f2 = ((mode * np.conj(mode)).sum(axis=0) / (2 * Z)).reshape(6, sp["ntri"])
+        pfield = np.sum(const * (DP[0] @ f1) * sp["area"])             # _fast_integral_c
+        pmode = np.sum(const * (DP[0] @ f2) * sp["area"])
+        return pfield, pmode
+
+    def assemble_frequency(self, freq):
+        """Forms A(f) and the port right-hand sides on the device (Assembler.assemble_freq_matrix, assembler.py:312-388)."""
+        k0 = 2 * np.pi * freq / 299792458
+        sids, gammas = [], []
+        for b in self.robin:
+            sid = self.sid[id(b)]
+            if b._include_force:
+                xy = self.points[id(b)]
+                U = np.asarray(b.get_Uinc(xy[0].ravel(), xy[1].ravel(), k0), dtype=np.complex128)
+                self.ctx.surface_set_U(sid, U.reshape(3, 6, self.ntri[id(b)]))
+            if b._include_stiff:
+                sids.append(sid)
+                gammas.append(complex(b.get_gamma(k0)))
+        self.ctx.form_A(k0, sids, gammas)
+        return k0
+
+    def run(self, freqs, keep_fields=False, raise_on_fail=True) -> SweepResult:
+        if not self._setup_done:
+            self.setup()
+        ports = self.ports
+        pn = [p.port_number for p in ports]
+        S = np.zeros((len(freqs), len(ports), len(ports)), dtype=np.complex128)
+        res = SweepResult(np.asarray(freqs, dtype=float), pn, S)
+        for p in ports:
+            p.active = False
+        for i, f in enumerate(freqs):
+            k0 = self.assemble_frequency(f)
+            for ja, pa in enumerate(ports):
+                pa.active = True
+                x, info = self.ctx.solve(self.sid[id(pa)], want_x=True, raise_on_fail=raise_on_fail, **self.solver_opts)
+                info.update(freq=float(f), port=pa.port_number)
+                res.stats.append(info)
+                if keep_fields:
+                    res.fields[(i, pa.port_number)] = x
+                _, pout = self._s_data(pa, k0, None)
+                for ib, pb in enumerate(ports):
+                    pf, _ = self._s_data(pb, k0, None)
+                    S[i, ib, ja] = pf / pout
+                pa.active = False
+        res.timings = dict(self.timings)
+        return res

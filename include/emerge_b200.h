@@ -1,0 +1,127 @@
+/* emerge_b200 — C ABI of the B200-native EMerge frequency-domain hot path.
+ *
+ * Plain pointers and sizes only; every pointer is a HOST pointer unless the name starts with d_.
+ * The library copies what it needs during the call and never retains host pointers.  All device
+ * state lives in an opaque context bound to one GPU and one CUDA stream; a context is owned by one
+ * host thread.  Return value: 0 ok, <0 error (emb_last_error gives the text), >0 non-convergence.
+ *
+ * Each entry point names the reference interface it replaces (paths relative to the EMerge tree).
+ * Arrays use the reference's own memory layouts so the Python seam can pass the
+ * numpy buffers it already holds:
+ *   nodes   (nN,3) f64 row-major  = memory of mesh.nodes (3,nN) F-order view   fem/mesh3d.py:227-230
+ *   tets    (nT,4) i64 row-major  = memory of mesh.tets (4,nT) view             fem/mesh3d.py:245
+ *   tris    (nTri,3) i64 row-major                                              fem/mesh3d.py:271
+ *   tet_to_field (20,nT) i64 C-order, tri_to_field (8,nTri) i64 C-order         fem/elements/nedelec2.py:46-62
+ *   er, ur  (3,3,nT) c128 C-order                                               fem/mesh3d.py:358-378
+ */
+#ifndef EMERGE_B200_H
+#define EMERGE_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct emb_ctx emb_ctx;
+typedef struct { double re, im; } emb_c128;
+
+/* ---- context ------------------------------------------------------------------------------ */
+int emb_create(int device, emb_ctx** out);
+void emb_destroy(emb_ctx* ctx);
+const char* emb_last_error(const emb_ctx* ctx);
+const char* emb_version(void);
+/* number of kernels this library launched since the context was created (bench.py gpu_launches) */
+int64_t emb_launch_count(const emb_ctx* ctx);
+/* device time (ms, CUDA events on the context stream) of the last call of the named phase:
+ * "symbolic", "tet_kernel", "reduce", "form_A", "spmv", "solve", "surface" */
+double emb_last_ms(const emb_ctx* ctx, const char* phase);
+
+/* ---- mesh + DOF tables (input contract of Nedelec2 / Mesh3D; consumed, never renumbered) ---- */
+/* replaces the array gathering at fem/physics/edm/optimized_assembly.py:47-57 */
+int emb_upload_mesh(emb_ctx* ctx, int64_t nN, int64_t nT, int64_t nE, int64_t nTri,
+                    const double* nodes_n3, const int64_t* tets_n4, const int64_t* tris_n3,
+                    const int64_t* tet_to_field_20xnT, const int64_t* tri_to_field_8xnTri);
+/* er/ur per tet (fem/physics/edm/emfreq3d.py:615-616) */
+int emb_upload_materials(emb_ctx* ctx, const emb_c128* er_3x3xnT, const emb_c128* ur_3x3xnT);
+
+/* ---- assembly ------------------------------------------------------------------------------- */
+/* One-time symbolic phase: canonical CSR pattern of E/B (sorted columns, duplicates merged, explicit
+ * zeros kept) = the pattern coo_matrix(...).tocsr() produces at optimized_assembly.py:61-62. */
+int emb_symbolic(emb_ctx* ctx);
+/* Numeric phase: element kernel + deterministic reduction -> E (curl-curl) and B (mass) values.
+ * Replaces tet_mass_stiffness_matrices(field, er, ur) (optimized_assembly.py:43-64). */
+int emb_assemble_KM(emb_ctx* ctx);
+int64_t emb_n_field(const emb_ctx* ctx);
+int64_t emb_nnz(const emb_ctx* ctx);
+/* copy the CSR out (parity checks, and the scipy csr_matrix the Assembler seam must return).
+ * which: 0=E (K), 1=B (M), 2=A(f) of the last emb_form_A (solve-space pattern).  Any pointer may be NULL. */
+int emb_get_csr(emb_ctx* ctx, int which, int64_t* indptr, int32_t* indices, emb_c128* data);
+int64_t emb_csr_rows(const emb_ctx* ctx, int which);
+int64_t emb_csr_nnz(const emb_ctx* ctx, int which);
+/* element matrices of tets [t0,t1) in the reference's slot order p=400(t-t0)+20i+j
+ * (optimized_assembly.py:109-115); debug/parity only */
+int emb_element_matrices(emb_ctx* ctx, int64_t t0, int64_t t1, emb_c128* E400, emb_c128* B400);
+
+/* ---- surface (Robin) terms --------------------------------------------------------------------- */
+/* Define surface `sid` (0..15) on global triangle ids.  frame=0: port frame, local = basis_inv @ (x - origin)
+ * as assemble_robin_bc_excited does (assembler.py:100-123); frame=1: per-triangle frame of ned2_tri_stiff
+ * (fem/mth/tri.py:709-723) as assemble_robin_bc does (assembler.py:125-144).  Computes the gamma-free
+ * matrix S (B_p = gamma*S) on the global pattern once. */
+int emb_surface_define(emb_ctx* ctx, int sid, int64_t ntri, const int64_t* tri_ids, int frame,
+                       const double* basis_inv_3x3, const double* origin_3);
+/* Dunavant-4 points of the surface in its local frame, xy (2,6,ntri): generate_points (assembler.py:63-81) */
+int emb_surface_points(emb_ctx* ctx, int sid, double* xy_2x6xntri);
+/* forcing vector from incident field samples U (3,6,ntri) c128 (compute_bc_entries, assembler.py:83-98);
+ * result kept on the device as the RHS of surface sid and optionally copied to b_full (length n_field). */
+int emb_surface_set_U(emb_ctx* ctx, int sid, const emb_c128* U_3x6xntri, emb_c128* b_full);
+/* B_p = gamma*S as COO over the surface's triangles in the reference's order (64 per triangle); parity only */
+int emb_surface_blocks(emb_ctx* ctx, int sid, double* S_ntrix64);
+
+/* ---- Dirichlet elimination + A(f) ----------------------------------------------------------- */
+/* PEC dof ids (assembler.py:348-359,384-385).  Builds the solve-space pattern (rows/cols of solve_ids only),
+ * i.e. A[np.ix_(solve_ids, solve_ids)] of fem/solver.py:434, once instead of per solve. */
+int emb_set_dirichlet(emb_ctx* ctx, int64_t npec, const int64_t* pec_ids);
+int64_t emb_n_solve(const emb_ctx* ctx);
+int emb_get_solve_ids(emb_ctx* ctx, int64_t* solve_ids);
+/* A(f) = E - k0^2 B + sum_s gamma[s] S_s on the solve-space pattern (assembler.py:333,383) */
+int emb_form_A(emb_ctx* ctx, double k0, int nsurf, const int* sids, const emb_c128* gammas);
+
+/* ---- linear algebra ------------------------------------------------------------------------------ */
+/* y = A x on the solve space (host vectors of length n_solve); parity + SpMV benchmark */
+int emb_spmv_host(emb_ctx* ctx, const emb_c128* x, emb_c128* y);
+/* times `reps` SpMVs on resident device vectors, returns avg ms per SpMV */
+int emb_spmv_bench(emb_ctx* ctx, int reps, double* ms_per_spmv);
+
+typedef struct {
+    int method;        /* 0 = GMRES(restart), 1 = BiCGStab, 2 = COCG (complex-symmetric) */
+    int precond;       /* 0 = none, 1 = Jacobi, 2 = block-Jacobi (2x2 edge/face pairs) */
+    int restart;       /* GMRES restart length */
+    int maxit;
+    double rtol;       /* ||b-Ax||/||b|| */
+    int use_x0;        /* 1: x_full holds an initial guess */
+} emb_solve_opts;
+typedef struct {
+    int iters;
+    double relres;     /* true relative residual recomputed at exit */
+    double ms;         /* device time */
+    int spmvs;
+} emb_solve_info;
+/* Solve A x = b_sid (RHS of surface sid from emb_surface_set_U) on the solve space; x_full has n_field
+ * entries with zeros at Dirichlet DOFs, as SolveRoutine.solve returns it (fem/solver.py:405-469). */
+int emb_solve(emb_ctx* ctx, int sid, const emb_solve_opts* opts, emb_c128* x_full, emb_solve_info* info);
+/* same with an explicit host RHS of length n_field (the b + port_vectors[p] of emfreq3d.py:691) */
+int emb_solve_rhs(emb_ctx* ctx, const emb_c128* b_full, const emb_solve_opts* opts, emb_c128* x_full,
+                  emb_solve_info* info);
+
+/* ---- field evaluation (S-parameter extraction) -------------------------------------------------- */
+/* E-field of solution x_full (host, n_field) at npts points, point k lying in tet tet_ids[k]:
+ * the per-point part of ned2_tet_interp (fem/mth/tet.py:371-497).  E_3xnpts is (3,npts) c128. */
+int emb_interp(emb_ctx* ctx, const emb_c128* x_full, int64_t npts, const int64_t* tet_ids,
+               const double* xyz_3xnpts, emb_c128* E_3xnpts);
+/* same, using the device-resident solution of the last emb_solve (no x upload) */
+int emb_interp_last(emb_ctx* ctx, int64_t npts, const int64_t* tet_ids, const double* xyz_3xnpts,
+                    emb_c128* E_3xnpts);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
