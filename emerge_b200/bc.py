@@ -106,8 +106,11 @@ class PortBC(RobinBC):
 
 
 class RectangularWaveguide(PortBC):
-    """TE_mn rectangular port with analytic mode field (fem/bc.py:496-618)."""
-    modetype = "TE"
+    """TE_mn rectangular port with analytic mode field (fem/bc.py:496-618).
+    Quirk kept for parity: the reference sets `self.type = 'TE'` (fem/bc.py:530) but its `modetype` property is the
+    inherited PortBC one and always answers 'TEM' (fem/bc.py:203-205), so S-parameter normalisation uses the TEM
+    constants (Zvac, sqrt(eps/mu))."""
+    modetype = "TEM"
 
     def __init__(self, tri_ids, port_number, cs, dims, active=False, power=1.0, mode=(1, 0)):
         super().__init__(tri_ids, port_number, cs, active)
