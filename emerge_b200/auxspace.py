@@ -1,0 +1,110 @@
+"""Auxiliary spaces for the multilevel preconditioner (host side, numpy; one-time per mesh).
+
+The second-order Nedelec space of the reference contains
+  * the gradients of the quadratic Lagrange space  (the null-space of the curl-curl matrix E), and
+  * the lowest-order (Whitney) Nedelec space.
+This module builds the two sparse transfer matrices in the reference's dof numbering,
+    G  (n_field x (nN + nE)) : coefficients of grad(phi_k), phi_k the P2 nodal functions
+                               (vertex functions lam_v(2 lam_v - 1), edge functions 4 lam_A lam_B),
+    P  (n_field x nE)        : coefficients of the Whitney functions w_AB = lam_B grad lam_A - lam_A grad lam_B,
+and G1 (nE x nN), the P1 gradient in the Whitney basis.  They are used by the CUDA solver as an additive
+multilevel preconditioner  M^-1 = D^-1 + G D_G^-1 G^T + P (D_P^-1 + G1 D_G1^-1 G1^T) P^T.
+
+Derivation of the entries (no quadrature, no per-tet work): the dofs of the reference's basis are point
+functionals of the tangential field,
+    c_edge-a(A,B) = -E(v_A).t_AB,  c_edge-b(A,B) = -E(v_B).t_AB            (t_AB = (v_B - v_A)/l_AB),
+and, on a face (A,B,E) with centroid c, the two face coefficients follow from E_t(c):
+    u = c_fa l_AE,  w = c_fb l_AB:   u - 2w = R1,  2u - w = R2,
+    R1 = 9 E(c).d_AB + 2 s_AB - s_BE + s_AE,   R2 = 9 E(c).d_AE + s_AB + s_BE + 2 s_AE,   s_PQ = -(E_P + E_Q).d_PQ,
+because at the centroid every edge function of edge (P,Q) equals l_PQ (g_P - g_Q)/9, face-a = -l_AE (g_A - g_E)/9,
+face-b = l_AB (g_A - g_B)/9, and g_P.d_QR = delta_PR - delta_PQ.  All targets are linear fields, so only their
+vertex values dotted with edge vectors enter; these are integers (delta combinations), hence every entry of G and P
+is (small integer)/(edge length).
+"""
+from __future__ import annotations
+
+import numpy as np
+import scipy.sparse as sp
+
+
+def _gdot(V, Q, R):
+    """grad(lam_V) . (v_R - v_Q) = delta_VR - delta_VQ (local indices 0..2)."""
+    return float(V == R) - float(V == Q)
+
+
+def _face_tables():
+    """For the 6 P2 targets (3 vertex, 3 edge fns) and 3 Whitney targets on a face with local vertices (0,1,2) =
+    (A,B,E) and local edges e0=(0,1), e1=(1,2), e2=(0,2): the pair (u, w) = (c_fa*l_AE, c_fb*l_AB)."""
+    edges = [(0, 1), (1, 2), (0, 2)]
+
+    def solve(Edot):           # Edot(u, Q, R) = E_u . (v_R - v_Q)
+        s = {e: -(Edot(e[0], *e) + Edot(e[1], *e)) for e in edges}
+        Ec_AB = sum(Edot(u, 0, 1) for u in range(3)) / 3.0
+        Ec_AE = sum(Edot(u, 0, 2) for u in range(3)) / 3.0
+        R1 = 9 * Ec_AB + 2 * s[(0, 1)] - s[(1, 2)] + s[(0, 2)]
+        R2 = 9 * Ec_AE + s[(0, 1)] + s[(1, 2)] + 2 * s[(0, 2)]
+        return (2 * R2 - R1) / 3.0, (R2 - 2 * R1) / 3.0
+
+    vert = [solve(lambda u, Q, R, V=V: (4.0 * (u == V) - 1.0) * _gdot(V, Q, R)) for V in range(3)]
+    edge = [solve(lambda u, Q, R, P_=P_, Q_=Q_: 4.0 * ((u == P_) * _gdot(Q_, Q, R) + (u == Q_) * _gdot(P_, Q, R)))
+            for (P_, Q_) in edges]
+    whit = [solve(lambda u, Q, R, P_=P_, Q_=Q_: (u == Q_) * _gdot(P_, Q, R) - (u == P_) * _gdot(Q_, Q, R))
+            for (P_, Q_) in edges]
+    return np.array(vert), np.array(edge), np.array(whit)
+
+
+def build_aux_spaces(tables):
+    """tables: MeshTables-like (nodes (3,nN), edges (2,nE), tris (3,nTri), tri_to_edge (3,nTri), edge_lengths).
+    Returns (G, P, G1) as scipy CSR in the reference's dof numbering
+    [edge-a | face-a | edge-b | face-b] (fem/elements/nedelec2.py:46-62)."""
+    nodes = np.asarray(tables.nodes)
+    edges = np.asarray(tables.edges)
+    tris = np.asarray(tables.tris)
+    t2e = np.asarray(tables.tri_to_edge)
+    nN, nE, nTri = nodes.shape[1], edges.shape[1], tris.shape[1]
+    N = 2 * nE + 2 * nTri
+    d = nodes[:, edges[1]] - nodes[:, edges[0]]
+    ell = np.sqrt((d ** 2).sum(axis=0))
+    il = 1.0 / ell
+    ea, eb = np.arange(nE), np.arange(nE) + nE + nTri
+    fa, fb = np.arange(nTri) + nE, np.arange(nTri) + 2 * nE + nTri
+    A, Bv = edges[0], edges[1]
+    ecol = nN + np.arange(nE)
+    # edge rows of G: c_a = -grad(phi)(v_A).t, c_b = -grad(phi)(v_B).t
+    rows = [ea, ea, ea, eb, eb, eb]
+    cols = [A, Bv, ecol, A, Bv, ecol]
+    vals = [3 * il, 1 * il, -4 * il, -1 * il, -3 * il, 4 * il]
+    # face rows
+    vt, et, wt = _face_tables()
+    lAE = ell[t2e[2]]         # tri edges (1-2, 2-3, 1-3) = (A,B),(B,E),(A,E)  (fem/mesh3d.py:330-335)
+    lAB = ell[t2e[0]]
+    for k in range(3):        # vertex targets
+        rows += [fa, fb]
+        cols += [tris[k], tris[k]]
+        vals += [vt[k, 0] / lAE, vt[k, 1] / lAB]
+    for k in range(3):        # edge targets
+        rows += [fa, fb]
+        cols += [nN + t2e[k], nN + t2e[k]]
+        vals += [et[k, 0] / lAE, et[k, 1] / lAB]
+    r = np.concatenate([np.broadcast_to(x, v.shape) for x, v in zip(rows, vals)])
+    c = np.concatenate([np.broadcast_to(x, v.shape) for x, v in zip(cols, vals)])
+    v = np.concatenate(vals)
+    keep = v != 0
+    G = sp.coo_matrix((v[keep], (r[keep], c[keep])), shape=(N, nN + nE)).tocsr()
+    # Whitney prolongation
+    rows = [ea, eb]
+    cols = [ea, ea]
+    vals = [il, il]
+    for k in range(3):
+        rows += [fa, fb]
+        cols += [t2e[k], t2e[k]]
+        vals += [wt[k, 0] / lAE, wt[k, 1] / lAB]
+    r = np.concatenate([np.broadcast_to(x, v.shape) for x, v in zip(rows, vals)])
+    c = np.concatenate([np.broadcast_to(x, v.shape) for x, v in zip(cols, vals)])
+    v = np.concatenate(vals)
+    keep = v != 0
+    P = sp.coo_matrix((v[keep], (r[keep], c[keep])), shape=(N, nE)).tocsr()
+    # P1 gradient in the Whitney basis: grad(lam_v) = sum_e G1[e,v] w_e ; w_AB.t_AB = -1/l  =>  G1[e,A]=+1, G1[e,B]=-1
+    G1 = sp.coo_matrix((np.concatenate([np.ones(nE), -np.ones(nE)]),
+                        (np.concatenate([ea, ea]), np.concatenate([A, Bv]))), shape=(nE, nN)).tocsr()
+    return G, P, G1

@@ -12,7 +12,8 @@ extern "C" int emb_create(int device, emb_ctx** out) {
     emb_ctx* c = new emb_ctx();
     c->device = device;
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess) {
+        cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess ||
+        cudaEventCreate(&c->evs0) != cudaSuccess || cudaEventCreate(&c->evs1) != cudaSuccess) {
         delete c;
         return EMB_ERR_CUDA;
     }
@@ -36,7 +37,13 @@ extern "C" void emb_destroy(emb_ctx* c) {
     c->K.release(); c->M.release(); c->newid.release(); c->solve_ids.release(); c->rowptr_s.release();
     c->col_s.release(); c->src.release(); c->A.release(); c->xs.release(); c->xfull.release();
     for (auto& w : c->work) w.release();
-    c->dinv.release(); c->pairmate.release(); c->red.release();
+    c->dinv.release(); c->pairmate.release(); c->red.release(); c->As.release();
+    for (auto& a : c->aux) {
+        a.rptr.release(); a.tptr.release(); a.rcol.release(); a.tcol.release(); a.rval.release(); a.tval.release();
+        a.dinv.release(); a.tmp.release();
+    }
+    cudaEventDestroy(c->evs0);
+    cudaEventDestroy(c->evs1);
     for (auto& s : c->surf) release_surface(s);
     cudaEventDestroy(c->ev0);
     cudaEventDestroy(c->ev1);

@@ -40,6 +40,15 @@ struct Surface {
     bool has_rhs = false;
 };
 
+// auxiliary space of the additive multilevel preconditioner: real transfer matrix R (Ns x ncol) and R^T, both CSR
+struct AuxSpace {
+    int64_t ncol = 0, nnz = 0;
+    DevBuf<int64_t> rptr, tptr;     // R rows [Ns+1], R^T rows [ncol+1]
+    DevBuf<int> rcol, tcol;
+    DevBuf<double> rval, tval;
+    DevBuf<cx> dinv, tmp;           // 1/diag(R^T A R), scratch [ncol]
+};
+
 struct emb_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -90,6 +99,13 @@ struct emb_ctx {
     DevBuf<cx> dinv;          // Jacobi / block-Jacobi inverse blocks
     DevBuf<int> pairmate;     // solve-space index of the paired dof (block-Jacobi) or -1
     DevBuf<double> red;       // reduction scratch
+    std::vector<AuxSpace> aux;
+    DevBuf<cx> As;            // symmetric part of A (COCR operator), cached between solves of one frequency
+    bool have_As = false;
+    int As_precond = -1;
+    double spmv_ms_sum = 0;   // sampled SpMV timings inside solves (CUDA events)
+    int64_t spmv_ms_cnt = 0;
+    cudaEvent_t evs0 = nullptr, evs1 = nullptr;
 };
 
 template <typename T>

@@ -569,5 +569,6 @@ extern "C" int emb_form_A(emb_ctx* c, double k0, int nsurf, const int* sids, con
     }
     c->k0 = k0;
     c->have_A = true;
+    c->have_As = false;
     return EMB_OK;
 }

@@ -208,6 +208,87 @@ __global__ void k_precond_apply(int64_t ns, const cx* __restrict__ dinv, const i
     z[i] = v;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// auxiliary-space corrections  z += R diag(R^T A R)^-1 R^T r   (R real, CSR; R^T CSR)
+// ------------------------------------------------------------------------------------------------
+// one warp per aux column k: d_k = sum_{i,j in supp(k)} R_ik A_ij R_jk, supp(k) = row k of R^T (sorted by i)
+__global__ void __launch_bounds__(256) k_aux_diag(int64_t ncol, const int64_t* __restrict__ tptr, const int* __restrict__ tcol,
+                                                  const double* __restrict__ tval, const int64_t* __restrict__ rowptr,
+                                                  const int* __restrict__ col, const cx* __restrict__ A, cx* __restrict__ dinv) {
+    const int lane = threadIdx.x & 31;
+    const int64_t k = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (k >= ncol) return;
+    const int64_t p0 = tptr[k], p1 = tptr[k + 1];
+    double ar = 0, ai = 0;
+    for (int64_t m = p0; m < p1; ++m) {
+        const int i = tcol[m];
+        const double ri = tval[m];
+        for (int64_t e = rowptr[i] + lane; e < rowptr[i + 1]; e += 32) {
+            const int j = col[e];
+            int64_t lo = p0, hi = p1 - 1;
+            while (lo < hi) {
+                int64_t mid = (lo + hi) >> 1;
+                if (tcol[mid] < j) lo = mid + 1; else hi = mid;
+            }
+            if (tcol[lo] == j) {
+                const double w = ri * tval[lo];
+                const cx a = A[e];
+                ar += w * a.re;
+                ai += w * a.im;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        ar += __shfl_down_sync(0xffffffffu, ar, o);
+        ai += __shfl_down_sync(0xffffffffu, ai, o);
+    }
+    if (lane == 0) {
+        const double n2 = ar * ar + ai * ai;
+        dinv[k] = n2 > 0 ? cdiv(mk(1.0), cx{ar, ai}) : mk(0.0);
+    }
+}
+// t[k] = dinv[k] * sum_i RT[k,i] r[i]     (8 lanes per aux column)
+__global__ void __launch_bounds__(256) k_aux_restrict(int64_t ncol, const int64_t* __restrict__ tptr, const int* __restrict__ tcol,
+                                                      const double* __restrict__ tval, const cx* __restrict__ dinv,
+                                                      const cx* __restrict__ r, cx* __restrict__ t) {
+    const int64_t gt = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t k = gt >> 3;
+    const int sub = (int)(gt & 7);
+    double ar = 0, ai = 0;
+    if (k < ncol)
+        for (int64_t m = tptr[k] + sub; m < tptr[k + 1]; m += 8) {
+            const double w = tval[m];
+            const double2 v = __ldg(reinterpret_cast<const double2*>(r + tcol[m]));
+            ar += w * v.x;
+            ai += w * v.y;
+        }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+        ar += __shfl_down_sync(0xffffffffu, ar, o, 8);
+        ai += __shfl_down_sync(0xffffffffu, ai, o, 8);
+    }
+    if (k < ncol && sub == 0) t[k] = dinv[k] * cx{ar, ai};
+}
+// z[i] += sum_k R[i,k] t[k]     (thread per row; rows of R are short)
+__global__ void __launch_bounds__(256) k_aux_prolong(int64_t n, const int64_t* __restrict__ rptr, const int* __restrict__ rcol,
+                                                     const double* __restrict__ rval, const cx* __restrict__ t, cx* __restrict__ z) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double ar = 0, ai = 0;
+    for (int64_t m = rptr[i]; m < rptr[i + 1]; ++m) {
+        const double w = rval[m];
+        const double2 v = __ldg(reinterpret_cast<const double2*>(t + rcol[m]));
+        ar += w * v.x;
+        ai += w * v.y;
+    }
+    cx zi = z[i];
+    zi.re += ar;
+    zi.im += ai;
+    z[i] = zi;
+}
+
 // ------------------------------------------------------------------------------------------------
 // fused COCR kernels (device scalars: sc[0]=zAz, sc[1]=alpha, sc[2]=beta, sc[3]=|r|^2, sc[4]=zAz_new)
 // ------------------------------------------------------------------------------------------------
@@ -284,7 +365,16 @@ static int dot_host(emb_ctx* c, bool conj, const cx* a, const cx* b, cx* out) {
     return EMB_OK;
 }
 
-static int precond_setup(emb_ctx* c, int mode, const cx* val) {
+static int precond_setup(emb_ctx* c, int mode_in, const cx* val) {
+    const int mode = mode_in == 3 ? 2 : mode_in;
+    if (mode_in == 3) {
+        if (c->aux.empty()) { c->err = "precond=3 needs auxiliary spaces (emb_aux_add)"; return EMB_ERR_STATE; }
+        for (auto& a : c->aux) {
+            k_aux_diag<<<blocks_for(a.ncol * 32, 256), 256, 0, c->stream>>>(a.ncol, a.tptr.p, a.tcol.p, a.tval.p, c->rowptr_s.p,
+                                                                            c->col_s.p, val, a.dinv.p);
+            EMB_LAUNCH_CHECK(c);
+        }
+    }
     EMB_TRY(dev_alloc(c, c->dinv, (size_t)c->Ns * 2));
     if (mode == 2 && !c->pairmate.p) {
         EMB_TRY(dev_alloc(c, c->pairmate, (size_t)c->Ns));
@@ -297,8 +387,15 @@ static int precond_setup(emb_ctx* c, int mode, const cx* val) {
     return EMB_OK;
 }
 static int precond_apply(emb_ctx* c, int mode, const cx* r, cx* z) {
-    k_precond_apply<<<blocks_for(c->Ns, 256), 256, 0, c->stream>>>(c->Ns, c->dinv.p, mode == 2 ? c->pairmate.p : nullptr, r, z);
+    k_precond_apply<<<blocks_for(c->Ns, 256), 256, 0, c->stream>>>(c->Ns, c->dinv.p, mode >= 2 ? c->pairmate.p : nullptr, r, z);
     EMB_LAUNCH_CHECK(c);
+    if (mode == 3)
+        for (auto& a : c->aux) {
+            k_aux_restrict<<<blocks_for(a.ncol * 8, 256), 256, 0, c->stream>>>(a.ncol, a.tptr.p, a.tcol.p, a.tval.p, a.dinv.p, r, a.tmp.p);
+            EMB_LAUNCH_CHECK(c);
+            k_aux_prolong<<<blocks_for(c->Ns, 256), 256, 0, c->stream>>>(c->Ns, a.rptr.p, a.rcol.p, a.rval.p, a.tmp.p, z);
+            EMB_LAUNCH_CHECK(c);
+        }
     return EMB_OK;
 }
 
@@ -325,7 +422,10 @@ static int cocr(emb_ctx* c, int pmode, const cx* As, const cx* rhs, cx* d, doubl
         EMB_TRY(precond_apply(c, pmode, Ap, MAp));
         k_dot<false><<<NPART, VBLOCK, 0, c->stream>>>(n, Ap, MAp, partA); EMB_LAUNCH_CHECK(c);
         k_cocr_update<<<NPART, VBLOCK, 0, c->stream>>>(n, partA, sc, p, Ap, MAp, d, r, z, partR); EMB_LAUNCH_CHECK(c);
+        const bool sample = ((it + 1) % check == 0);
+        if (sample) cudaEventRecord(c->evs0, c->stream);
         EMB_TRY(spmv(c, As, z, Az)); ++*spmvs;
+        if (sample) cudaEventRecord(c->evs1, c->stream);
         k_dot<false><<<NPART, VBLOCK, 0, c->stream>>>(n, z, Az, partZ); EMB_LAUNCH_CHECK(c);
         k_cocr_dir<<<NPART, VBLOCK, 0, c->stream>>>(n, partZ, partR, sc, z, Az, p, Ap); EMB_LAUNCH_CHECK(c);
         k_cocr_commit<<<1, 1, 0, c->stream>>>(sc); EMB_LAUNCH_CHECK(c);
@@ -334,6 +434,10 @@ static int cocr(emb_ctx* c, int pmode, const cx* As, const cx* rhs, cx* d, doubl
             cx h[5];
             EMB_CUDA(c, cudaMemcpyAsync(h, sc, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
             EMB_CUDA(c, cudaStreamSynchronize(c->stream));
+            if (it % check == 0) {
+                float sms = 0;
+                if (cudaEventElapsedTime(&sms, c->evs0, c->evs1) == cudaSuccess) { c->spmv_ms_sum += sms; c->spmv_ms_cnt++; }
+            }
             rn = sqrt(fabs(h[3].re));
             if (!(rn == rn)) { c->err = "COCR breakdown (NaN)"; *its = it; *rnorm_out = rn; return EMB_NOT_CONVERGED; }
             if (rn <= stop_abs) break;
@@ -526,13 +630,21 @@ static int solve_device(emb_ctx* c, const emb_solve_opts* o, const cx* bs, cx* x
         EMB_TRY(bicgstab(c, o->precond, c->A.p, bs, xs, bnorm, o, &its, &spmvs, &relres));
     } else {
         // defect correction on A with COCR on the symmetric part
-        DevBuf<cx> As, rr, dd;
-        EMB_TRY(dev_alloc(c, As, (size_t)c->nnz_s));
+        DevBuf<cx> rr, dd;
+        DevBuf<cx>& As = c->As;
         EMB_TRY(dev_alloc(c, rr, (size_t)n));
         EMB_TRY(dev_alloc(c, dd, (size_t)n));
-        k_sym_part<<<blocks_for(n * 32, 256), 256, 0, c->stream>>>(n, c->rowptr_s.p, c->col_s.p, c->A.p, As.p);
-        EMB_LAUNCH_CHECK(c);
-        EMB_TRY(precond_setup(c, o->precond, As.p));
+        if (!c->have_As) {
+            EMB_TRY(dev_alloc(c, As, (size_t)c->nnz_s));
+            k_sym_part<<<blocks_for(n * 32, 256), 256, 0, c->stream>>>(n, c->rowptr_s.p, c->col_s.p, c->A.p, As.p);
+            EMB_LAUNCH_CHECK(c);
+            EMB_TRY(precond_setup(c, o->precond, As.p));
+            c->have_As = true;
+            c->As_precond = o->precond;
+        } else if (c->As_precond != o->precond) {
+            EMB_TRY(precond_setup(c, o->precond, As.p));
+            c->As_precond = o->precond;
+        }
         if (!o->use_x0) { k_zero<<<vb, 256, 0, c->stream>>>(n, xs); EMB_LAUNCH_CHECK(c); }
         double prev = 1e300;
         for (int outer = 0; outer < 30 && its < o->maxit; ++outer) {
@@ -564,7 +676,7 @@ static int solve_device(emb_ctx* c, const emb_solve_opts* o, const cx* bs, cx* x
             EMB_TRY(dot_host(c, true, rr.p, rr.p, &r2));
             relres = sqrt(r2.re) / bnorm;
         }
-        As.release(); rr.release(); dd.release();
+        rr.release(); dd.release();
         if (rc < 0) return rc;
     }
     if (o->method != 2 && bnorm > 0) {   // true residual at exit
@@ -776,4 +888,47 @@ extern "C" int emb_interp_last(emb_ctx* c, int64_t npts, const int64_t* tet_ids,
     if (!c || npts <= 0 || !tet_ids || !xyz || !E) return EMB_ERR_ARG;
     if (!c->xfull.p) { c->err = "emb_interp_last: no solution on the device"; return EMB_ERR_STATE; }
     return interp_impl(c, c->xfull.p, npts, tet_ids, xyz, E);
+}
+
+extern "C" int emb_aux_clear(emb_ctx* c) {
+    if (!c) return EMB_ERR_ARG;
+    for (auto& a : c->aux) {
+        a.rptr.release(); a.tptr.release(); a.rcol.release(); a.tcol.release(); a.rval.release(); a.tval.release();
+        a.dinv.release(); a.tmp.release();
+    }
+    c->aux.clear();
+    c->have_As = false;
+    return EMB_OK;
+}
+
+extern "C" int emb_aux_add(emb_ctx* c, int64_t ncol, const int64_t* Rp, const int32_t* Ri, const double* Rv, const int64_t* Tp,
+                           const int32_t* Ti, const double* Tv) {
+    if (!c || ncol <= 0 || !Rp || !Ri || !Rv || !Tp || !Ti || !Tv) return EMB_ERR_ARG;
+    if (!c->have_dirichlet) { c->err = "emb_aux_add: needs emb_set_dirichlet first (solve-space rows)"; return EMB_ERR_STATE; }
+    const int64_t nnz = Rp[c->Ns];
+    if (Tp[ncol] != nnz) { c->err = "emb_aux_add: R and R^T disagree on nnz"; return EMB_ERR_ARG; }
+    c->aux.emplace_back();
+    AuxSpace& a = c->aux.back();
+    a.ncol = ncol;
+    a.nnz = nnz;
+    EMB_TRY(h2d(c, a.rptr, Rp, (size_t)c->Ns + 1));
+    EMB_TRY(h2d(c, a.rcol, reinterpret_cast<const int*>(Ri), (size_t)nnz));
+    EMB_TRY(h2d(c, a.rval, Rv, (size_t)nnz));
+    EMB_TRY(h2d(c, a.tptr, Tp, (size_t)ncol + 1));
+    EMB_TRY(h2d(c, a.tcol, reinterpret_cast<const int*>(Ti), (size_t)nnz));
+    EMB_TRY(h2d(c, a.tval, Tv, (size_t)nnz));
+    EMB_TRY(dev_alloc(c, a.dinv, (size_t)ncol));
+    EMB_TRY(dev_alloc(c, a.tmp, (size_t)ncol));
+    EMB_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->have_As = false;
+    return EMB_OK;
+}
+
+extern "C" int emb_spmv_sampled(emb_ctx* c, double* avg_ms, int64_t* count) {
+    if (!c || !avg_ms || !count) return EMB_ERR_ARG;
+    *count = c->spmv_ms_cnt;
+    *avg_ms = c->spmv_ms_cnt ? c->spmv_ms_sum / c->spmv_ms_cnt : 0.0;
+    c->spmv_ms_sum = 0;
+    c->spmv_ms_cnt = 0;
+    return EMB_OK;
 }

@@ -26,7 +26,7 @@ class SolveInfo(C.Structure):
 
 
 METHODS = {"gmres": 0, "bicgstab": 1, "cocr": 2}
-PRECONDS = {"none": 0, "jacobi": 1, "block": 2}
+PRECONDS = {"none": 0, "jacobi": 1, "block": 2, "multilevel": 3}
 
 _SIGS = {
     "emb_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
@@ -55,6 +55,9 @@ _SIGS = {
     "emb_form_A": (C.c_int, [C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_void_p]),
     "emb_spmv_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "emb_spmv_bench": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double)]),
+    "emb_aux_clear": (C.c_int, [C.c_void_p]),
+    "emb_aux_add": (C.c_int, [C.c_void_p, C.c_int64] + [C.c_void_p] * 6),
+    "emb_spmv_sampled": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "emb_solve": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(SolveOpts), C.c_void_p, C.POINTER(SolveInfo)]),
     "emb_solve_rhs": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(SolveOpts), C.c_void_p, C.POINTER(SolveInfo)]),
     "emb_interp": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -243,6 +246,25 @@ class Context:
         ms = C.c_double()
         self._check(self.lib.emb_spmv_bench(self.h, reps, C.byref(ms)))
         return ms.value
+
+    def aux_clear(self):
+        self._check(self.lib.emb_aux_clear(self.h))
+
+    def aux_add(self, R):
+        """R: scipy sparse (n_solve x ncol) real transfer matrix of one auxiliary space."""
+        R = R.tocsr().astype(np.float64)
+        R.sort_indices()
+        T = R.T.tocsr()
+        T.sort_indices()
+        assert R.shape[0] == self.n_solve
+        a = [_c(R.indptr, np.int64), _c(R.indices, np.int32), _c(R.data, np.float64),
+             _c(T.indptr, np.int64), _c(T.indices, np.int32), _c(T.data, np.float64)]
+        self._check(self.lib.emb_aux_add(self.h, R.shape[1], *[_p(x) for x in a]))
+
+    def spmv_sampled(self):
+        ms, cnt = C.c_double(), C.c_int64()
+        self._check(self.lib.emb_spmv_sampled(self.h, C.byref(ms), C.byref(cnt)))
+        return ms.value, cnt.value
 
     @staticmethod
     def _opts(method="cocr", precond="block", restart=50, maxit=100000, rtol=1e-8, use_x0=False):

@@ -69,7 +69,7 @@ class FrequencySweep:
         self.ctx = ctx if ctx is not None else Context(device)
         self.timings = {}
         self._setup_done = False
-        self.solver_opts = dict(method="cocr", precond="block", rtol=1e-8, maxit=200000, restart=50)
+        self.solver_opts = dict(method="cocr", precond="multilevel", rtol=1e-8, maxit=200000, restart=50)
 
     # ------------------------------------------------------------------ setup (once)
     def setup(self):
@@ -103,6 +103,10 @@ class FrequencySweep:
             self.ntri[id(b)] = n
         ctx.set_dirichlet(pec)
         self.pec_ids = pec
+        if self.solver_opts.get("precond") == "multilevel":
+            t1 = time.perf_counter()
+            self._setup_aux_spaces()
+            self.timings["aux_setup_s"] = time.perf_counter() - t1
         # S-parameter sample points per port
         DP = dunavant4()
         nodes = np.asarray(t.nodes)
@@ -122,6 +126,33 @@ class FrequencySweep:
             if getattr(b, "v_integration", False):
                 self._setup_vline(b, ids)
         self._setup_done = True
+
+    def _setup_aux_spaces(self):
+        """Transfer matrices of the additive multilevel preconditioner restricted to the solve space; columns whose
+        support touches an eliminated dof are dropped (their potential / Whitney dof is fixed by the PEC condition)."""
+        from .auxspace import build_aux_spaces
+        G, P, G1 = build_aux_spaces(self.t)
+        N = G.shape[0]
+        keep = np.ones(N, dtype=bool)
+        keep[self.pec_ids] = False
+        elim = ~keep
+
+        def restrict(R):
+            bad = np.asarray(abs(R[elim]).sum(axis=0)).ravel() > 0
+            return R[keep][:, ~bad].tocsr(), bad
+        Gs, _ = restrict(G)
+        Ps, badP = restrict(P)
+        G1r = G1[~badP]
+        badN = np.asarray(abs(G1[badP]).sum(axis=0)).ravel() > 0
+        G1s = G1r[:, ~badN].tocsr()
+        self.ctx.aux_clear()
+        spaces = [Gs, Ps]
+        if G1s.shape[1] > 0:
+            spaces.append((Ps @ G1s).tocsr())
+        for R in spaces:
+            if R.shape[1] > 0:
+                self.ctx.aux_add(R)
+        self.aux_dims = [R.shape[1] for R in spaces]
 
     def _setup_vline(self, b, ids):
         """define_lumped_port_integration_points (emfreq3d.py:366-389) + point location for the 10 midpoints."""

@@ -91,9 +91,20 @@ int emb_spmv_host(emb_ctx* ctx, const emb_c128* x, emb_c128* y);
 /* times `reps` SpMVs on resident device vectors, returns avg ms per SpMV */
 int emb_spmv_bench(emb_ctx* ctx, int reps, double* ms_per_spmv);
 
+/* Auxiliary spaces of the additive multilevel preconditioner (precond = 3):
+ *   M^-1 = D^-1 + sum_k R_k diag(R_k^T A R_k)^-1 R_k^T
+ * R_k is a real sparse transfer matrix on the SOLVE space (n_solve x ncol), given as CSR together with its transpose
+ * (gradients of the quadratic Lagrange space, the Whitney space, and P1 gradients: emerge_b200/auxspace.py).
+ * The reference has no counterpart (it solves directly, fem/solver.py:243-309). */
+int emb_aux_clear(emb_ctx* ctx);
+int emb_aux_add(emb_ctx* ctx, int64_t ncol, const int64_t* R_indptr, const int32_t* R_indices, const double* R_data,
+                const int64_t* RT_indptr, const int32_t* RT_indices, const double* RT_data);
+/* average device time (ms) of the SpMVs sampled with CUDA events inside the solves since the last call, and their count */
+int emb_spmv_sampled(emb_ctx* ctx, double* avg_ms, int64_t* count);
+
 typedef struct {
-    int method;        /* 0 = GMRES(restart), 1 = BiCGStab, 2 = COCG (complex-symmetric) */
-    int precond;       /* 0 = none, 1 = Jacobi, 2 = block-Jacobi (2x2 edge/face pairs) */
+    int method;        /* 0 = GMRES(restart), 1 = BiCGStab, 2 = COCR on the symmetric part + defect correction */
+    int precond;       /* 0 = none, 1 = Jacobi, 2 = block-Jacobi (2x2 edge/face pairs), 3 = block-Jacobi + auxiliary spaces */
     int restart;       /* GMRES restart length */
     int maxit;
     double rtol;       /* ||b-Ax||/||b|| */

@@ -114,7 +114,8 @@ def test_Af_rhs_solution_sparams(name):
     ctx.close()
 
 
-@pytest.mark.parametrize("method,precond", [("gmres", "jacobi"), ("bicgstab", "block"), ("cocr", "jacobi")])
+@pytest.mark.parametrize("method,precond", [("gmres", "jacobi"), ("bicgstab", "block"), ("cocr", "jacobi"),
+                                            ("cocr", "block"), ("gmres", "multilevel")])
 def test_other_solvers_agree(method, precond):
     from emerge_b200.sweep import FrequencySweep
     g, t = load_golden("wg_tiny")
