@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+"""bench.py - frequency points/s of the EMerge frequency-domain hot path on B200 (BASELINE.json metric).
+
+A "step" is one frequency point of the sweep on the synthetic ~1M-tet rectangular waveguide (BASELINE config 4):
+numeric assembly of K and M (element kernel + deterministic reduction), A(f) formation, one Krylov solve per port
+(2 ports), S-parameter extraction.  `value` = frequency points per second with all inputs resident in HBM;
+`e2e` = the same through the host-buffer API (materials H2D from pinned memory, solved fields D2H every step).
+Multi-GPU: the sweep is sharded by contiguous frequency blocks, one process per GPU, no collective on the data
+path (NCCL only gathers the S-parameters and the timings) -> weak scaling.
+
+`--impl reference` times the reference's CPU path for the same metric on the host cores: the reference is pure
+Python + numba + SciPy and does not exist on the GPU box, so its CPU port (oracle/) runs it: closed-form element
+matrices, SciPy COO->CSR, K - k0^2 M + B_p, RCM + SuperLU direct solve (the reference's own fallback solver,
+fem/solver.py:535-573), on a bounded sub-sampled mesh of the same waveguide.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+METRIC = "freq_points_per_s"
+UNIT = "freq-points/s"
+A_WG, B_WG = 22.86e-3, 10.16e-3
+FREQS = np.linspace(8e9, 12e9, 201)
+
+
+def make_waveguide(nx, ny, nz):
+    from emerge_b200.synthmesh import box_mesh, mesh_tables, tri_ids_of
+    from emerge_b200 import bc as B
+    L = nz * A_WG / nx
+    box = box_mesh(nx, ny, nz, A_WG, B_WG, L)
+    t = mesh_tables(box.nodes_xyz, box.tets)
+    nT = t.tets.shape[1]
+    er = np.zeros((3, 3, nT), complex)
+    er[0, 0] = er[1, 1] = er[2, 2] = 1
+    ur = er.copy()
+    tag = lambda k: tri_ids_of(t, box.face_tris[box.face_tag == k])
+    bcs = [B.PEC(np.concatenate([tag(k) for k in (1, 2, 3, 4)])),
+           B.RectangularWaveguide(tag(5), 1, B.CoordSys(origin=(0, 0, 0)), (A_WG, B_WG)),
+           B.RectangularWaveguide(tag(6), 2, B.CoordSys(origin=(0, 0, L)), (A_WG, B_WG))]
+    return box, t, er, ur, bcs, L
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.samples, self.stop = index, [], False
+        self.th = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self.stop:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.samples.append([v.strip() for v in out.strip().split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def __enter__(self):
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop = True
+        self.th.join(timeout=6)
+
+    def summary(self):
+        sm = [float(s[0]) for s in self.samples if len(s) >= 6 and s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if len(s) >= 6 and s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for s in self.samples if len(s) >= 6 for n, v in zip(names, s[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def peaks():
+    p = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------------------ CPU port
+def cpu_port_setup(nx, ny, nz):
+    """Reference CPU path on a bounded sample (oracle port): returns a closure running one frequency point."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    from scipy.sparse.csgraph import reverse_cuthill_mckee
+    from oracle import ned2_oracle as O
+    box, t, er, ur, bcs, L = make_waveguide(nx, ny, nz)
+    N = t.n_field
+    state = {}
+
+    def assemble():
+        E, Bm = O.assemble_EB(t.nodes, t.tets, t.edges, t.tris, t.edge_lengths, t.tet_to_field, t.tet_to_edge, ur, er)
+        state["E"], state["B"] = E, Bm
+    pec = np.unique(np.asarray(t.tri_to_field)[:, bcs[0].tri_ids].ravel())
+    solve_ids = np.setdiff1d(np.arange(N), pec)
+    DP = O.dunavant4()
+    surf = []
+    for p in bcs[1:]:
+        ids = p.tri_ids
+        v = t.nodes[:, t.tris[:, ids]]
+        loc = np.einsum("ij,jvn->ivn", p.get_inv_basis(), v - p.cs.origin[:, None, None])
+        x, y = loc[0].T, loc[1].T
+        surf.append((p, ids, x, y, O.gen_csr_tri(N, t.tri_to_field, ids, O.tri_surface_matrix(x, y))))
+
+    def point(f):
+        k0 = 2 * np.pi * f / 299792458
+        K = (state["E"] - state["B"] * k0 ** 2).tocsr()                      # assembler.py:333
+        rhs = []
+        for p, ids, x, y, S in surf:
+            K = K + complex(p.get_gamma(k0)) * S                             # assembler.py:383
+            xq, yq = x @ DP[1:4], y @ DP[1:4]
+            U = p.get_Uinc(xq.T.ravel(), yq.T.ravel(), k0).reshape(3, 6, len(ids))
+            bv = np.zeros(N, dtype=complex)
+            np.add.at(bv, t.tri_to_field[:, ids].T, O.tri_forcing(x, y, U[:2]))
+            rhs.append(bv)
+        Asel = K.tocsc()[np.ix_(solve_ids, solve_ids)]                       # solver.py:434
+        perm = reverse_cuthill_mckee(Asel.tocsr(), symmetric_mode=False)     # solver.py:146
+        Asort = Asel[perm][:, perm].tocsc()
+        lu = spla.splu(Asort, permc_spec="MMD_AT_PLUS_A", diag_pivot_thresh=0.01,
+                       options=dict(SymmetricMode=True))                     # solver.py:269
+        out = []
+        for bv in rhs:
+            xs = lu.solve(bv[solve_ids][perm])
+            out.append(xs)
+        return out
+    return t, assemble, point
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    nx, ny, nz = args.ref_cells
+    t0 = time.perf_counter()
+    t, assemble, point = cpu_port_setup(nx, ny, nz)
+    assemble()
+    setup_s = time.perf_counter() - t0
+    fr = FREQS
+    for i in range(args.warmup):
+        point(fr[i % len(fr)])
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        point(fr[(args.warmup + i) % len(fr)])
+    dt = time.perf_counter() - t0
+    val = args.steps / dt
+    cores = os.cpu_count()
+    sample = (f"{t.tets.shape[1]}-tet / {t.n_field}-dof sub-sampled WR-90 waveguide ({nx}x{ny}x{nz} cells), per step: "
+              f"K(f) formation + RCM + SuperLU factorisation + 2 port solves (SciPy, 1 thread by construction: "
+              f"SuperLU is serial); assembly ({setup_s:.1f}s) outside the steps as the reference caches E,B")
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64/c128", "data": "synthetic",
+            "config": workload_config(args),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "host_cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args):
+    nx, ny, nz = args.cells
+    return {"workload": f"synthetic WR-90 rectangular waveguide, {nx}x{ny}x{nz} cells x 6 Kuhn tets = {6*nx*ny*nz} tets, "
+                        f"2 RectangularWaveguide ports + PEC walls, 201-point sweep 8-12 GHz (BASELINE config 4); "
+                        f"step = one frequency point (K/M assembly + A(f) + 2 port solves + S-parameters)",
+            "cells": [nx, ny, nz], "rtol": args.rtol, "solver": "COCR(sym. part)+defect correction, additive multilevel preconditioner",
+            "l2_policy": "inputs larger than L2 (A(f) alone is 5.3 GB at 1M tets)", "parallelism": f"freq-block x{args.gpus}"}
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_gpu(args):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from emerge_b200.sweep import FrequencySweep
+    nx, ny, nz = args.cells
+    t0 = time.perf_counter()
+    box, t, er, ur, bcs, L = make_waveguide(nx, ny, nz)
+    host_mesh_s = time.perf_counter() - t0
+    sw = FrequencySweep(t, er, ur, bcs, device=local)
+    sw.solver_opts.update(rtol=args.rtol, precond=args.precond)
+    t0 = time.perf_counter()
+    sw.setup()
+    setup_s = time.perf_counter() - t0
+    ctx = sw.ctx
+    nnz_s, Ns, N = int(ctx.lib.emb_csr_nnz(ctx.h, 2)), ctx.n_solve, ctx.n_field
+    # frequency block of this rank (contiguous), W warm-up + K timed points
+    nf = len(FREQS)
+    blk = nf // world
+    f0 = rank * blk
+    mine = [FREQS[(f0 + i) % nf] for i in range(args.warmup + args.steps)]
+    for p in sw.ports:
+        p.active = False
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(f, out_bufs=None):
+        ctx.assemble_KM()
+        return sw.solve_point(f, out_bufs=out_bufs)
+
+    for f in mine[:args.warmup]:
+        step(f)
+    ctx.spmv_sampled()
+    iters, S_list = [], []
+    barrier()
+    l0 = ctx.launches
+    with ClockSampler(local) as cs:
+        ctx.timer_start()
+        for f in mine[args.warmup:]:
+            S, st, _ = step(f)
+            S_list.append(S)
+            iters.extend(s["iters"] for s in st)
+        ms = ctx.timer_stop()
+    barrier()
+    launches = ctx.launches - l0
+    spmv_ms, spmv_cnt = ctx.spmv_sampled()
+    # e2e: host buffers in pinned memory, H2D of the materials and D2H of the fields inside the timed region
+    er_p = torch.from_numpy(er).pin_memory().numpy()
+    ur_p = torch.from_numpy(ur).pin_memory().numpy()
+    outs = {p.port_number: torch.empty(N, dtype=torch.complex128).pin_memory().numpy() for p in sw.ports}
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    barrier()
+    ctx.timer_start()
+    for f in mine[args.warmup:args.warmup + e2e_steps]:
+        ctx.upload_materials(er_p, ur_p)
+        step(f, out_bufs=outs)
+    ms_e2e = ctx.timer_stop()
+    barrier()
+    h2d = er_p.nbytes + ur_p.nbytes + sum(18 * 16 * sw.ntri[id(p)] for p in sw.ports)
+    d2h = sum(o.nbytes for o in outs.values()) + sum(2 * 3 * 16 * sw._sp[id(p)]["pts"].shape[1] * len(sw.ports) for p in sw.ports)
+    # max over ranks
+    tm = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=f"cuda:{local}")
+    if dist is not None:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        Sg = [None] * world
+        dist.all_gather_object(Sg, [s.tolist() for s in S_list] if False else None)
+        St = torch.view_as_real(torch.tensor(np.array(S_list), device=f"cuda:{local}")).contiguous()
+        gath = [torch.empty_like(St) for _ in range(world)]
+        dist.all_gather(gath, St)                      # NCCL: S-parameter blocks (the only data-path-adjacent collective)
+    ms_max, ms_e2e_max = float(tm[0]), float(tm[1])
+    if rank == 0:
+        value = world * args.steps / (ms_max / 1e3)
+        e2e_val = world * e2e_steps / (ms_e2e_max / 1e3)
+        peak, peak_src = peaks()
+        spmv_bytes = 20 * nnz_s + 36 * Ns + 4
+        achieved = spmv_bytes / (spmv_ms * 1e-3) / 1e9 if spmv_ms > 0 else None
+        traffic = None
+        tp = os.path.join(REPO, "profiles", "spmv_traffic.json")
+        if os.path.exists(tp) and (nx, ny, nz) == (44, 20, 190):
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        S21 = [abs(s[1, 0]) for s in S_list]
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64/c128", "data": "synthetic", "config": workload_config(args),
+                "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                        "steps": e2e_steps},
+                "gpu_launches": int(launches),
+                "roofline": {"kernel": "k_spmv<8> (complex CSR SpMV inside COCR)", "bound": "hbm", "achieved": achieved,
+                             "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                             "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+                             "algorithmic_bytes_per_launch": spmv_bytes, "avg_launch_ms": spmv_ms, "sampled_launches": spmv_cnt},
+                "assembly": {"tet_kernel_ms": ctx.last_ms("tet_kernel"), "reduce_ms": ctx.last_ms("reduce"),
+                             "Mtet_per_s": t.tets.shape[1] / ((ctx.last_ms("tet_kernel") + ctx.last_ms("reduce")) * 1e3),
+                             "symbolic_ms": sw.timings.get("symbolic_ms"), "form_A_ms": ctx.last_ms("form_A")},
+                "solver": {"iters_per_solve": float(np.mean(iters)), "max_iters": int(max(iters)), "rtol": args.rtol,
+                           "abs_S21_minmax": [min(S21), max(S21)]},
+                "sizes": {"tets": int(t.tets.shape[1]), "n_field": N, "n_solve": Ns, "nnz_solve": nnz_s},
+                "setup": {"host_mesh_tables_s": host_mesh_s, "gpu_setup_s": setup_s, **{k: v for k, v in sw.timings.items()}},
+                "clocks": cs.summary()}
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args)
+            line["same_size_as_cpu_sample"] = gpu_same_size(args, local)
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def gpu_same_size(args, device):
+    """This GPU path on exactly the mesh the CPU baseline / reference arm uses (equal-size comparison)."""
+    from emerge_b200.sweep import FrequencySweep
+    nx, ny, nz = args.ref_cells
+    box, t, er, ur, bcs, L = make_waveguide(nx, ny, nz)
+    sw = FrequencySweep(t, er, ur, bcs, device=device)
+    sw.solver_opts.update(rtol=args.rtol, precond=args.precond)
+    sw.setup()
+    for f in FREQS[:2]:
+        sw.ctx.assemble_KM()
+        sw.solve_point(f)
+    n = 4
+    sw.ctx.timer_start()
+    for i in range(n):
+        sw.ctx.assemble_KM()
+        sw.solve_point(FREQS[i * 50])
+    ms = sw.ctx.timer_stop()
+    sw.ctx.close()
+    return {"cells": [nx, ny, nz], "tets": int(t.tets.shape[1]), "value": n / (ms / 1e3), "unit": UNIT}
+
+
+def cpu_baseline(args):
+    """Oracle port (kind "port") on rank 0's host cores, bounded sample of the same workload."""
+    nx, ny, nz = args.ref_cells
+    t0 = time.perf_counter()
+    t, assemble, point = cpu_port_setup(nx, ny, nz)
+    assemble()
+    asm_s = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    n = 2
+    for i in range(n):
+        point(FREQS[i * 50])
+    dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": UNIT, "cores": 1, "host_cores": os.cpu_count(), "kind": "port",
+            "sample": f"{t.tets.shape[1]}-tet / {t.n_field}-dof sub-sampled waveguide ({nx}x{ny}x{nz} cells), {n} frequency points: "
+                      f"K(f) + RCM + SuperLU + 2 solves per point (SciPy; SuperLU is serial); oracle assembly {asm_s:.1f}s "
+                      f"({t.tets.shape[1]/asm_s/1e6:.4f} Mtet/s, numpy port) not included"}
+
+
+REF_CANDIDATES = [(6, 3, 10), (8, 4, 16), (10, 5, 20), (12, 6, 24), (12, 6, 30), (14, 7, 30), (16, 8, 36)]
+
+
+def pick_ref_cells(total_steps, budget_s=150.0):
+    """Largest sub-sampled waveguide whose SuperLU steps fit the time budget: step ~ 27.7 s x (tets/12960)^2.3
+    (27.7 s per frequency at 12,960 tets on this class of host)."""
+    best = REF_CANDIDATES[0]
+    for c in REF_CANDIDATES:
+        nT = 6 * c[0] * c[1] * c[2]
+        if total_steps * 27.7 * (nT / 12960.0) ** 2.3 <= budget_s:
+            best = c
+    return best
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="emerge_b200", choices=["emerge_b200", "reference"])
+    ap.add_argument("--cells", type=lambda s: tuple(int(v) for v in s.split(",")), default=(44, 20, 190))
+    ap.add_argument("--ref-cells", type=lambda s: tuple(int(v) for v in s.split(",")), default=None)
+    ap.add_argument("--rtol", type=float, default=1e-8)
+    ap.add_argument("--precond", default="multilevel")
+    ap.add_argument("--e2e-steps", type=int, default=1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.ref_cells is None:
+        args.ref_cells = pick_ref_cells(args.steps + args.warmup) if args.impl == "reference" else pick_ref_cells(3, 60.0)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -96,3 +96,20 @@ extern "C" int emb_get_csr(emb_ctx* c, int which, int64_t* indptr, int32_t* indi
     EMB_CUDA(c, cudaStreamSynchronize(c->stream));
     return EMB_OK;
 }
+
+extern "C" int emb_timer_start(emb_ctx* c) {
+    if (!c) return EMB_ERR_ARG;
+    if (!c->evt0) { EMB_CUDA(c, cudaEventCreate(&c->evt0)); EMB_CUDA(c, cudaEventCreate(&c->evt1)); }
+    EMB_CUDA(c, cudaStreamSynchronize(c->stream));
+    EMB_CUDA(c, cudaEventRecord(c->evt0, c->stream));
+    return EMB_OK;
+}
+extern "C" int emb_timer_stop(emb_ctx* c, double* ms) {
+    if (!c || !ms || !c->evt0) return EMB_ERR_ARG;
+    EMB_CUDA(c, cudaEventRecord(c->evt1, c->stream));
+    EMB_CUDA(c, cudaEventSynchronize(c->evt1));
+    float f = 0;
+    EMB_CUDA(c, cudaEventElapsedTime(&f, c->evt0, c->evt1));
+    *ms = f;
+    return EMB_OK;
+}

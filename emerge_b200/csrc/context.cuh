@@ -105,7 +105,7 @@ struct emb_ctx {
     int As_precond = -1;
     double spmv_ms_sum = 0;   // sampled SpMV timings inside solves (CUDA events)
     int64_t spmv_ms_cnt = 0;
-    cudaEvent_t evs0 = nullptr, evs1 = nullptr;
+    cudaEvent_t evs0 = nullptr, evs1 = nullptr, evt0 = nullptr, evt1 = nullptr;
 };
 
 template <typename T>

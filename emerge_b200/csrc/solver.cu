@@ -120,7 +120,9 @@ __global__ void k_axpby(int64_t n, const cx* __restrict__ sa, double fa, const c
                         double fb, cx* __restrict__ y) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const cx a = sa ? fa * (*sa) : mk(fa), b = sb ? fb * (*sb) : mk(fb);
+    const cx a = sa ? fa * (*sa) : mk(fa);
+    if (!sb && fb == 0.0) { y[i] = a * x[i]; return; }      // do not read an uninitialised y
+    const cx b = sb ? fb * (*sb) : mk(fb);
     y[i] = a * x[i] + b * y[i];
 }
 __global__ void k_gather(int64_t ns, const int* __restrict__ ids, const cx* __restrict__ full, cx* __restrict__ sub) {

@@ -35,6 +35,8 @@ _SIGS = {
     "emb_version": (C.c_char_p, []),
     "emb_launch_count": (C.c_int64, [C.c_void_p]),
     "emb_last_ms": (C.c_double, [C.c_void_p, C.c_char_p]),
+    "emb_timer_start": (C.c_int, [C.c_void_p]),
+    "emb_timer_stop": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "emb_upload_mesh": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64] + [C.c_void_p] * 5),
     "emb_upload_materials": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "emb_symbolic": (C.c_int, [C.c_void_p]),
@@ -144,6 +146,14 @@ class Context:
 
     def last_ms(self, phase: str) -> float:
         return float(self.lib.emb_last_ms(self.h, phase.encode()))
+
+    def timer_start(self):
+        self._check(self.lib.emb_timer_start(self.h))
+
+    def timer_stop(self) -> float:
+        ms = C.c_double()
+        self._check(self.lib.emb_timer_stop(self.h, C.byref(ms)))
+        return ms.value
 
     @property
     def n_field(self) -> int:
@@ -270,10 +280,10 @@ class Context:
     def _opts(method="cocr", precond="block", restart=50, maxit=100000, rtol=1e-8, use_x0=False):
         return SolveOpts(METHODS[method], PRECONDS[precond], restart, maxit, rtol, int(use_x0))
 
-    def solve(self, sid, want_x=True, raise_on_fail=True, **kw):
+    def solve(self, sid, want_x=True, raise_on_fail=True, out=None, **kw):
         o = self._opts(**kw)
         info = SolveInfo()
-        x = np.zeros(self.n_field, dtype=np.complex128) if want_x else None
+        x = out if out is not None else (np.zeros(self.n_field, dtype=np.complex128) if want_x else None)
         rc = self._check(self.lib.emb_solve(self.h, sid, C.byref(o), _p(x), C.byref(info)), allow_positive=not raise_on_fail)
         return x, dict(iters=info.iters, relres=info.relres, ms=info.ms, spmvs=info.spmvs, converged=rc == 0)
 

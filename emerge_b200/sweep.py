@@ -234,6 +234,29 @@ class FrequencySweep:
         self.ctx.form_A(k0, sids, gammas)
         return k0
 
+    def solve_point(self, freq, keep_fields=False, raise_on_fail=True, out_bufs=None):
+        """One frequency point: A(f), one solve per port, S-parameters.  Returns (S (P,P), stats list, fields dict).
+        out_bufs: optional {port_number: preallocated (pinned) complex128[n_field]} receiving the fields."""
+        ports = self.ports
+        S = np.zeros((len(ports), len(ports)), dtype=np.complex128)
+        stats, fields = [], {}
+        k0 = self.assemble_frequency(freq)
+        for ja, pa in enumerate(ports):
+            pa.active = True
+            want = keep_fields or (out_bufs is not None)
+            out = out_bufs.get(pa.port_number) if out_bufs else None
+            x, info = self.ctx.solve(self.sid[id(pa)], want_x=want, raise_on_fail=raise_on_fail, out=out, **self.solver_opts)
+            info.update(freq=float(freq), port=pa.port_number)
+            stats.append(info)
+            if keep_fields:
+                fields[pa.port_number] = x
+            _, pout = self._s_data(pa, k0, None)
+            for ib, pb in enumerate(ports):
+                pf, _ = self._s_data(pb, k0, None)
+                S[ib, ja] = pf / pout
+            pa.active = False
+        return S, stats, fields
+
     def run(self, freqs, keep_fields=False, raise_on_fail=True) -> SweepResult:
         if not self._setup_done:
             self.setup()
@@ -244,18 +267,9 @@ class FrequencySweep:
         for p in ports:
             p.active = False
         for i, f in enumerate(freqs):
-            k0 = self.assemble_frequency(f)
-            for ja, pa in enumerate(ports):
-                pa.active = True
-                x, info = self.ctx.solve(self.sid[id(pa)], want_x=True, raise_on_fail=raise_on_fail, **self.solver_opts)
-                info.update(freq=float(f), port=pa.port_number)
-                res.stats.append(info)
-                if keep_fields:
-                    res.fields[(i, pa.port_number)] = x
-                _, pout = self._s_data(pa, k0, None)
-                for ib, pb in enumerate(ports):
-                    pf, _ = self._s_data(pb, k0, None)
-                    S[i, ib, ja] = pf / pout
-                pa.active = False
+            S[i], st, fl = self.solve_point(f, keep_fields, raise_on_fail)
+            res.stats.extend(st)
+            for k, v in fl.items():
+                res.fields[(i, k)] = v
         res.timings = dict(self.timings)
         return res

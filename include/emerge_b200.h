@@ -35,6 +35,11 @@ int64_t emb_launch_count(const emb_ctx* ctx);
  * "symbolic", "tet_kernel", "reduce", "form_A", "spmv", "solve", "surface" */
 double emb_last_ms(const emb_ctx* ctx, const char* phase);
 
+/* CUDA-event stopwatch on the context's stream (bench.py times whole steps with it: torch.cuda.Event only sees
+ * torch's own stream).  stop returns the elapsed device-timeline milliseconds since start. */
+int emb_timer_start(emb_ctx* ctx);
+int emb_timer_stop(emb_ctx* ctx, double* ms);
+
 /* ---- mesh + DOF tables (input contract of Nedelec2 / Mesh3D; consumed, never renumbered) ---- */
 /* replaces the array gathering at fem/physics/edm/optimized_assembly.py:47-57 */
 int emb_upload_mesh(emb_ctx* ctx, int64_t nN, int64_t nT, int64_t nE, int64_t nTri,
