@@ -37,7 +37,8 @@ extern "C" void emb_destroy(emb_ctx* c) {
     c->K.release(); c->M.release(); c->newid.release(); c->solve_ids.release(); c->rowptr_s.release();
     c->col_s.release(); c->src.release(); c->A.release(); c->xs.release(); c->xfull.release();
     for (auto& w : c->work) w.release();
-    c->dinv.release(); c->pairmate.release(); c->red.release(); c->As.release();
+    c->dinv.release(); c->pairmate.release(); c->red.release(); c->As.release(); c->rc_x0.release();
+    c->rcU.release(); c->rcC.release(); c->rc_part.release(); c->bs.release();
     for (auto& a : c->aux) {
         a.rptr.release(); a.tptr.release(); a.rcol.release(); a.tcol.release(); a.rval.release(); a.tval.release();
         a.dinv.release(); a.tmp.release();

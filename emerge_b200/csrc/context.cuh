@@ -94,6 +94,7 @@ struct emb_ctx {
 
     // solver workspace
     DevBuf<cx> xs;            // last solution (solve space)
+    DevBuf<cx> bs;            // right-hand side of the current solve (solve space)
     DevBuf<cx> xfull;         // last solution (full space)
     std::vector<DevBuf<cx>> work;
     DevBuf<cx> dinv;          // Jacobi / block-Jacobi inverse blocks
@@ -103,6 +104,17 @@ struct emb_ctx {
     DevBuf<cx> As;            // symmetric part of A (COCR operator), cached between solves of one frequency
     bool have_As = false;
     int As_precond = -1;
+    // Subspace recycling across the frequency points of a sweep (solver.cu): U spans previous Krylov corrections,
+    // C = A(f) U is re-formed and orthonormalised once per frequency; x0 = U C^H b is the minimum-residual start.
+    int rc_cap = 0, rc_n = 0;
+    DevBuf<cx> rcU, rcC;                // [rc_cap][Ns]; ring, NEWEST first: slot (rc_head + j) % rc_cap is the j-th newest
+    int rc_head = 0;
+    bool rc_C_valid = false;
+    double rc_snap = 0.1;               // solves that feed the recycled space run to rc_snap * rtol
+    DevBuf<cx> rc_x0;                   // start vector of the current solve (new direction = x - x0)
+    DevBuf<cx> rc_part;                 // [rc_cap][RC_NP] dot partials + [rc_cap] coefficients
+    int64_t rc_spmvs = 0;               // SpMVs spent on C = A U so far (reported by emb_recycle_info)
+    double rc_last_proj_relres = -1;    // relative residual left by the projection in the last solve
     double spmv_ms_sum = 0;   // sampled SpMV timings inside solves (CUDA events)
     int64_t spmv_ms_cnt = 0;
     cudaEvent_t evs0 = nullptr, evs1 = nullptr, evt0 = nullptr, evt1 = nullptr;

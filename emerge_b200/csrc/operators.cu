@@ -470,6 +470,11 @@ extern "C" int emb_set_dirichlet(emb_ctx* c, int64_t npec, const int64_t* pec_id
     for (auto& s : c->surf) s.slot_s.release();
     c->have_dirichlet = true;
     c->have_A = false;
+    c->rc_n = 0; c->rc_head = 0; c->rc_C_valid = false;
+    if (c->rc_cap > 0) {   // vectors are sized by the solve space
+        c->rcU.release(); c->rcC.release(); c->rc_part.release();
+        c->rc_cap = 0;
+    }
     return EMB_OK;
 }
 
@@ -570,5 +575,6 @@ extern "C" int emb_form_A(emb_ctx* c, double k0, int nsurf, const int* sids, con
     c->k0 = k0;
     c->have_A = true;
     c->have_As = false;
+    c->rc_C_valid = false;
     return EMB_OK;
 }

@@ -607,6 +607,188 @@ static int bicgstab(emb_ctx* c, int pmode, const cx* A, const cx* b, cx* x, doub
     return EMB_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Subspace recycling across frequency points (the sweep solves A(f) x = b(f) for a dense list of f).
+// U holds previous Krylov corrections (any port); once per frequency C = A(f) U is re-formed and (C, U) are
+// orthonormalised together (modified Gram-Schmidt on C, same column operations on U, so C = A U keeps holding).
+// For a right-hand side b the start vector x0 = sum_i <c_i, b - A x> u_i minimises the residual over span(U);
+// the Krylov method then only has to remove what the recycled space cannot represent.  The true residual is
+// always recomputed from A afterwards, so the accuracy contract (relres <= rtol in FP64) is unchanged.
+// The reference has no counterpart (it refactorises at every frequency, fem/solver.py:243-309).
+// ------------------------------------------------------------------------------------------------
+constexpr int RC_NP = 256;       // partials per dot product of the batched Gram-Schmidt kernels
+
+// part[k][blockIdx.x] = partial of <c_k, v> over this block's range, k = blockIdx.y (column k = slot (head+k)%cap)
+__global__ void __launch_bounds__(VBLOCK) k_rc_dots(int64_t n, const cx* __restrict__ Cb, int head, int cap,
+                                                    const cx* __restrict__ v, cx* __restrict__ part) {
+    const cx* ck = Cb + (int64_t)((head + blockIdx.y) % cap) * n;
+    cx acc = mk(0.0);
+    const int64_t per = (n + RC_NP - 1) / RC_NP;
+    const int64_t i0 = blockIdx.x * per, i1 = (i0 + per < n) ? i0 + per : n;
+    for (int64_t i = i0 + threadIdx.x; i < i1; i += VBLOCK) {
+        const cx u = ck[i], w = v[i];
+        acc.re += u.re * w.re + u.im * w.im;
+        acc.im += u.re * w.im - u.im * w.re;
+    }
+    cx t = block_sum(acc);
+    if (threadIdx.x == 0) part[(int64_t)blockIdx.y * RC_NP + blockIdx.x] = t;
+}
+// coef[k] = sum of the RC_NP partials of column k in fixed order (one block per column)
+__global__ void __launch_bounds__(VBLOCK) k_rc_coef(const cx* __restrict__ part, cx* __restrict__ coef) {
+    cx v = part[(int64_t)blockIdx.x * RC_NP + threadIdx.x];     // RC_NP == VBLOCK
+    cx t = block_sum(v);
+    if (threadIdx.x == 0) coef[blockIdx.x] = t;
+}
+// cj -= sum_k coef[k] c_k ; uj -= sum_k coef[k] u_k   (k < m, columns counted from `head`)
+__global__ void __launch_bounds__(256) k_rc_sub(int64_t n, int m, const cx* __restrict__ coef, const cx* __restrict__ Cb,
+                                                const cx* __restrict__ Ub, int head, int cap, cx* __restrict__ cj,
+                                                cx* __restrict__ uj) {
+    extern __shared__ cx s_h[];
+    for (int k = threadIdx.x; k < m; k += blockDim.x) s_h[k] = coef[k];
+    __syncthreads();
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    cx a = cj[i], b = uj[i];
+    for (int k = 0; k < m; ++k) {
+        const int64_t off = (int64_t)((head + k) % cap) * n + i;
+        const cx h = -s_h[k];
+        fma_c(a, h, Cb[off]);
+        fma_c(b, h, Ub[off]);
+    }
+    cj[i] = a; uj[i] = b;
+}
+// x += sum_k coef[k] u_k
+__global__ void __launch_bounds__(256) k_rc_combine(int64_t n, int m, const cx* __restrict__ coef, const cx* __restrict__ Ub,
+                                                    int head, int cap, cx* __restrict__ x) {
+    extern __shared__ cx s_h[];
+    for (int k = threadIdx.x; k < m; k += blockDim.x) s_h[k] = coef[k];
+    __syncthreads();
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    cx a = x[i];
+    for (int k = 0; k < m; ++k) fma_c(a, s_h[k], Ub[(int64_t)((head + k) % cap) * n + i]);
+    x[i] = a;
+}
+// cj, uj *= 1/sqrt(sum(part).re); the norm goes to norm_out[0] (0 => vector zeroed)
+__global__ void __launch_bounds__(VBLOCK) k_rc_scale(int64_t n, const cx* __restrict__ part, cx* __restrict__ cj,
+                                                     cx* __restrict__ uj, double* __restrict__ norm_out) {
+    const cx t = sum_partials(part);
+    const double nrm = sqrt(fabs(t.re));
+    const double s = nrm > 0 ? 1.0 / nrm : 0.0;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && norm_out) *norm_out = nrm;
+    const int64_t per = (n + NPART - 1) / NPART;
+    const int64_t i0 = blockIdx.x * per, i1 = (i0 + per < n) ? i0 + per : n;
+    for (int64_t i = i0 + threadIdx.x; i < i1; i += VBLOCK) {
+        cj[i] = s * cj[i];
+        uj[i] = s * uj[i];
+    }
+}
+
+static inline cx* rc_U(emb_ctx* c, int j) { return c->rcU.p + (int64_t)((c->rc_head + j) % c->rc_cap) * c->Ns; }
+static inline cx* rc_C(emb_ctx* c, int j) { return c->rcC.p + (int64_t)((c->rc_head + j) % c->rc_cap) * c->Ns; }
+
+static void rc_clear(emb_ctx* c) {
+    c->rc_n = 0;
+    c->rc_head = 0;
+    c->rc_C_valid = false;
+}
+
+// classical Gram-Schmidt of column j of (C, U) against columns [0, j) (batched: one pass over the 2j vectors),
+// `passes` times, then normalisation; *norm_dev receives the norm
+static int rc_orth_column(emb_ctx* c, int j, int passes, double* norm_dev) {
+    const int64_t n = c->Ns;
+    cx* part = c->rc_part.p;
+    cx* coef = part + (int64_t)c->rc_cap * RC_NP;
+    cx *Cj = rc_C(c, j), *Uj = rc_U(c, j);
+    if (j > 0)
+        for (int pass = 0; pass < passes; ++pass) {
+            k_rc_dots<<<dim3(RC_NP, j), VBLOCK, 0, c->stream>>>(n, c->rcC.p, c->rc_head, c->rc_cap, Cj, part); EMB_LAUNCH_CHECK(c);
+            k_rc_coef<<<j, VBLOCK, 0, c->stream>>>(part, coef); EMB_LAUNCH_CHECK(c);
+            k_rc_sub<<<blocks_for(n, 256), 256, j * sizeof(cx), c->stream>>>(n, j, coef, c->rcC.p, c->rcU.p, c->rc_head, c->rc_cap, Cj, Uj);
+            EMB_LAUNCH_CHECK(c);
+        }
+    cx* pn = reinterpret_cast<cx*>(c->red.p) + 3 * NPART;
+    k_dot<true><<<NPART, VBLOCK, 0, c->stream>>>(n, Cj, Cj, pn); EMB_LAUNCH_CHECK(c);
+    k_rc_scale<<<NPART, VBLOCK, 0, c->stream>>>(n, pn, Cj, Uj, norm_dev); EMB_LAUNCH_CHECK(c);
+    return EMB_OK;
+}
+
+// C = A(f) U, orthonormalised, newest direction first (once per frequency)
+static int rc_rebuild(emb_ctx* c) {
+    for (int j = 0; j < c->rc_n; ++j) {
+        EMB_TRY(spmv(c, c->A.p, rc_U(c, j), rc_C(c, j)));
+        c->rc_spmvs++;
+        EMB_TRY(rc_orth_column(c, j, 1, nullptr));
+    }
+    c->rc_C_valid = true;
+    return EMB_OK;
+}
+
+// xs += U C^H r
+static int rc_project(emb_ctx* c, const cx* r, cx* xs) {
+    const int64_t n = c->Ns;
+    const int m = c->rc_n;
+    cx* part = c->rc_part.p;
+    cx* coef = part + (int64_t)c->rc_cap * RC_NP;
+    k_rc_dots<<<dim3(RC_NP, m), VBLOCK, 0, c->stream>>>(n, c->rcC.p, c->rc_head, c->rc_cap, r, part); EMB_LAUNCH_CHECK(c);
+    k_rc_coef<<<m, VBLOCK, 0, c->stream>>>(part, coef); EMB_LAUNCH_CHECK(c);
+    k_rc_combine<<<blocks_for(n, 256), 256, m * sizeof(cx), c->stream>>>(n, m, coef, c->rcU.p, c->rc_head, c->rc_cap, xs);
+    EMB_LAUNCH_CHECK(c);
+    return EMB_OK;
+}
+
+// add direction d (or d - minus) to the recycled space as its NEWEST member.  It is orthogonalised against the
+// current members first, so the member dropped when the ring is full (the last in Gram-Schmidt order) only carries
+// what was unique to the oldest direction.
+static int rc_append(emb_ctx* c, const cx* d, const cx* minus) {
+    const int64_t n = c->Ns;
+    const unsigned vb = blocks_for(n, 256);
+    if (!c->rc_C_valid && c->rc_n > 0) EMB_TRY(rc_rebuild(c));
+    const int m = c->rc_n < c->rc_cap ? c->rc_n : c->rc_cap - 1;     // members kept
+    // stage the candidate in the slot just before the head (it becomes column 0 if accepted); when the ring is
+    // full that slot is the oldest member's, which is the one being replaced
+    const int slot = (c->rc_head - 1 + c->rc_cap) % c->rc_cap;
+    cx *Un = c->rcU.p + (int64_t)slot * n, *Cn = c->rcC.p + (int64_t)slot * n;
+    if (minus) {
+        k_copy<<<vb, 256, 0, c->stream>>>(n, minus, Un); EMB_LAUNCH_CHECK(c);
+        k_axpby<<<vb, 256, 0, c->stream>>>(n, nullptr, 1.0, d, nullptr, -1.0, Un); EMB_LAUNCH_CHECK(c);
+    } else {
+        k_copy<<<vb, 256, 0, c->stream>>>(n, d, Un); EMB_LAUNCH_CHECK(c);
+    }
+    EMB_TRY(spmv(c, c->A.p, Un, Cn));
+    c->rc_spmvs++;
+    double* nd = c->red.p + (size_t)(4 * NPART + 16) * 2 - 4;     // scalar area: |A d|^2 (cx) then the final norm
+    cx* pn = reinterpret_cast<cx*>(c->red.p) + 3 * NPART;
+    k_dot<true><<<NPART, VBLOCK, 0, c->stream>>>(n, Cn, Cn, pn); EMB_LAUNCH_CHECK(c);
+    k_finish<<<1, VBLOCK, 0, c->stream>>>(pn, reinterpret_cast<cx*>(nd)); EMB_LAUNCH_CHECK(c);
+    // orthogonalise against members 0..m-1 (two passes: the candidate may be nearly inside the space)
+    {
+        cx* part = c->rc_part.p;
+        cx* coef = part + (int64_t)c->rc_cap * RC_NP;
+        if (m > 0)
+            for (int pass = 0; pass < 2; ++pass) {
+                k_rc_dots<<<dim3(RC_NP, m), VBLOCK, 0, c->stream>>>(n, c->rcC.p, c->rc_head, c->rc_cap, Cn, part); EMB_LAUNCH_CHECK(c);
+                k_rc_coef<<<m, VBLOCK, 0, c->stream>>>(part, coef); EMB_LAUNCH_CHECK(c);
+                k_rc_sub<<<vb, 256, m * sizeof(cx), c->stream>>>(n, m, coef, c->rcC.p, c->rcU.p, c->rc_head, c->rc_cap, Cn, Un);
+                EMB_LAUNCH_CHECK(c);
+            }
+        k_dot<true><<<NPART, VBLOCK, 0, c->stream>>>(n, Cn, Cn, pn); EMB_LAUNCH_CHECK(c);
+        k_rc_scale<<<NPART, VBLOCK, 0, c->stream>>>(n, pn, Cn, Un, nd + 2); EMB_LAUNCH_CHECK(c);
+    }
+    double h[3];
+    EMB_CUDA(c, cudaMemcpyAsync(h, nd, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    EMB_CUDA(c, cudaStreamSynchronize(c->stream));
+    const double before = sqrt(fabs(h[0])), after = h[2];
+    if (!(after > 1e-9 * before) || !(after == after)) {     // numerically inside the space: not kept
+        if (c->rc_n == c->rc_cap) c->rc_n = c->rc_cap - 1;     // its slot was overwritten by the candidate
+        return EMB_OK;
+    }
+    c->rc_head = slot;
+    c->rc_n = m + 1;
+    return EMB_OK;
+}
+
 // solves A xs = bs (device, solve space); xs is in/out (initial guess when use_x0)
 static int solve_device(emb_ctx* c, const emb_solve_opts* o, const cx* bs, cx* xs, emb_solve_info* info) {
     const int64_t n = c->Ns;
@@ -619,23 +801,41 @@ static int solve_device(emb_ctx* c, const emb_solve_opts* o, const cx* bs, cx* x
     EMB_TRY(dot_host(c, true, bs, bs, &bb));
     const double bnorm = sqrt(bb.re);
     int rc = EMB_OK;
+    const bool recycle = c->rc_cap > 0 && bnorm > 0;
+    c->rc_last_proj_relres = -1;
+    if (bnorm > 0 && !o->use_x0) { k_zero<<<vb, 256, 0, c->stream>>>(n, xs); EMB_LAUNCH_CHECK(c); }
+    if (recycle) {
+        EMB_TRY(dev_alloc(c, c->rc_x0, (size_t)n));
+        if (c->rc_n > 0) {
+            if (!c->rc_C_valid) EMB_TRY(rc_rebuild(c));
+            const cx* r0 = bs;
+            if (o->use_x0) {    // residual of the caller's guess
+                cx* t = c->work[0].p;
+                EMB_TRY(spmv(c, c->A.p, xs, t)); ++spmvs;
+                k_axpby<<<vb, 256, 0, c->stream>>>(n, nullptr, 1.0, bs, nullptr, -1.0, t); EMB_LAUNCH_CHECK(c);
+                r0 = t;
+            }
+            EMB_TRY(rc_project(c, r0, xs));
+        }
+        k_copy<<<vb, 256, 0, c->stream>>>(n, xs, c->rc_x0.p); EMB_LAUNCH_CHECK(c);
+    }
+    const bool have_guess = o->use_x0 || (recycle && c->rc_n > 0);
+    const double target = recycle ? o->rtol * c->rc_snap : o->rtol;
+    emb_solve_opts ot = *o;
+    ot.rtol = target;
     if (bnorm == 0) {
         k_zero<<<vb, 256, 0, c->stream>>>(n, xs); EMB_LAUNCH_CHECK(c);
         relres = 0;
     } else if (o->method == 0) {
-        if (!o->use_x0) { k_zero<<<vb, 256, 0, c->stream>>>(n, xs); EMB_LAUNCH_CHECK(c); }
         EMB_TRY(precond_setup(c, o->precond, c->A.p));
-        EMB_TRY(gmres(c, o->precond, c->A.p, bs, xs, bnorm, o, &its, &spmvs, &relres));
+        EMB_TRY(gmres(c, o->precond, c->A.p, bs, xs, bnorm, &ot, &its, &spmvs, &relres));
     } else if (o->method == 1) {
-        if (!o->use_x0) { k_zero<<<vb, 256, 0, c->stream>>>(n, xs); EMB_LAUNCH_CHECK(c); }
         EMB_TRY(precond_setup(c, o->precond, c->A.p));
-        EMB_TRY(bicgstab(c, o->precond, c->A.p, bs, xs, bnorm, o, &its, &spmvs, &relres));
+        EMB_TRY(bicgstab(c, o->precond, c->A.p, bs, xs, bnorm, &ot, &its, &spmvs, &relres));
     } else {
         // defect correction on A with COCR on the symmetric part
-        DevBuf<cx> rr, dd;
+        struct { cx* p; } rr{c->work[8].p}, dd{c->work[9].p};      // persistent workspace (no per-solve cudaMalloc)
         DevBuf<cx>& As = c->As;
-        EMB_TRY(dev_alloc(c, rr, (size_t)n));
-        EMB_TRY(dev_alloc(c, dd, (size_t)n));
         if (!c->have_As) {
             EMB_TRY(dev_alloc(c, As, (size_t)c->nnz_s));
             k_sym_part<<<blocks_for(n * 32, 256), 256, 0, c->stream>>>(n, c->rowptr_s.p, c->col_s.p, c->A.p, As.p);
@@ -647,21 +847,28 @@ static int solve_device(emb_ctx* c, const emb_solve_opts* o, const cx* bs, cx* x
             EMB_TRY(precond_setup(c, o->precond, As.p));
             c->As_precond = o->precond;
         }
-        if (!o->use_x0) { k_zero<<<vb, 256, 0, c->stream>>>(n, xs); EMB_LAUNCH_CHECK(c); }
         double prev = 1e300;
         for (int outer = 0; outer < 30 && its < o->maxit; ++outer) {
-            EMB_TRY(spmv(c, c->A.p, xs, rr.p)); ++spmvs;
-            k_axpby<<<vb, 256, 0, c->stream>>>(n, nullptr, 1.0, bs, nullptr, -1.0, rr.p); EMB_LAUNCH_CHECK(c);
-            cx r2;
-            EMB_TRY(dot_host(c, true, rr.p, rr.p, &r2));
-            const double rn = sqrt(r2.re);
+            double rn = bnorm;
+            if (outer > 0 || have_guess) {
+                EMB_TRY(spmv(c, c->A.p, xs, rr.p)); ++spmvs;
+                k_axpby<<<vb, 256, 0, c->stream>>>(n, nullptr, 1.0, bs, nullptr, -1.0, rr.p); EMB_LAUNCH_CHECK(c);
+                cx r2;
+                EMB_TRY(dot_host(c, true, rr.p, rr.p, &r2));
+                rn = sqrt(r2.re);
+            } else {
+                k_copy<<<vb, 256, 0, c->stream>>>(n, bs, rr.p); EMB_LAUNCH_CHECK(c);
+            }
             relres = rn / bnorm;
-            if (relres <= o->rtol) break;
+            if (outer == 0 && recycle && c->rc_n > 0) c->rc_last_proj_relres = relres;
+            // a start vector that already meets rtol is accepted as is; once the solve has to iterate it feeds the
+            // recycled space and is run to the tighter snapshot tolerance
+            if (relres <= (outer == 0 ? o->rtol : target)) break;
             if (outer > 2 && rn > 0.5 * prev) { /* stagnation of the correction: keep going, but it is visible in info */ }
             prev = rn;
             // inner target: two digits below the current residual, never below what the outer loop needs
             double stop = 1e-2 * rn;
-            const double need = 0.3 * o->rtol * bnorm;
+            const double need = 0.3 * target * bnorm;
             if (stop < need) stop = need;
             int iit = 0;
             double irn = 0;
@@ -678,7 +885,6 @@ static int solve_device(emb_ctx* c, const emb_solve_opts* o, const cx* bs, cx* x
             EMB_TRY(dot_host(c, true, rr.p, rr.p, &r2));
             relres = sqrt(r2.re) / bnorm;
         }
-        rr.release(); dd.release();
         if (rc < 0) return rc;
     }
     if (o->method != 2 && bnorm > 0) {   // true residual at exit
@@ -689,6 +895,7 @@ static int solve_device(emb_ctx* c, const emb_solve_opts* o, const cx* bs, cx* x
         EMB_TRY(dot_host(c, true, t, t, &r2));
         relres = sqrt(r2.re) / bnorm;
     }
+    if (recycle && its > 0 && relres <= 1e2 * o->rtol) EMB_TRY(rc_append(c, xs, c->rc_x0.p));
     cudaEventRecord(c->ev1, c->stream);
     cudaEventSynchronize(c->ev1);
     float ms = 0;
@@ -722,7 +929,7 @@ extern "C" int emb_solve(emb_ctx* c, int sid, const emb_solve_opts* opts, emb_c1
     }
     const emb_solve_opts* o = opts ? opts : &kDefaultOpts;
     Surface& s = c->surf[sid];
-    DevBuf<cx> bs;
+    DevBuf<cx>& bs = c->bs;
     EMB_TRY(dev_alloc(c, bs, (size_t)c->Ns));
     EMB_TRY(dev_alloc(c, c->xs, (size_t)c->Ns));
     k_zero<<<blocks_for(c->Ns, 256), 256, 0, c->stream>>>(c->Ns, bs.p); EMB_LAUNCH_CHECK(c);
@@ -735,7 +942,6 @@ extern "C" int emb_solve(emb_ctx* c, int sid, const emb_solve_opts* opts, emb_c1
         EMB_LAUNCH_CHECK(c);
     }
     int rc = solve_device(c, o, bs.p, c->xs.p, info);
-    bs.release();
     if (rc < 0) return rc;
     EMB_TRY(finish_solution(c, x_full));
     return rc;
@@ -746,7 +952,8 @@ extern "C" int emb_solve_rhs(emb_ctx* c, const emb_c128* b_full, const emb_solve
     if (!c || !b_full) return EMB_ERR_ARG;
     if (!c->have_A) { c->err = "emb_solve_rhs: needs emb_form_A first"; return EMB_ERR_STATE; }
     const emb_solve_opts* o = opts ? opts : &kDefaultOpts;
-    DevBuf<cx> bf, bs;
+    DevBuf<cx> bf;
+    DevBuf<cx>& bs = c->bs;
     EMB_TRY(h2d(c, bf, reinterpret_cast<const cx*>(b_full), (size_t)c->N));
     EMB_TRY(dev_alloc(c, bs, (size_t)c->Ns));
     EMB_TRY(dev_alloc(c, c->xs, (size_t)c->Ns));
@@ -759,10 +966,48 @@ extern "C" int emb_solve_rhs(emb_ctx* c, const emb_c128* b_full, const emb_solve
         EMB_LAUNCH_CHECK(c);
     }
     int rc = solve_device(c, o, bs.p, c->xs.p, info);
-    bf.release(); bs.release();
+    bf.release();
     if (rc < 0) return rc;
     EMB_TRY(finish_solution(c, x_full));
     return rc;
+}
+
+
+// ---- recycling control --------------------------------------------------------------------------
+extern "C" int emb_recycle_config(emb_ctx* c, int max_vectors, double snapshot_rtol_factor) {
+    if (!c || max_vectors < 0 || max_vectors > 256) return EMB_ERR_ARG;
+    if (max_vectors > 0 && !c->have_dirichlet) { c->err = "emb_recycle_config: needs emb_set_dirichlet first"; return EMB_ERR_STATE; }
+    c->rcU.release(); c->rcC.release(); c->rc_part.release();
+    c->rc_cap = max_vectors;
+    c->rc_snap = (snapshot_rtol_factor > 0 && snapshot_rtol_factor <= 1) ? snapshot_rtol_factor : 0.1;
+    rc_clear(c);
+    if (max_vectors > 0) {
+        EMB_TRY(dev_alloc(c, c->rcU, (size_t)max_vectors * c->Ns));
+        EMB_TRY(dev_alloc(c, c->rcC, (size_t)max_vectors * c->Ns));
+        EMB_TRY(dev_alloc(c, c->rc_part, (size_t)max_vectors * (RC_NP + 1)));
+        EMB_TRY(ensure_work(c, 10));
+    }
+    return EMB_OK;
+}
+extern "C" int emb_recycle_info(emb_ctx* c, int* n, int64_t* spmvs, double* last_proj_relres) {
+    if (!c) return EMB_ERR_ARG;
+    if (n) *n = c->rc_n;
+    if (spmvs) *spmvs = c->rc_spmvs;
+    if (last_proj_relres) *last_proj_relres = c->rc_last_proj_relres;
+    return EMB_OK;
+}
+// Device-to-device exchange of recycled directions between the ranks of a sharded sweep (the host side moves the
+// buffers with NCCL over NVLink).  d_dst / d_src are DEVICE pointers to Ns complex128 values.
+extern "C" int emb_recycle_export(emb_ctx* c, int j, void* d_dst) {
+    if (!c || !d_dst || j < 0 || j >= c->rc_n) return EMB_ERR_ARG;
+    EMB_CUDA(c, cudaMemcpyAsync(d_dst, rc_U(c, j), (size_t)c->Ns * sizeof(cx), cudaMemcpyDeviceToDevice, c->stream));
+    EMB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return EMB_OK;
+}
+extern "C" int emb_recycle_import(emb_ctx* c, const void* d_src) {
+    if (!c || !d_src) return EMB_ERR_ARG;
+    if (c->rc_cap <= 0 || !c->have_A) { c->err = "emb_recycle_import: recycling not configured or no A(f)"; return EMB_ERR_STATE; }
+    return rc_append(c, reinterpret_cast<const cx*>(d_src), nullptr);
 }
 
 extern "C" int emb_spmv_host(emb_ctx* c, const emb_c128* x, emb_c128* y) {

@@ -62,6 +62,10 @@ _SIGS = {
     "emb_spmv_sampled": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "emb_solve": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(SolveOpts), C.c_void_p, C.POINTER(SolveInfo)]),
     "emb_solve_rhs": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(SolveOpts), C.c_void_p, C.POINTER(SolveInfo)]),
+    "emb_recycle_config": (C.c_int, [C.c_void_p, C.c_int, C.c_double]),
+    "emb_recycle_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
+    "emb_recycle_export": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "emb_recycle_import": (C.c_int, [C.c_void_p, C.c_void_p]),
     "emb_interp": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "emb_interp_last": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
@@ -275,6 +279,21 @@ class Context:
         ms, cnt = C.c_double(), C.c_int64()
         self._check(self.lib.emb_spmv_sampled(self.h, C.byref(ms), C.byref(cnt)))
         return ms.value, cnt.value
+
+    # ---- subspace recycling across frequency points
+    def recycle_config(self, max_vectors: int, snapshot_rtol_factor: float = 0.1):
+        self._check(self.lib.emb_recycle_config(self.h, int(max_vectors), float(snapshot_rtol_factor)))
+
+    def recycle_info(self):
+        n, sp, rr = C.c_int(), C.c_int64(), C.c_double()
+        self._check(self.lib.emb_recycle_info(self.h, C.byref(n), C.byref(sp), C.byref(rr)))
+        return dict(n=n.value, spmvs=sp.value, last_proj_relres=rr.value)
+
+    def recycle_export(self, j: int, device_ptr: int):
+        self._check(self.lib.emb_recycle_export(self.h, int(j), C.c_void_p(device_ptr)))
+
+    def recycle_import(self, device_ptr: int):
+        self._check(self.lib.emb_recycle_import(self.h, C.c_void_p(device_ptr)))
 
     @staticmethod
     def _opts(method="cocr", precond="block", restart=50, maxit=100000, rtol=1e-8, use_x0=False):

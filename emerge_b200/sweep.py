@@ -35,6 +35,25 @@ def dunavant4() -> np.ndarray:
     return np.array(rows).T
 
 
+def hierarchical_order(n: int) -> list:
+    """Processing order of n frequency points for a sweep with subspace recycling: both ends first, then midpoints of
+    ever finer bisection.  Later points are then INTERPOLATED by the recycled space (combination weights O(1)) instead of
+    extrapolated (weights growing like binomials, which amplifies the 1e-9 solver noise of the stored directions above
+    rtol)."""
+    if n <= 2:
+        return list(range(n))
+    out, seg = [0, n - 1], [(0, n - 1)]
+    while seg:
+        nxt = []
+        for a, b in seg:
+            if b - a > 1:
+                m = (a + b) // 2
+                out.append(m)
+                nxt += [(a, m), (m, b)]
+        seg = nxt
+    return out
+
+
 def _is(bc, name):
     """isinstance by class name through the MRO so reference objects (fem.bc.*) are accepted too."""
     return any(k.__name__ == name for k in type(bc).__mro__)
@@ -60,7 +79,8 @@ class FrequencySweep:
     """tables: emerge_b200.synthmesh.MeshTables-like object (or any object exposing the reference's arrays:
     nodes, tets, tris, edges, tri_to_tet, tet_to_field, tri_to_field).  bcs: PEC / RobinBC objects (ours or fem's)."""
 
-    def __init__(self, tables, er, ur, bcs, device: int = 0, get_triangles=None, ctx: Context | None = None):
+    def __init__(self, tables, er, ur, bcs, device: int = 0, get_triangles=None, ctx: Context | None = None,
+                 recycle: int = 24):
         self.t = tables
         self.er = np.ascontiguousarray(er, dtype=np.complex128)
         self.ur = np.ascontiguousarray(ur, dtype=np.complex128)
@@ -69,6 +89,7 @@ class FrequencySweep:
         self.ctx = ctx if ctx is not None else Context(device)
         self.timings = {}
         self._setup_done = False
+        self.recycle = int(recycle)        # directions kept from previous frequency points (0 = every point solved cold)
         self.solver_opts = dict(method="cocr", precond="multilevel", rtol=1e-8, maxit=200000, restart=50)
 
     # ------------------------------------------------------------------ setup (once)
@@ -103,6 +124,7 @@ class FrequencySweep:
             self.ntri[id(b)] = n
         ctx.set_dirichlet(pec)
         self.pec_ids = pec
+        ctx.recycle_config(self.recycle)
         if self.solver_opts.get("precond") == "multilevel":
             t1 = time.perf_counter()
             self._setup_aux_spaces()
@@ -247,6 +269,9 @@ class FrequencySweep:
             out = out_bufs.get(pa.port_number) if out_bufs else None
             x, info = self.ctx.solve(self.sid[id(pa)], want_x=want, raise_on_fail=raise_on_fail, out=out, **self.solver_opts)
             info.update(freq=float(freq), port=pa.port_number)
+            if self.recycle:
+                ri = self.ctx.recycle_info()
+                info.update(recycled=ri["n"], proj_relres=ri["last_proj_relres"])
             stats.append(info)
             if keep_fields:
                 fields[pa.port_number] = x
@@ -257,7 +282,9 @@ class FrequencySweep:
             pa.active = False
         return S, stats, fields
 
-    def run(self, freqs, keep_fields=False, raise_on_fail=True) -> SweepResult:
+    def run(self, freqs, keep_fields=False, raise_on_fail=True, order=None) -> SweepResult:
+        """Solves every frequency point; results are returned in the order of `freqs` (as emfreq3d.py:658 does).
+        order: processing order (list of indices); default hierarchical when recycling is on, else as given."""
         if not self._setup_done:
             self.setup()
         ports = self.ports
@@ -266,10 +293,15 @@ class FrequencySweep:
         res = SweepResult(np.asarray(freqs, dtype=float), pn, S)
         for p in ports:
             p.active = False
-        for i, f in enumerate(freqs):
-            S[i], st, fl = self.solve_point(f, keep_fields, raise_on_fail)
-            res.stats.extend(st)
+        if order is None:
+            order = hierarchical_order(len(freqs)) if self.recycle else list(range(len(freqs)))
+        stats = {}
+        for i in order:
+            S[i], st, fl = self.solve_point(freqs[i], keep_fields, raise_on_fail)
+            stats[i] = st
             for k, v in fl.items():
                 res.fields[(i, k)] = v
+        for i in range(len(freqs)):
+            res.stats.extend(stats.get(i, []))
         res.timings = dict(self.timings)
         return res

@@ -128,6 +128,23 @@ int emb_solve(emb_ctx* ctx, int sid, const emb_solve_opts* opts, emb_c128* x_ful
 int emb_solve_rhs(emb_ctx* ctx, const emb_c128* b_full, const emb_solve_opts* opts, emb_c128* x_full,
                   emb_solve_info* info);
 
+/* ---- subspace recycling across the frequency points of a sweep ------------------------------------------
+ * The reference refactorises A(f) at every frequency (fem/solver.py:264-275, emfreq3d.py:658-694).  Here every
+ * converged solve leaves its Krylov correction in a ring of at most max_vectors directions U (shared by all ports);
+ * at the next frequency C = A(f) U is formed and orthonormalised once, and each solve starts from the minimum-
+ * residual combination x0 = U C^H b.  The exit test is unchanged (true residual of A(f) in FP64 <= rtol).
+ * A solve that does have to iterate is run to snapshot_rtol_factor * rtol (0 < factor <= 1, default 0.1) so that the
+ * direction it leaves is accurate enough for neighbouring points to be accepted without iterating.
+ * max_vectors = 0 switches it off and frees the vectors (2 * max_vectors * n_solve * 16 B of HBM). */
+int emb_recycle_config(emb_ctx* ctx, int max_vectors, double snapshot_rtol_factor);
+/* n: directions held; spmvs: SpMVs spent forming C = A U so far; last_proj_relres: relative residual of the recycled
+ * start vector in the last solve (-1 if none) */
+int emb_recycle_info(emb_ctx* ctx, int* n, int64_t* spmvs, double* last_proj_relres);
+/* exchange of directions between the ranks of a frequency-sharded sweep; d_dst / d_src are DEVICE pointers to
+ * n_solve complex128 values (the host side moves them with NCCL).  j = 0 is the oldest direction. */
+int emb_recycle_export(emb_ctx* ctx, int j, void* d_dst);
+int emb_recycle_import(emb_ctx* ctx, const void* d_src);
+
 /* ---- field evaluation (S-parameter extraction) -------------------------------------------------- */
 /* E-field of solution x_full (host, n_field) at npts points, point k lying in tet tet_ids[k]:
  * the per-point part of ned2_tet_interp (fem/mth/tet.py:371-497).  E_3xnpts is (3,npts) c128. */

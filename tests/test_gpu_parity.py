@@ -172,3 +172,43 @@ def test_oracle_parity_larger_mesh(gpu_ctx):
     N = t.n_field
     Em = sp.csr_matrix((E, ix, ip), shape=(N, N))
     assert abs(Em - Em.T).max() <= 1e-13 * np.abs(E).max()
+
+
+def test_recycled_sweep_matches_cold_sweep():
+    """Subspace recycling across frequency points only changes the start vector of each solve: every point still meets
+    rtol on the true residual, S-parameters agree with the cold sweep, results come back in the caller's frequency
+    order, and most points are accepted without a Krylov iteration."""
+    from emerge_b200.sweep import FrequencySweep, hierarchical_order
+    from emerge_b200.synthmesh import box_mesh, mesh_tables, tri_ids_of
+    from emerge_b200 import bc as B
+    a, b, L = 22.86e-3, 10.16e-3, 45e-3
+    box = box_mesh(6, 3, 12, a, b, L, jitter=0.1, seed=2)
+    t = mesh_tables(box.nodes_xyz, box.tets)
+    nT = t.tets.shape[1]
+    er = np.repeat(np.eye(3, dtype=complex)[:, :, None], nT, axis=2)
+    ur = er.copy()
+    tag = lambda k: tri_ids_of(t, box.face_tris[box.face_tag == k])
+
+    def bcs():
+        return [B.PEC(np.concatenate([tag(k) for k in (1, 2, 3, 4)])),
+                B.RectangularWaveguide(tag(5), 1, B.CoordSys(origin=(0, 0, 0)), (a, b)),
+                B.RectangularWaveguide(tag(6), 2, B.CoordSys(origin=(0, 0, L)), (a, b))]
+    freqs = np.linspace(8e9, 12e9, 41)
+    assert sorted(hierarchical_order(41)) == list(range(41))
+    cold = FrequencySweep(t, er, ur, bcs(), recycle=0)
+    cold.solver_opts.update(rtol=1e-9)
+    rc = cold.run(freqs)
+    cold.ctx.close()
+    warm = FrequencySweep(t, er, ur, bcs(), recycle=32)
+    warm.solver_opts.update(rtol=1e-9)
+    rw = warm.run(freqs)
+    assert warm.ctx.recycle_info()["n"] > 0
+    warm.ctx.close()
+    assert all(s["converged"] and s["relres"] <= 1e-9 for s in rw.stats)
+    assert [s["freq"] for s in rw.stats[::2]] == list(freqs)
+    assert db_deg_close(rw.S, rc.S), np.abs(rw.S - rc.S).max()
+    it_cold = sum(s["iters"] for s in rc.stats)
+    it_warm = sum(s["iters"] for s in rw.stats)
+    free = sum(1 for s in rw.stats if s["iters"] == 0)
+    assert it_warm * 3 < it_cold, (it_warm, it_cold)
+    assert free >= len(rw.stats) // 2, free
