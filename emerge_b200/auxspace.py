@@ -108,3 +108,40 @@ def build_aux_spaces(tables):
     G1 = sp.coo_matrix((np.concatenate([np.ones(nE), -np.ones(nE)]),
                         (np.concatenate([ea, ea]), np.concatenate([A, Bv]))), shape=(nE, nN)).tocsr()
     return G, P, G1
+
+
+def nodal_interpolation(tables):
+    """Pi_c (nE x nN), c = x, y, z: Whitney coefficients of the nodal vector field e_c * lam_v.  With the reference's sign
+    convention w_AB.t_AB = -1/l on edge (A,B), the coefficient of a field E is -(E(v_A) + E(v_B))/2 . (v_B - v_A)."""
+    nodes = np.asarray(tables.nodes)
+    edges = np.asarray(tables.edges)
+    nN, nE = nodes.shape[1], edges.shape[1]
+    d = nodes[:, edges[1]] - nodes[:, edges[0]]
+    ea = np.arange(nE)
+    out = []
+    for c in range(3):
+        v = -0.5 * d[c]
+        out.append(sp.coo_matrix((np.concatenate([v, v]), (np.concatenate([ea, ea]), np.concatenate([edges[0], edges[1]]))),
+                                 shape=(nE, nN)).tocsr())
+    return out
+
+
+def p1_stiffness_mass(tables, weight=None):
+    """P1 Lagrange stiffness (grad lam_i, w grad lam_j) with a per-tet scalar weight, and the lumped mass vector."""
+    nodes = np.asarray(tables.nodes)
+    tets = np.asarray(tables.tets)
+    nN, nT = nodes.shape[1], tets.shape[1]
+    X = nodes[:, tets]                                             # (3, 4, nT)
+    e1, e2, e3 = X[:, 1] - X[:, 0], X[:, 2] - X[:, 0], X[:, 3] - X[:, 0]
+    g1, g2, g3 = np.cross(e2.T, e3.T).T, np.cross(e3.T, e1.T).T, np.cross(e1.T, e2.T).T
+    det = np.einsum("it,it->t", e1, g1)
+    grad = np.stack([-(g1 + g2 + g3), g1, g2, g3], axis=0) / det   # (4, 3, nT)
+    vol = np.abs(det) / 6.0
+    w = vol if weight is None else vol * np.asarray(weight, dtype=float)
+    loc = np.einsum("ixt,jxt->ijt", grad, grad) * w                # (4, 4, nT)
+    ii = np.broadcast_to(tets[:, None, :], (4, 4, nT))
+    jj = np.broadcast_to(tets[None, :, :], (4, 4, nT))
+    L = sp.coo_matrix((loc.ravel(), (ii.ravel(), jj.ravel())), shape=(nN, nN)).tocsr()
+    mass = np.zeros(nN)
+    np.add.at(mass, tets.ravel(), np.repeat(vol[None, :] / 4.0, 4, axis=0).ravel())
+    return L, mass

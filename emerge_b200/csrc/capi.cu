@@ -39,10 +39,7 @@ extern "C" void emb_destroy(emb_ctx* c) {
     for (auto& w : c->work) w.release();
     c->dinv.release(); c->pairmate.release(); c->red.release(); c->As.release(); c->rc_x0.release();
     c->rcU.release(); c->rcC.release(); c->rc_part.release(); c->bs.release();
-    for (auto& a : c->aux) {
-        a.rptr.release(); a.tptr.release(); a.rcol.release(); a.tcol.release(); a.rval.release(); a.tval.release();
-        a.dinv.release(); a.tmp.release();
-    }
+    emb_aux_clear(c);
     cudaEventDestroy(c->evs0);
     cudaEventDestroy(c->evs1);
     for (auto& s : c->surf) release_surface(s);

@@ -40,13 +40,33 @@ struct Surface {
     bool has_rhs = false;
 };
 
-// auxiliary space of the additive multilevel preconditioner: real transfer matrix R (Ns x ncol) and R^T, both CSR
+// One level of a smoothed-aggregation hierarchy (set up on the host, emerge_b200/amg.py): real SPD matrix A, prolongator
+// P to the next coarser level and its transpose, damped-Jacobi data, complex work vectors of the V-cycle.
+struct AmgLevel {
+    int64_t n = 0, nc = 0;
+    DevBuf<int64_t> aptr, pptr, tptr;
+    DevBuf<int> acol, pcol, tcol;
+    DevBuf<double> aval, pval, tval, dinv;
+    double omega = 1.0;
+    DevBuf<cx> b, xa, xb, t;
+};
+struct AmgHierarchy {
+    std::vector<AmgLevel> lev;
+    DevBuf<double> cinv;            // dense inverse of the coarsest matrix, row-major [n][n]
+    int64_t ncinv = 0;
+};
+
+// auxiliary space of the additive multilevel preconditioner: real transfer matrix R (rows of the parent space x ncol)
+// and R^T, both CSR.  parent < 0: the parent is the solve space.  solver 0: diagonal of R^T A R (top-level spaces only,
+// recomputed per frequency); solver 1: V-cycle of hierarchy `hid` times scale (scale_mode 0: 1, 1: -1/k0^2).
 struct AuxSpace {
-    int64_t ncol = 0, nnz = 0;
-    DevBuf<int64_t> rptr, tptr;     // R rows [Ns+1], R^T rows [ncol+1]
+    int64_t ncol = 0, nnz = 0, nrow = 0;
+    int parent = -1, solver = 0, hid = -1, scale_mode = 0;
+    bool has_children = false;
+    DevBuf<int64_t> rptr, tptr;     // R rows [nrow+1], R^T rows [ncol+1]
     DevBuf<int> rcol, tcol;
     DevBuf<double> rval, tval;
-    DevBuf<cx> dinv, tmp;           // 1/diag(R^T A R), scratch [ncol]
+    DevBuf<cx> dinv, tmp, traw;     // 1/diag(R^T A R); correction x [ncol]; raw restricted residual [ncol] (if children)
 };
 
 struct emb_ctx {
@@ -101,6 +121,7 @@ struct emb_ctx {
     DevBuf<int> pairmate;     // solve-space index of the paired dof (block-Jacobi) or -1
     DevBuf<double> red;       // reduction scratch
     std::vector<AuxSpace> aux;
+    std::vector<AmgHierarchy> amg;
     DevBuf<cx> As;            // symmetric part of A (COCR operator), cached between solves of one frequency
     bool have_As = false;
     int As_precond = -1;

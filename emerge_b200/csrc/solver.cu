@@ -14,6 +14,7 @@
 // iteration of COCR is 4 launches and no host synchronisation (scalars live on the device, block partial
 // sums are reduced in a fixed order by the consumer kernel => bitwise reproducible).
 #include "context.cuh"
+#include "amg.cuh"
 #include <vector>
 
 constexpr int NPART = 1024;          // block partials per reduction (fixed => deterministic)
@@ -251,10 +252,10 @@ __global__ void __launch_bounds__(256) k_aux_diag(int64_t ncol, const int64_t* _
         dinv[k] = n2 > 0 ? cdiv(mk(1.0), cx{ar, ai}) : mk(0.0);
     }
 }
-// t[k] = dinv[k] * sum_i RT[k,i] r[i]     (8 lanes per aux column)
+// s = sum_i RT[k,i] r[i];  traw[k] = s (if traw);  t[k] = dinv ? dinv[k]*s : s     (8 lanes per aux column)
 __global__ void __launch_bounds__(256) k_aux_restrict(int64_t ncol, const int64_t* __restrict__ tptr, const int* __restrict__ tcol,
                                                       const double* __restrict__ tval, const cx* __restrict__ dinv,
-                                                      const cx* __restrict__ r, cx* __restrict__ t) {
+                                                      const cx* __restrict__ r, cx* __restrict__ t, cx* __restrict__ traw) {
     const int64_t gt = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int64_t k = gt >> 3;
     const int sub = (int)(gt & 7);
@@ -271,23 +272,28 @@ __global__ void __launch_bounds__(256) k_aux_restrict(int64_t ncol, const int64_
         ar += __shfl_down_sync(0xffffffffu, ar, o, 8);
         ai += __shfl_down_sync(0xffffffffu, ai, o, 8);
     }
-    if (k < ncol && sub == 0) t[k] = dinv[k] * cx{ar, ai};
+    if (k < ncol && sub == 0) {
+        if (traw) traw[k] = cx{ar, ai};
+        if (t) t[k] = dinv ? dinv[k] * cx{ar, ai} : cx{ar, ai};
+    }
 }
-// z[i] += sum_k R[i,k] t[k]     (thread per row; rows of R are short)
+// z[i] += s * sum_k R[i,k] t[k]     (thread per row; rows of R are short)
 __global__ void __launch_bounds__(256) k_aux_prolong(int64_t n, const int64_t* __restrict__ rptr, const int* __restrict__ rcol,
-                                                     const double* __restrict__ rval, const cx* __restrict__ t, cx* __restrict__ z) {
+                                                     const double* __restrict__ rval, const cx* __restrict__ t, cx s,
+                                                     cx* __restrict__ z) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
+    const int64_t m0 = rptr[i], m1 = rptr[i + 1];
+    if (m0 == m1) return;
     double ar = 0, ai = 0;
-    for (int64_t m = rptr[i]; m < rptr[i + 1]; ++m) {
+    for (int64_t m = m0; m < m1; ++m) {
         const double w = rval[m];
         const double2 v = __ldg(reinterpret_cast<const double2*>(t + rcol[m]));
         ar += w * v.x;
         ai += w * v.y;
     }
     cx zi = z[i];
-    zi.re += ar;
-    zi.im += ai;
+    fma_c(zi, s, cx{ar, ai});
     z[i] = zi;
 }
 
@@ -372,6 +378,7 @@ static int precond_setup(emb_ctx* c, int mode_in, const cx* val) {
     if (mode_in == 3) {
         if (c->aux.empty()) { c->err = "precond=3 needs auxiliary spaces (emb_aux_add)"; return EMB_ERR_STATE; }
         for (auto& a : c->aux) {
+            if (a.solver != 0) continue;
             k_aux_diag<<<blocks_for(a.ncol * 32, 256), 256, 0, c->stream>>>(a.ncol, a.tptr.p, a.tcol.p, a.tval.p, c->rowptr_s.p,
                                                                             c->col_s.p, val, a.dinv.p);
             EMB_LAUNCH_CHECK(c);
@@ -388,16 +395,38 @@ static int precond_setup(emb_ctx* c, int mode_in, const cx* val) {
     EMB_LAUNCH_CHECK(c);
     return EMB_OK;
 }
+// z = M^-1 r.  mode 3: block-Jacobi on the solve space plus the tree of auxiliary spaces (additive):
+// restrict down the tree (parents before children), solve every space (diagonal, or AMG V-cycle), prolong up.
 static int precond_apply(emb_ctx* c, int mode, const cx* r, cx* z) {
     k_precond_apply<<<blocks_for(c->Ns, 256), 256, 0, c->stream>>>(c->Ns, c->dinv.p, mode >= 2 ? c->pairmate.p : nullptr, r, z);
     EMB_LAUNCH_CHECK(c);
-    if (mode == 3)
-        for (auto& a : c->aux) {
-            k_aux_restrict<<<blocks_for(a.ncol * 8, 256), 256, 0, c->stream>>>(a.ncol, a.tptr.p, a.tcol.p, a.tval.p, a.dinv.p, r, a.tmp.p);
-            EMB_LAUNCH_CHECK(c);
-            k_aux_prolong<<<blocks_for(c->Ns, 256), 256, 0, c->stream>>>(c->Ns, a.rptr.p, a.rcol.p, a.rval.p, a.tmp.p, z);
-            EMB_LAUNCH_CHECK(c);
+    if (mode != 3) return EMB_OK;
+    const int na = (int)c->aux.size();
+    for (int i = 0; i < na; ++i) {
+        AuxSpace& a = c->aux[i];
+        const cx* src = a.parent < 0 ? r : c->aux[a.parent].traw.p;
+        cx* traw = (a.has_children || a.solver == 1) ? a.traw.p : nullptr;
+        cx* t = a.solver == 0 ? a.tmp.p : nullptr;
+        k_aux_restrict<<<blocks_for(a.ncol * 8, 256), 256, 0, c->stream>>>(a.ncol, a.tptr.p, a.tcol.p, a.tval.p,
+                                                                           a.solver == 0 ? a.dinv.p : nullptr, src, t, traw);
+        EMB_LAUNCH_CHECK(c);
+    }
+    for (int i = na - 1; i >= 0; --i) {
+        AuxSpace& a = c->aux[i];
+        const cx* x = a.tmp.p;
+        cx scale = mk(1.0);
+        if (a.solver == 1) {
+            AmgHierarchy& H = c->amg[a.hid];
+            EMB_CUDA(c, cudaMemcpyAsync(H.lev[0].b.p, a.traw.p, (size_t)a.ncol * sizeof(cx), cudaMemcpyDeviceToDevice, c->stream));
+            cx* res = nullptr;
+            EMB_TRY(amg_vcycle(c, H, &res));
+            x = res;
+            if (a.scale_mode == 1) scale = mk(-1.0 / (c->k0 * c->k0));
         }
+        cx* dst = a.parent < 0 ? z : c->aux[a.parent].tmp.p;
+        k_aux_prolong<<<blocks_for(a.nrow, 256), 256, 0, c->stream>>>(a.nrow, a.rptr.p, a.rcol.p, a.rval.p, x, scale, dst);
+        EMB_LAUNCH_CHECK(c);
+    }
     return EMB_OK;
 }
 
@@ -836,17 +865,21 @@ static int solve_device(emb_ctx* c, const emb_solve_opts* o, const cx* bs, cx* x
         // defect correction on A with COCR on the symmetric part
         struct { cx* p; } rr{c->work[8].p}, dd{c->work[9].p};      // persistent workspace (no per-solve cudaMalloc)
         DevBuf<cx>& As = c->As;
-        if (!c->have_As) {
-            EMB_TRY(dev_alloc(c, As, (size_t)c->nnz_s));
-            k_sym_part<<<blocks_for(n * 32, 256), 256, 0, c->stream>>>(n, c->rowptr_s.p, c->col_s.p, c->A.p, As.p);
-            EMB_LAUNCH_CHECK(c);
-            EMB_TRY(precond_setup(c, o->precond, As.p));
-            c->have_As = true;
-            c->As_precond = o->precond;
-        } else if (c->As_precond != o->precond) {
-            EMB_TRY(precond_setup(c, o->precond, As.p));
-            c->As_precond = o->precond;
-        }
+        // the symmetric part and the preconditioner are only built when a point really has to iterate
+        auto ensure_operator = [&]() -> int {
+            if (!c->have_As) {
+                EMB_TRY(dev_alloc(c, As, (size_t)c->nnz_s));
+                k_sym_part<<<blocks_for(n * 32, 256), 256, 0, c->stream>>>(n, c->rowptr_s.p, c->col_s.p, c->A.p, As.p);
+                EMB_LAUNCH_CHECK(c);
+                EMB_TRY(precond_setup(c, o->precond, As.p));
+                c->have_As = true;
+                c->As_precond = o->precond;
+            } else if (c->As_precond != o->precond) {
+                EMB_TRY(precond_setup(c, o->precond, As.p));
+                c->As_precond = o->precond;
+            }
+            return EMB_OK;
+        };
         double prev = 1e300;
         for (int outer = 0; outer < 30 && its < o->maxit; ++outer) {
             double rn = bnorm;
@@ -867,13 +900,17 @@ static int solve_device(emb_ctx* c, const emb_solve_opts* o, const cx* bs, cx* x
             if (outer > 2 && rn > 0.5 * prev) { /* stagnation of the correction: keep going, but it is visible in info */ }
             prev = rn;
             // inner target: two digits below the current residual, never below what the outer loop needs
-            double stop = 1e-2 * rn;
+            static const double inner_red = getenv("EMB_INNER") ? atof(getenv("EMB_INNER")) : 1e-2;
+            double stop = inner_red * rn;
             const double need = 0.3 * target * bnorm;
             if (stop < need) stop = need;
             int iit = 0;
             double irn = 0;
+            EMB_TRY(ensure_operator());
             rc = cocr(c, o->precond, As.p, rr.p, dd.p, stop, o->maxit - its, &iit, &spmvs, &irn);
             its += iit;
+            static const bool verbose = getenv("EMB_VERBOSE") != nullptr;
+            if (verbose) fprintf(stderr, "[emb] outer %d relres %.3e -> inner %d its, inner residual %.3e (target %.3e)\n", outer, relres, iit, irn / bnorm, stop / bnorm);
             if (rc < 0) break;
             k_axpby<<<vb, 256, 0, c->stream>>>(n, nullptr, 1.0, dd.p, nullptr, 1.0, xs); EMB_LAUNCH_CHECK(c);
             if (rc == EMB_NOT_CONVERGED) break;
@@ -1141,24 +1178,38 @@ extern "C" int emb_aux_clear(emb_ctx* c) {
     if (!c) return EMB_ERR_ARG;
     for (auto& a : c->aux) {
         a.rptr.release(); a.tptr.release(); a.rcol.release(); a.tcol.release(); a.rval.release(); a.tval.release();
-        a.dinv.release(); a.tmp.release();
+        a.dinv.release(); a.tmp.release(); a.traw.release();
     }
     c->aux.clear();
+    for (auto& h : c->amg) amg_release(h);
+    c->amg.clear();
     c->have_As = false;
     return EMB_OK;
 }
 
-extern "C" int emb_aux_add(emb_ctx* c, int64_t ncol, const int64_t* Rp, const int32_t* Ri, const double* Rv, const int64_t* Tp,
-                           const int32_t* Ti, const double* Tv) {
-    if (!c || ncol <= 0 || !Rp || !Ri || !Rv || !Tp || !Ti || !Tv) return EMB_ERR_ARG;
+extern "C" int emb_aux_add_ex(emb_ctx* c, int64_t nrow, int64_t ncol, const int64_t* Rp, const int32_t* Ri, const double* Rv,
+                              const int64_t* Tp, const int32_t* Ti, const double* Tv, int parent, int solver, int hid,
+                              int scale_mode) {
+    if (!c || ncol <= 0 || nrow <= 0 || !Rp || !Ri || !Rv || !Tp || !Ti || !Tv) return EMB_ERR_ARG;
     if (!c->have_dirichlet) { c->err = "emb_aux_add: needs emb_set_dirichlet first (solve-space rows)"; return EMB_ERR_STATE; }
-    const int64_t nnz = Rp[c->Ns];
+    const int na = (int)c->aux.size();
+    if (parent >= na || (parent < 0 && nrow != c->Ns) || (parent >= 0 && nrow != c->aux[parent].ncol)) {
+        c->err = "emb_aux_add: row count does not match the parent space";
+        return EMB_ERR_ARG;
+    }
+    if (solver == 0 && parent >= 0) { c->err = "emb_aux_add: the diagonal solver needs a top-level space"; return EMB_ERR_ARG; }
+    if (solver == 1 && (hid < 0 || hid >= (int)c->amg.size() || c->amg[hid].lev.empty() || c->amg[hid].lev[0].n != ncol ||
+                        !c->amg[hid].cinv.p)) {
+        c->err = "emb_aux_add: AMG hierarchy missing, incomplete or of the wrong size";
+        return EMB_ERR_ARG;
+    }
+    const int64_t nnz = Rp[nrow];
     if (Tp[ncol] != nnz) { c->err = "emb_aux_add: R and R^T disagree on nnz"; return EMB_ERR_ARG; }
     c->aux.emplace_back();
     AuxSpace& a = c->aux.back();
-    a.ncol = ncol;
-    a.nnz = nnz;
-    EMB_TRY(h2d(c, a.rptr, Rp, (size_t)c->Ns + 1));
+    a.ncol = ncol; a.nrow = nrow; a.nnz = nnz;
+    a.parent = parent; a.solver = solver; a.hid = hid; a.scale_mode = scale_mode;
+    EMB_TRY(h2d(c, a.rptr, Rp, (size_t)nrow + 1));
     EMB_TRY(h2d(c, a.rcol, reinterpret_cast<const int*>(Ri), (size_t)nnz));
     EMB_TRY(h2d(c, a.rval, Rv, (size_t)nnz));
     EMB_TRY(h2d(c, a.tptr, Tp, (size_t)ncol + 1));
@@ -1166,8 +1217,63 @@ extern "C" int emb_aux_add(emb_ctx* c, int64_t ncol, const int64_t* Rp, const in
     EMB_TRY(h2d(c, a.tval, Tv, (size_t)nnz));
     EMB_TRY(dev_alloc(c, a.dinv, (size_t)ncol));
     EMB_TRY(dev_alloc(c, a.tmp, (size_t)ncol));
+    EMB_TRY(dev_alloc(c, a.traw, (size_t)ncol));
+    if (parent >= 0) c->aux[parent].has_children = true;
     EMB_CUDA(c, cudaStreamSynchronize(c->stream));
     c->have_As = false;
+    return EMB_OK;
+}
+extern "C" int emb_aux_add(emb_ctx* c, int64_t ncol, const int64_t* Rp, const int32_t* Ri, const double* Rv, const int64_t* Tp,
+                           const int32_t* Ti, const double* Tv) {
+    if (!c) return EMB_ERR_ARG;
+    return emb_aux_add_ex(c, c->Ns, ncol, Rp, Ri, Rv, Tp, Ti, Tv, -1, 0, -1, 0);
+}
+
+extern "C" int emb_amg_create(emb_ctx* c, int* hid) {
+    if (!c || !hid) return EMB_ERR_ARG;
+    c->amg.emplace_back();
+    *hid = (int)c->amg.size() - 1;
+    return EMB_OK;
+}
+extern "C" int emb_amg_add_level(emb_ctx* c, int hid, int64_t n, const int64_t* Ap, const int32_t* Ai, const double* Av,
+                                 const double* dinv, double omega, int64_t ncoarse, const int64_t* Pp, const int32_t* Pi,
+                                 const double* Pv, const int64_t* Tp, const int32_t* Ti, const double* Tv) {
+    if (!c || hid < 0 || hid >= (int)c->amg.size() || n <= 0) return EMB_ERR_ARG;
+    AmgHierarchy& H = c->amg[hid];
+    if (!H.lev.empty() && H.lev.back().nc != n) { c->err = "emb_amg_add_level: size does not match the previous level"; return EMB_ERR_ARG; }
+    H.lev.emplace_back();
+    AmgLevel& v = H.lev.back();
+    v.n = n; v.nc = ncoarse; v.omega = omega;
+    EMB_TRY(dev_alloc(c, v.b, (size_t)n));
+    EMB_TRY(dev_alloc(c, v.xa, (size_t)n));
+    if (ncoarse > 0) {
+        if (!Ap || !Ai || !Av || !dinv || !Pp || !Pi || !Pv || !Tp || !Ti || !Tv) return EMB_ERR_ARG;
+        EMB_TRY(h2d(c, v.aptr, Ap, (size_t)n + 1));
+        EMB_TRY(h2d(c, v.acol, reinterpret_cast<const int*>(Ai), (size_t)Ap[n]));
+        EMB_TRY(h2d(c, v.aval, Av, (size_t)Ap[n]));
+        EMB_TRY(h2d(c, v.dinv, dinv, (size_t)n));
+        EMB_TRY(h2d(c, v.pptr, Pp, (size_t)n + 1));
+        EMB_TRY(h2d(c, v.pcol, reinterpret_cast<const int*>(Pi), (size_t)Pp[n]));
+        EMB_TRY(h2d(c, v.pval, Pv, (size_t)Pp[n]));
+        EMB_TRY(h2d(c, v.tptr, Tp, (size_t)ncoarse + 1));
+        EMB_TRY(h2d(c, v.tcol, reinterpret_cast<const int*>(Ti), (size_t)Tp[ncoarse]));
+        EMB_TRY(h2d(c, v.tval, Tv, (size_t)Tp[ncoarse]));
+        EMB_TRY(dev_alloc(c, v.xb, (size_t)n));
+        EMB_TRY(dev_alloc(c, v.t, (size_t)n));
+    }
+    EMB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return EMB_OK;
+}
+extern "C" int emb_amg_set_coarse_inverse(emb_ctx* c, int hid, int64_t n, const double* Ainv) {
+    if (!c || hid < 0 || hid >= (int)c->amg.size() || n <= 0 || !Ainv) return EMB_ERR_ARG;
+    AmgHierarchy& H = c->amg[hid];
+    if (H.lev.empty() || H.lev.back().n != n || H.lev.back().nc != 0) {
+        c->err = "emb_amg_set_coarse_inverse: the last level must be the coarsest (ncoarse = 0) and of size n";
+        return EMB_ERR_ARG;
+    }
+    EMB_TRY(h2d(c, H.cinv, Ainv, (size_t)n * n));
+    H.ncinv = n;
+    EMB_CUDA(c, cudaStreamSynchronize(c->stream));
     return EMB_OK;
 }
 

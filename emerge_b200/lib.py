@@ -59,6 +59,10 @@ _SIGS = {
     "emb_spmv_bench": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double)]),
     "emb_aux_clear": (C.c_int, [C.c_void_p]),
     "emb_aux_add": (C.c_int, [C.c_void_p, C.c_int64] + [C.c_void_p] * 6),
+    "emb_aux_add_ex": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64] + [C.c_void_p] * 6 + [C.c_int] * 4),
+    "emb_amg_create": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
+    "emb_amg_add_level": (C.c_int, [C.c_void_p, C.c_int, C.c_int64] + [C.c_void_p] * 4 + [C.c_double, C.c_int64] + [C.c_void_p] * 6),
+    "emb_amg_set_coarse_inverse": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p]),
     "emb_spmv_sampled": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "emb_solve": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(SolveOpts), C.c_void_p, C.POINTER(SolveInfo)]),
     "emb_solve_rhs": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(SolveOpts), C.c_void_p, C.POINTER(SolveInfo)]),
@@ -263,6 +267,7 @@ class Context:
 
     def aux_clear(self):
         self._check(self.lib.emb_aux_clear(self.h))
+        self._n_aux = 0
 
     def aux_add(self, R):
         """R: scipy sparse (n_solve x ncol) real transfer matrix of one auxiliary space."""
@@ -274,6 +279,40 @@ class Context:
         a = [_c(R.indptr, np.int64), _c(R.indices, np.int32), _c(R.data, np.float64),
              _c(T.indptr, np.int64), _c(T.indices, np.int32), _c(T.data, np.float64)]
         self._check(self.lib.emb_aux_add(self.h, R.shape[1], *[_p(x) for x in a]))
+        self._n_aux = getattr(self, "_n_aux", 0) + 1
+        return self._n_aux - 1
+
+    @staticmethod
+    def _csr_args(M):
+        M = M.tocsr().astype(np.float64)
+        M.sort_indices()
+        return [_c(M.indptr, np.int64), _c(M.indices, np.int32), _c(M.data, np.float64)]
+
+    def aux_add_ex(self, R, parent=-1, solver="diag", hid=-1, scale="one"):
+        """R: scipy sparse (rows of the parent space x ncol) real transfer matrix; returns the index of the new space."""
+        a = self._csr_args(R) + self._csr_args(R.T)
+        self._check(self.lib.emb_aux_add_ex(self.h, R.shape[0], R.shape[1], *[_p(x) for x in a], int(parent),
+                                            {"diag": 0, "amg": 1}[solver], int(hid), {"one": 0, "minus_inv_k0sq": 1}[scale]))
+        self._n_aux = getattr(self, "_n_aux", 0) + 1
+        return self._n_aux - 1
+
+    def amg_upload(self, levels):
+        """levels: output of emerge_b200.amg.sa_hierarchy (finest first); returns the hierarchy id."""
+        hid = C.c_int()
+        self._check(self.lib.emb_amg_create(self.h, C.byref(hid)))
+        for lev in levels:
+            A, P = lev["A"], lev["P"]
+            if P is None:
+                n = A.shape[0]
+                self._check(self.lib.emb_amg_add_level(self.h, hid.value, n, None, None, None, None, 1.0, 0, *([None] * 6)))
+                inv = _c(np.linalg.inv(A.toarray()), np.float64)
+                self._check(self.lib.emb_amg_set_coarse_inverse(self.h, hid.value, n, _p(inv)))
+                break
+            a = self._csr_args(A) + [_c(lev["dinv"], np.float64)]
+            pt = self._csr_args(P) + self._csr_args(P.T)
+            self._check(self.lib.emb_amg_add_level(self.h, hid.value, A.shape[0], *[_p(x) for x in a],
+                                                   float(4.0 / (3.0 * lev["rho"])), P.shape[1], *[_p(x) for x in pt]))
+        return hid.value
 
     def spmv_sampled(self):
         ms, cnt = C.c_double(), C.c_int64()

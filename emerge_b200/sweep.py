@@ -80,7 +80,7 @@ class FrequencySweep:
     nodes, tets, tris, edges, tri_to_tet, tet_to_field, tri_to_field).  bcs: PEC / RobinBC objects (ours or fem's)."""
 
     def __init__(self, tables, er, ur, bcs, device: int = 0, get_triangles=None, ctx: Context | None = None,
-                 recycle: int = 24):
+                 recycle: int = 40, multilevel: bool = True, f_ref: float = 10e9):
         self.t = tables
         self.er = np.ascontiguousarray(er, dtype=np.complex128)
         self.ur = np.ascontiguousarray(ur, dtype=np.complex128)
@@ -89,6 +89,8 @@ class FrequencySweep:
         self.ctx = ctx if ctx is not None else Context(device)
         self.timings = {}
         self._setup_done = False
+        self.multilevel = bool(multilevel)  # AMG V-cycles on the nodal auxiliary problems (False: Jacobi on every space)
+        self.f_ref = float(f_ref)           # frequency whose k0^2 shifts the nodal Helmholtz-type auxiliary operator
         self.recycle = int(recycle)        # directions kept from previous frequency points (0 = every point solved cold)
         self.solver_opts = dict(method="cocr", precond="multilevel", rtol=1e-8, maxit=200000, restart=50)
 
@@ -150,9 +152,17 @@ class FrequencySweep:
         self._setup_done = True
 
     def _setup_aux_spaces(self):
-        """Transfer matrices of the additive multilevel preconditioner restricted to the solve space; columns whose
-        support touches an eliminated dof are dropped (their potential / Whitney dof is fixed by the PEC condition)."""
-        from .auxspace import build_aux_spaces
+        """Auxiliary spaces of the additive multilevel preconditioner, restricted to the solve space; columns whose
+        support touches an eliminated dof are dropped (their potential / Whitney / nodal dof is fixed by the PEC condition).
+
+            M^-1 = D_blk^-1 + G D_G^-1 G^T + P [ D_P^-1 + G1 (-k0^-2 V_eps) G1^T + sum_c Pi_c V_mu Pi_c^T ] P^T
+
+        G: gradients of the P2 Lagrange space (the kernel of the curl-curl matrix), P: the Whitney space, G1: gradients
+        of P1 inside the Whitney space, Pi_c: nodal vector fields (Hiptmair-Xu); V_eps / V_mu are V-cycles of
+        smoothed-aggregation hierarchies of the P1 operators (grad, eps grad) and (grad, mu^-1 grad) + k^2 (lumped mass),
+        set up once per mesh (emerge_b200/amg.py).  With multilevel=False the nodal problems are not solved and the
+        P1 gradients only get a Jacobi scaling (the round-1 first version)."""
+        from .auxspace import build_aux_spaces, nodal_interpolation, p1_stiffness_mass
         G, P, G1 = build_aux_spaces(self.t)
         N = G.shape[0]
         keep = np.ones(N, dtype=bool)
@@ -167,14 +177,40 @@ class FrequencySweep:
         G1r = G1[~badP]
         badN = np.asarray(abs(G1[badP]).sum(axis=0)).ravel() > 0
         G1s = G1r[:, ~badN].tocsr()
-        self.ctx.aux_clear()
-        spaces = [Gs, Ps]
-        if G1s.shape[1] > 0:
-            spaces.append((Ps @ G1s).tocsr())
-        for R in spaces:
-            if R.shape[1] > 0:
-                self.ctx.aux_add(R)
-        self.aux_dims = [R.shape[1] for R in spaces]
+        ctx = self.ctx
+        ctx.aux_clear()
+        self.aux_dims = []
+        if Gs.shape[1] > 0:
+            ctx.aux_add(Gs)
+            self.aux_dims.append(Gs.shape[1])
+        if Ps.shape[1] == 0:
+            return
+        if not self.multilevel or G1s.shape[1] == 0:
+            ctx.aux_add(Ps)
+            self.aux_dims.append(Ps.shape[1])
+            if G1s.shape[1] > 0:
+                ctx.aux_add((Ps @ G1s).tocsr())
+                self.aux_dims.append(G1s.shape[1])
+            return
+        from .amg import sa_hierarchy
+        ip = ctx.aux_add_ex(Ps, parent=-1, solver="diag")
+        self.aux_dims.append(Ps.shape[1])
+        tr = lambda T: np.real(T[0, 0] + T[1, 1] + T[2, 2]) / 3.0
+        w_eps, w_mu = tr(self.er), 1.0 / tr(self.ur)
+        kmid2 = (2 * np.pi * self.f_ref / C0) ** 2
+        Le, mass = p1_stiffness_mass(self.t, w_eps)
+        same = np.allclose(w_eps, w_mu)
+        Lm = Le if same else p1_stiffness_mass(self.t, w_mu)[0]
+        kn = ~badN
+        import scipy.sparse as sp
+        He = sa_hierarchy((Le[kn][:, kn] + 1e-3 * kmid2 * sp.diags(mass[kn] * np.mean(w_eps))).tocsr())
+        Hm = sa_hierarchy((Lm[kn][:, kn] + kmid2 * sp.diags(mass[kn] * np.mean(w_mu))).tocsr())
+        he, hm = ctx.amg_upload(He), ctx.amg_upload(Hm)
+        self.amg_levels = dict(eps=[l["A"].shape[0] for l in He], mu=[l["A"].shape[0] for l in Hm])
+        ctx.aux_add_ex(G1s, parent=ip, solver="amg", hid=he, scale="minus_inv_k0sq")
+        for Pc in nodal_interpolation(self.t):
+            ctx.aux_add_ex(Pc[~badP][:, kn].tocsr(), parent=ip, solver="amg", hid=hm, scale="one")
+        self.aux_dims += [G1s.shape[1]] * 4
 
     def _setup_vline(self, b, ids):
         """define_lumped_port_integration_points (emfreq3d.py:366-389) + point location for the 10 midpoints."""
@@ -286,6 +322,7 @@ class FrequencySweep:
         """Solves every frequency point; results are returned in the order of `freqs` (as emfreq3d.py:658 does).
         order: processing order (list of indices); default hierarchical when recycling is on, else as given."""
         if not self._setup_done:
+            self.f_ref = float(np.median(np.asarray(freqs, dtype=float)))
             self.setup()
         ports = self.ports
         pn = [p.port_number for p in ports]

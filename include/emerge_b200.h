@@ -104,6 +104,23 @@ int emb_spmv_bench(emb_ctx* ctx, int reps, double* ms_per_spmv);
 int emb_aux_clear(emb_ctx* ctx);
 int emb_aux_add(emb_ctx* ctx, int64_t ncol, const int64_t* R_indptr, const int32_t* R_indices, const double* R_data,
                 const int64_t* RT_indptr, const int32_t* RT_indices, const double* RT_data);
+/* Tree of auxiliary spaces with multilevel solvers.  A space is given by its real transfer matrix R (nrow x ncol) to its
+ * parent (parent < 0: the solve space, else the index of an earlier emb_aux_add* call, nrow = that space's ncol).
+ * solver 0: diagonal of R^T A R (top-level only); solver 1: V-cycle of AMG hierarchy hid on an ncol-sized real SPD matrix,
+ * times 1 (scale_mode 0) or -1/k0^2 (scale_mode 1: the gradient spaces, on which A(f) = -k0^2 (grad, eps grad)).
+ * emb_aux_clear also frees the hierarchies. */
+int emb_aux_add_ex(emb_ctx* ctx, int64_t nrow, int64_t ncol, const int64_t* R_indptr, const int32_t* R_indices,
+                   const double* R_data, const int64_t* RT_indptr, const int32_t* RT_indices, const double* RT_data,
+                   int parent, int solver, int hid, int scale_mode);
+/* Smoothed-aggregation hierarchy, built on the host (emerge_b200/amg.py), finest level first.  Every level but the last
+ * carries its matrix A (real CSR), 1/diag(A), the Jacobi damping omega, the prolongator P (n x ncoarse) and P^T; the last
+ * level has ncoarse = 0, null matrices, and gets the dense inverse of its matrix (row-major n x n). */
+int emb_amg_create(emb_ctx* ctx, int* hid);
+int emb_amg_add_level(emb_ctx* ctx, int hid, int64_t n, const int64_t* A_indptr, const int32_t* A_indices,
+                      const double* A_data, const double* dinv, double omega, int64_t ncoarse, const int64_t* P_indptr,
+                      const int32_t* P_indices, const double* P_data, const int64_t* PT_indptr, const int32_t* PT_indices,
+                      const double* PT_data);
+int emb_amg_set_coarse_inverse(emb_ctx* ctx, int hid, int64_t n, const double* Ainv_nxn);
 /* average device time (ms) of the SpMVs sampled with CUDA events inside the solves since the last call, and their count */
 int emb_spmv_sampled(emb_ctx* ctx, double* avg_ms, int64_t* count);
 
