@@ -13,7 +13,8 @@ extern "C" int emb_create(int device, emb_ctx** out) {
     c->device = device;
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess ||
-        cudaEventCreate(&c->evs0) != cudaSuccess || cudaEventCreate(&c->evs1) != cudaSuccess) {
+        cudaEventCreate(&c->evs0) != cudaSuccess || cudaEventCreate(&c->evs1) != cudaSuccess ||
+        cudaEventCreate(&c->evr0) != cudaSuccess || cudaEventCreate(&c->evr1) != cudaSuccess) {
         delete c;
         return EMB_ERR_CUDA;
     }
@@ -40,6 +41,8 @@ extern "C" void emb_destroy(emb_ctx* c) {
     c->dinv.release(); c->pairmate.release(); c->red.release(); c->As.release(); c->rc_x0.release();
     c->rcU.release(); c->rcC.release(); c->rc_part.release(); c->bs.release();
     emb_aux_clear(c);
+    cudaEventDestroy(c->evr0);
+    cudaEventDestroy(c->evr1);
     cudaEventDestroy(c->evs0);
     cudaEventDestroy(c->evs1);
     for (auto& s : c->surf) release_surface(s);

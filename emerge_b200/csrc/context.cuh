@@ -138,7 +138,8 @@ struct emb_ctx {
     double rc_last_proj_relres = -1;    // relative residual left by the projection in the last solve
     double spmv_ms_sum = 0;   // sampled SpMV timings inside solves (CUDA events)
     int64_t spmv_ms_cnt = 0;
-    cudaEvent_t evs0 = nullptr, evs1 = nullptr, evt0 = nullptr, evt1 = nullptr;
+    cudaEvent_t evs0 = nullptr, evs1 = nullptr, evt0 = nullptr, evt1 = nullptr, evr0 = nullptr, evr1 = nullptr;
+    bool rc_sample_pending = false;
 };
 
 template <typename T>

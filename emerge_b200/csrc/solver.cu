@@ -746,7 +746,10 @@ static int rc_orth_column(emb_ctx* c, int j, int passes, double* norm_dev) {
 // C = A(f) U, orthonormalised, newest direction first (once per frequency)
 static int rc_rebuild(emb_ctx* c) {
     for (int j = 0; j < c->rc_n; ++j) {
+        const bool sample = (j == c->rc_n / 2) && !c->rc_sample_pending;     // one timed SpMV per frequency point
+        if (sample) cudaEventRecord(c->evr0, c->stream);
         EMB_TRY(spmv(c, c->A.p, rc_U(c, j), rc_C(c, j)));
+        if (sample) { cudaEventRecord(c->evr1, c->stream); c->rc_sample_pending = true; }
         c->rc_spmvs++;
         EMB_TRY(rc_orth_column(c, j, 1, nullptr));
     }
@@ -938,6 +941,11 @@ static int solve_device(emb_ctx* c, const emb_solve_opts* o, const cx* bs, cx* x
     float ms = 0;
     cudaEventElapsedTime(&ms, c->ev0, c->ev1);
     c->ms["solve"] = ms;
+    if (c->rc_sample_pending) {
+        float sms = 0;
+        if (cudaEventElapsedTime(&sms, c->evr0, c->evr1) == cudaSuccess) { c->spmv_ms_sum += sms; c->spmv_ms_cnt++; }
+        c->rc_sample_pending = false;
+    }
     if (info) { info->iters = its; info->relres = relres; info->ms = ms; info->spmvs = spmvs; }
     if (!(relres <= o->rtol)) {
         c->err = "solver did not reach rtol: relres=" + std::to_string(relres) + " after " + std::to_string(its) + " iterations";

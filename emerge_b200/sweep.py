@@ -318,9 +318,11 @@ class FrequencySweep:
             pa.active = False
         return S, stats, fields
 
-    def run(self, freqs, keep_fields=False, raise_on_fail=True, order=None) -> SweepResult:
+    def run(self, freqs, keep_fields=False, raise_on_fail=True, order=None, out_bufs=None, on_point=None) -> SweepResult:
         """Solves every frequency point; results are returned in the order of `freqs` (as emfreq3d.py:658 does).
-        order: processing order (list of indices); default hierarchical when recycling is on, else as given."""
+        order: processing order (list of indices); default hierarchical when recycling is on, else as given.
+        out_bufs: optional {port_number: complex128[n_field] host buffer (pinned)} receiving every solved field (D2H each
+        point, like data._fields[port] = x at emfreq3d.py:699); on_point(i, S_i, stats) is called after every point."""
         if not self._setup_done:
             self.f_ref = float(np.median(np.asarray(freqs, dtype=float)))
             self.setup()
@@ -334,8 +336,10 @@ class FrequencySweep:
             order = hierarchical_order(len(freqs)) if self.recycle else list(range(len(freqs)))
         stats = {}
         for i in order:
-            S[i], st, fl = self.solve_point(freqs[i], keep_fields, raise_on_fail)
+            S[i], st, fl = self.solve_point(freqs[i], keep_fields, raise_on_fail, out_bufs=out_bufs)
             stats[i] = st
+            if on_point is not None:
+                on_point(i, S[i], st)
             for k, v in fl.items():
                 res.fields[(i, k)] = v
         for i in range(len(freqs)):
