@@ -1,125 +1,137 @@
-// V-cycle of a smoothed-aggregation hierarchy on the GPU: real CSR matrices acting on complex vectors.
+// V-cycle of a smoothed-aggregation hierarchy on the GPU: real CSR matrices acting on NV interleaved complex vectors.
 //
 // The hierarchy (aggregates, smoothed prolongators, Galerkin operators, coarsest dense inverse) is built once per mesh on
 // the host (emerge_b200/amg.py) for the nodal auxiliary problems of the preconditioner; only the cycle runs here.
 // The reference has no counterpart (sparse direct solves, fem/solver.py:243-309).
 // Cycle (symmetric, so the preconditioner stays complex-symmetric for COCR):
 //   x = w D^-1 b;  b_c = P^T (b - A x);  x += P V(b_c);  x += w D^-1 (b - A x);   coarsest: x = A^-1 b (dense).
-// All kernels are short-row gathers (7-30 nonzeros per row): LPR lanes per row, 12 B per nonzero + 16 B gathers.
+// The matrices are shared by every auxiliary space that uses the hierarchy; the level vectors belong to the space
+// (AmgWork), so the cycles of different spaces run concurrently on different streams.
+// All kernels are short-row gathers: LPR lanes per row chosen from the average row length, 12 B per nonzero + gathers.
 #pragma once
-#include "context.cuh"
+#include "krylov.cuh"
 
 // MODE 0: y = A x        MODE 1: y = b - A x        MODE 2: y = x + w d (b - A x)   (out of place)
-template <int LPR, int MODE>
+// MODE 3: y += A x
+template <int LPR, int MODE, int NV>
 __global__ void __launch_bounds__(256) k_rcsr(int64_t n, const int64_t* __restrict__ ptr, const int* __restrict__ col,
                                               const double* __restrict__ val, const cx* __restrict__ x, cx* __restrict__ y,
                                               const cx* __restrict__ b, const double* __restrict__ d, double w) {
     const int64_t gt = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int64_t r = gt / LPR;
     const int sub = (int)(gt % LPR);
-    double ar = 0, ai = 0;
+    double ar[NV], ai[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) ar[v] = ai[v] = 0.0;
     if (r < n)
         for (int64_t k = ptr[r] + sub; k < ptr[r + 1]; k += LPR) {
             const double a = val[k];
-            const double2 v = __ldg(reinterpret_cast<const double2*>(x + col[k]));
-            ar += a * v.x;
-            ai += a * v.y;
+            const cx* xp = x + (int64_t)col[k] * NV;
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                const cx u = ldx(xp + v);
+                ar[v] += a * u.re;
+                ai[v] += a * u.im;
+            }
         }
 #pragma unroll
-    for (int o = LPR / 2; o > 0; o >>= 1) {
-        ar += __shfl_down_sync(0xffffffffu, ar, o, LPR);
-        ai += __shfl_down_sync(0xffffffffu, ai, o, LPR);
-    }
+    for (int o = LPR / 2; o > 0; o >>= 1)
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            ar[v] += __shfl_down_sync(0xffffffffu, ar[v], o, LPR);
+            ai[v] += __shfl_down_sync(0xffffffffu, ai[v], o, LPR);
+        }
     if (r < n && sub == 0) {
-        if (MODE == 0) y[r] = cx{ar, ai};
-        else if (MODE == 1) { const cx bb = b[r]; y[r] = cx{bb.re - ar, bb.im - ai}; }
-        else {
-            const cx bb = b[r], xx = x[r];
-            const double s = w * d[r];
-            y[r] = cx{xx.re + s * (bb.re - ar), xx.im + s * (bb.im - ai)};
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            const int64_t o = r * NV + v;
+            if (MODE == 0) y[o] = cx{ar[v], ai[v]};
+            else if (MODE == 1) { const cx bb = b[o]; y[o] = cx{bb.re - ar[v], bb.im - ai[v]}; }
+            else if (MODE == 2) {
+                const cx bb = b[o], xx = x[o];
+                const double s = w * d[r];
+                y[o] = cx{xx.re + s * (bb.re - ar[v]), xx.im + s * (bb.im - ai[v])};
+            } else {
+                const cx yy = y[o];
+                y[o] = cx{yy.re + ar[v], yy.im + ai[v]};
+            }
         }
     }
 }
-// y += s * (A x), complex s
-template <int LPR>
-__global__ void __launch_bounds__(256) k_rcsr_add(int64_t n, const int64_t* __restrict__ ptr, const int* __restrict__ col,
-                                                  const double* __restrict__ val, const cx* __restrict__ x, cx s,
-                                                  cx* __restrict__ y) {
-    const int64_t gt = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    const int64_t r = gt / LPR;
-    const int sub = (int)(gt % LPR);
-    double ar = 0, ai = 0;
-    if (r < n)
-        for (int64_t k = ptr[r] + sub; k < ptr[r + 1]; k += LPR) {
-            const double a = val[k];
-            const double2 v = __ldg(reinterpret_cast<const double2*>(x + col[k]));
-            ar += a * v.x;
-            ai += a * v.y;
-        }
-#pragma unroll
-    for (int o = LPR / 2; o > 0; o >>= 1) {
-        ar += __shfl_down_sync(0xffffffffu, ar, o, LPR);
-        ai += __shfl_down_sync(0xffffffffu, ai, o, LPR);
-    }
-    if (r < n && sub == 0) {
-        cx yy = y[r];
-        fma_c(yy, s, cx{ar, ai});
-        y[r] = yy;
-    }
-}
-// x = w d b
-__global__ void k_amg_smooth0(int64_t n, const double* __restrict__ d, double w, const cx* __restrict__ b, cx* __restrict__ x) {
+// x = w d b   (flat over n * nv entries)
+__global__ void k_amg_smooth0(int64_t n, int nv, const double* __restrict__ d, double w, const cx* __restrict__ b,
+                              cx* __restrict__ x) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i < n) { const double s = w * d[i]; const cx v = b[i]; x[i] = cx{s * v.re, s * v.im}; }
+    if (i < n * nv) { const double s = w * d[i / nv]; const cx v = b[i]; x[i] = cx{s * v.re, s * v.im}; }
 }
-// dense real matrix times complex vector, one warp per row
-__global__ void __launch_bounds__(256) k_dense_mv(int64_t n, const double* __restrict__ M, const cx* __restrict__ b, cx* __restrict__ x) {
+// dense real matrix times NV interleaved complex vectors, one warp per row
+template <int NV>
+__global__ void __launch_bounds__(256) k_dense_mv(int64_t n, const double* __restrict__ M, const cx* __restrict__ b,
+                                                  cx* __restrict__ x) {
     const int lane = threadIdx.x & 31;
     const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     if (r >= n) return;
-    double ar = 0, ai = 0;
+    double ar[NV], ai[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) ar[v] = ai[v] = 0.0;
     for (int64_t k = lane; k < n; k += 32) {
         const double a = M[r * n + k];
-        const cx v = b[k];
-        ar += a * v.re;
-        ai += a * v.im;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            const cx u = b[k * NV + v];
+            ar[v] += a * u.re;
+            ai[v] += a * u.im;
+        }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        ar += __shfl_down_sync(0xffffffffu, ar, o);
-        ai += __shfl_down_sync(0xffffffffu, ai, o);
-    }
-    if (lane == 0) x[r] = cx{ar, ai};
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            ar[v] += __shfl_down_sync(0xffffffffu, ar[v], o);
+            ai[v] += __shfl_down_sync(0xffffffffu, ai[v], o);
+        }
+    if (lane == 0)
+#pragma unroll
+        for (int v = 0; v < NV; ++v) x[r * NV + v] = cx{ar[v], ai[v]};
 }
 
-constexpr int AMG_LPR = 4;
+// lanes per row from the average row length (rows of P^T hold a whole aggregate neighbourhood: 50-200 entries)
+static inline int pick_lpr(int64_t nnz, int64_t n) {
+    const double avg = n > 0 ? (double)nnz / (double)n : 0.0;
+    return avg <= 12.0 ? 4 : (avg <= 48.0 ? 8 : 32);
+}
+template <int MODE, int NV>
+static int rcsr_launch(emb_ctx* c, cudaStream_t s, int lpr, int64_t n, const int64_t* ptr, const int* col, const double* val,
+                       const cx* x, cx* y, const cx* b, const double* d, double w) {
+    if (lpr == 4) k_rcsr<4, MODE, NV><<<blocks_for(n * 4, 256), 256, 0, s>>>(n, ptr, col, val, x, y, b, d, w);
+    else if (lpr == 8) k_rcsr<8, MODE, NV><<<blocks_for(n * 8, 256), 256, 0, s>>>(n, ptr, col, val, x, y, b, d, w);
+    else k_rcsr<32, MODE, NV><<<blocks_for(n * 32, 256), 256, 0, s>>>(n, ptr, col, val, x, y, b, d, w);
+    EMB_LAUNCH_CHECK(c);
+    return EMB_OK;
+}
 
-// V-cycle with right-hand side in lev[0].b; returns the device pointer holding the result (a level-0 buffer)
-static int amg_vcycle(emb_ctx* c, AmgHierarchy& H, cx** result) {
+// V-cycle on stream s with right-hand side in W.b[0]; returns the device pointer holding the result (a level-0 buffer)
+template <int NV>
+static int amg_vcycle(emb_ctx* c, cudaStream_t s, AmgHierarchy& H, AmgWork& W, cx** result) {
     const int L = (int)H.lev.size();
     std::vector<cx*> xs(L, nullptr);
     for (int l = 0; l < L; ++l) {
         AmgLevel& v = H.lev[l];
         if (l == L - 1) {
-            k_dense_mv<<<blocks_for(v.n * 32, 256), 256, 0, c->stream>>>(v.n, H.cinv.p, v.b.p, v.xa.p); EMB_LAUNCH_CHECK(c);
-            xs[l] = v.xa.p;
+            k_dense_mv<NV><<<blocks_for(v.n * 32, 256), 256, 0, s>>>(v.n, H.cinv.p, W.b[l].p, W.xa[l].p); EMB_LAUNCH_CHECK(c);
+            xs[l] = W.xa[l].p;
             break;
         }
-        AmgLevel& nx = H.lev[l + 1];
-        k_amg_smooth0<<<blocks_for(v.n, 256), 256, 0, c->stream>>>(v.n, v.dinv.p, v.omega, v.b.p, v.xa.p); EMB_LAUNCH_CHECK(c);
-        k_rcsr<AMG_LPR, 1><<<blocks_for(v.n * AMG_LPR, 256), 256, 0, c->stream>>>(v.n, v.aptr.p, v.acol.p, v.aval.p, v.xa.p, v.t.p,
-                                                                                 v.b.p, nullptr, 0.0); EMB_LAUNCH_CHECK(c);
-        k_rcsr<AMG_LPR, 0><<<blocks_for(v.nc * AMG_LPR, 256), 256, 0, c->stream>>>(v.nc, v.tptr.p, v.tcol.p, v.tval.p, v.t.p, nx.b.p,
-                                                                                  nullptr, nullptr, 0.0); EMB_LAUNCH_CHECK(c);
-        xs[l] = v.xa.p;
+        k_amg_smooth0<<<blocks_for(v.n * NV, 256), 256, 0, s>>>(v.n, NV, v.dinv.p, v.omega, W.b[l].p, W.xa[l].p); EMB_LAUNCH_CHECK(c);
+        EMB_TRY((rcsr_launch<1, NV>(c, s, v.lpr_a, v.n, v.aptr.p, v.acol.p, v.aval.p, W.xa[l].p, W.t[l].p, W.b[l].p, nullptr, 0.0)));
+        EMB_TRY((rcsr_launch<0, NV>(c, s, v.lpr_t, v.nc, v.tptr.p, v.tcol.p, v.tval.p, W.t[l].p, W.b[l + 1].p, nullptr, nullptr, 0.0)));
+        xs[l] = W.xa[l].p;
     }
     for (int l = L - 2; l >= 0; --l) {
         AmgLevel& v = H.lev[l];
-        k_rcsr_add<AMG_LPR><<<blocks_for(v.n * AMG_LPR, 256), 256, 0, c->stream>>>(v.n, v.pptr.p, v.pcol.p, v.pval.p, xs[l + 1],
-                                                                                  mk(1.0), v.xa.p); EMB_LAUNCH_CHECK(c);
-        k_rcsr<AMG_LPR, 2><<<blocks_for(v.n * AMG_LPR, 256), 256, 0, c->stream>>>(v.n, v.aptr.p, v.acol.p, v.aval.p, v.xa.p, v.xb.p,
-                                                                                 v.b.p, v.dinv.p, v.omega); EMB_LAUNCH_CHECK(c);
-        xs[l] = v.xb.p;
+        EMB_TRY((rcsr_launch<3, NV>(c, s, v.lpr_p, v.n, v.pptr.p, v.pcol.p, v.pval.p, xs[l + 1], W.xa[l].p, nullptr, nullptr, 0.0)));
+        EMB_TRY((rcsr_launch<2, NV>(c, s, v.lpr_a, v.n, v.aptr.p, v.acol.p, v.aval.p, W.xa[l].p, W.xb[l].p, W.b[l].p, v.dinv.p, v.omega)));
+        xs[l] = W.xb[l].p;
     }
     *result = xs[0];
     return EMB_OK;
@@ -129,8 +141,28 @@ static void amg_release(AmgHierarchy& H) {
     for (auto& v : H.lev) {
         v.aptr.release(); v.pptr.release(); v.tptr.release(); v.acol.release(); v.pcol.release(); v.tcol.release();
         v.aval.release(); v.pval.release(); v.tval.release(); v.dinv.release();
-        v.b.release(); v.xa.release(); v.xb.release(); v.t.release();
     }
     H.lev.clear();
     H.cinv.release();
+}
+static void amg_work_release(AmgWork& W) {
+    for (auto& b : W.b) b.release();
+    for (auto& b : W.xa) b.release();
+    for (auto& b : W.xb) b.release();
+    for (auto& b : W.t) b.release();
+    W.b.clear(); W.xa.clear(); W.xb.clear(); W.t.clear();
+}
+static int amg_work_alloc(emb_ctx* c, const AmgHierarchy& H, AmgWork& W) {
+    const size_t L = H.lev.size();
+    W.b.resize(L); W.xa.resize(L); W.xb.resize(L); W.t.resize(L);
+    for (size_t l = 0; l < L; ++l) {
+        const size_t n = (size_t)H.lev[l].n * NVMAX;
+        EMB_TRY(dev_alloc(c, W.b[l], n));
+        EMB_TRY(dev_alloc(c, W.xa[l], n));
+        if (H.lev[l].nc > 0) {
+            EMB_TRY(dev_alloc(c, W.xb[l], n));
+            EMB_TRY(dev_alloc(c, W.t[l], n));
+        }
+    }
+    return EMB_OK;
 }

@@ -240,6 +240,8 @@ extern "C" int emb_symbolic(emb_ctx* c) {
     rowlen.release(); errflag.release(); tmp.release();
     c->have_pattern = true;
     c->have_KM = c->have_dirichlet = c->have_A = false;
+    c->asm_items.release();
+    c->asm_chunk = 0;
     return EMB_OK;
 }
 
@@ -405,7 +407,8 @@ __global__ void __launch_bounds__(TWARPS * 32) k_tet(int64_t t0, int64_t t1, int
 constexpr int RWARPS = 4;
 constexpr int ROWCAP = 192;    // row entries cached in shared memory per warp; longer rows use global memory
 
-__global__ void __launch_bounds__(RWARPS * 32) k_reduce_rows(int64_t N, int64_t t0, int64_t t1, int first,
+__global__ void __launch_bounds__(RWARPS * 32) k_reduce_rows(int64_t N, int64_t t0, int64_t t1, int first_launch,
+                                                             const unsigned long long* __restrict__ items,
                                                              const int64_t* __restrict__ rowptr, const int* __restrict__ col,
                                                              const int64_t* __restrict__ adjptr, const int* __restrict__ adj,
                                                              const int* __restrict__ gid, const cx* __restrict__ cooK,
@@ -414,8 +417,19 @@ __global__ void __launch_bounds__(RWARPS * 32) k_reduce_rows(int64_t N, int64_t 
     __shared__ double2 s_K[RWARPS][ROWCAP];
     __shared__ double2 s_M[RWARPS][ROWCAP];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t r = blockIdx.x * (int64_t)RWARPS + warp;
-    if (r >= N) return;
+    // work unit: a whole row (items == nullptr, N rows), or the part of a row that lies in the tet chunk [t0, t1)
+    // (items: N packed (row << 32 | first adjacency index of the chunk) entries, see build_chunk_items)
+    const int64_t w = blockIdx.x * (int64_t)RWARPS + warp;
+    if (w >= N) return;
+    int64_t r = w, ai0 = -1;
+    if (items) {
+        const unsigned long long it = items[w];
+        r = (int64_t)(it >> 32);
+        ai0 = (int64_t)(it & 0xffffffffull);
+    }
+    const int64_t a0 = adjptr[r], a1 = adjptr[r + 1];
+    const bool first = items ? (ai0 == a0) : (first_launch != 0);
+    if (!items) ai0 = a0;
     const int64_t p0 = rowptr[r];
     const int len = (int)(rowptr[r + 1] - p0);
     const bool in_smem = len <= ROWCAP;
@@ -439,11 +453,11 @@ __global__ void __launch_bounds__(RWARPS * 32) k_reduce_rows(int64_t N, int64_t 
         }
     }
     __syncwarp();
-    const int64_t a0 = adjptr[r], a1 = adjptr[r + 1];
-    for (int64_t ai = a0; ai < a1; ++ai) {
+    for (int64_t ai = ai0; ai < a1; ++ai) {
         const int a = adj[ai];            // tet*20 + canonical local row, ascending in tet
         const int t = a / 20;
-        if (t < t0 || t >= t1) continue;
+        if (t < t0) continue;
+        if (t >= t1) break;
         if (lane < 20) {
             const int cj = gid[(int64_t)t * 20 + lane];
             const int64_t src = ((int64_t)(a - t0 * 20)) * 20 + lane;
@@ -474,6 +488,93 @@ __global__ void __launch_bounds__(RWARPS * 32) k_reduce_rows(int64_t N, int64_t 
         }
 }
 
+// ---- chunk work lists ------------------------------------------------------------------------------------
+// The numeric phase runs chunk by chunk over the tetrahedra so that the COO scratch of one chunk (12.8 KB per tet)
+// stays resident in the 126 MB L2 between the element kernel that writes it and the reduction that reads it: HBM then
+// only sees the inputs and the K/M rows.  A row is touched by every chunk that owns one of its tets; the partial sums
+// are carried in K/M themselves, chunks run in ascending tet order, so the additions happen in exactly the order of
+// the single-pass reduction (bitwise identical result).
+__global__ void k_count_items(int64_t N, int64_t CT, const int64_t* __restrict__ adjptr, const int* __restrict__ adj,
+                              int* __restrict__ cnt) {
+    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= N) return;
+    int n = 0;
+    int64_t prev = -1;
+    for (int64_t ai = adjptr[r]; ai < adjptr[r + 1]; ++ai) {
+        const int64_t ch = (adj[ai] / 20) / CT;
+        if (ch != prev) { ++n; prev = ch; }
+    }
+    cnt[r] = n;
+}
+__global__ void k_fill_items(int64_t N, int64_t CT, const int64_t* __restrict__ adjptr, const int* __restrict__ adj,
+                             const int* __restrict__ off, int* __restrict__ key, unsigned long long* __restrict__ val) {
+    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= N) return;
+    int o = off[r];
+    int64_t prev = -1;
+    for (int64_t ai = adjptr[r]; ai < adjptr[r + 1]; ++ai) {
+        const int64_t ch = (adj[ai] / 20) / CT;
+        if (ch != prev) {
+            key[o] = (int)ch;
+            val[o] = ((unsigned long long)r << 32) | (unsigned long long)(unsigned)ai;
+            ++o;
+            prev = ch;
+        }
+    }
+}
+
+static int build_chunk_items(emb_ctx* c, int64_t CT) {
+    if (c->asm_chunk == CT && c->asm_items.p) return EMB_OK;
+    const int64_t N = c->N;
+    const int64_t nch = (c->nT + CT - 1) / CT;
+    DevBuf<int> cnt, off, key, key2;
+    DevBuf<unsigned long long> val;
+    DevBuf<char> tmp;
+    EMB_TRY(dev_alloc(c, cnt, (size_t)N + 1));
+    EMB_TRY(dev_alloc(c, off, (size_t)N + 1));
+    EMB_CUDA(c, cudaMemsetAsync(cnt.p + N, 0, sizeof(int), c->stream));
+    k_count_items<<<blocks_for(N, 256), 256, 0, c->stream>>>(N, CT, c->adjptr.p, c->adj.p, cnt.p);
+    EMB_LAUNCH_CHECK(c);
+    size_t tb = 0;
+    EMB_CUDA(c, cub::DeviceScan::ExclusiveSum(nullptr, tb, cnt.p, off.p, (int)(N + 1), c->stream));
+    EMB_TRY(dev_alloc(c, tmp, tb));
+    EMB_CUDA(c, cub::DeviceScan::ExclusiveSum(tmp.p, tb, cnt.p, off.p, (int)(N + 1), c->stream));
+    int nitems = 0;
+    EMB_CUDA(c, cudaMemcpyAsync(&nitems, off.p + N, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    EMB_CUDA(c, cudaStreamSynchronize(c->stream));
+    EMB_TRY(dev_alloc(c, key, (size_t)nitems));
+    EMB_TRY(dev_alloc(c, key2, (size_t)nitems));
+    EMB_TRY(dev_alloc(c, val, (size_t)nitems));
+    EMB_TRY(dev_alloc(c, c->asm_items, (size_t)nitems));
+    k_fill_items<<<blocks_for(N, 256), 256, 0, c->stream>>>(N, CT, c->adjptr.p, c->adj.p, off.p, key.p, val.p);
+    EMB_LAUNCH_CHECK(c);
+    int bits = 1;
+    while (((int64_t)1 << bits) < nch) ++bits;
+    // stable sort by chunk: inside a chunk the items stay in ascending row order
+    size_t tb2 = 0;
+    EMB_CUDA(c, cub::DeviceRadixSort::SortPairs(nullptr, tb2, key.p, key2.p, val.p, c->asm_items.p, nitems, 0, bits, c->stream));
+    if (tb2 > tmp.n) EMB_TRY(dev_alloc(c, tmp, tb2));
+    EMB_CUDA(c, cub::DeviceRadixSort::SortPairs(tmp.p, tb2, key.p, key2.p, val.p, c->asm_items.p, nitems, 0, bits, c->stream));
+    DevBuf<int64_t> ptr;
+    EMB_TRY(dev_alloc(c, ptr, (size_t)nch + 1));
+    k_segptr<<<blocks_for(nitems, 256), 256, 0, c->stream>>>(key2.p, nitems, nch, ptr.p);
+    EMB_LAUNCH_CHECK(c);
+    c->launches += 6;
+    c->asm_chunk_ptr.resize((size_t)nch + 1);
+    EMB_CUDA(c, cudaMemcpyAsync(c->asm_chunk_ptr.data(), ptr.p, (size_t)(nch + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+    EMB_CUDA(c, cudaStreamSynchronize(c->stream));
+    cnt.release(); off.release(); key.release(); key2.release(); val.release(); tmp.release(); ptr.release();
+    c->asm_chunk = CT;
+    return EMB_OK;
+}
+
+extern "C" int emb_assemble_config(emb_ctx* c, int64_t chunk_tets, int persist_l2) {
+    if (!c || chunk_tets < 0) return EMB_ERR_ARG;
+    c->asm_chunk_req = chunk_tets;
+    c->asm_persist = persist_l2 != 0;
+    return EMB_OK;
+}
+
 extern "C" int emb_assemble_KM(emb_ctx* c) {
     if (!c || !c->have_pattern || !c->have_mat) {
         if (c) c->err = "emb_assemble_KM: needs emb_symbolic and emb_upload_materials first";
@@ -481,36 +582,90 @@ extern "C" int emb_assemble_KM(emb_ctx* c) {
     }
     EMB_TRY(dev_alloc(c, c->K, (size_t)c->nnz));
     EMB_TRY(dev_alloc(c, c->M, (size_t)c->nnz));
-    // COO scratch: 12.8 KB per tet; chunk so that it stays below ~48 GB
-    const int64_t max_chunk = (int64_t)(48.0e9 / 12800.0);
-    const int64_t chunk = c->nT < max_chunk ? c->nT : max_chunk;
-    DevBuf<cx> cooK, cooM;
-    EMB_TRY(dev_alloc(c, cooK, (size_t)chunk * 400));
-    EMB_TRY(dev_alloc(c, cooM, (size_t)chunk * 400));
-    double ms_tet = 0, ms_red = 0;
-    for (int64_t t0 = 0; t0 < c->nT; t0 += chunk) {
-        const int64_t t1 = (t0 + chunk < c->nT) ? t0 + chunk : c->nT;
+    // chunk size in tets: 0 (default) = single pass, the COO scratch makes one round trip through HBM.  Chunks of one
+    // wave of element-kernel blocks (32 tets x 148 SMs = 60 MB of COO, pinned in L2) were measured on a B200 and LOSE
+    // (1M tets: 16.6 ms vs 14.4 ms, profiles/r1_asm_chunk_sweep.json): one block per SM leaves the element kernel
+    // latency-bound and the per-chunk reductions re-read partially summed rows.  The option stays for experiments.
+    int64_t CT = c->asm_chunk_req;
+    if (const char* e = getenv("EMB_ASM_CHUNK")) CT = atoll(e);
+    if (CT <= 0) CT = c->nT;
+    const int64_t max_chunk = (int64_t)(48.0e9 / 12800.0);      // single-pass scratch stays below ~48 GB
+    if (CT > max_chunk) CT = max_chunk;
+    const bool chunked = CT < c->nT;
+    const int64_t chunk = chunked ? CT : c->nT;
+    DevBuf<cx> coo;                                              // [K | M] of one chunk, one allocation (one L2 window)
+    EMB_TRY(dev_alloc(c, coo, (size_t)chunk * 800));
+    cx* cooK = coo.p;
+    cx* cooM = coo.p + chunk * 400;
+    if (!chunked) {
+        double ms_tet = 0, ms_red = 0;
         {
             PhaseTimer pt(c, "tet_kernel");
-            k_tet<<<blocks_for(t1 - t0, 32), TWARPS * 32, 0, c->stream>>>(t0, t1, c->nT, c->tetc.p, c->nodes.p, c->er.p, c->ur.p,
-                                                                  cooK.p, cooM.p);
+            k_tet<<<blocks_for(c->nT, 32), TWARPS * 32, 0, c->stream>>>(0, c->nT, c->nT, c->tetc.p, c->nodes.p, c->er.p, c->ur.p,
+                                                                       cooK, cooM);
             EMB_LAUNCH_CHECK(c);
         }
-        ms_tet += c->ms["tet_kernel"];
+        ms_tet = c->ms["tet_kernel"];
         {
             PhaseTimer pt(c, "reduce");
             k_reduce_rows<<<blocks_for(c->N, RWARPS), RWARPS * 32, 0, c->stream>>>(
-                c->N, t0, t1, t0 == 0 ? 1 : 0, c->rowptr.p, c->col.p, c->adjptr.p, c->adj.p, c->gid.p, cooK.p, cooM.p,
-                c->K.p, c->M.p);
+                c->N, 0, c->nT, 1, nullptr, c->rowptr.p, c->col.p, c->adjptr.p, c->adj.p, c->gid.p, cooK, cooM, c->K.p, c->M.p);
             EMB_LAUNCH_CHECK(c);
         }
-        ms_red += c->ms["reduce"];
+        ms_red = c->ms["reduce"];
+        c->ms["assemble"] = ms_tet + ms_red;
+    } else {
+        EMB_TRY(build_chunk_items(c, CT));
+        bool window = false;
+        bool persist = c->asm_persist;
+        if (const char* e = getenv("EMB_ASM_PERSIST")) persist = atoi(e) != 0;
+        if (persist) {
+            cudaDeviceProp prop;
+            if (cudaGetDeviceProperties(&prop, c->device) == cudaSuccess && prop.persistingL2CacheMaxSize > 0) {
+                const size_t bytes = (size_t)chunk * 800 * sizeof(cx);
+                const size_t carve = bytes < (size_t)prop.persistingL2CacheMaxSize ? bytes : (size_t)prop.persistingL2CacheMaxSize;
+                cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve);
+                cudaStreamAttrValue av;
+                memset(&av, 0, sizeof(av));
+                av.accessPolicyWindow.base_ptr = coo.p;
+                av.accessPolicyWindow.num_bytes = bytes < (size_t)prop.accessPolicyMaxWindowSize ? bytes : (size_t)prop.accessPolicyMaxWindowSize;
+                av.accessPolicyWindow.hitRatio = (float)((double)carve / (double)av.accessPolicyWindow.num_bytes);
+                if (av.accessPolicyWindow.hitRatio > 1.0f) av.accessPolicyWindow.hitRatio = 1.0f;
+                av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+                av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+                window = cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &av) == cudaSuccess;
+                cudaGetLastError();
+            }
+        }
+        {
+            PhaseTimer pt(c, "assemble");
+            const int64_t nch = (c->nT + CT - 1) / CT;
+            for (int64_t ch = 0; ch < nch; ++ch) {
+                const int64_t t0 = ch * CT, t1 = (t0 + CT < c->nT) ? t0 + CT : c->nT;
+                k_tet<<<blocks_for(t1 - t0, 32), TWARPS * 32, 0, c->stream>>>(t0, t1, c->nT, c->tetc.p, c->nodes.p, c->er.p,
+                                                                             c->ur.p, cooK, cooM);
+                EMB_LAUNCH_CHECK(c);
+                const int64_t i0 = c->asm_chunk_ptr[(size_t)ch], i1 = c->asm_chunk_ptr[(size_t)ch + 1];
+                if (i1 > i0) {
+                    k_reduce_rows<<<blocks_for(i1 - i0, RWARPS), RWARPS * 32, 0, c->stream>>>(
+                        i1 - i0, t0, t1, 0, c->asm_items.p + i0, c->rowptr.p, c->col.p, c->adjptr.p, c->adj.p, c->gid.p, cooK,
+                        cooM, c->K.p, c->M.p);
+                    EMB_LAUNCH_CHECK(c);
+                }
+            }
+        }
+        if (window) {
+            cudaStreamAttrValue av;
+            memset(&av, 0, sizeof(av));
+            cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &av);
+            cudaCtxResetPersistingL2Cache();
+            cudaGetLastError();
+        }
+        c->ms.erase("tet_kernel");
+        c->ms.erase("reduce");
     }
-    c->ms["tet_kernel"] = ms_tet;
-    c->ms["reduce"] = ms_red;
     EMB_CUDA(c, cudaStreamSynchronize(c->stream));
-    cooK.release();
-    cooM.release();
+    coo.release();
     c->have_KM = true;
     c->have_A = false;
     return EMB_OK;

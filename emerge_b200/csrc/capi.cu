@@ -35,7 +35,7 @@ extern "C" void emb_destroy(emb_ctx* c) {
     cudaStreamSynchronize(c->stream);
     c->nodes.release(); c->tris.release(); c->tri2f.release(); c->tetc.release(); c->tetord.release(); c->gid.release();
     c->er.release(); c->ur.release(); c->adjptr.release(); c->adj.release(); c->rowptr.release(); c->col.release();
-    c->K.release(); c->M.release(); c->newid.release(); c->solve_ids.release(); c->rowptr_s.release();
+    c->K.release(); c->M.release(); c->asm_items.release(); c->newid.release(); c->solve_ids.release(); c->rowptr_s.release();
     c->col_s.release(); c->src.release(); c->A.release(); c->xs.release(); c->xfull.release();
     for (auto& w : c->work) w.release();
     c->dinv.release(); c->pairmate.release(); c->red.release(); c->As.release(); c->rc_x0.release();
@@ -112,5 +112,15 @@ extern "C" int emb_timer_stop(emb_ctx* c, double* ms) {
     float f = 0;
     EMB_CUDA(c, cudaEventElapsedTime(&f, c->evt0, c->evt1));
     *ms = f;
+    return EMB_OK;
+}
+
+// cudaProfilerStart/Stop for `ncu --profile-from-start off` windows (the library links cudart statically, so the
+// host side cannot reach the same runtime instance through ctypes)
+#include <cuda_profiler_api.h>
+extern "C" int emb_profiler(emb_ctx* c, int on) {
+    if (!c) return EMB_ERR_ARG;
+    EMB_CUDA(c, cudaStreamSynchronize(c->stream));
+    EMB_CUDA(c, on ? cudaProfilerStart() : cudaProfilerStop());
     return EMB_OK;
 }

@@ -2,6 +2,7 @@
 #pragma once
 #include "emb_common.cuh"
 #include "emerge_b200.h"
+#include <complex>
 #include <map>
 #include <vector>
 
@@ -48,12 +49,16 @@ struct AmgLevel {
     DevBuf<int> acol, pcol, tcol;
     DevBuf<double> aval, pval, tval, dinv;
     double omega = 1.0;
-    DevBuf<cx> b, xa, xb, t;
+    int lpr_a = 4, lpr_p = 4, lpr_t = 4;      // lanes per row of the A, P and P^T kernels (from the average row length)
 };
 struct AmgHierarchy {
     std::vector<AmgLevel> lev;
     DevBuf<double> cinv;            // dense inverse of the coarsest matrix, row-major [n][n]
     int64_t ncinv = 0;
+};
+// level vectors of one user of a hierarchy (NVMAX interleaved columns each)
+struct AmgWork {
+    std::vector<DevBuf<cx>> b, xa, xb, t;
 };
 
 // auxiliary space of the additive multilevel preconditioner: real transfer matrix R (rows of the parent space x ncol)
@@ -66,7 +71,8 @@ struct AuxSpace {
     DevBuf<int64_t> rptr, tptr;     // R rows [nrow+1], R^T rows [ncol+1]
     DevBuf<int> rcol, tcol;
     DevBuf<double> rval, tval;
-    DevBuf<cx> dinv, tmp, traw;     // 1/diag(R^T A R); correction x [ncol]; raw restricted residual [ncol] (if children)
+    DevBuf<cx> dinv, tmp, traw;     // 1/diag(R^T A R) [ncol]; correction x, raw restricted residual [ncol][NVMAX]
+    AmgWork wk;                     // V-cycle vectors (solver 1)
 };
 
 struct emb_ctx {
@@ -98,6 +104,11 @@ struct emb_ctx {
     bool have_pattern = false;
     DevBuf<cx> K, M;          // [nnz]
     bool have_KM = false;
+    // chunked numeric phase (assembly.cu): (row, chunk) work items sorted by chunk, host copy of the chunk offsets
+    int64_t asm_chunk_req = 0, asm_chunk = 0;
+    bool asm_persist = true;
+    DevBuf<unsigned long long> asm_items;
+    std::vector<int64_t> asm_chunk_ptr;
 
     // solve space
     int64_t Ns = 0, nnz_s = 0;
@@ -122,24 +133,46 @@ struct emb_ctx {
     DevBuf<double> red;       // reduction scratch
     std::vector<AuxSpace> aux;
     std::vector<AmgHierarchy> amg;
-    DevBuf<cx> As;            // symmetric part of A (COCR operator), cached between solves of one frequency
+    // inner operator of COCR: symmetric part of A(f), stored complex64 (default) or complex128; cached between the
+    // solves of one frequency
+    DevBuf<cx> As;
+    DevBuf<float> As32;       // [nnz_s][2]
+    bool as_fp32 = true;
     bool have_As = false;
     int As_precond = -1;
-    // Subspace recycling across the frequency points of a sweep (solver.cu): U spans previous Krylov corrections,
-    // C = A(f) U is re-formed and orthonormalised once per frequency; x0 = U C^H b is the minimum-residual start.
-    int rc_cap = 0, rc_n = 0;
-    DevBuf<cx> rcU, rcC;                // [rc_cap][Ns]; ring, NEWEST first: slot (rc_head + j) % rc_cap is the j-th newest
-    int rc_head = 0;
-    bool rc_C_valid = false;
+    // side streams of the additive preconditioner (independent auxiliary spaces run concurrently) and their events
+    static constexpr int NSIDE = 6;
+    cudaStream_t side[NSIDE] = {};
+    cudaEvent_t ev_fork = nullptr;
+    std::vector<cudaEvent_t> ev_restr, ev_done;
+    bool use_side_streams = true;
+    // Reduced-basis recycling across the frequency points of a sweep (recycle.cuh).  U: solution directions of earlier
+    // solves (any port, any frequency).  A(f) = sum_t coef_t(f) W_t is affine in T = 2 + nsurf fixed matrices
+    // (K, M, S_p), so W_t u is computed ONCE per direction and kept in an orthonormal basis Q with small host-side
+    // coefficient matrices R_t:  W_t U = Q R_t,  A(f) U = Q G(f),  G(f) = sum_t coef_t(f) R_t.
+    int rc_cap = 0, rc_n = 0;           // directions held: slots 0..rc_n-1, oldest first
+    int rc_nq = 0, rc_qcap = 0;         // columns of Q in use / allocated
+    DevBuf<cx> rcU, rcQ;                // [rc_cap][Ns], [rc_qcap][Ns]
+    std::vector<int> rc_terms;          // surface ids of the affine terms 2.. (terms 0, 1 are K and M)
+    std::vector<std::vector<std::complex<double>>> rc_R;   // [T] column-major rc_qcap x rc_cap
+    std::vector<double> rc_uscale;      // x0 = sum_j y_j * uscale_j * U_j
+    std::vector<std::complex<double>> aff_coef;            // coefficients of the last emb_form_A: 1, -k0^2, gamma_p...
+    std::vector<int> aff_sids;
     double rc_snap = 0.1;               // solves that feed the recycled space run to rc_snap * rtol
-    DevBuf<cx> rc_x0;                   // start vector of the current solve (new direction = x - x0)
-    DevBuf<cx> rc_part;                 // [rc_cap][RC_NP] dot partials + [rc_cap] coefficients
-    int64_t rc_spmvs = 0;               // SpMVs spent on C = A U so far (reported by emb_recycle_info)
+    DevBuf<cx> rc_x0;                   // start vectors of the current solve (new direction = x - x0)
+    DevBuf<cx> rc_part;                 // dot partials + coefficients of the batched Gram-Schmidt / projection kernels
+    DevBuf<cx> rc_tmp;                  // one contiguous vector
+    int64_t rc_spmvs = 0;               // SpMVs spent on W_t u so far (reported by emb_recycle_info)
+    int64_t rc_rebuilds = 0;
     double rc_last_proj_relres = -1;    // relative residual left by the projection in the last solve
+    int nsol = 0;                       // columns of the last lockstep solve held in xs
     double spmv_ms_sum = 0;   // sampled SpMV timings inside solves (CUDA events)
     int64_t spmv_ms_cnt = 0;
+    double prec_ms_sum = 0;   // sampled preconditioner applications
+    int64_t prec_ms_cnt = 0;
     cudaEvent_t evs0 = nullptr, evs1 = nullptr, evt0 = nullptr, evt1 = nullptr, evr0 = nullptr, evr1 = nullptr;
-    bool rc_sample_pending = false;
+    cudaEvent_t evp0 = nullptr, evp1 = nullptr;
+    int64_t graph_launches = 0;
 };
 
 template <typename T>

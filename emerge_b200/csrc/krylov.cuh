@@ -1,0 +1,285 @@
+// Multi-right-hand-side building blocks of the frequency-domain solve (sm_100a, FP64 arithmetic).
+//
+// All ports of one frequency point are solved in lockstep: NV (1, 2 or 4) vectors are stored INTERLEAVED,
+// v[i * NV + k] = entry i of right-hand side k.  The operator is then read ONCE per iteration for all ports
+// (the matrix is 93 % of the SpMV traffic), every gather of x is a full 32-byte sector or more, and the
+// latency-bound multilevel kernels are shared.  Every reduction is per column, in a fixed order (block partials
+// summed by the consumer kernel), so results are bitwise reproducible and column k does not depend on what the
+// other columns hold.
+//
+// Reference path replaced: the per-port loop around SolveRoutine.solve (fem/physics/edm/emfreq3d.py:683-694,
+// fem/solver.py:405-469), which factorises once and back-substitutes per port.
+#pragma once
+#include "context.cuh"
+
+constexpr int NPART = 1024;          // block partials per reduction (fixed => deterministic)
+constexpr int VBLOCK = 256;
+constexpr int NVMAX = 4;             // widest lockstep group
+
+// complex64 storage of the inner (preconditioned, complex-symmetric) operator; arithmetic stays FP64
+struct cf {
+    float re, im;
+};
+__device__ __forceinline__ cx ldval(const cx* __restrict__ v, int64_t k) {
+    const double2 a = __ldg(reinterpret_cast<const double2*>(v + k));
+    return cx{a.x, a.y};
+}
+__device__ __forceinline__ cx ldval(const cf* __restrict__ v, int64_t k) {
+    const float2 a = __ldg(reinterpret_cast<const float2*>(v + k));
+    return cx{(double)a.x, (double)a.y};
+}
+__device__ __forceinline__ void stval(cx* v, int64_t k, cx a) { *reinterpret_cast<double2*>(v + k) = make_double2(a.re, a.im); }
+__device__ __forceinline__ void stval(cf* v, int64_t k, cx a) {
+    *reinterpret_cast<float2*>(v + k) = make_float2((float)a.re, (float)a.im);
+}
+__device__ __forceinline__ cx ldx(const cx* __restrict__ p) {
+    const double2 a = __ldg(reinterpret_cast<const double2*>(p));
+    return cx{a.x, a.y};
+}
+// a / b, 0 when b == 0 (a frozen column: zero right-hand side or an exactly converged recurrence)
+__device__ __forceinline__ cx sdiv(cx a, cx b) {
+    const double d = b.re * b.re + b.im * b.im;
+    if (!(d > 0.0)) return cx{0.0, 0.0};
+    const double s = 1.0 / d;
+    return cx{(a.re * b.re + a.im * b.im) * s, (a.im * b.re - a.re * b.im) * s};
+}
+
+// ------------------------------------------------------------------------------------------------
+// SpMV / SpMM: LPR lanes per row, NV interleaved vectors.  RESID: y = b - A x.
+// Algorithmic bytes: nnz * (sizeof(VT) + 4) + n * (8 + 32 * NV)   (+16 * NV * n for b when RESID)
+// ------------------------------------------------------------------------------------------------
+template <int NV, typename VT, int LPR, bool RESID>
+__global__ void __launch_bounds__(256) k_spmv(int64_t n, const int64_t* __restrict__ rowptr, const int* __restrict__ col,
+                                              const VT* __restrict__ val, const cx* __restrict__ x, const cx* __restrict__ b,
+                                              cx* __restrict__ y) {
+    const int64_t gt = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t r = gt / LPR;
+    const int sub = (int)(gt % LPR);
+    double ar[NV], ai[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) ar[v] = ai[v] = 0.0;
+    if (r < n) {
+        const int64_t p0 = rowptr[r], p1 = rowptr[r + 1];
+#pragma unroll 2
+        for (int64_t k = p0 + sub; k < p1; k += LPR) {
+            const cx a = ldval(val, k);
+            const cx* xp = x + (int64_t)__ldg(col + k) * NV;
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                const cx w = ldx(xp + v);
+                ar[v] += a.re * w.re - a.im * w.im;
+                ai[v] += a.re * w.im + a.im * w.re;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1)
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            ar[v] += __shfl_down_sync(0xffffffffu, ar[v], o, LPR);
+            ai[v] += __shfl_down_sync(0xffffffffu, ai[v], o, LPR);
+        }
+    if (r < n && sub == 0) {
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            double2 o2 = make_double2(ar[v], ai[v]);
+            if (RESID) {
+                const double2 bb = *reinterpret_cast<const double2*>(b + r * NV + v);
+                o2 = make_double2(bb.x - ar[v], bb.y - ai[v]);
+            }
+            *reinterpret_cast<double2*>(y + r * NV + v) = o2;
+        }
+    }
+}
+
+constexpr int SPMV_LPR = 8;      // ~43 nonzeros per row of the order-2 Nedelec operator
+template <int NV, typename VT>
+static int spmv(emb_ctx* c, const VT* val, const cx* x, cx* y) {
+    k_spmv<NV, VT, SPMV_LPR, false><<<blocks_for(c->Ns * SPMV_LPR, 256), 256, 0, c->stream>>>(c->Ns, c->rowptr_s.p, c->col_s.p,
+                                                                                              val, x, nullptr, y);
+    EMB_LAUNCH_CHECK(c);
+    return EMB_OK;
+}
+// y = b - A x
+template <int NV, typename VT>
+static int spmv_resid(emb_ctx* c, const VT* val, const cx* x, const cx* b, cx* y) {
+    k_spmv<NV, VT, SPMV_LPR, true><<<blocks_for(c->Ns * SPMV_LPR, 256), 256, 0, c->stream>>>(c->Ns, c->rowptr_s.p, c->col_s.p, val,
+                                                                                             x, b, y);
+    EMB_LAUNCH_CHECK(c);
+    return EMB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// deterministic per-column reductions over interleaved vectors (flat index: column = idx % NV; VBLOCK % NV == 0)
+// ------------------------------------------------------------------------------------------------
+// sum of `v` over the threads of the block that share (threadIdx.x % NV); valid in threads 0..NV-1
+template <int NV>
+__device__ __forceinline__ cx block_sum_cols(cx v) {
+    __shared__ double s_re[VBLOCK / 32][NVMAX], s_im[VBLOCK / 32][NVMAX];
+#pragma unroll
+    for (int o = 16; o >= NV; o >>= 1) {
+        v.re += __shfl_xor_sync(0xffffffffu, v.re, o);
+        v.im += __shfl_xor_sync(0xffffffffu, v.im, o);
+    }
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane < NV) { s_re[w][lane] = v.re; s_im[w][lane] = v.im; }
+    __syncthreads();
+    cx out = mk(0.0);
+    if (threadIdx.x < NV)
+        for (int i = 0; i < VBLOCK / 32; ++i) { out.re += s_re[i][threadIdx.x]; out.im += s_im[i][threadIdx.x]; }
+    return out;
+}
+// tot[k] = sum of the NPART partials of column k (part[i * NV + k]); fixed order; all threads read s_tot afterwards
+template <int NV>
+__device__ __forceinline__ void sum_partials(const cx* __restrict__ part, cx* s_tot /* shared, NV entries */) {
+    cx v = mk(0.0);
+    for (int i = threadIdx.x; i < NPART * NV; i += VBLOCK) v += part[i];      // i % NV == threadIdx.x % NV
+    const cx t = block_sum_cols<NV>(v);
+    __syncthreads();
+    if (threadIdx.x < NV) s_tot[threadIdx.x] = t;
+    __syncthreads();
+}
+
+// rows of block b: [row_lo, row_hi)
+__device__ __forceinline__ void block_rows(int64_t n, int64_t& lo, int64_t& hi) {
+    const int64_t per = (n + NPART - 1) / NPART;
+    lo = blockIdx.x * per;
+    hi = (lo + per < n) ? lo + per : n;
+    if (lo > n) lo = n;
+}
+
+// part[blockIdx * NV + k] = partial of sum_i a[i][k] * b[i][k] (CONJ: conj(a) * b)
+template <int NV, bool CONJ>
+__global__ void __launch_bounds__(VBLOCK) k_dot(int64_t n, const cx* __restrict__ a, const cx* __restrict__ b,
+                                                cx* __restrict__ part) {
+    cx acc = mk(0.0);
+    int64_t lo, hi;
+    block_rows(n, lo, hi);
+    for (int64_t i = lo * NV + threadIdx.x; i < hi * NV; i += VBLOCK) {
+        const cx u = a[i], v = b[i];
+        if (CONJ) { acc.re += u.re * v.re + u.im * v.im; acc.im += u.re * v.im - u.im * v.re; }
+        else fma_c(acc, u, v);
+    }
+    const cx t = block_sum_cols<NV>(acc);
+    if (threadIdx.x < NV) part[blockIdx.x * NV + threadIdx.x] = t;
+}
+template <int NV>
+__global__ void __launch_bounds__(VBLOCK) k_finish(const cx* __restrict__ part, cx* __restrict__ out) {
+    __shared__ cx s_tot[NVMAX];
+    sum_partials<NV>(part, s_tot);
+    if (threadIdx.x < NV) out[threadIdx.x] = s_tot[threadIdx.x];
+}
+
+// ------------------------------------------------------------------------------------------------
+// small vector kernels (flat, any layout)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_copy(int64_t n, const cx* __restrict__ a, cx* __restrict__ b) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) b[i] = a[i];
+}
+__global__ void k_zero(int64_t n, cx* __restrict__ a) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) a[i] = cx{0, 0};
+}
+// y = a*x + b*y with device scalars sa[0]*fa, sb[0]*fb (null => 1)
+__global__ void k_axpby(int64_t n, const cx* __restrict__ sa, double fa, const cx* __restrict__ x, const cx* __restrict__ sb,
+                        double fb, cx* __restrict__ y) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const cx a = sa ? fa * (*sa) : mk(fa);
+    if (!sb && fb == 0.0) { y[i] = a * x[i]; return; }      // do not read an uninitialised y
+    const cx b = sb ? fb * (*sb) : mk(fb);
+    y[i] = a * x[i] + b * y[i];
+}
+__global__ void k_gather(int64_t ns, const int* __restrict__ ids, const cx* __restrict__ full, cx* __restrict__ sub) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < ns) sub[i] = full[ids[i]];
+}
+// full[ids[i]] = sub[i * nv + k]
+__global__ void k_scatter_col(int64_t ns, const int* __restrict__ ids, const cx* __restrict__ sub, int nv, int k,
+                              cx* __restrict__ full) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < ns) full[ids[i]] = sub[i * nv + k];
+}
+// sub[i * nv + k] = full[ids[i]]
+__global__ void k_gather_col(int64_t ns, const int* __restrict__ ids, const cx* __restrict__ full, int nv, int k,
+                             cx* __restrict__ sub) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < ns) sub[i * nv + k] = full[ids[i]];
+}
+// bs[newid[dof[i]] * nv + k] = bval[i]
+__global__ void k_scatter_rhs(int64_t nd, const int* __restrict__ dof, const cx* __restrict__ bval, const int* __restrict__ newid,
+                              int nv, int k, cx* __restrict__ bs) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= nd) return;
+    const int s = newid[dof[i]];
+    if (s >= 0) bs[(int64_t)s * nv + k] = bval[i];
+}
+// out[i] = a[i * nv + k] - (b ? b[i * nv + k] : 0)      (column k of an interleaved vector, contiguous)
+__global__ void k_extract_col(int64_t n, const cx* __restrict__ a, const cx* __restrict__ b, int nv, int k, cx* __restrict__ out) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    cx v = a[i * nv + k];
+    if (b) v -= b[i * nv + k];
+    out[i] = v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused COCR kernels.  Device scalars sc[q * NV + k]: q = 0 zAz, 1 alpha, 2 beta, 3 |r|^2, 4 zAz_new
+// ------------------------------------------------------------------------------------------------
+// alpha = zAz / sum(partA);  x += alpha p; r -= alpha Ap; z -= alpha MAp;  partial |r|^2
+template <int NV>
+__global__ void __launch_bounds__(VBLOCK) k_cocr_update(int64_t n, const cx* __restrict__ partA, cx* __restrict__ sc,
+                                                        const cx* __restrict__ p, const cx* __restrict__ Ap,
+                                                        const cx* __restrict__ MAp, cx* __restrict__ x, cx* __restrict__ r,
+                                                        cx* __restrict__ z, cx* __restrict__ partR) {
+    __shared__ cx s_den[NVMAX];
+    sum_partials<NV>(partA, s_den);
+    const int k = threadIdx.x % NV;
+    const cx alpha = sdiv(sc[k], s_den[k]);
+    if (blockIdx.x == 0 && threadIdx.x < NV) sc[NV + k] = alpha;
+    const cx na = -alpha;
+    cx acc = mk(0.0);
+    int64_t lo, hi;
+    block_rows(n, lo, hi);
+    for (int64_t i = lo * NV + threadIdx.x; i < hi * NV; i += VBLOCK) {
+        cx xi = x[i], ri = r[i], zi = z[i];
+        fma_c(xi, alpha, p[i]);
+        fma_c(ri, na, Ap[i]);
+        fma_c(zi, na, MAp[i]);
+        x[i] = xi; r[i] = ri; z[i] = zi;
+        acc.re += ri.re * ri.re + ri.im * ri.im;
+    }
+    const cx t = block_sum_cols<NV>(acc);
+    if (threadIdx.x < NV) partR[blockIdx.x * NV + threadIdx.x] = t;
+}
+// beta = sum(partZ)/zAz; p = z + beta p; Ap = Az + beta Ap; also finishes |r|^2.  sc[0] (zAz) is read by every block,
+// so the new value goes to sc[4] and k_cocr_commit moves it afterwards.
+template <int NV>
+__global__ void __launch_bounds__(VBLOCK) k_cocr_dir(int64_t n, const cx* __restrict__ partZ, const cx* __restrict__ partR,
+                                                     cx* __restrict__ sc, const cx* __restrict__ z, const cx* __restrict__ Az,
+                                                     cx* __restrict__ p, cx* __restrict__ Ap) {
+    __shared__ cx s_z[NVMAX], s_r[NVMAX];
+    sum_partials<NV>(partZ, s_z);
+    sum_partials<NV>(partR, s_r);
+    const int k = threadIdx.x % NV;
+    const cx beta = sdiv(s_z[k], sc[k]);
+    int64_t lo, hi;
+    block_rows(n, lo, hi);
+    for (int64_t i = lo * NV + threadIdx.x; i < hi * NV; i += VBLOCK) {
+        cx pi = z[i], api = Az[i];
+        fma_c(pi, beta, p[i]);
+        fma_c(api, beta, Ap[i]);
+        p[i] = pi; Ap[i] = api;
+    }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x < NV) {
+        sc[2 * NV + k] = beta;
+        sc[3 * NV + k] = s_r[k];
+        sc[4 * NV + k] = s_z[k];
+    }
+}
+template <int NV>
+__global__ void k_cocr_commit(cx* sc) {
+    if (threadIdx.x < NV) sc[threadIdx.x] = sc[4 * NV + threadIdx.x];
+}

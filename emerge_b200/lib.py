@@ -37,10 +37,12 @@ _SIGS = {
     "emb_last_ms": (C.c_double, [C.c_void_p, C.c_char_p]),
     "emb_timer_start": (C.c_int, [C.c_void_p]),
     "emb_timer_stop": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
+    "emb_profiler": (C.c_int, [C.c_void_p, C.c_int]),
     "emb_upload_mesh": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64] + [C.c_void_p] * 5),
     "emb_upload_materials": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "emb_symbolic": (C.c_int, [C.c_void_p]),
     "emb_assemble_KM": (C.c_int, [C.c_void_p]),
+    "emb_assemble_config": (C.c_int, [C.c_void_p, C.c_int64, C.c_int]),
     "emb_n_field": (C.c_int64, [C.c_void_p]),
     "emb_nnz": (C.c_int64, [C.c_void_p]),
     "emb_get_csr": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -163,6 +165,10 @@ class Context:
         self._check(self.lib.emb_timer_stop(self.h, C.byref(ms)))
         return ms.value
 
+    def profiler(self, on: bool):
+        """cudaProfilerStart/Stop window for `ncu --profile-from-start off`."""
+        self._check(self.lib.emb_profiler(self.h, int(bool(on))))
+
     @property
     def n_field(self) -> int:
         return int(self.lib.emb_n_field(self.h))
@@ -199,6 +205,10 @@ class Context:
 
     def assemble_KM(self):
         self._check(self.lib.emb_assemble_KM(self.h))
+
+    def assemble_config(self, chunk_tets: int = 0, persist_l2: bool = True):
+        """tets per chunk of the numeric phase (0: default = single pass) and L2 pinning of a chunk's COO scratch."""
+        self._check(self.lib.emb_assemble_config(self.h, int(chunk_tets), int(bool(persist_l2))))
 
     def get_csr(self, which: int, values: bool = True, pattern: bool = True):
         rows = int(self.lib.emb_csr_rows(self.h, which))

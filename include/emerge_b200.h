@@ -39,6 +39,8 @@ double emb_last_ms(const emb_ctx* ctx, const char* phase);
  * torch's own stream).  stop returns the elapsed device-timeline milliseconds since start. */
 int emb_timer_start(emb_ctx* ctx);
 int emb_timer_stop(emb_ctx* ctx, double* ms);
+/* cudaProfilerStart (on=1) / cudaProfilerStop (on=0) after a stream sync: window for `ncu --profile-from-start off` */
+int emb_profiler(emb_ctx* ctx, int on);
 
 /* ---- mesh + DOF tables (input contract of Nedelec2 / Mesh3D; consumed, never renumbered) ---- */
 /* replaces the array gathering at fem/physics/edm/optimized_assembly.py:47-57 */
@@ -55,6 +57,11 @@ int emb_symbolic(emb_ctx* ctx);
 /* Numeric phase: element kernel + deterministic reduction -> E (curl-curl) and B (mass) values.
  * Replaces tet_mass_stiffness_matrices(field, er, ur) (optimized_assembly.py:43-64). */
 int emb_assemble_KM(emb_ctx* ctx);
+/* Numeric-phase tuning (no reference counterpart): tets per chunk of the element kernel -> reduction pipeline
+ * (0 = default = single pass through HBM; e.g. 32 x SM count keeps the COO scratch of a chunk resident in L2)
+ * and whether the scratch is pinned in L2 with a persisting access-policy window.  Results are bitwise independent
+ * of both settings. */
+int emb_assemble_config(emb_ctx* ctx, int64_t chunk_tets, int persist_l2);
 int64_t emb_n_field(const emb_ctx* ctx);
 int64_t emb_nnz(const emb_ctx* ctx);
 /* copy the CSR out (parity checks, and the scipy csr_matrix the Assembler seam must return).
