@@ -191,8 +191,9 @@ def workload_config(args):
                         f"2 RectangularWaveguide ports + PEC walls, 201-point sweep 8-12 GHz (BASELINE config 4); "
                         f"step = one frequency point (A(f) + 2 port solves + S-parameters), K/M assembly once per job",
             "cells": [nx, ny, nz], "rtol": args.rtol,
-            "solver": "subspace recycling across points + COCR(sym. part)/defect correction, additive multilevel "
-                      "(Hiptmair-Xu + smoothed-aggregation AMG) preconditioner",
+            "solver": "reduced-basis recycling across points (affine A(f)) + lockstep COCR over the ports on the complex64 "
+                      "symmetric part / FP64 defect correction, additive multilevel (Hiptmair-Xu + smoothed-aggregation AMG) "
+                      "preconditioner, iteration replayed from a CUDA graph",
             "recycle_vectors": args.recycle, "order": "hierarchical (bisection) within each rank's frequency block",
             "l2_policy": "inputs larger than L2 (A(f) alone is 5.3 GB at 1M tets)", "parallelism": f"freq-block x{args.gpus}"}
 
@@ -239,6 +240,7 @@ def run_gpu(args):
         sw.solve_point(FREQS[i], raise_on_fail=False)
     ctx.recycle_config(args.recycle)
     ctx.spmv_sampled()
+    ctx.precond_sampled()
     barrier()
     l0 = ctx.launches
     with ClockSampler(local) as cs:
@@ -249,6 +251,10 @@ def run_gpu(args):
     barrier()
     launches = ctx.launches - l0
     spmv_ms, spmv_cnt = ctx.spmv_sampled()
+    prec_ms, prec_cnt = ctx.precond_sampled()
+    graph_iters = ctx.graph_launches
+    nv = min(4, len(sw.ports)) if sw.lockstep > 1 else 1
+    nv = 4 if nv == 3 else nv
     asm = {"tet_kernel_ms": ctx.last_ms("tet_kernel"), "reduce_ms": ctx.last_ms("reduce")}
     rinfo = ctx.recycle_info()
     # e2e: a fresh sweep object through the host API, host buffers in pinned memory
@@ -296,15 +302,22 @@ def run_gpu(args):
         value = world * K / (ms_max / 1e3)
         e2e_val = world * e2e_K / (ms_e2e_max / 1e3) if e2e_K > 0 else None
         peak, peak_src = peaks()
-        spmv_bytes = 20 * nnz_s + 36 * Ns + 4
+        # dominant kernel: the lockstep operator application of COCR, k_spmv<NV, complex64 values, 8 lanes/row>:
+        # per nonzero 8 B value + 4 B column, per row 8 B rowptr + NV x (16 B x + 16 B y)   
+        spmv_bytes = 12 * nnz_s + (8 + 32 * nv) * Ns + 8
         achieved = spmv_bytes / (spmv_ms * 1e-3) / 1e9 if spmv_ms > 0 else None
         traffic = None
         tp = os.path.join(REPO, "profiles", "spmv_traffic.json")
         if os.path.exists(tp) and os.path.getsize(tp) > 0 and (nx, ny, nz) == (44, 20, 190):
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            tj = json.load(open(tp))
+            if tj.get("nv") == nv and tj.get("values") == "complex64":
+                traffic = tj.get("dram_bytes_per_launch")
         S21 = np.abs(S_all[:, 1, 0])
-        iters = [s["iters"] for s in res.stats]
-        iterating = sorted({s["freq"] for s in res.stats if s["iters"] > 0})
+        by_freq = {}
+        for s_ in res.stats:                  # the ports of a lockstep group share one iteration count
+            by_freq[s_["freq"]] = max(by_freq.get(s_["freq"], 0), s_["iters"])
+        iters = list(by_freq.values())
+        iterating = sorted(f for f, n in by_freq.items() if n > 0)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
                 "ms_per_step": ms_max / K, "higher_is_better": True,
                 "scaling": "strong" if K * world >= len(FREQS) - world else "weak", "vs_baseline": None,
@@ -312,17 +325,20 @@ def run_gpu(args):
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "steps": e2e_K, "timed": "host wall clock around FrequencySweep() construction, setup() and the points"},
                 "gpu_launches": int(launches),
-                "roofline": {"kernel": "k_spmv<8> (complex CSR SpMV: C = A(f) U of the recycled space and inside COCR)",
+                "roofline": {"kernel": f"k_spmv<NV={nv}, complex64 values, 8 lanes/row> (operator application of the lockstep "
+                                       f"COCR iteration on {nv} interleaved right-hand sides)",
                              "bound": "hbm", "achieved": achieved,
                              "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                              "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                              "algorithmic_bytes_per_launch": spmv_bytes, "avg_launch_ms": spmv_ms, "sampled_launches": spmv_cnt},
                 "assembly": {**asm, "Mtet_per_s": t.tets.shape[1] / ((asm["tet_kernel_ms"] + asm["reduce_ms"]) * 1e3),
                              "form_A_ms": ctx.last_ms("form_A")},
-                "solver": {"krylov_iterations_total": int(np.sum(iters)), "points_that_iterated": len(iterating),
-                           "points": K, "max_iters_per_solve": int(max(iters)), "rtol": args.rtol,
+                "solver": {"lockstep_iterations_total": int(np.sum(iters)), "lockstep_width": nv,
+                           "points_that_iterated": len(iterating),
+                           "points": K, "max_iters_per_point": int(max(iters)), "rtol": args.rtol,
+                           "precond_apply_ms": prec_ms, "precond_samples": prec_cnt, "graph_replayed_iterations": int(graph_iters),
                            "max_relres": float(max(s["relres"] for s in res.stats)),
-                           "recycled_directions": rinfo["n"], "recycle_spmvs": rinfo["spmvs"],
+                           "recycled_directions": rinfo["n"], "recycle_term_products": rinfo["spmvs"],
                            "abs_S21_minmax": [float(S21.min()), float(S21.max())]},
                 "sizes": {"tets": int(t.tets.shape[1]), "n_field": N, "n_solve": Ns, "nnz_solve": nnz_s},
                 "setup": {"host_mesh_tables_s": host_mesh_s, "gpu_setup_s": setup_s, **{k: v for k, v in sw.timings.items()}},

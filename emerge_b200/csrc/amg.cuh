@@ -13,48 +13,40 @@
 
 // MODE 0: y = A x        MODE 1: y = b - A x        MODE 2: y = x + w d (b - A x)   (out of place)
 // MODE 3: y += A x
-template <int LPR, int MODE, int NV>
+// KPR x NV lanes per row: lane (ks, v) walks nonzeros ks, ks + KPR, ... for column v (one gather wavefront per nonzero).
+template <int KPR, int MODE, int NV>
 __global__ void __launch_bounds__(256) k_rcsr(int64_t n, const int64_t* __restrict__ ptr, const int* __restrict__ col,
                                               const double* __restrict__ val, const cx* __restrict__ x, cx* __restrict__ y,
                                               const cx* __restrict__ b, const double* __restrict__ d, double w) {
+    constexpr int LPR = KPR * NV;
     const int64_t gt = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int64_t r = gt / LPR;
-    const int sub = (int)(gt % LPR);
-    double ar[NV], ai[NV];
-#pragma unroll
-    for (int v = 0; v < NV; ++v) ar[v] = ai[v] = 0.0;
+    const int s = (int)(gt % LPR);
+    const int v = s % NV, ks = s / NV;
+    double ar = 0.0, ai = 0.0;
     if (r < n)
-        for (int64_t k = ptr[r] + sub; k < ptr[r + 1]; k += LPR) {
+        for (int64_t k = ptr[r] + ks; k < ptr[r + 1]; k += KPR) {
             const double a = val[k];
-            const cx* xp = x + (int64_t)col[k] * NV;
-#pragma unroll
-            for (int v = 0; v < NV; ++v) {
-                const cx u = ldx(xp + v);
-                ar[v] += a * u.re;
-                ai[v] += a * u.im;
-            }
+            const cx u = ldx(x + (int64_t)col[k] * NV + v);
+            ar += a * u.re;
+            ai += a * u.im;
         }
 #pragma unroll
-    for (int o = LPR / 2; o > 0; o >>= 1)
-#pragma unroll
-        for (int v = 0; v < NV; ++v) {
-            ar[v] += __shfl_down_sync(0xffffffffu, ar[v], o, LPR);
-            ai[v] += __shfl_down_sync(0xffffffffu, ai[v], o, LPR);
-        }
-    if (r < n && sub == 0) {
-#pragma unroll
-        for (int v = 0; v < NV; ++v) {
-            const int64_t o = r * NV + v;
-            if (MODE == 0) y[o] = cx{ar[v], ai[v]};
-            else if (MODE == 1) { const cx bb = b[o]; y[o] = cx{bb.re - ar[v], bb.im - ai[v]}; }
-            else if (MODE == 2) {
-                const cx bb = b[o], xx = x[o];
-                const double s = w * d[r];
-                y[o] = cx{xx.re + s * (bb.re - ar[v]), xx.im + s * (bb.im - ai[v])};
-            } else {
-                const cx yy = y[o];
-                y[o] = cx{yy.re + ar[v], yy.im + ai[v]};
-            }
+    for (int o = LPR / 2; o >= NV; o >>= 1) {
+        ar += __shfl_down_sync(0xffffffffu, ar, o, LPR);
+        ai += __shfl_down_sync(0xffffffffu, ai, o, LPR);
+    }
+    if (r < n && ks == 0) {
+        const int64_t o = r * NV + v;
+        if (MODE == 0) y[o] = cx{ar, ai};
+        else if (MODE == 1) { const cx bb = b[o]; y[o] = cx{bb.re - ar, bb.im - ai}; }
+        else if (MODE == 2) {
+            const cx bb = b[o], xx = x[o];
+            const double sc = w * d[r];
+            y[o] = cx{xx.re + sc * (bb.re - ar), xx.im + sc * (bb.im - ai)};
+        } else {
+            const cx yy = y[o];
+            y[o] = cx{yy.re + ar, yy.im + ai};
         }
     }
 }
@@ -103,9 +95,10 @@ static inline int pick_lpr(int64_t nnz, int64_t n) {
 template <int MODE, int NV>
 static int rcsr_launch(emb_ctx* c, cudaStream_t s, int lpr, int64_t n, const int64_t* ptr, const int* col, const double* val,
                        const cx* x, cx* y, const cx* b, const double* d, double w) {
-    if (lpr == 4) k_rcsr<4, MODE, NV><<<blocks_for(n * 4, 256), 256, 0, s>>>(n, ptr, col, val, x, y, b, d, w);
-    else if (lpr == 8) k_rcsr<8, MODE, NV><<<blocks_for(n * 8, 256), 256, 0, s>>>(n, ptr, col, val, x, y, b, d, w);
-    else k_rcsr<32, MODE, NV><<<blocks_for(n * 32, 256), 256, 0, s>>>(n, ptr, col, val, x, y, b, d, w);
+    constexpr int KMAX = 32 / NV;          // KPR * NV lanes must fit a warp
+    if (lpr <= 4 || KMAX <= 4) k_rcsr<4, MODE, NV><<<blocks_for(n * 4 * NV, 256), 256, 0, s>>>(n, ptr, col, val, x, y, b, d, w);
+    else if (lpr == 8 || KMAX == 8) k_rcsr<8, MODE, NV><<<blocks_for(n * 8 * NV, 256), 256, 0, s>>>(n, ptr, col, val, x, y, b, d, w);
+    else k_rcsr<KMAX, MODE, NV><<<blocks_for(n * KMAX * NV, 256), 256, 0, s>>>(n, ptr, col, val, x, y, b, d, w);
     EMB_LAUNCH_CHECK(c);
     return EMB_OK;
 }

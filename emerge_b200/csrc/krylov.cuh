@@ -48,63 +48,57 @@ __device__ __forceinline__ cx sdiv(cx a, cx b) {
 // SpMV / SpMM: LPR lanes per row, NV interleaved vectors.  RESID: y = b - A x.
 // Algorithmic bytes: nnz * (sizeof(VT) + 4) + n * (8 + 32 * NV)   (+16 * NV * n for b when RESID)
 // ------------------------------------------------------------------------------------------------
-template <int NV, typename VT, int LPR, bool RESID>
+// Lane mapping: KPR x NV lanes per row; lane (ks, v) walks nonzeros ks, ks + KPR, ... of the row for column v, so the
+// NV lanes of one nonzero read ONE contiguous 16*NV-byte piece of x (one L1 wavefront per nonzero whatever NV is; the
+// gather wavefronts, not HBM, are what bounds this kernel once the values are complex64).
+template <int NV, typename VT, int KPR, bool RESID>
 __global__ void __launch_bounds__(256) k_spmv(int64_t n, const int64_t* __restrict__ rowptr, const int* __restrict__ col,
                                               const VT* __restrict__ val, const cx* __restrict__ x, const cx* __restrict__ b,
                                               cx* __restrict__ y) {
+    constexpr int LPR = KPR * NV;
     const int64_t gt = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int64_t r = gt / LPR;
-    const int sub = (int)(gt % LPR);
-    double ar[NV], ai[NV];
-#pragma unroll
-    for (int v = 0; v < NV; ++v) ar[v] = ai[v] = 0.0;
+    const int s = (int)(gt % LPR);
+    const int v = s % NV, ks = s / NV;
+    double ar = 0.0, ai = 0.0;
     if (r < n) {
         const int64_t p0 = rowptr[r], p1 = rowptr[r + 1];
 #pragma unroll 2
-        for (int64_t k = p0 + sub; k < p1; k += LPR) {
+        for (int64_t k = p0 + ks; k < p1; k += KPR) {
             const cx a = ldval(val, k);
-            const cx* xp = x + (int64_t)__ldg(col + k) * NV;
-#pragma unroll
-            for (int v = 0; v < NV; ++v) {
-                const cx w = ldx(xp + v);
-                ar[v] += a.re * w.re - a.im * w.im;
-                ai[v] += a.re * w.im + a.im * w.re;
-            }
+            const cx w = ldx(x + (int64_t)__ldg(col + k) * NV + v);
+            ar += a.re * w.re - a.im * w.im;
+            ai += a.re * w.im + a.im * w.re;
         }
     }
 #pragma unroll
-    for (int o = LPR / 2; o > 0; o >>= 1)
-#pragma unroll
-        for (int v = 0; v < NV; ++v) {
-            ar[v] += __shfl_down_sync(0xffffffffu, ar[v], o, LPR);
-            ai[v] += __shfl_down_sync(0xffffffffu, ai[v], o, LPR);
+    for (int o = LPR / 2; o >= NV; o >>= 1) {
+        ar += __shfl_down_sync(0xffffffffu, ar, o, LPR);
+        ai += __shfl_down_sync(0xffffffffu, ai, o, LPR);
+    }
+    if (r < n && ks == 0) {
+        double2 o2 = make_double2(ar, ai);
+        if (RESID) {
+            const double2 bb = *reinterpret_cast<const double2*>(b + r * NV + v);
+            o2 = make_double2(bb.x - ar, bb.y - ai);
         }
-    if (r < n && sub == 0) {
-#pragma unroll
-        for (int v = 0; v < NV; ++v) {
-            double2 o2 = make_double2(ar[v], ai[v]);
-            if (RESID) {
-                const double2 bb = *reinterpret_cast<const double2*>(b + r * NV + v);
-                o2 = make_double2(bb.x - ar[v], bb.y - ai[v]);
-            }
-            *reinterpret_cast<double2*>(y + r * NV + v) = o2;
-        }
+        *reinterpret_cast<double2*>(y + r * NV + v) = o2;
     }
 }
 
-constexpr int SPMV_LPR = 8;      // ~43 nonzeros per row of the order-2 Nedelec operator
+constexpr int SPMV_KPR = 8;      // ~43 nonzeros per row of the order-2 Nedelec operator
 template <int NV, typename VT>
 static int spmv(emb_ctx* c, const VT* val, const cx* x, cx* y) {
-    k_spmv<NV, VT, SPMV_LPR, false><<<blocks_for(c->Ns * SPMV_LPR, 256), 256, 0, c->stream>>>(c->Ns, c->rowptr_s.p, c->col_s.p,
-                                                                                              val, x, nullptr, y);
+    k_spmv<NV, VT, SPMV_KPR, false><<<blocks_for(c->Ns * SPMV_KPR * NV, 256), 256, 0, c->stream>>>(c->Ns, c->rowptr_s.p, c->col_s.p,
+                                                                                                   val, x, nullptr, y);
     EMB_LAUNCH_CHECK(c);
     return EMB_OK;
 }
 // y = b - A x
 template <int NV, typename VT>
 static int spmv_resid(emb_ctx* c, const VT* val, const cx* x, const cx* b, cx* y) {
-    k_spmv<NV, VT, SPMV_LPR, true><<<blocks_for(c->Ns * SPMV_LPR, 256), 256, 0, c->stream>>>(c->Ns, c->rowptr_s.p, c->col_s.p, val,
-                                                                                             x, b, y);
+    k_spmv<NV, VT, SPMV_KPR, true><<<blocks_for(c->Ns * SPMV_KPR * NV, 256), 256, 0, c->stream>>>(c->Ns, c->rowptr_s.p, c->col_s.p,
+                                                                                                  val, x, b, y);
     EMB_LAUNCH_CHECK(c);
     return EMB_OK;
 }

@@ -470,11 +470,14 @@ extern "C" int emb_set_dirichlet(emb_ctx* c, int64_t npec, const int64_t* pec_id
     for (auto& s : c->surf) s.slot_s.release();
     c->have_dirichlet = true;
     c->have_A = false;
-    c->rc_n = 0; c->rc_head = 0; c->rc_C_valid = false;
+    c->rc_n = 0; c->rc_nq = 0;
     if (c->rc_cap > 0) {   // vectors are sized by the solve space
-        c->rcU.release(); c->rcC.release(); c->rc_part.release();
+        c->rcU.release(); c->rcQ.release(); c->rc_part.release(); c->rc_tmp.release(); c->rc_x0.release();
         c->rc_cap = 0;
     }
+    // every solve-space buffer is sized by Ns
+    for (auto& w : c->work) w.release();
+    c->xs.release(); c->bs.release(); c->As.release(); c->As32.release(); c->have_As = false;
     return EMB_OK;
 }
 
@@ -575,6 +578,10 @@ extern "C" int emb_form_A(emb_ctx* c, double k0, int nsurf, const int* sids, con
     c->k0 = k0;
     c->have_A = true;
     c->have_As = false;
-    c->rc_C_valid = false;
+    // affine coefficients of this A(f) for the reduced-basis projection (recycle.cuh): K, M, surfaces in caller order
+    c->aff_coef.assign(1, std::complex<double>(1.0, 0.0));
+    c->aff_coef.push_back(std::complex<double>(-k0 * k0, 0.0));
+    c->aff_sids.assign(sids, sids + nsurf);
+    for (int i = 0; i < nsurf; ++i) c->aff_coef.push_back(std::complex<double>(gammas[i].re, gammas[i].im));
     return EMB_OK;
 }

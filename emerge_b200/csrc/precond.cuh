@@ -1,0 +1,269 @@
+// Additive multilevel preconditioner of the complex-symmetric inner operator As (symmetric part of A(f)):
+//
+//     M^-1 = D_blk^-1 + sum_k R_k S_k R_k^T        (tree of auxiliary spaces, emerge_b200/sweep.py::_setup_aux_spaces)
+//
+// D_blk: 2x2 blocks over the two functions of an edge / face; S_k: diagonal of R^T As R, or a V-cycle of a
+// smoothed-aggregation hierarchy (amg.cuh).  The spaces are independent given the residual, so each one runs on its
+// own side stream (fork / join with events); the contributions are added into z in a FIXED order on the parent's
+// stream, so the result is bitwise identical to the serial schedule.  Vectors hold NV interleaved columns.
+// The reference has no counterpart (it factorises, fem/solver.py:243-309).
+#pragma once
+#include "amg.cuh"
+
+// one warp per row: As[k] = (A[k] + A[k^T])/2; the pattern is structurally symmetric
+template <typename VT>
+__global__ void k_sym_part(int64_t n, const int64_t* __restrict__ rowptr, const int* __restrict__ col, const cx* __restrict__ A,
+                           VT* __restrict__ As) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (r >= n) return;
+    for (int64_t k = rowptr[r] + lane; k < rowptr[r + 1]; k += 32) {
+        const int j = col[k];
+        int64_t lo = rowptr[j], hi = rowptr[j + 1] - 1;
+        while (lo < hi) {
+            int64_t mid = (lo + hi) >> 1;
+            if (col[mid] < (int)r) lo = mid + 1; else hi = mid;
+        }
+        cx a = A[k];
+        if (col[lo] == (int)r) { const cx b = A[lo]; a = cx{0.5 * (a.re + b.re), 0.5 * (a.im + b.im)}; }
+        stval(As, k, a);
+    }
+}
+
+// mate[s] = solve-space index of the other function of the same edge/face (or -1)
+__global__ void k_pairmate(int64_t ns, const int* __restrict__ solve_ids, const int* __restrict__ newid, int64_t nE, int64_t nTri,
+                           int* __restrict__ mate) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= ns) return;
+    const int64_t d = solve_ids[i];
+    int64_t m;
+    if (d < nE) m = d + nE + nTri;                    // edge-a -> edge-b   (fem/elements/nedelec2.py:46-50)
+    else if (d < nE + nTri) m = d + nE + nTri;        // face-a -> face-b
+    else m = d - nE - nTri;                           // b -> a
+    mate[i] = newid[m];
+}
+
+template <typename VT>
+__device__ __forceinline__ cx csr_get(const int64_t* rowptr, const int* col, const VT* val, int r, int cidx) {
+    int64_t lo = rowptr[r], hi = rowptr[r + 1] - 1;
+    while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if (col[mid] < cidx) lo = mid + 1; else hi = mid;
+    }
+    return (lo <= hi && col[lo] == cidx) ? ldval(val, lo) : cx{0, 0};
+}
+
+// dinv[2i], dinv[2i+1]: row i of the inverse 2x2 block (acting on (x_i, x_mate));  Jacobi: (1/a_ii, 0)
+template <typename VT>
+__global__ void k_precond_setup(int64_t ns, int mode, const int64_t* __restrict__ rowptr, const int* __restrict__ col,
+                                const VT* __restrict__ val, const int* __restrict__ mate, cx* __restrict__ dinv) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= ns) return;
+    const cx aii = csr_get(rowptr, col, val, (int)i, (int)i);
+    const int m = (mode == 2) ? mate[i] : -1;
+    if (mode == 0) { dinv[2 * i] = mk(1.0); dinv[2 * i + 1] = mk(0.0); return; }
+    if (m < 0) { dinv[2 * i] = cdiv(mk(1.0), aii); dinv[2 * i + 1] = mk(0.0); return; }
+    const cx aim = csr_get(rowptr, col, val, (int)i, m), ami = csr_get(rowptr, col, val, m, (int)i);
+    const cx amm = csr_get(rowptr, col, val, m, m);
+    const cx det = aii * amm - aim * ami;
+    dinv[2 * i] = cdiv(amm, det);
+    dinv[2 * i + 1] = cdiv(-aim, det);
+}
+// z = D_blk^-1 r   (flat over ns * nv entries)
+__global__ void k_precond_apply(int64_t ns, int nv, const cx* __restrict__ dinv, const int* __restrict__ mate,
+                                const cx* __restrict__ r, cx* __restrict__ z) {
+    int64_t f = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (f >= ns * nv) return;
+    const int64_t i = f / nv;
+    const int k = (int)(f % nv);
+    cx v = dinv[2 * i] * r[f];
+    const int m = mate ? mate[i] : -1;
+    if (m >= 0) fma_c(v, dinv[2 * i + 1], r[(int64_t)m * nv + k]);
+    z[f] = v;
+}
+
+// one warp per aux column k: d_k = sum_{i,j in supp(k)} R_ik A_ij R_jk, supp(k) = row k of R^T (sorted by i)
+template <typename VT>
+__global__ void __launch_bounds__(256) k_aux_diag(int64_t ncol, const int64_t* __restrict__ tptr, const int* __restrict__ tcol,
+                                                  const double* __restrict__ tval, const int64_t* __restrict__ rowptr,
+                                                  const int* __restrict__ col, const VT* __restrict__ A, cx* __restrict__ dinv) {
+    const int lane = threadIdx.x & 31;
+    const int64_t k = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (k >= ncol) return;
+    const int64_t p0 = tptr[k], p1 = tptr[k + 1];
+    double ar = 0, ai = 0;
+    for (int64_t m = p0; m < p1; ++m) {
+        const int i = tcol[m];
+        const double ri = tval[m];
+        for (int64_t e = rowptr[i] + lane; e < rowptr[i + 1]; e += 32) {
+            const int j = col[e];
+            int64_t lo = p0, hi = p1 - 1;
+            while (lo < hi) {
+                int64_t mid = (lo + hi) >> 1;
+                if (tcol[mid] < j) lo = mid + 1; else hi = mid;
+            }
+            if (tcol[lo] == j) {
+                const double w = ri * tval[lo];
+                const cx a = ldval(A, e);
+                ar += w * a.re;
+                ai += w * a.im;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        ar += __shfl_down_sync(0xffffffffu, ar, o);
+        ai += __shfl_down_sync(0xffffffffu, ai, o);
+    }
+    if (lane == 0) {
+        const double n2 = ar * ar + ai * ai;
+        dinv[k] = n2 > 0 ? cdiv(mk(1.0), cx{ar, ai}) : mk(0.0);
+    }
+}
+// s = sum_i RT[k,i] r[i];  traw[k] = s (if traw);  t[k] = dinv ? dinv[k]*s : s     (8 x NV lanes per aux column)
+template <int NV>
+__global__ void __launch_bounds__(256) k_aux_restrict(int64_t ncol, const int64_t* __restrict__ tptr, const int* __restrict__ tcol,
+                                                      const double* __restrict__ tval, const cx* __restrict__ dinv,
+                                                      const cx* __restrict__ r, cx* __restrict__ t, cx* __restrict__ traw) {
+    constexpr int LPR = 8 * NV;
+    const int64_t gt = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t k = gt / LPR;
+    const int s = (int)(gt % LPR);
+    const int v = s % NV, ks = s / NV;
+    double ar = 0.0, ai = 0.0;
+    if (k < ncol)
+        for (int64_t m = tptr[k] + ks; m < tptr[k + 1]; m += 8) {
+            const double w = tval[m];
+            const cx u = ldx(r + (int64_t)tcol[m] * NV + v);
+            ar += w * u.re;
+            ai += w * u.im;
+        }
+#pragma unroll
+    for (int o = LPR / 2; o >= NV; o >>= 1) {
+        ar += __shfl_down_sync(0xffffffffu, ar, o, LPR);
+        ai += __shfl_down_sync(0xffffffffu, ai, o, LPR);
+    }
+    if (k < ncol && ks == 0) {
+        const cx sum = cx{ar, ai};
+        if (traw) traw[k * NV + v] = sum;
+        if (t) t[k * NV + v] = dinv ? dinv[k] * sum : sum;
+    }
+}
+// z[i] += s * sum_k R[i,k] t[k]     (NV threads per row; rows of R are short)
+template <int NV>
+__global__ void __launch_bounds__(256) k_aux_prolong(int64_t n, const int64_t* __restrict__ rptr, const int* __restrict__ rcol,
+                                                     const double* __restrict__ rval, const cx* __restrict__ t, cx s,
+                                                     cx* __restrict__ z) {
+    const int64_t f = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (f >= n * NV) return;
+    const int64_t i = f / NV;
+    const int v = (int)(f % NV);
+    const int64_t m0 = rptr[i], m1 = rptr[i + 1];
+    if (m0 == m1) return;
+    double ar = 0.0, ai = 0.0;
+    for (int64_t m = m0; m < m1; ++m) {
+        const double w = rval[m];
+        const cx u = ldx(t + (int64_t)rcol[m] * NV + v);
+        ar += w * u.re;
+        ai += w * u.im;
+    }
+    cx zi = z[f];
+    fma_c(zi, s, cx{ar, ai});
+    z[f] = zi;
+}
+
+static int precond_streams(emb_ctx* c) {
+    if (c->side[0]) return EMB_OK;
+    for (int i = 0; i < emb_ctx::NSIDE; ++i) EMB_CUDA(c, cudaStreamCreateWithFlags(&c->side[i], cudaStreamNonBlocking));
+    EMB_CUDA(c, cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    return EMB_OK;
+}
+static int precond_events(emb_ctx* c) {
+    const size_t na = c->aux.size();
+    while (c->ev_restr.size() < na) {
+        cudaEvent_t a = nullptr, b = nullptr;
+        EMB_CUDA(c, cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+        EMB_CUDA(c, cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+        c->ev_restr.push_back(a);
+        c->ev_done.push_back(b);
+    }
+    return EMB_OK;
+}
+
+template <typename VT>
+static int precond_setup(emb_ctx* c, int mode_in, const VT* val) {
+    const int mode = mode_in == 3 ? 2 : mode_in;
+    if (mode_in == 3) {
+        if (c->aux.empty()) { c->err = "precond=3 needs auxiliary spaces (emb_aux_add)"; return EMB_ERR_STATE; }
+        for (auto& a : c->aux) {
+            if (a.solver != 0) continue;
+            k_aux_diag<VT><<<blocks_for(a.ncol * 32, 256), 256, 0, c->stream>>>(a.ncol, a.tptr.p, a.tcol.p, a.tval.p, c->rowptr_s.p,
+                                                                                c->col_s.p, val, a.dinv.p);
+            EMB_LAUNCH_CHECK(c);
+        }
+        EMB_TRY(precond_streams(c));
+        EMB_TRY(precond_events(c));
+    }
+    EMB_TRY(dev_alloc(c, c->dinv, (size_t)c->Ns * 2));
+    if (mode == 2 && !c->pairmate.p) {
+        EMB_TRY(dev_alloc(c, c->pairmate, (size_t)c->Ns));
+        k_pairmate<<<blocks_for(c->Ns, 256), 256, 0, c->stream>>>(c->Ns, c->solve_ids.p, c->newid.p, c->nE, c->nTri, c->pairmate.p);
+        EMB_LAUNCH_CHECK(c);
+    }
+    k_precond_setup<VT><<<blocks_for(c->Ns, 256), 256, 0, c->stream>>>(c->Ns, mode, c->rowptr_s.p, c->col_s.p, val,
+                                                                      mode == 2 ? c->pairmate.p : nullptr, c->dinv.p);
+    EMB_LAUNCH_CHECK(c);
+    return EMB_OK;
+}
+
+// z = M^-1 r on NV interleaved columns.  mode 3: block-Jacobi on the solve space plus the tree of auxiliary spaces
+// (additive): restrict down the tree (parents before children), solve every space, prolong up.
+template <int NV>
+static int precond_apply(emb_ctx* c, int mode, const cx* r, cx* z) {
+    cudaStream_t main = c->stream;
+    const int na = (mode == 3) ? (int)c->aux.size() : 0;
+    const bool par = c->use_side_streams && na > 0;
+    if (par) EMB_CUDA(c, cudaEventRecord(c->ev_fork, main));       // r is complete here
+    k_precond_apply<<<blocks_for(c->Ns * NV, 256), 256, 0, main>>>(c->Ns, NV, c->dinv.p, mode >= 2 ? c->pairmate.p : nullptr, r, z);
+    EMB_LAUNCH_CHECK(c);
+    if (na == 0) return EMB_OK;
+    auto strm = [&](int i) { return par ? c->side[i % emb_ctx::NSIDE] : main; };
+    std::vector<cx*> xres((size_t)na, nullptr);
+    for (int i = 0; i < na; ++i) {
+        AuxSpace& a = c->aux[i];
+        cudaStream_t s = strm(i);
+        if (par) EMB_CUDA(c, cudaStreamWaitEvent(s, a.parent < 0 ? c->ev_fork : c->ev_restr[a.parent], 0));
+        const cx* src = a.parent < 0 ? r : c->aux[a.parent].traw.p;
+        cx* traw = (a.has_children || a.solver == 1) ? a.traw.p : nullptr;
+        cx* t = a.solver == 0 ? a.tmp.p : nullptr;
+        // solver 1 restricts straight into the right-hand side of its V-cycle
+        if (a.solver == 1 && !a.has_children) traw = a.wk.b[0].p;
+        k_aux_restrict<NV><<<blocks_for(a.ncol * 8 * NV, 256), 256, 0, s>>>(a.ncol, a.tptr.p, a.tcol.p, a.tval.p,
+                                                                      a.solver == 0 ? a.dinv.p : nullptr, src, t, traw);
+        EMB_LAUNCH_CHECK(c);
+        if (par) EMB_CUDA(c, cudaEventRecord(c->ev_restr[i], s));
+        xres[i] = a.tmp.p;
+        if (a.solver == 1) {
+            AmgHierarchy& H = c->amg[a.hid];
+            if (a.has_children)
+                EMB_CUDA(c, cudaMemcpyAsync(a.wk.b[0].p, a.traw.p, (size_t)a.ncol * NV * sizeof(cx), cudaMemcpyDeviceToDevice, s));
+            cx* res = nullptr;
+            EMB_TRY(amg_vcycle<NV>(c, s, H, a.wk, &res));
+            xres[i] = res;
+        }
+    }
+    for (int i = na - 1; i >= 0; --i) {
+        AuxSpace& a = c->aux[i];
+        cx scale = mk(1.0);
+        if (a.solver == 1 && a.scale_mode == 1) scale = mk(-1.0 / (c->k0 * c->k0));
+        cudaStream_t dst_s = a.parent < 0 ? main : strm(a.parent);
+        if (par && dst_s != strm(i)) {
+            EMB_CUDA(c, cudaEventRecord(c->ev_done[i], strm(i)));
+            EMB_CUDA(c, cudaStreamWaitEvent(dst_s, c->ev_done[i], 0));
+        }
+        cx* dst = a.parent < 0 ? z : c->aux[a.parent].tmp.p;
+        k_aux_prolong<NV><<<blocks_for(a.nrow * NV, 256), 256, 0, dst_s>>>(a.nrow, a.rptr.p, a.rcol.p, a.rval.p, xres[i], scale, dst);
+        EMB_LAUNCH_CHECK(c);
+    }
+    return EMB_OK;
+}

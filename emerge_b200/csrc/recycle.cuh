@@ -1,0 +1,423 @@
+// Reduced-basis recycling across the frequency points of a sweep.
+//
+// The sweep solves A(f) x = b_p(f) for a dense list of f.  A(f) = K - k0^2 M + sum_p gamma_p(f) S_p is AFFINE in T fixed
+// matrices W_t (K, M and the port / absorbing-boundary matrices S_p), so for the solution directions U kept from
+// earlier solves the products W_t U never change.  They are computed once per direction (T SpMVs) and held as
+//      W_t U = Q R_t        Q: orthonormal columns in HBM (classical Gram-Schmidt, two passes, batched dots),
+//                           R_t: small coefficient matrices on the host.
+// At a new frequency  A(f) U = Q G(f)  with  G(f) = sum_t coef_t(f) R_t  - no SpMV and no orthogonalisation on the device.
+// The start vector of a solve is the minimum-residual combination over span(U):
+//      y = argmin || Q^H r0 - G(f) y ||  (Householder QR of the small matrix on the host),   x0 += U y,
+// which costs one pass over Q (batched dots for all ports at once) and one pass over U.  The residual of x0 is then
+// recomputed from A(f) itself in FP64 - the accuracy contract (relres <= rtol on the true operator) does not depend on
+// anything in this file.  A point whose start vector already meets rtol is accepted without iterating; a point that
+// iterates contributes its correction as a new direction.
+// The reference has no counterpart: it factorises A(f) at every point (fem/solver.py:243-309, emfreq3d.py:658-694).
+#pragma once
+#include "krylov.cuh"
+#include <complex>
+#include <vector>
+
+typedef std::complex<double> zc;
+constexpr int RC_NP = 256;       // partials per dot product of the batched kernels (== VBLOCK)
+
+// ---- W_t x on the solve space ------------------------------------------------------------------------------
+// y = F_s x where F is K or M on the FULL pattern and src maps solve-space entries to full-pattern slots
+__global__ void __launch_bounds__(256) k_spmv_src(int64_t n, const int64_t* __restrict__ rowptr, const int* __restrict__ col,
+                                                  const int64_t* __restrict__ src, const cx* __restrict__ F,
+                                                  const cx* __restrict__ x, cx* __restrict__ y) {
+    constexpr int LPR = 8;
+    const int64_t gt = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t r = gt / LPR;
+    const int sub = (int)(gt % LPR);
+    double ar = 0, ai = 0;
+    if (r < n)
+        for (int64_t k = rowptr[r] + sub; k < rowptr[r + 1]; k += LPR) {
+            const cx a = ldx(F + __ldg(src + k));
+            const cx w = ldx(x + __ldg(col + k));
+            ar += a.re * w.re - a.im * w.im;
+            ai += a.re * w.im + a.im * w.re;
+        }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) {
+        ar += __shfl_down_sync(0xffffffffu, ar, o, LPR);
+        ai += __shfl_down_sync(0xffffffffu, ai, o, LPR);
+    }
+    if (r < n && sub == 0) y[r] = cx{ar, ai};
+}
+// y += S x for a surface matrix held as (solve-pattern slot, real value) pairs in ascending slot order; y is zeroed
+// by the caller.  The thread that owns the first entry of a row sums the whole row in list order (deterministic).
+__device__ __forceinline__ int64_t row_of_slot(const int64_t* __restrict__ rowptr, int64_t n, int64_t p) {
+    int64_t lo = 0, hi = n - 1;          // last r with rowptr[r] <= p
+    while (lo < hi) {
+        const int64_t mid = (lo + hi + 1) >> 1;
+        if (rowptr[mid] <= p) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+__global__ void k_surf_mv(int64_t nslot, const int64_t* __restrict__ slot_s, const double* __restrict__ Sval, int64_t n,
+                          const int64_t* __restrict__ rowptr, const int* __restrict__ col, const cx* __restrict__ x,
+                          cx* __restrict__ y) {
+    const int64_t u = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (u >= nslot) return;
+    const int64_t p = slot_s[u];
+    if (p < 0) return;
+    const int64_t r = row_of_slot(rowptr, n, p);
+    for (int64_t w = u - 1; w >= 0; --w) {       // previous kept entry in the same row => not the owner
+        const int64_t q = slot_s[w];
+        if (q < 0) continue;
+        if (q >= rowptr[r]) return;
+        break;
+    }
+    const int64_t pend = rowptr[r + 1];
+    double ar = 0, ai = 0;
+    for (int64_t w = u; w < nslot; ++w) {
+        const int64_t q = slot_s[w];
+        if (q < 0) continue;
+        if (q >= pend) break;
+        const double s = Sval[w];
+        const cx v = x[col[q]];
+        ar += s * v.re;
+        ai += s * v.im;
+    }
+    y[r] = cx{ar, ai};
+}
+
+// ---- batched dots and combinations ---------------------------------------------------------------------------
+__device__ __forceinline__ cx block_sum1(cx v) {
+    __shared__ double s_re[VBLOCK / 32], s_im[VBLOCK / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        v.re += __shfl_down_sync(0xffffffffu, v.re, o);
+        v.im += __shfl_down_sync(0xffffffffu, v.im, o);
+    }
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) { s_re[w] = v.re; s_im[w] = v.im; }
+    __syncthreads();
+    cx out = mk(0.0);
+    if (threadIdx.x == 0)
+        for (int i = 0; i < VBLOCK / 32; ++i) { out.re += s_re[i]; out.im += s_im[i]; }
+    return out;   // valid in thread 0
+}
+// part[(j * RC_NP + blockIdx.x) * NV + v] = partial of <q_j, r_v> over this block's rows;  j = blockIdx.y;
+// Q: contiguous columns of length n, r: NV interleaved columns
+template <int NV>
+__global__ void __launch_bounds__(VBLOCK) k_rc_dots(int64_t n, const cx* __restrict__ Q, const cx* __restrict__ r,
+                                                    cx* __restrict__ part) {
+    const cx* q = Q + (int64_t)blockIdx.y * n;
+    cx acc[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) acc[v] = mk(0.0);
+    const int64_t per = (n + RC_NP - 1) / RC_NP;
+    const int64_t i0 = blockIdx.x * per, i1 = (i0 + per < n) ? i0 + per : n;
+    for (int64_t i = i0 + threadIdx.x; i < i1; i += VBLOCK) {
+        const cx u = q[i];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            const cx w = r[i * NV + v];
+            acc[v].re += u.re * w.re + u.im * w.im;
+            acc[v].im += u.re * w.im - u.im * w.re;
+        }
+    }
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+        const cx t = block_sum1(acc[v]);
+        if (threadIdx.x == 0) part[((int64_t)blockIdx.y * RC_NP + blockIdx.x) * NV + v] = t;
+    }
+}
+// coef[j * NV + v] = sum of the RC_NP partials in fixed order (one block per column j, RC_NP == VBLOCK threads)
+template <int NV>
+__global__ void __launch_bounds__(VBLOCK) k_rc_coef(const cx* __restrict__ part, cx* __restrict__ coef) {
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+        const cx t = block_sum1(part[((int64_t)blockIdx.x * RC_NP + threadIdx.x) * NV + v]);
+        if (threadIdx.x == 0) coef[blockIdx.x * NV + v] = t;
+    }
+}
+// w -= sum_{j<m} coef[j] q_j      (contiguous w)
+__global__ void __launch_bounds__(256) k_rc_sub(int64_t n, int m, const cx* __restrict__ coef, const cx* __restrict__ Q,
+                                                cx* __restrict__ w) {
+    extern __shared__ cx s_h[];
+    for (int k = threadIdx.x; k < m; k += blockDim.x) s_h[k] = coef[k];
+    __syncthreads();
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    cx a = w[i];
+    for (int k = 0; k < m; ++k) fma_c(a, -s_h[k], Q[(int64_t)k * n + i]);
+    w[i] = a;
+}
+// x[i][v] += sum_{j<m} y[j * NV + v] u_j[i]
+template <int NV>
+__global__ void __launch_bounds__(256) k_rc_combine(int64_t n, int m, const cx* __restrict__ y, const cx* __restrict__ U,
+                                                    cx* __restrict__ x) {
+    extern __shared__ cx s_h[];
+    for (int k = threadIdx.x; k < m * NV; k += blockDim.x) s_h[k] = y[k];
+    __syncthreads();
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    cx a[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) a[v] = x[i * NV + v];
+    for (int k = 0; k < m; ++k) {
+        const cx u = U[(int64_t)k * n + i];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) fma_c(a[v], s_h[k * NV + v], u);
+    }
+#pragma unroll
+    for (int v = 0; v < NV; ++v) x[i * NV + v] = a[v];
+}
+__global__ void k_scale_real(int64_t n, double s, cx* __restrict__ w) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) w[i] = s * w[i];
+}
+
+// ---- small dense least squares on the host --------------------------------------------------------------------
+// min || g_v - G y_v ||, G: nq x m column-major (destroyed), g: nq x nv column-major (destroyed -> Q^H g).
+// Householder QR; columns whose pivot is negligible get y = 0.  resid[v] = || g_v - G y_v ||.
+static void ls_solve(int nq, int m, std::vector<zc>& G, int nv, std::vector<zc>& g, std::vector<zc>& y, std::vector<double>& resid) {
+    const int kmax = m < nq ? m : nq;
+    std::vector<double> piv((size_t)m, 0.0);
+    double pmax = 0;
+    for (int j = 0; j < kmax; ++j) {
+        zc* x = &G[(size_t)j * nq];
+        double nx2 = 0;
+        for (int i = j; i < nq; ++i) nx2 += std::norm(x[i]);
+        const double nx = std::sqrt(nx2);
+        if (nx == 0) { piv[j] = 0; continue; }
+        const double a0 = std::abs(x[j]);
+        const zc ph = a0 > 0 ? x[j] / a0 : zc(1.0, 0.0);
+        std::vector<zc> v((size_t)(nq - j));
+        for (int i = j; i < nq; ++i) v[(size_t)(i - j)] = x[i];
+        v[0] += ph * nx;
+        double vn2 = 0;
+        for (auto& t : v) vn2 += std::norm(t);
+        if (vn2 == 0) { piv[j] = nx; continue; }
+        auto reflect = [&](zc* colp) {
+            zc w(0.0, 0.0);
+            for (int i = j; i < nq; ++i) w += std::conj(v[(size_t)(i - j)]) * colp[i];
+            w *= 2.0 / vn2;
+            for (int i = j; i < nq; ++i) colp[i] -= w * v[(size_t)(i - j)];
+        };
+        for (int k = j + 1; k < m; ++k) reflect(&G[(size_t)k * nq]);
+        for (int k = 0; k < nv; ++k) reflect(&g[(size_t)k * nq]);
+        x[j] = -ph * nx;
+        for (int i = j + 1; i < nq; ++i) x[i] = zc(0.0, 0.0);
+        piv[j] = nx;
+        if (nx > pmax) pmax = nx;
+    }
+    y.assign((size_t)m * nv, zc(0.0, 0.0));
+    resid.assign((size_t)nv, 0.0);
+    for (int k = 0; k < nv; ++k) {
+        const zc* gk = &g[(size_t)k * nq];
+        for (int j = kmax - 1; j >= 0; --j) {
+            if (!(piv[j] > 1e-14 * pmax)) { y[(size_t)j * nv + k] = zc(0.0, 0.0); continue; }
+            zc s = gk[j];
+            for (int l = j + 1; l < kmax; ++l) s -= G[(size_t)l * nq + j] * y[(size_t)l * nv + k];
+            y[(size_t)j * nv + k] = s / G[(size_t)j * nq + j];
+        }
+        double r2 = 0;
+        for (int i = kmax; i < nq; ++i) r2 += std::norm(gk[i]);
+        for (int j = 0; j < kmax; ++j)
+            if (!(piv[j] > 1e-14 * pmax)) r2 += std::norm(gk[j]);
+        resid[(size_t)k] = std::sqrt(r2);
+    }
+}
+
+// ---- state ----------------------------------------------------------------------------------------------------
+static inline int rc_T(const emb_ctx* c) { return 2 + (int)c->rc_terms.size(); }
+static inline cx* rc_U(emb_ctx* c, int j) { return c->rcU.p + (int64_t)j * c->Ns; }
+static inline cx* rc_Q(emb_ctx* c, int j) { return c->rcQ.p + (int64_t)j * c->Ns; }
+
+static void rc_clear(emb_ctx* c) {
+    c->rc_n = 0;
+    c->rc_nq = 0;
+    for (auto& R : c->rc_R) std::fill(R.begin(), R.end(), zc(0.0, 0.0));
+}
+
+// (re)allocates U, Q and the coefficient matrices for the affine terms of the current A(f)
+static int rc_prepare(emb_ctx* c) {
+    if (c->rc_cap <= 0) return EMB_OK;
+    const bool same_terms = c->rc_terms == c->aff_sids && c->rcU.p && c->rcQ.p;
+    if (same_terms) return EMB_OK;
+    c->rc_terms = c->aff_sids;
+    const int T = rc_T(c);
+    c->rc_qcap = T * c->rc_cap;
+    EMB_TRY(dev_alloc(c, c->rcU, (size_t)c->rc_cap * c->Ns));
+    EMB_TRY(dev_alloc(c, c->rcQ, (size_t)c->rc_qcap * c->Ns));
+    EMB_TRY(dev_alloc(c, c->rc_part, (size_t)c->rc_qcap * RC_NP * NVMAX + (size_t)(3 * c->rc_qcap + c->rc_cap + 8) * NVMAX));
+    EMB_TRY(dev_alloc(c, c->rc_tmp, (size_t)c->Ns));
+    c->rc_R.assign((size_t)T, std::vector<zc>((size_t)c->rc_qcap * c->rc_cap, zc(0.0, 0.0)));
+    c->rc_uscale.assign((size_t)c->rc_cap, 1.0);
+    rc_clear(c);
+    return EMB_OK;
+}
+static inline cx* rc_coef_area(emb_ctx* c) { return c->rc_part.p + (size_t)c->rc_qcap * RC_NP * NVMAX; }
+
+// w = W_t u   (t = 0: K, 1: M, >= 2: surface rc_terms[t-2]) on the solve space; contiguous vectors
+static int rc_term_mv(emb_ctx* c, int t, const cx* u, cx* w) {
+    const int64_t n = c->Ns;
+    if (t < 2) {
+        k_spmv_src<<<blocks_for(n * 8, 256), 256, 0, c->stream>>>(n, c->rowptr_s.p, c->col_s.p, c->src.p, t == 0 ? c->K.p : c->M.p, u, w);
+        EMB_LAUNCH_CHECK(c);
+    } else {
+        Surface& s = c->surf[c->rc_terms[(size_t)t - 2]];
+        EMB_CUDA(c, cudaMemsetAsync(w, 0, (size_t)n * sizeof(cx), c->stream));
+        k_surf_mv<<<blocks_for(s.nslot, 128), 128, 0, c->stream>>>(s.nslot, s.slot_s.p, s.Sval.p, n, c->rowptr_s.p, c->col_s.p, u, w);
+        EMB_LAUNCH_CHECK(c);
+    }
+    c->rc_spmvs++;
+    return EMB_OK;
+}
+
+// G(f) = sum_t coef_t R_t restricted to the first m directions (nq x m, column-major)
+static void rc_build_G(const emb_ctx* c, int m, std::vector<zc>& G) {
+    const int nq = c->rc_nq, T = rc_T(c);
+    G.assign((size_t)nq * m, zc(0.0, 0.0));
+    for (int t = 0; t < T; ++t) {
+        const zc ct = c->aff_coef[(size_t)t];
+        const std::vector<zc>& R = c->rc_R[(size_t)t];
+        for (int j = 0; j < m; ++j)
+            for (int i = 0; i < nq; ++i) G[(size_t)j * nq + i] += ct * R[(size_t)j * c->rc_qcap + i];
+    }
+}
+
+// U[slot] holds a new direction: compute its T products, extend Q, fill column `slot` of every R_t.
+// accept_test: keep the direction only if A(f) u is not (numerically) inside span(A(f) U[0..slot)).
+static int rc_insert(emb_ctx* c, int slot, bool accept_test, bool* accepted) {
+    const int64_t n = c->Ns;
+    const int T = rc_T(c);
+    const unsigned vb = blocks_for(n, 256);
+    cx* part = c->rc_part.p;
+    cx* coef = rc_coef_area(c);                 // h1 [qcap], h2 [qcap], norms [2]
+    const int qc = c->rc_qcap;
+    std::vector<cx> host((size_t)2 * qc + 2);
+    for (int t = 0; t < T; ++t) {
+        const int nq = c->rc_nq;
+        if (nq >= qc) { c->err = "recycling: orthonormal basis is full"; return EMB_ERR_LIMIT; }
+        cx* w = rc_Q(c, nq);
+        EMB_TRY(rc_term_mv(c, t, rc_U(c, slot), w));
+        cx* pn = part;                          // NPART partials fit: qcap * RC_NP * NVMAX >= NPART (qcap >= 2, RC_NP = 256, NVMAX = 4)
+        k_dot<1, true><<<NPART, VBLOCK, 0, c->stream>>>(n, w, w, pn); EMB_LAUNCH_CHECK(c);
+        k_finish<1><<<1, VBLOCK, 0, c->stream>>>(pn, coef + 2 * qc); EMB_LAUNCH_CHECK(c);
+        for (int pass = 0; pass < 2 && nq > 0; ++pass) {
+            cx* h = coef + (size_t)pass * qc;
+            k_rc_dots<1><<<dim3(RC_NP, nq), VBLOCK, 0, c->stream>>>(n, c->rcQ.p, w, part); EMB_LAUNCH_CHECK(c);
+            k_rc_coef<1><<<nq, VBLOCK, 0, c->stream>>>(part, h); EMB_LAUNCH_CHECK(c);
+            k_rc_sub<<<vb, 256, nq * sizeof(cx), c->stream>>>(n, nq, h, c->rcQ.p, w); EMB_LAUNCH_CHECK(c);
+        }
+        k_dot<1, true><<<NPART, VBLOCK, 0, c->stream>>>(n, w, w, pn); EMB_LAUNCH_CHECK(c);
+        k_finish<1><<<1, VBLOCK, 0, c->stream>>>(pn, coef + 2 * qc + 1); EMB_LAUNCH_CHECK(c);
+        EMB_CUDA(c, cudaMemcpyAsync(host.data(), coef, host.size() * sizeof(cx), cudaMemcpyDeviceToHost, c->stream));
+        EMB_CUDA(c, cudaStreamSynchronize(c->stream));
+        const double n0 = std::sqrt(std::fabs(host[(size_t)2 * qc].re)), n1 = std::sqrt(std::fabs(host[(size_t)2 * qc + 1].re));
+        std::vector<zc>& R = c->rc_R[(size_t)t];
+        for (int i = 0; i < qc; ++i) R[(size_t)slot * qc + i] = zc(0.0, 0.0);
+        for (int i = 0; i < nq; ++i)
+            R[(size_t)slot * qc + i] = zc(host[(size_t)i].re + host[(size_t)qc + i].re, host[(size_t)i].im + host[(size_t)qc + i].im);
+        if (n0 > 0 && n1 > 1e-11 * n0 && n1 == n1) {
+            k_scale_real<<<vb, 256, 0, c->stream>>>(n, 1.0 / n1, w); EMB_LAUNCH_CHECK(c);
+            R[(size_t)slot * qc + nq] = zc(n1, 0.0);
+            c->rc_nq = nq + 1;
+        }
+    }
+    // scale so that A(f) u has unit norm at its birth frequency; acceptance against the existing directions
+    const int nq = c->rc_nq;
+    std::vector<zc> cn((size_t)nq, zc(0.0, 0.0));
+    for (int t = 0; t < T; ++t)
+        for (int i = 0; i < nq; ++i) cn[(size_t)i] += c->aff_coef[(size_t)t] * c->rc_R[(size_t)t][(size_t)slot * qc + i];
+    double cnorm = 0;
+    for (auto& v : cn) cnorm += std::norm(v);
+    cnorm = std::sqrt(cnorm);
+    bool ok = cnorm > 0 && cnorm == cnorm;
+    if (ok && accept_test && slot > 0) {
+        std::vector<zc> G, y;
+        std::vector<double> res;
+        rc_build_G(c, slot, G);
+        std::vector<zc> g = cn;
+        ls_solve(nq, slot, G, 1, g, y, res);
+        ok = res[0] > 1e-9 * cnorm;
+    }
+    if (ok) {
+        const double s = 1.0 / cnorm;
+        c->rc_uscale[(size_t)slot] = s;
+        for (int t = 0; t < T; ++t)
+            for (int i = 0; i < nq; ++i) c->rc_R[(size_t)t][(size_t)slot * qc + i] *= s;
+    } else {
+        for (int t = 0; t < T; ++t)
+            for (int i = 0; i < qc; ++i) c->rc_R[(size_t)t][(size_t)slot * qc + i] = zc(0.0, 0.0);
+    }
+    if (accepted) *accepted = ok;
+    return EMB_OK;
+}
+
+// drops the oldest `drop` directions and recomputes Q and R from the remaining ones
+static int rc_compact(emb_ctx* c, int drop) {
+    const int keep = c->rc_n - drop;
+    for (int j = 0; j < keep; ++j)
+        EMB_CUDA(c, cudaMemcpyAsync(rc_U(c, j), rc_U(c, j + drop), (size_t)c->Ns * sizeof(cx), cudaMemcpyDeviceToDevice, c->stream));
+    rc_clear(c);
+    for (int j = 0; j < keep; ++j) {
+        if (c->rc_n != j)           // an earlier direction was dropped: keep the slots dense
+            EMB_CUDA(c, cudaMemcpyAsync(rc_U(c, c->rc_n), rc_U(c, j), (size_t)c->Ns * sizeof(cx), cudaMemcpyDeviceToDevice, c->stream));
+        bool ok = false;
+        EMB_TRY(rc_insert(c, c->rc_n, false, &ok));
+        if (ok) c->rc_n++;
+    }
+    c->rc_rebuilds++;
+    return EMB_OK;
+}
+
+// add direction d (contiguous, solve space) as the NEWEST member; needs the A(f) it was computed with (aff_coef)
+static int rc_append(emb_ctx* c, const cx* d) {
+    EMB_TRY(rc_prepare(c));
+    const int T = rc_T(c);
+    if (c->rc_n >= c->rc_cap || c->rc_nq + T > c->rc_qcap) {
+        int drop = c->rc_cap / 4 > 0 ? c->rc_cap / 4 : 1;
+        if (c->rc_n < c->rc_cap) drop = 0;
+        if (drop > c->rc_n) drop = c->rc_n;
+        EMB_TRY(rc_compact(c, drop));
+        if (c->rc_n >= c->rc_cap) return EMB_OK;      // cap == 1 and nothing could be dropped
+    }
+    const int slot = c->rc_n;
+    if (d != rc_U(c, slot))
+        EMB_CUDA(c, cudaMemcpyAsync(rc_U(c, slot), d, (size_t)c->Ns * sizeof(cx), cudaMemcpyDeviceToDevice, c->stream));
+    bool ok = false;
+    EMB_TRY(rc_insert(c, slot, true, &ok));
+    if (ok) c->rc_n = slot + 1;
+    return EMB_OK;
+}
+
+// xs += U y,  y = argmin || r0 - A(f) U y ||  for NV interleaved right-hand sides
+template <int NV>
+static int rc_project(emb_ctx* c, const cx* r0, cx* xs) {
+    const int64_t n = c->Ns;
+    if (c->rc_n > 0 && c->rc_terms != c->aff_sids) rc_clear(c);      // A(f) has other affine terms than the stored products
+    const int m = c->rc_n, nq = c->rc_nq;
+    if (m == 0 || nq == 0) return EMB_OK;
+    cx* part = c->rc_part.p;
+    cx* coef = rc_coef_area(c);
+    k_rc_dots<NV><<<dim3(RC_NP, nq), VBLOCK, 0, c->stream>>>(n, c->rcQ.p, r0, part); EMB_LAUNCH_CHECK(c);
+    k_rc_coef<NV><<<nq, VBLOCK, 0, c->stream>>>(part, coef); EMB_LAUNCH_CHECK(c);
+    std::vector<cx> h((size_t)nq * NV);
+    EMB_CUDA(c, cudaMemcpyAsync(h.data(), coef, h.size() * sizeof(cx), cudaMemcpyDeviceToHost, c->stream));
+    EMB_CUDA(c, cudaStreamSynchronize(c->stream));
+    std::vector<zc> G, y, g((size_t)nq * NV);
+    std::vector<double> res;
+    rc_build_G(c, m, G);
+    for (int v = 0; v < NV; ++v)
+        for (int i = 0; i < nq; ++i) g[(size_t)v * nq + i] = zc(h[(size_t)i * NV + v].re, h[(size_t)i * NV + v].im);
+    ls_solve(nq, m, G, NV, g, y, res);
+    std::vector<cx> yd((size_t)m * NV);
+    for (int j = 0; j < m; ++j)
+        for (int v = 0; v < NV; ++v) {
+            const zc t = y[(size_t)j * NV + v] * c->rc_uscale[(size_t)j];
+            yd[(size_t)j * NV + v] = cx{t.real(), t.imag()};
+        }
+    cx* ydev = coef + (size_t)3 * c->rc_qcap * NVMAX;
+    EMB_CUDA(c, cudaMemcpyAsync(ydev, yd.data(), yd.size() * sizeof(cx), cudaMemcpyHostToDevice, c->stream));
+    EMB_CUDA(c, cudaStreamSynchronize(c->stream));      // yd is a stack-lifetime host buffer
+    k_rc_combine<NV><<<blocks_for(n, 256), 256, (size_t)m * NV * sizeof(cx), c->stream>>>(n, m, ydev, c->rcU.p, xs);
+    EMB_LAUNCH_CHECK(c);
+    return EMB_OK;
+}

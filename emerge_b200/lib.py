@@ -67,6 +67,12 @@ _SIGS = {
     "emb_amg_set_coarse_inverse": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p]),
     "emb_spmv_sampled": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "emb_solve": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(SolveOpts), C.c_void_p, C.POINTER(SolveInfo)]),
+    "emb_solve_multi": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(SolveOpts), C.c_void_p, C.c_void_p]),
+    "emb_select_solution": (C.c_int, [C.c_void_p, C.c_int]),
+    "emb_precond_sampled": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
+    "emb_spmv_bench_ex": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]),
+    "emb_solver_config": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "emb_graph_launch_count": (C.c_int64, [C.c_void_p]),
     "emb_solve_rhs": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(SolveOpts), C.c_void_p, C.POINTER(SolveInfo)]),
     "emb_recycle_config": (C.c_int, [C.c_void_p, C.c_int, C.c_double]),
     "emb_recycle_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
@@ -270,10 +276,24 @@ class Context:
         self._check(self.lib.emb_spmv_host(self.h, _p(x), _p(y)))
         return y
 
-    def spmv_bench(self, reps=20):
+    def spmv_bench(self, reps=20, nv=1, fp32=False):
+        """avg ms of one operator application on resident vectors (nv interleaved right-hand sides; fp32: the complex64
+        inner operator instead of A(f))"""
         ms = C.c_double()
-        self._check(self.lib.emb_spmv_bench(self.h, reps, C.byref(ms)))
+        self._check(self.lib.emb_spmv_bench_ex(self.h, reps, int(nv), int(bool(fp32)), C.byref(ms)))
         return ms.value
+
+    def solver_config(self, inner_fp32=True, side_streams=True):
+        self._check(self.lib.emb_solver_config(self.h, int(bool(inner_fp32)), int(bool(side_streams))))
+
+    @property
+    def graph_launches(self) -> int:
+        return int(self.lib.emb_graph_launch_count(self.h))
+
+    def precond_sampled(self):
+        ms, cnt = C.c_double(), C.c_int64()
+        self._check(self.lib.emb_precond_sampled(self.h, C.byref(ms), C.byref(cnt)))
+        return ms.value, cnt.value
 
     def aux_clear(self):
         self._check(self.lib.emb_aux_clear(self.h))
@@ -354,6 +374,30 @@ class Context:
         x = out if out is not None else (np.zeros(self.n_field, dtype=np.complex128) if want_x else None)
         rc = self._check(self.lib.emb_solve(self.h, sid, C.byref(o), _p(x), C.byref(info)), allow_positive=not raise_on_fail)
         return x, dict(iters=info.iters, relres=info.relres, ms=info.ms, spmvs=info.spmvs, converged=rc == 0)
+
+    def solve_multi(self, sids, want_x=True, raise_on_fail=True, outs=None, **kw):
+        """All right-hand sides `sids` (1..4 surfaces) of the current A(f) in lockstep.  Returns (list of x or None, list
+        of info dicts).  outs: optional list of preallocated complex128[n_field] host buffers (None entries allowed)."""
+        sids = [int(s) for s in sids]
+        n = len(sids)
+        o = self._opts(**kw)
+        infos = (SolveInfo * n)()
+        xs = []
+        for k in range(n):
+            x = outs[k] if outs is not None and outs[k] is not None else (np.zeros(self.n_field, dtype=np.complex128) if want_x else None)
+            xs.append(x)
+        ptrs = (C.c_void_p * n)(*[None if x is None else x.ctypes.data for x in xs])
+        sid_arr = (C.c_int * n)(*sids)
+        rc = self._check(self.lib.emb_solve_multi(self.h, n, sid_arr, C.byref(o), ptrs, infos), allow_positive=not raise_on_fail)
+        out = [dict(iters=i.iters, relres=i.relres, ms=i.ms, spmvs=i.spmvs, converged=bool(i.relres <= o.rtol)) for i in infos]
+        if rc == 0:
+            for d in out:
+                d["converged"] = True
+        return xs, out
+
+    def select_solution(self, k: int):
+        """column k of the last solve_multi becomes the device-resident solution used by interp(None, ...)"""
+        self._check(self.lib.emb_select_solution(self.h, int(k)))
 
     def solve_rhs(self, b_full, x0=None, raise_on_fail=True, **kw):
         b = _c(b_full, np.complex128)

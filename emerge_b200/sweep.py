@@ -92,6 +92,7 @@ class FrequencySweep:
         self.multilevel = bool(multilevel)  # AMG V-cycles on the nodal auxiliary problems (False: Jacobi on every space)
         self.f_ref = float(f_ref)           # frequency whose k0^2 shifts the nodal Helmholtz-type auxiliary operator
         self.recycle = int(recycle)        # directions kept from previous frequency points (0 = every point solved cold)
+        self.lockstep = 4                   # ports solved together per lockstep group (1 = one port at a time)
         self.solver_opts = dict(method="cocr", precond="multilevel", rtol=1e-8, maxit=200000, restart=50)
 
     # ------------------------------------------------------------------ setup (once)
@@ -299,23 +300,32 @@ class FrequencySweep:
         S = np.zeros((len(ports), len(ports)), dtype=np.complex128)
         stats, fields = [], {}
         k0 = self.assemble_frequency(freq)
-        for ja, pa in enumerate(ports):
-            pa.active = True
-            want = keep_fields or (out_bufs is not None)
-            out = out_bufs.get(pa.port_number) if out_bufs else None
-            x, info = self.ctx.solve(self.sid[id(pa)], want_x=want, raise_on_fail=raise_on_fail, out=out, **self.solver_opts)
-            info.update(freq=float(freq), port=pa.port_number)
-            if self.recycle:
-                ri = self.ctx.recycle_info()
-                info.update(recycled=ri["n"], proj_relres=ri["last_proj_relres"])
-            stats.append(info)
-            if keep_fields:
-                fields[pa.port_number] = x
-            _, pout = self._s_data(pa, k0, None)
-            for ib, pb in enumerate(ports):
-                pf, _ = self._s_data(pb, k0, None)
-                S[ib, ja] = pf / pout
-            pa.active = False
+        want = keep_fields or (out_bufs is not None)
+        lock = self.lockstep if self.solver_opts.get("method", "cocr") == "cocr" else 1
+        ja0 = 0
+        while ja0 < len(ports):
+            group = ports[ja0:ja0 + max(1, min(4, lock))]       # lockstep groups of up to 4 ports
+            outs = [out_bufs.get(p.port_number) if out_bufs else None for p in group]
+            xs, infos = self.ctx.solve_multi([self.sid[id(p)] for p in group], want_x=want, raise_on_fail=raise_on_fail,
+                                             outs=outs, **self.solver_opts)
+            ri = self.ctx.recycle_info() if self.recycle else None
+            for k, pa in enumerate(group):
+                ja = ja0 + k
+                info = infos[k]
+                info.update(freq=float(freq), port=pa.port_number, lockstep=len(group))
+                if ri is not None:
+                    info.update(recycled=ri["n"], proj_relres=ri["last_proj_relres"])
+                stats.append(info)
+                if keep_fields:
+                    fields[pa.port_number] = xs[k]
+                self.ctx.select_solution(k)
+                pa.active = True
+                _, pout = self._s_data(pa, k0, None)
+                for ib, pb in enumerate(ports):
+                    pf, _ = self._s_data(pb, k0, None)
+                    S[ib, ja] = pf / pout
+                pa.active = False
+            ja0 += len(group)
         return S, stats, fields
 
     def run(self, freqs, keep_fields=False, raise_on_fail=True, order=None, out_bufs=None, on_point=None) -> SweepResult:

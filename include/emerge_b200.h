@@ -128,8 +128,18 @@ int emb_amg_add_level(emb_ctx* ctx, int hid, int64_t n, const int64_t* A_indptr,
                       const int32_t* P_indices, const double* P_data, const int64_t* PT_indptr, const int32_t* PT_indices,
                       const double* PT_data);
 int emb_amg_set_coarse_inverse(emb_ctx* ctx, int hid, int64_t n, const double* Ainv_nxn);
-/* average device time (ms) of the SpMVs sampled with CUDA events inside the solves since the last call, and their count */
+/* average device time (ms) of the operator applications sampled with CUDA events inside the solves since the last
+ * call, and their count; same for the preconditioner applications sampled next to them */
 int emb_spmv_sampled(emb_ctx* ctx, double* avg_ms, int64_t* count);
+int emb_precond_sampled(emb_ctx* ctx, double* avg_ms, int64_t* count);
+/* operator application on resident vectors: nv = 1, 2, 4 interleaved right-hand sides; fp32 = 1: the complex64
+ * symmetric-part operator of the inner iteration, 0: A(f) in complex128 */
+int emb_spmv_bench_ex(emb_ctx* ctx, int reps, int nv, int fp32, double* ms_per_spmv);
+/* solver switches (no reference counterpart): complex64 storage of the inner operator (default 1), auxiliary spaces of
+ * the preconditioner on concurrent streams (default 1).  Results of the second are bitwise independent of it. */
+int emb_solver_config(emb_ctx* ctx, int inner_fp32, int side_streams);
+/* iterations replayed from the captured CUDA graph so far (the kernels inside are counted by emb_launch_count) */
+int64_t emb_graph_launch_count(const emb_ctx* ctx);
 
 typedef struct {
     int method;        /* 0 = GMRES(restart), 1 = BiCGStab, 2 = COCR on the symmetric part + defect correction */
@@ -148,24 +158,35 @@ typedef struct {
 /* Solve A x = b_sid (RHS of surface sid from emb_surface_set_U) on the solve space; x_full has n_field
  * entries with zeros at Dirichlet DOFs, as SolveRoutine.solve returns it (fem/solver.py:405-469). */
 int emb_solve(emb_ctx* ctx, int sid, const emb_solve_opts* opts, emb_c128* x_full, emb_solve_info* info);
+/* All ports of a frequency point in LOCKSTEP (the per-port loop of emfreq3d.py:683-694): nrhs = 1..4 surfaces whose
+ * right-hand sides are solved together on interleaved vectors, so A(f) and the preconditioner are read once per
+ * iteration for all of them.  x_full: NULL, or nrhs host pointers (each NULL or n_field entries; initial guesses when
+ * use_x0).  infos: nrhs entries (iters / ms are those of the group).  Column 0 becomes the device-resident "last
+ * solution"; emb_select_solution(k) switches emb_interp_last to column k. */
+int emb_solve_multi(emb_ctx* ctx, int nrhs, const int* sids, const emb_solve_opts* opts, emb_c128* const* x_full,
+                    emb_solve_info* infos);
+int emb_select_solution(emb_ctx* ctx, int k);
 /* same with an explicit host RHS of length n_field (the b + port_vectors[p] of emfreq3d.py:691) */
 int emb_solve_rhs(emb_ctx* ctx, const emb_c128* b_full, const emb_solve_opts* opts, emb_c128* x_full,
                   emb_solve_info* info);
 
 /* ---- subspace recycling across the frequency points of a sweep ------------------------------------------
  * The reference refactorises A(f) at every frequency (fem/solver.py:264-275, emfreq3d.py:658-694).  Here every
- * converged solve leaves its Krylov correction in a ring of at most max_vectors directions U (shared by all ports);
- * at the next frequency C = A(f) U is formed and orthonormalised once, and each solve starts from the minimum-
- * residual combination x0 = U C^H b.  The exit test is unchanged (true residual of A(f) in FP64 <= rtol).
+ * solve that iterated leaves its correction in a set of at most max_vectors directions U (shared by all ports).
+ * A(f) is affine in K, M and the surface matrices, so the products W_t U are formed once per direction and kept in an
+ * orthonormal basis; at a new frequency A(f) U is a small host-side matrix combination and each solve starts from the
+ * minimum-residual combination over span(U) (csrc/recycle.cuh).  The exit test is unchanged (true residual of A(f) in
+ * FP64 <= rtol).
  * A solve that does have to iterate is run to snapshot_rtol_factor * rtol (0 < factor <= 1, default 0.1) so that the
  * direction it leaves is accurate enough for neighbouring points to be accepted without iterating.
- * max_vectors = 0 switches it off and frees the vectors (2 * max_vectors * n_solve * 16 B of HBM). */
+ * max_vectors = 0 switches it off and frees the vectors ((1 + T) * max_vectors * n_solve * 16 B of HBM, T = 2 + number
+ * of surfaces in A(f)). */
 int emb_recycle_config(emb_ctx* ctx, int max_vectors, double snapshot_rtol_factor);
-/* n: directions held; spmvs: SpMVs spent forming C = A U so far; last_proj_relres: relative residual of the recycled
+/* n: directions held; spmvs: matrix-vector products spent on W_t u so far; last_proj_relres: relative residual of the recycled
  * start vector in the last solve (-1 if none) */
 int emb_recycle_info(emb_ctx* ctx, int* n, int64_t* spmvs, double* last_proj_relres);
 /* exchange of directions between the ranks of a frequency-sharded sweep; d_dst / d_src are DEVICE pointers to
- * n_solve complex128 values (the host side moves them with NCCL).  j = 0 is the oldest direction. */
+ * n_solve complex128 values (the host side moves them with NCCL).  j = 0 is the NEWEST direction. */
 int emb_recycle_export(emb_ctx* ctx, int j, void* d_dst);
 int emb_recycle_import(emb_ctx* ctx, const void* d_src);
 

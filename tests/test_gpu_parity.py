@@ -212,3 +212,70 @@ def test_recycled_sweep_matches_cold_sweep():
     free = sum(1 for s in rw.stats if s["iters"] == 0)
     assert it_warm * 3 < it_cold, (it_warm, it_cold)
     assert free >= len(rw.stats) // 2, free
+
+
+def _medium_sweep(**kw):
+    from emerge_b200.sweep import FrequencySweep
+    g, t = load_golden("wg_medium")
+    sw = FrequencySweep(t, g["er"], g["ur"], golden_bcs(g, t), **kw)
+    sw.solver_opts.update(rtol=1e-10)
+    return g, sw
+
+
+def test_lockstep_matches_port_by_port():
+    """All ports of a point solved in lockstep (interleaved vectors, one operator read per iteration) give the fields
+    of the port-by-port solves to the solver tolerance, and the same S-parameters."""
+    g, one = _medium_sweep(recycle=0)
+    one.lockstep = 1
+    f = list(g["freqs"][:2])
+    ra = one.run(f, keep_fields=True)
+    one.ctx.close()
+    g, lock = _medium_sweep(recycle=0)
+    rb = lock.run(f, keep_fields=True)
+    assert all(s["lockstep"] == 2 and s["converged"] and s["relres"] <= 1e-10 for s in rb.stats)
+    for key, xa in ra.fields.items():
+        assert np.linalg.norm(rb.fields[key] - xa) <= 1e-8 * np.linalg.norm(xa)
+    assert db_deg_close(rb.S, ra.S)
+    assert db_deg_close(rb.S, g["S"][:2])
+    # a group of three right-hand sides is padded with a zero column; equal columns stay bitwise equal
+    lock.assemble_frequency(f[0])
+    sids = [lock.sid[id(p)] for p in lock.ports]
+    xs, infos = lock.ctx.solve_multi([sids[0], sids[1], sids[0]], **lock.solver_opts)
+    assert all(i["converged"] for i in infos)
+    assert np.array_equal(xs[0].view(np.float64), xs[2].view(np.float64))
+    assert np.linalg.norm(xs[1] - rb.fields[(0, lock.ports[1].port_number)]) <= 1e-8 * np.linalg.norm(xs[1])
+    lock.ctx.close()
+
+
+def test_inner_precision_and_stream_schedule():
+    """The complex64 inner operator only changes the path of the defect correction (the exit test is the FP64 residual
+    of A(f)); running the auxiliary spaces on concurrent streams does not change a single bit."""
+    f = None
+    out = {}
+    for name, fp32, side in (("fp32", True, True), ("fp64", False, True), ("serial", True, False)):
+        g, sw = _medium_sweep(recycle=0)
+        sw.ctx.solver_config(inner_fp32=fp32, side_streams=side)
+        f = list(g["freqs"][:1])
+        r = sw.run(f, keep_fields=True)
+        assert all(s["converged"] and s["relres"] <= 1e-10 for s in r.stats)
+        out[name] = r
+        sw.ctx.close()
+    for key, x in out["fp32"].fields.items():
+        assert np.linalg.norm(out["fp64"].fields[key] - x) <= 1e-8 * np.linalg.norm(x)
+        assert np.array_equal(out["serial"].fields[key].view(np.float64), x.view(np.float64))
+
+
+def test_chunked_numeric_phase_is_bitwise_identical(gpu_ctx):
+    g, t = load_golden("wg_medium")
+    gpu_ctx.assemble_config(0, True)
+    _assembled(gpu_ctx, g, t)
+    _, _, E = gpu_ctx.get_csr(0, pattern=False)
+    _, _, B = gpu_ctx.get_csr(1, pattern=False)
+    for chunk, persist in ((64, True), (1000, False)):
+        gpu_ctx.assemble_config(chunk, persist)
+        gpu_ctx.assemble_KM()
+        _, _, E2 = gpu_ctx.get_csr(0, pattern=False)
+        _, _, B2 = gpu_ctx.get_csr(1, pattern=False)
+        assert np.array_equal(E.view(np.float64), E2.view(np.float64))
+        assert np.array_equal(B.view(np.float64), B2.view(np.float64))
+    gpu_ctx.assemble_config(0, True)
