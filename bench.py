@@ -302,9 +302,10 @@ def run_gpu(args):
         value = world * K / (ms_max / 1e3)
         e2e_val = world * e2e_K / (ms_e2e_max / 1e3) if e2e_K > 0 else None
         peak, peak_src = peaks()
-        # dominant kernel: the lockstep operator application of COCR, k_spmv<NV, complex64 values, 8 lanes/row>:
-        # per nonzero 8 B value + 4 B column, per row 8 B rowptr + NV x (16 B x + 16 B y)   
-        spmv_bytes = 12 * nnz_s + (8 + 32 * nv) * Ns + 8
+        # dominant kernel: the lockstep operator application of COCR, k_bspmv<NV, complex64 values> (2x2 block-CSR):
+        # per nonzero 8 B value + 1 B (one 4 B column per 2x2 block), per row 4 B rowptr (8 B per block-row) +
+        # NV x (16 B x + 16 B y)   
+        spmv_bytes = 9 * nnz_s + (4 + 32 * nv) * Ns + 8
         achieved = spmv_bytes / (spmv_ms * 1e-3) / 1e9 if spmv_ms > 0 else None
         traffic = None
         tp = os.path.join(REPO, "profiles", "spmv_traffic.json")
@@ -325,7 +326,7 @@ def run_gpu(args):
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "steps": e2e_K, "timed": "host wall clock around FrequencySweep() construction, setup() and the points"},
                 "gpu_launches": int(launches),
-                "roofline": {"kernel": f"k_spmv<NV={nv}, complex64 values, 8 lanes/row> (operator application of the lockstep "
+                "roofline": {"kernel": f"k_bspmv<NV={nv}, complex64 values> (2x2 block-CSR operator application of the lockstep "
                                        f"COCR iteration on {nv} interleaved right-hand sides)",
                              "bound": "hbm", "achieved": achieved,
                              "peak": peak, "peak_source": peak_src, "unit": "GB/s",

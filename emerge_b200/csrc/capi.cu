@@ -24,7 +24,7 @@ extern "C" int emb_create(int device, emb_ctx** out) {
 
 static void release_surface(Surface& s) {
     s.tri.release(); s.xy.release(); s.S.release(); s.slot.release(); s.segptr.release(); s.ent.release();
-    s.Sval.release(); s.slot_s.release(); s.dof.release(); s.dsegptr.release(); s.dent.release();
+    s.Sval.release(); s.slot_s.release(); s.mv_slot.release(); s.mv_val.release(); s.dof.release(); s.dsegptr.release(); s.dent.release();
     s.bloc.release(); s.bval.release();
     s = Surface();
 }
@@ -35,7 +35,7 @@ extern "C" void emb_destroy(emb_ctx* c) {
     cudaStreamSynchronize(c->stream);
     c->nodes.release(); c->tris.release(); c->tri2f.release(); c->tetc.release(); c->tetord.release(); c->gid.release();
     c->er.release(); c->ur.release(); c->adjptr.release(); c->adj.release(); c->rowptr.release(); c->col.release();
-    c->K.release(); c->M.release(); c->asm_items.release(); c->newid.release(); c->solve_ids.release(); c->rowptr_s.release();
+    c->K.release(); c->M.release(); c->asm_items.release(); c->sperm.release(); c->blkcol.release(); c->newid.release(); c->solve_ids.release(); c->rowptr_s.release();
     c->col_s.release(); c->src.release(); c->A.release(); c->xs.release(); c->xfull.release();
     for (auto& w : c->work) w.release();
     c->dinv.release(); c->pairmate.release(); c->red.release(); c->As.release(); c->rc_x0.release();

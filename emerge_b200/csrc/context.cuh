@@ -31,6 +31,8 @@ struct Surface {
     DevBuf<int> ent;          // entry ids (tri*64 + i*8 + j)
     DevBuf<double> Sval;      // summed value per unique slot
     DevBuf<int64_t> slot_s;   // same slots mapped to the solve-space pattern (-1 if eliminated)
+    DevBuf<int64_t> mv_slot;  // slot_s sorted ascending with the matching values (matrix-vector product S x, recycle.cuh)
+    DevBuf<double> mv_val;
     // forcing vector
     int64_t ndof = 0;
     DevBuf<int> dof;          // unique dofs, ascending
@@ -117,6 +119,13 @@ struct emb_ctx {
     DevBuf<int64_t> rowptr_s; // [Ns+1]
     DevBuf<int> col_s;        // [nnz_s]
     DevBuf<int64_t> src;      // [nnz_s] full-pattern slot of each solve-space entry
+    // Pair ordering of the solve space: when both functions of every kept edge / face are kept (PEC elimination always
+    // does that), solve index 2j is the first and 2j+1 the second function of kept entity j.  Rows 2j and 2j+1 then share
+    // one column list made of pairs (2c, 2c+1): the operator is a block-CSR matrix of 2x2 blocks whose column index is
+    // stored once per block (blkcol), and the two x entries of a block are adjacent in memory.
+    bool paired = false;
+    DevBuf<int> sperm;        // [Ns] ascending-dof position -> solve index (identity when not paired)
+    DevBuf<int> blkcol;       // [nnz_s / 4] entity column of each 2x2 block (paired only)
     DevBuf<cx> A;             // [nnz_s]
     bool have_dirichlet = false, have_A = false;
     double k0 = 0;

@@ -86,22 +86,91 @@ __global__ void __launch_bounds__(256) k_spmv(int64_t n, const int64_t* __restri
     }
 }
 
-constexpr int SPMV_KPR = 8;      // ~43 nonzeros per row of the order-2 Nedelec operator
-template <int NV, typename VT>
-static int spmv(emb_ctx* c, const VT* val, const cx* x, cx* y) {
-    k_spmv<NV, VT, SPMV_KPR, false><<<blocks_for(c->Ns * SPMV_KPR * NV, 256), 256, 0, c->stream>>>(c->Ns, c->rowptr_s.p, c->col_s.p,
-                                                                                                   val, x, nullptr, y);
+// Pair-ordered solve space (context.cuh: paired): the operator is block-CSR with 2x2 blocks.  One block-row (rows 2j, 2j+1)
+// per lane group of KPR x 2NV lanes; lane (ks, h, k) walks blocks ks, ks + KPR, ... holding x[2c + h][k], which it
+// multiplies with the two entries A[2j][2c + h] and A[2j+1][2c + h].  Per block (4 nonzeros): ONE column index, one
+// contiguous 32*NV-byte piece of x, two contiguous value pairs - a quarter of the L1 wavefronts of the scalar kernel,
+// which is what bounds it (ncu: l1tex 68 %, DRAM 41 % on the scalar kernel at 1M tets, profiles/).
+// Algorithmic bytes: nnz * sizeof(VT) + nnz / 4 * 4 + n * (4 + 32 * NV).
+template <int NV, typename VT, int KPR, bool RESID>
+__global__ void __launch_bounds__(256) k_bspmv(int64_t nbr, const int64_t* __restrict__ rowptr, const int* __restrict__ blkcol,
+                                               const VT* __restrict__ val, const cx* __restrict__ x, const cx* __restrict__ b,
+                                               cx* __restrict__ y) {
+    constexpr int LPB = 2 * NV;           // lanes per block
+    constexpr int LPR = KPR * LPB;        // lanes per block-row (<= 32)
+    const int64_t gt = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t j = gt / LPR;
+    const int s = (int)(gt % LPR);
+    const int u = s % LPB, ks = s / LPB;
+    const int h = u / NV;
+    double a0r = 0.0, a0i = 0.0, a1r = 0.0, a1i = 0.0;
+    if (j < nbr) {
+        const int64_t p0 = rowptr[2 * j], p1 = rowptr[2 * j + 1];
+        const int64_t nb = (p1 - p0) >> 1;
+        const int* bc = blkcol + (p0 >> 2);
+#pragma unroll 4
+        for (int64_t q = ks; q < nb; q += KPR) {
+            const int cb = __ldg(bc + q);
+            const cx w = ldx(x + (int64_t)cb * LPB + u);
+            const cx e0 = ldval(val, p0 + 2 * q + h);
+            const cx e1 = ldval(val, p1 + 2 * q + h);
+            a0r += e0.re * w.re - e0.im * w.im;
+            a0i += e0.re * w.im + e0.im * w.re;
+            a1r += e1.re * w.re - e1.im * w.im;
+            a1i += e1.re * w.im + e1.im * w.re;
+        }
+    }
+#pragma unroll
+    for (int o = LPR / 2; o >= NV; o >>= 1) {
+        a0r += __shfl_down_sync(0xffffffffu, a0r, o, LPR);
+        a0i += __shfl_down_sync(0xffffffffu, a0i, o, LPR);
+        a1r += __shfl_down_sync(0xffffffffu, a1r, o, LPR);
+        a1i += __shfl_down_sync(0xffffffffu, a1i, o, LPR);
+    }
+    if (j < nbr && s < NV) {
+        double2 o0 = make_double2(a0r, a0i), o1 = make_double2(a1r, a1i);
+        const int64_t i0 = (2 * j) * NV + s, i1 = (2 * j + 1) * NV + s;
+        if (RESID) {
+            const double2 b0 = *reinterpret_cast<const double2*>(b + i0), b1 = *reinterpret_cast<const double2*>(b + i1);
+            o0 = make_double2(b0.x - a0r, b0.y - a0i);
+            o1 = make_double2(b1.x - a1r, b1.y - a1i);
+        }
+        *reinterpret_cast<double2*>(y + i0) = o0;
+        *reinterpret_cast<double2*>(y + i1) = o1;
+    }
+}
+
+constexpr int SPMV_KPR = 8;      // ~43 nonzeros per row / ~21 blocks per block-row of the order-2 Nedelec operator
+template <int NV, typename VT, bool RESID>
+static int spmv_any(emb_ctx* c, const VT* val, const cx* x, const cx* b, cx* y) {
+    if (c->paired) {
+        // block slots per block-row (KPR x 2NV lanes): few lanes with several independent gathers each - the kernel is
+        // bound by memory-level parallelism per warp, not by bandwidth, when every warp owns a single short row
+        static const int kpr_env = getenv("EMB_SPMV_KPR") ? atoi(getenv("EMB_SPMV_KPR")) : 0;
+        const int64_t nbr = c->Ns / 2;
+        int kpr = kpr_env > 0 ? kpr_env : (NV == 1 ? 2 : 1);      // measured on B200 at 1M tets (profiles/r1_spmv_tuning.txt)
+        if (kpr * 2 * NV > 32) kpr = 32 / (2 * NV);
+        if (kpr >= 8)
+            k_bspmv<NV, VT, (NV == 4 ? 4 : 8), RESID><<<blocks_for(nbr * (NV == 4 ? 4 : 8) * 2 * NV, 256), 256, 0, c->stream>>>(
+                nbr, c->rowptr_s.p, c->blkcol.p, val, x, b, y);
+        else if (kpr >= 4)
+            k_bspmv<NV, VT, 4, RESID><<<blocks_for(nbr * 4 * 2 * NV, 256), 256, 0, c->stream>>>(nbr, c->rowptr_s.p, c->blkcol.p, val, x, b, y);
+        else if (kpr >= 2)
+            k_bspmv<NV, VT, 2, RESID><<<blocks_for(nbr * 2 * 2 * NV, 256), 256, 0, c->stream>>>(nbr, c->rowptr_s.p, c->blkcol.p, val, x, b, y);
+        else
+            k_bspmv<NV, VT, 1, RESID><<<blocks_for(nbr * 1 * 2 * NV, 256), 256, 0, c->stream>>>(nbr, c->rowptr_s.p, c->blkcol.p, val, x, b, y);
+    } else {
+        k_spmv<NV, VT, SPMV_KPR, RESID><<<blocks_for(c->Ns * SPMV_KPR * NV, 256), 256, 0, c->stream>>>(c->Ns, c->rowptr_s.p,
+                                                                                                       c->col_s.p, val, x, b, y);
+    }
     EMB_LAUNCH_CHECK(c);
     return EMB_OK;
 }
+template <int NV, typename VT>
+static int spmv(emb_ctx* c, const VT* val, const cx* x, cx* y) { return spmv_any<NV, VT, false>(c, val, x, nullptr, y); }
 // y = b - A x
 template <int NV, typename VT>
-static int spmv_resid(emb_ctx* c, const VT* val, const cx* x, const cx* b, cx* y) {
-    k_spmv<NV, VT, SPMV_KPR, true><<<blocks_for(c->Ns * SPMV_KPR * NV, 256), 256, 0, c->stream>>>(c->Ns, c->rowptr_s.p, c->col_s.p,
-                                                                                                  val, x, b, y);
-    EMB_LAUNCH_CHECK(c);
-    return EMB_OK;
-}
+static int spmv_resid(emb_ctx* c, const VT* val, const cx* x, const cx* b, cx* y) { return spmv_any<NV, VT, true>(c, val, x, b, y); }
 
 // ------------------------------------------------------------------------------------------------
 // deterministic per-column reductions over interleaved vectors (flat index: column = idx % NV; VBLOCK % NV == 0)

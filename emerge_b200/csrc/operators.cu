@@ -382,16 +382,27 @@ __global__ void k_fill_int(int* v, int64_t n, int val) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i < n) v[i] = val;
 }
-__global__ void k_newid(int64_t N, const int* __restrict__ keep, const int* __restrict__ scan, int* __restrict__ newid,
-                        int* __restrict__ solve_ids) {
+// pair check: keep[d] == keep[d + H] for every d < H
+__global__ void k_check_pairs(int64_t H, const int* __restrict__ keep, int* __restrict__ flag) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < H && keep[i] != keep[i + H]) atomicExch(flag, 1);
+}
+// H > 0: pair ordering (solve index = 2 * rank inside its half + half); H == 0: ascending dof order
+__global__ void k_newid(int64_t N, int64_t H, int64_t Ns, const int* __restrict__ keep, const int* __restrict__ scan,
+                        int* __restrict__ newid, int* __restrict__ solve_ids, int* __restrict__ sperm) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= N) return;
-    if (keep[i]) { newid[i] = scan[i]; solve_ids[scan[i]] = (int)i; }
-    else newid[i] = -1;
+    if (!keep[i]) { newid[i] = -1; return; }
+    int id = scan[i];
+    if (H > 0) id = i < H ? 2 * scan[i] : 2 * (scan[i] - (int)(Ns / 2)) + 1;
+    newid[i] = id;
+    solve_ids[id] = (int)i;
+    sperm[scan[i]] = id;
 }
-// one warp per kept row
+// one warp per kept row.  H > 0 (pair ordering): the kept columns of a row are its first-half entities followed by
+// the same entities in the second half; they are emitted interleaved (2q, 2q+1) so the row stays sorted.
 template <bool FILL>
-__global__ void k_compact_rows(int64_t Ns, const int* __restrict__ solve_ids, const int* __restrict__ newid,
+__global__ void k_compact_rows(int64_t Ns, int64_t H, const int* __restrict__ solve_ids, const int* __restrict__ newid,
                                const int64_t* __restrict__ rowptr, const int* __restrict__ col, int64_t* __restrict__ rowlen,
                                const int64_t* __restrict__ rowptr_s, int* __restrict__ col_s, int64_t* __restrict__ src) {
     const int lane = threadIdx.x & 31;
@@ -399,21 +410,46 @@ __global__ void k_compact_rows(int64_t Ns, const int* __restrict__ solve_ids, co
     if (rs >= Ns) return;
     const int r = solve_ids[rs];
     const int64_t p0 = rowptr[r], p1 = rowptr[r + 1];
+    int na = 0;                      // kept columns in the first half (pair ordering)
+    if (FILL && H > 0)
+        for (int64_t k0 = p0; k0 < p1; k0 += 32) {
+            const int64_t k = k0 + lane;
+            bool f = false;
+            if (k < p1) { const int cc = col[k]; f = cc < H && newid[cc] >= 0; }
+            na += __popc(__ballot_sync(0xffffffffu, f));
+        }
     int base = 0;
     const int64_t o0 = FILL ? rowptr_s[rs] : 0;
     for (int64_t k0 = p0; k0 < p1; k0 += 32) {
         const int64_t k = k0 + lane;
-        int nc = -1;
-        if (k < p1) nc = newid[col[k]];
+        int nc = -1, cc = 0;
+        if (k < p1) { cc = col[k]; nc = newid[cc]; }
         const unsigned m = __ballot_sync(0xffffffffu, nc >= 0);
         if (FILL && nc >= 0) {
-            const int64_t o = o0 + base + __popc(m & ((1u << lane) - 1));
+            const int rank = base + __popc(m & ((1u << lane) - 1));
+            int64_t o = o0 + rank;
+            if (H > 0) o = o0 + (cc < H ? 2 * rank : 2 * (rank - na) + 1);
             col_s[o] = nc;
             src[o] = k;
         }
         base += __popc(m);
     }
     if (!FILL && lane == 0) rowlen[rs] = base;
+}
+// entity column of every 2x2 block: block q of block row j sits at entries rowptr_s[2j] + 2q (+1) of rows 2j, 2j+1
+__global__ void k_blkcol(int64_t nblkrow, const int64_t* __restrict__ rowptr_s, const int* __restrict__ col_s,
+                         int* __restrict__ blkcol, int* __restrict__ flag) {
+    const int lane = threadIdx.x & 31;
+    const int64_t j = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (j >= nblkrow) return;
+    const int64_t p0 = rowptr_s[2 * j], p1 = rowptr_s[2 * j + 1], p2 = rowptr_s[2 * j + 2];
+    if (p1 - p0 != p2 - p1 || ((p1 - p0) & 1) || (p0 & 3)) { if (lane == 0) atomicExch(flag, 1); return; }
+    const int64_t nb = (p1 - p0) >> 1;
+    for (int64_t q = lane; q < nb; q += 32) {
+        const int c0 = col_s[p0 + 2 * q], c1 = col_s[p0 + 2 * q + 1];
+        if ((c0 & 1) || c1 != c0 + 1 || col_s[p1 + 2 * q] != c0 || col_s[p1 + 2 * q + 1] != c1) atomicExch(flag, 1);
+        blkcol[(p0 >> 2) + q] = c0 >> 1;
+    }
 }
 
 extern "C" int emb_set_dirichlet(emb_ctx* c, int64_t npec, const int64_t* pec_ids) {
@@ -445,29 +481,61 @@ extern "C" int emb_set_dirichlet(emb_ctx* c, int64_t npec, const int64_t* pec_id
     c->Ns = (int64_t)last_scan + last_keep;
     if (c->Ns <= 0) { c->err = "emb_set_dirichlet: every dof is eliminated"; return EMB_ERR_ARG; }
     EMB_TRY(dev_alloc(c, c->solve_ids, (size_t)c->Ns));
-    k_newid<<<blocks_for(N, 256), 256, 0, c->stream>>>(N, keep.p, scan.p, c->newid.p, c->solve_ids.p);
-    EMB_LAUNCH_CHECK(c);
-    EMB_TRY(dev_alloc(c, rowlen, (size_t)c->Ns + 1));
-    EMB_TRY(dev_alloc(c, c->rowptr_s, (size_t)c->Ns + 1));
-    EMB_CUDA(c, cudaMemsetAsync(rowlen.p + c->Ns, 0, sizeof(int64_t), c->stream));
-    k_compact_rows<false><<<blocks_for(c->Ns * 32, 256), 256, 0, c->stream>>>(c->Ns, c->solve_ids.p, c->newid.p, c->rowptr.p,
-                                                                             c->col.p, rowlen.p, nullptr, nullptr, nullptr);
-    EMB_LAUNCH_CHECK(c);
-    size_t tb2 = 0;
-    EMB_CUDA(c, cub::DeviceScan::ExclusiveSum(nullptr, tb2, rowlen.p, c->rowptr_s.p, (int)(c->Ns + 1), c->stream));
-    if (tb2 > tmp.n) EMB_TRY(dev_alloc(c, tmp, tb2));
-    EMB_CUDA(c, cub::DeviceScan::ExclusiveSum(tmp.p, tb2, rowlen.p, c->rowptr_s.p, (int)(c->Ns + 1), c->stream));
-    c->launches += 2;
-    EMB_CUDA(c, cudaMemcpyAsync(&c->nnz_s, c->rowptr_s.p + c->Ns, sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
-    EMB_CUDA(c, cudaStreamSynchronize(c->stream));
-    EMB_TRY(dev_alloc(c, c->col_s, (size_t)c->nnz_s));
-    EMB_TRY(dev_alloc(c, c->src, (size_t)c->nnz_s));
-    k_compact_rows<true><<<blocks_for(c->Ns * 32, 256), 256, 0, c->stream>>>(c->Ns, c->solve_ids.p, c->newid.p, c->rowptr.p,
-                                                                            c->col.p, nullptr, c->rowptr_s.p, c->col_s.p, c->src.p);
-    EMB_LAUNCH_CHECK(c);
+    EMB_TRY(dev_alloc(c, c->sperm, (size_t)c->Ns));
+    // pair ordering when both functions of every entity share their fate (fem/elements/nedelec2.py:46-62: function b of an
+    // edge / face is dof a + nE + nTri)
+    const int64_t Hh = c->nE + c->nTri;
+    DevBuf<int> flag;
+    EMB_TRY(dev_alloc(c, flag, 1));
+    EMB_CUDA(c, cudaMemsetAsync(flag.p, 0, sizeof(int), c->stream));
+    bool paired = (2 * Hh == N) && (c->Ns % 2 == 0) && !(getenv("EMB_NO_PAIRING") && atoi(getenv("EMB_NO_PAIRING")));
+    if (paired) {
+        k_check_pairs<<<blocks_for(Hh, 256), 256, 0, c->stream>>>(Hh, keep.p, flag.p);
+        EMB_LAUNCH_CHECK(c);
+        int hf = 0;
+        EMB_CUDA(c, cudaMemcpyAsync(&hf, flag.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        EMB_CUDA(c, cudaStreamSynchronize(c->stream));
+        paired = hf == 0;
+    }
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        const int64_t H = paired ? Hh : 0;
+        k_newid<<<blocks_for(N, 256), 256, 0, c->stream>>>(N, H, c->Ns, keep.p, scan.p, c->newid.p, c->solve_ids.p, c->sperm.p);
+        EMB_LAUNCH_CHECK(c);
+        EMB_TRY(dev_alloc(c, rowlen, (size_t)c->Ns + 1));
+        EMB_TRY(dev_alloc(c, c->rowptr_s, (size_t)c->Ns + 1));
+        EMB_CUDA(c, cudaMemsetAsync(rowlen.p + c->Ns, 0, sizeof(int64_t), c->stream));
+        k_compact_rows<false><<<blocks_for(c->Ns * 32, 256), 256, 0, c->stream>>>(c->Ns, H, c->solve_ids.p, c->newid.p, c->rowptr.p,
+                                                                                 c->col.p, rowlen.p, nullptr, nullptr, nullptr);
+        EMB_LAUNCH_CHECK(c);
+        size_t tb2 = 0;
+        EMB_CUDA(c, cub::DeviceScan::ExclusiveSum(nullptr, tb2, rowlen.p, c->rowptr_s.p, (int)(c->Ns + 1), c->stream));
+        if (tb2 > tmp.n) EMB_TRY(dev_alloc(c, tmp, tb2));
+        EMB_CUDA(c, cub::DeviceScan::ExclusiveSum(tmp.p, tb2, rowlen.p, c->rowptr_s.p, (int)(c->Ns + 1), c->stream));
+        c->launches += 2;
+        EMB_CUDA(c, cudaMemcpyAsync(&c->nnz_s, c->rowptr_s.p + c->Ns, sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+        EMB_CUDA(c, cudaStreamSynchronize(c->stream));
+        EMB_TRY(dev_alloc(c, c->col_s, (size_t)c->nnz_s));
+        EMB_TRY(dev_alloc(c, c->src, (size_t)c->nnz_s));
+        k_compact_rows<true><<<blocks_for(c->Ns * 32, 256), 256, 0, c->stream>>>(c->Ns, H, c->solve_ids.p, c->newid.p, c->rowptr.p,
+                                                                                c->col.p, nullptr, c->rowptr_s.p, c->col_s.p, c->src.p);
+        EMB_LAUNCH_CHECK(c);
+        c->blkcol.release();
+        if (!paired) break;
+        // block structure (verified entry by entry; a mesh whose pattern is not pair-symmetric falls back to plain CSR)
+        EMB_TRY(dev_alloc(c, c->blkcol, (size_t)(c->nnz_s / 4 + 1)));
+        k_blkcol<<<blocks_for((c->Ns / 2) * 32, 256), 256, 0, c->stream>>>(c->Ns / 2, c->rowptr_s.p, c->col_s.p, c->blkcol.p, flag.p);
+        EMB_LAUNCH_CHECK(c);
+        int hf = 0;
+        EMB_CUDA(c, cudaMemcpyAsync(&hf, flag.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        EMB_CUDA(c, cudaStreamSynchronize(c->stream));
+        if (hf == 0) break;
+        paired = false;
+    }
+    c->paired = paired;
+    flag.release();
     EMB_CUDA(c, cudaStreamSynchronize(c->stream));
     keep.release(); scan.release(); dids.release(); rowlen.release(); tmp.release();
-    for (auto& s : c->surf) s.slot_s.release();
+    for (auto& s : c->surf) { s.slot_s.release(); s.mv_slot.release(); s.mv_val.release(); }
     c->have_dirichlet = true;
     c->have_A = false;
     c->rc_n = 0; c->rc_nq = 0;
@@ -484,12 +552,26 @@ extern "C" int emb_set_dirichlet(emb_ctx* c, int64_t npec, const int64_t* pec_id
 extern "C" int emb_get_solve_ids(emb_ctx* c, int64_t* out) {
     if (!c || !out) return EMB_ERR_ARG;
     if (!c->have_dirichlet) { c->err = "emb_get_solve_ids: emb_set_dirichlet not called"; return EMB_ERR_STATE; }
-    std::vector<int> h((size_t)c->Ns);
+    // ascending dof order, as the reference builds it (assembler.py:385); position s is solve index sperm[s]
+    std::vector<int> h((size_t)c->Ns), pm((size_t)c->Ns);
     EMB_CUDA(c, cudaMemcpyAsync(h.data(), c->solve_ids.p, h.size() * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    EMB_CUDA(c, cudaMemcpyAsync(pm.data(), c->sperm.p, pm.size() * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     EMB_CUDA(c, cudaStreamSynchronize(c->stream));
-    for (size_t i = 0; i < h.size(); ++i) out[i] = h[i];
+    for (size_t i = 0; i < h.size(); ++i) out[i] = h[(size_t)pm[i]];
     return EMB_OK;
 }
+// solve index of the s-th kept dof in ascending dof order (the order of emb_get_solve_ids); vectors and matrices that
+// cross the ABI on the solve space (emb_get_csr which=2, emb_spmv_host, emb_aux_add*) are in SOLVE-INDEX order
+extern "C" int emb_get_solve_perm(emb_ctx* c, int64_t* perm) {
+    if (!c || !perm) return EMB_ERR_ARG;
+    if (!c->have_dirichlet) { c->err = "emb_get_solve_perm: emb_set_dirichlet not called"; return EMB_ERR_STATE; }
+    std::vector<int> pm((size_t)c->Ns);
+    EMB_CUDA(c, cudaMemcpyAsync(pm.data(), c->sperm.p, pm.size() * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    EMB_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (size_t i = 0; i < pm.size(); ++i) perm[i] = pm[i];
+    return EMB_OK;
+}
+extern "C" int emb_is_paired(const emb_ctx* c) { return c && c->paired ? 1 : 0; }
 
 // ------------------------------------------------------------------------------------------------
 // A(f) = E - k0^2 B + sum gamma_s S_s  on the solve-space pattern

@@ -120,24 +120,28 @@ __global__ void __launch_bounds__(256) k_aux_diag(int64_t ncol, const int64_t* _
         dinv[k] = n2 > 0 ? cdiv(mk(1.0), cx{ar, ai}) : mk(0.0);
     }
 }
-// s = sum_i RT[k,i] r[i];  traw[k] = s (if traw);  t[k] = dinv ? dinv[k]*s : s     (8 x NV lanes per aux column)
-template <int NV>
+// s = sum_i RT[k,i] r[i];  traw[k] = s (if traw);  t[k] = dinv ? dinv[k]*s : s     (KPR x NV lanes per aux column;
+// the rows of R^T are short (5-30 entries), so few lanes with several independent loads each beat many idle lanes)
+template <int NV, int KPR>
 __global__ void __launch_bounds__(256) k_aux_restrict(int64_t ncol, const int64_t* __restrict__ tptr, const int* __restrict__ tcol,
                                                       const double* __restrict__ tval, const cx* __restrict__ dinv,
                                                       const cx* __restrict__ r, cx* __restrict__ t, cx* __restrict__ traw) {
-    constexpr int LPR = 8 * NV;
+    constexpr int LPR = KPR * NV;
     const int64_t gt = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int64_t k = gt / LPR;
     const int s = (int)(gt % LPR);
     const int v = s % NV, ks = s / NV;
     double ar = 0.0, ai = 0.0;
-    if (k < ncol)
-        for (int64_t m = tptr[k] + ks; m < tptr[k + 1]; m += 8) {
-            const double w = tval[m];
-            const cx u = ldx(r + (int64_t)tcol[m] * NV + v);
+    if (k < ncol) {
+        const int64_t m1 = tptr[k + 1];
+#pragma unroll 4
+        for (int64_t m = tptr[k] + ks; m < m1; m += KPR) {
+            const double w = __ldg(tval + m);
+            const cx u = ldx(r + (int64_t)__ldg(tcol + m) * NV + v);
             ar += w * u.re;
             ai += w * u.im;
         }
+    }
 #pragma unroll
     for (int o = LPR / 2; o >= NV; o >>= 1) {
         ar += __shfl_down_sync(0xffffffffu, ar, o, LPR);
@@ -148,6 +152,18 @@ __global__ void __launch_bounds__(256) k_aux_restrict(int64_t ncol, const int64_
         if (traw) traw[k * NV + v] = sum;
         if (t) t[k * NV + v] = dinv ? dinv[k] * sum : sum;
     }
+}
+template <int NV>
+static int aux_restrict_launch(emb_ctx* c, cudaStream_t s, const AuxSpace& a, const cx* dinv, const cx* src, cx* t, cx* traw) {
+    const double avg = a.ncol > 0 ? (double)a.nnz / (double)a.ncol : 0.0;
+    if (avg <= 16.0)
+        k_aux_restrict<NV, 2><<<blocks_for(a.ncol * 2 * NV, 256), 256, 0, s>>>(a.ncol, a.tptr.p, a.tcol.p, a.tval.p, dinv, src, t, traw);
+    else if (avg <= 48.0 || NV == 4)
+        k_aux_restrict<NV, 4><<<blocks_for(a.ncol * 4 * NV, 256), 256, 0, s>>>(a.ncol, a.tptr.p, a.tcol.p, a.tval.p, dinv, src, t, traw);
+    else
+        k_aux_restrict<NV, 8><<<blocks_for(a.ncol * 8 * NV, 256), 256, 0, s>>>(a.ncol, a.tptr.p, a.tcol.p, a.tval.p, dinv, src, t, traw);
+    EMB_LAUNCH_CHECK(c);
+    return EMB_OK;
 }
 // z[i] += s * sum_k R[i,k] t[k]     (NV threads per row; rows of R are short)
 template <int NV>
@@ -170,6 +186,41 @@ __global__ void __launch_bounds__(256) k_aux_prolong(int64_t n, const int64_t* _
     cx zi = z[f];
     fma_c(zi, s, cx{ar, ai});
     z[f] = zi;
+}
+
+// Top-level spaces whose prolongations are fused with the block-Jacobi term into the single pass that writes z
+struct TopSpaces {
+    int n;
+    const int64_t* rptr[4];
+    const int* rcol[4];
+    const double* rval[4];
+    const cx* t[4];
+    cx scale[4];
+};
+// z = D_blk^-1 r + sum_s scale_s R_s t_s   (flat over ns * NV entries; terms added in the order of the list)
+template <int NV>
+__global__ void __launch_bounds__(256) k_precond_final(int64_t ns, const cx* __restrict__ dinv, const int* __restrict__ mate,
+                                                       const cx* __restrict__ r, TopSpaces T, cx* __restrict__ z) {
+    const int64_t f = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (f >= ns * NV) return;
+    const int64_t i = f / NV;
+    const int v = (int)(f % NV);
+    cx acc = dinv[2 * i] * r[f];
+    const int m = mate ? mate[i] : -1;
+    if (m >= 0) fma_c(acc, dinv[2 * i + 1], r[(int64_t)m * NV + v]);
+    for (int s = 0; s < T.n; ++s) {
+        const int64_t m0 = T.rptr[s][i], m1 = T.rptr[s][i + 1];
+        if (m0 == m1) continue;
+        double ar = 0.0, ai = 0.0;
+        for (int64_t q = m0; q < m1; ++q) {
+            const double w = __ldg(T.rval[s] + q);
+            const cx u = ldx(T.t[s] + (int64_t)__ldg(T.rcol[s] + q) * NV + v);
+            ar += w * u.re;
+            ai += w * u.im;
+        }
+        fma_c(acc, T.scale[s], cx{ar, ai});
+    }
+    z[f] = acc;
 }
 
 static int precond_streams(emb_ctx* c) {
@@ -217,16 +268,20 @@ static int precond_setup(emb_ctx* c, int mode_in, const VT* val) {
 }
 
 // z = M^-1 r on NV interleaved columns.  mode 3: block-Jacobi on the solve space plus the tree of auxiliary spaces
-// (additive): restrict down the tree (parents before children), solve every space, prolong up.
+// (additive): restrict down the tree (parents before children), solve every space, prolong up; the prolongations of
+// the top-level spaces are fused with the block-Jacobi term into the one pass that writes z.
 template <int NV>
 static int precond_apply(emb_ctx* c, int mode, const cx* r, cx* z) {
     cudaStream_t main = c->stream;
     const int na = (mode == 3) ? (int)c->aux.size() : 0;
     const bool par = c->use_side_streams && na > 0;
+    const int* mate = mode >= 2 ? c->pairmate.p : nullptr;
+    if (na == 0) {
+        k_precond_apply<<<blocks_for(c->Ns * NV, 256), 256, 0, main>>>(c->Ns, NV, c->dinv.p, mate, r, z);
+        EMB_LAUNCH_CHECK(c);
+        return EMB_OK;
+    }
     if (par) EMB_CUDA(c, cudaEventRecord(c->ev_fork, main));       // r is complete here
-    k_precond_apply<<<blocks_for(c->Ns * NV, 256), 256, 0, main>>>(c->Ns, NV, c->dinv.p, mode >= 2 ? c->pairmate.p : nullptr, r, z);
-    EMB_LAUNCH_CHECK(c);
-    if (na == 0) return EMB_OK;
     auto strm = [&](int i) { return par ? c->side[i % emb_ctx::NSIDE] : main; };
     std::vector<cx*> xres((size_t)na, nullptr);
     for (int i = 0; i < na; ++i) {
@@ -238,9 +293,7 @@ static int precond_apply(emb_ctx* c, int mode, const cx* r, cx* z) {
         cx* t = a.solver == 0 ? a.tmp.p : nullptr;
         // solver 1 restricts straight into the right-hand side of its V-cycle
         if (a.solver == 1 && !a.has_children) traw = a.wk.b[0].p;
-        k_aux_restrict<NV><<<blocks_for(a.ncol * 8 * NV, 256), 256, 0, s>>>(a.ncol, a.tptr.p, a.tcol.p, a.tval.p,
-                                                                      a.solver == 0 ? a.dinv.p : nullptr, src, t, traw);
-        EMB_LAUNCH_CHECK(c);
+        EMB_TRY(aux_restrict_launch<NV>(c, s, a, a.solver == 0 ? a.dinv.p : nullptr, src, t, traw));
         if (par) EMB_CUDA(c, cudaEventRecord(c->ev_restr[i], s));
         xres[i] = a.tmp.p;
         if (a.solver == 1) {
@@ -252,6 +305,15 @@ static int precond_apply(emb_ctx* c, int mode, const cx* r, cx* z) {
             xres[i] = res;
         }
     }
+    TopSpaces T;
+    T.n = 0;
+    int ntop = 0;
+    for (int i = 0; i < na; ++i) ntop += c->aux[i].parent < 0;
+    const bool fuse = ntop <= 4;
+    if (!fuse) {
+        k_precond_apply<<<blocks_for(c->Ns * NV, 256), 256, 0, main>>>(c->Ns, NV, c->dinv.p, mate, r, z);
+        EMB_LAUNCH_CHECK(c);
+    }
     for (int i = na - 1; i >= 0; --i) {
         AuxSpace& a = c->aux[i];
         cx scale = mk(1.0);
@@ -261,8 +323,17 @@ static int precond_apply(emb_ctx* c, int mode, const cx* r, cx* z) {
             EMB_CUDA(c, cudaEventRecord(c->ev_done[i], strm(i)));
             EMB_CUDA(c, cudaStreamWaitEvent(dst_s, c->ev_done[i], 0));
         }
+        if (a.parent < 0 && fuse) {
+            const int q = T.n++;
+            T.rptr[q] = a.rptr.p; T.rcol[q] = a.rcol.p; T.rval[q] = a.rval.p; T.t[q] = xres[i]; T.scale[q] = scale;
+            continue;
+        }
         cx* dst = a.parent < 0 ? z : c->aux[a.parent].tmp.p;
         k_aux_prolong<NV><<<blocks_for(a.nrow * NV, 256), 256, 0, dst_s>>>(a.nrow, a.rptr.p, a.rcol.p, a.rval.p, xres[i], scale, dst);
+        EMB_LAUNCH_CHECK(c);
+    }
+    if (fuse) {
+        k_precond_final<NV><<<blocks_for(c->Ns * NV, 256), 256, 0, main>>>(c->Ns, c->dinv.p, mate, r, T, z);
         EMB_LAUNCH_CHECK(c);
     }
     return EMB_OK;

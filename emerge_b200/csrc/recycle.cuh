@@ -15,6 +15,7 @@
 // The reference has no counterpart: it factorises A(f) at every point (fem/solver.py:243-309, emfreq3d.py:658-694).
 #pragma once
 #include "krylov.cuh"
+#include <cub/cub.cuh>
 #include <complex>
 #include <vector>
 
@@ -45,8 +46,8 @@ __global__ void __launch_bounds__(256) k_spmv_src(int64_t n, const int64_t* __re
     }
     if (r < n && sub == 0) y[r] = cx{ar, ai};
 }
-// y += S x for a surface matrix held as (solve-pattern slot, real value) pairs in ascending slot order; y is zeroed
-// by the caller.  The thread that owns the first entry of a row sums the whole row in list order (deterministic).
+// y += S x for a surface matrix held as (solve-pattern slot, real value) pairs SORTED by slot (eliminated entries, slot
+// -1, first); y is zeroed by the caller.  The thread that owns the first entry of a row sums the whole row in list order (deterministic).
 __device__ __forceinline__ int64_t row_of_slot(const int64_t* __restrict__ rowptr, int64_t n, int64_t p) {
     int64_t lo = 0, hi = n - 1;          // last r with rowptr[r] <= p
     while (lo < hi) {
@@ -262,8 +263,20 @@ static int rc_term_mv(emb_ctx* c, int t, const cx* u, cx* w) {
         EMB_LAUNCH_CHECK(c);
     } else {
         Surface& s = c->surf[c->rc_terms[(size_t)t - 2]];
+        if (!s.mv_slot.p) {      // once per surface: entries in solve-pattern order (the list is in full-pattern order)
+            EMB_TRY(dev_alloc(c, s.mv_slot, (size_t)s.nslot));
+            EMB_TRY(dev_alloc(c, s.mv_val, (size_t)s.nslot));
+            DevBuf<char> tmp;
+            size_t tb = 0;
+            EMB_CUDA(c, cub::DeviceRadixSort::SortPairs(nullptr, tb, s.slot_s.p, s.mv_slot.p, s.Sval.p, s.mv_val.p, (int)s.nslot, 0, 64, c->stream));
+            EMB_TRY(dev_alloc(c, tmp, tb));
+            EMB_CUDA(c, cub::DeviceRadixSort::SortPairs(tmp.p, tb, s.slot_s.p, s.mv_slot.p, s.Sval.p, s.mv_val.p, (int)s.nslot, 0, 64, c->stream));
+            EMB_CUDA(c, cudaStreamSynchronize(c->stream));
+            tmp.release();
+            c->launches += 3;
+        }
         EMB_CUDA(c, cudaMemsetAsync(w, 0, (size_t)n * sizeof(cx), c->stream));
-        k_surf_mv<<<blocks_for(s.nslot, 128), 128, 0, c->stream>>>(s.nslot, s.slot_s.p, s.Sval.p, n, c->rowptr_s.p, c->col_s.p, u, w);
+        k_surf_mv<<<blocks_for(s.nslot, 128), 128, 0, c->stream>>>(s.nslot, s.mv_slot.p, s.mv_val.p, n, c->rowptr_s.p, c->col_s.p, u, w);
         EMB_LAUNCH_CHECK(c);
     }
     c->rc_spmvs++;

@@ -56,6 +56,8 @@ _SIGS = {
     "emb_set_dirichlet": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p]),
     "emb_n_solve": (C.c_int64, [C.c_void_p]),
     "emb_get_solve_ids": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "emb_get_solve_perm": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "emb_is_paired": (C.c_int, [C.c_void_p]),
     "emb_form_A": (C.c_int, [C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_void_p]),
     "emb_spmv_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "emb_spmv_bench": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double)]),
@@ -222,8 +224,20 @@ class Context:
         indptr = np.empty(rows + 1, dtype=np.int64) if pattern else None
         indices = np.empty(nnz, dtype=np.int32) if pattern else None
         data = np.empty(nnz, dtype=np.complex128) if values else None
-        self._check(self.lib.emb_get_csr(self.h, which, _p(indptr), _p(indices), _p(data)))
-        return indptr, indices, data
+        if which != 2 or not self.paired:
+            self._check(self.lib.emb_get_csr(self.h, which, _p(indptr), _p(indices), _p(data)))
+            return indptr, indices, data
+        # the library holds A(f) in solve-index (pair) order; callers get it in the reference's ascending-dof order
+        import scipy.sparse as sp
+        ip = np.empty(rows + 1, dtype=np.int64)
+        ix = np.empty(nnz, dtype=np.int32)
+        self._check(self.lib.emb_get_csr(self.h, which, _p(ip), _p(ix), _p(data)))
+        perm = self.solve_perm()
+        vals = data if data is not None else np.ones(nnz, dtype=np.complex128)
+        A = sp.csr_matrix((vals, ix, ip), shape=(rows, rows))[perm][:, perm].tocsr()
+        A.sort_indices()
+        return (A.indptr.astype(np.int64) if pattern else None, A.indices.astype(np.int32) if pattern else None,
+                A.data if values else None)
 
     def element_matrices(self, t0, t1):
         E = np.empty((t1 - t0, 20, 20), dtype=np.complex128)
@@ -259,6 +273,27 @@ class Context:
     def set_dirichlet(self, pec_ids):
         ids = _c(pec_ids, np.int64)
         self._check(self.lib.emb_set_dirichlet(self.h, len(ids), _p(ids)))
+        self._perm = None
+
+    @property
+    def paired(self) -> bool:
+        """True when the library numbers the solve space by (edge / face) function pairs (block-CSR operator)."""
+        return bool(self.lib.emb_is_paired(self.h))
+
+    def solve_perm(self):
+        """perm[s] = internal solve index of solve_ids()[s] (identity unless `paired`)."""
+        if getattr(self, "_perm", None) is None:
+            out = np.empty(self.n_solve, dtype=np.int64)
+            self._check(self.lib.emb_get_solve_perm(self.h, _p(out)))
+            self._perm = out
+        return self._perm
+
+    def _rows_to_internal(self, R):
+        """rows of a solve-space matrix given in ascending-dof order -> solve-index order"""
+        perm = self.solve_perm()
+        inv = np.empty_like(perm)
+        inv[perm] = np.arange(len(perm))
+        return R[inv]
 
     def solve_ids(self):
         out = np.empty(self.n_solve, dtype=np.int64)
@@ -271,10 +306,13 @@ class Context:
         self._check(self.lib.emb_form_A(self.h, float(k0), len(s), _p(s), _p(g)))
 
     def spmv(self, x):
-        x = _c(x, np.complex128)
-        y = np.empty_like(x)
-        self._check(self.lib.emb_spmv_host(self.h, _p(x), _p(y)))
-        return y
+        """y = A(f) x on the solve space, x and y in the order of solve_ids()"""
+        perm = self.solve_perm()
+        xi = np.empty(self.n_solve, dtype=np.complex128)
+        xi[perm] = _c(x, np.complex128)
+        y = np.empty_like(xi)
+        self._check(self.lib.emb_spmv_host(self.h, _p(xi), _p(y)))
+        return y[perm]
 
     def spmv_bench(self, reps=20, nv=1, fp32=False):
         """avg ms of one operator application on resident vectors (nv interleaved right-hand sides; fp32: the complex64
@@ -301,7 +339,7 @@ class Context:
 
     def aux_add(self, R):
         """R: scipy sparse (n_solve x ncol) real transfer matrix of one auxiliary space."""
-        R = R.tocsr().astype(np.float64)
+        R = self._rows_to_internal(R.tocsr().astype(np.float64)).tocsr()
         R.sort_indices()
         T = R.T.tocsr()
         T.sort_indices()
@@ -320,6 +358,8 @@ class Context:
 
     def aux_add_ex(self, R, parent=-1, solver="diag", hid=-1, scale="one"):
         """R: scipy sparse (rows of the parent space x ncol) real transfer matrix; returns the index of the new space."""
+        if parent < 0:
+            R = self._rows_to_internal(R.tocsr())
         a = self._csr_args(R) + self._csr_args(R.T)
         self._check(self.lib.emb_aux_add_ex(self.h, R.shape[0], R.shape[1], *[_p(x) for x in a], int(parent),
                                             {"diag": 0, "amg": 1}[solver], int(hid), {"one": 0, "minus_inv_k0sq": 1}[scale]))

@@ -93,7 +93,15 @@ int emb_surface_blocks(emb_ctx* ctx, int sid, double* S_ntrix64);
  * i.e. A[np.ix_(solve_ids, solve_ids)] of fem/solver.py:434, once instead of per solve. */
 int emb_set_dirichlet(emb_ctx* ctx, int64_t npec, const int64_t* pec_ids);
 int64_t emb_n_solve(const emb_ctx* ctx);
+/* kept dofs in ascending order = the reference's solve_ids (assembler.py:385) */
 int emb_get_solve_ids(emb_ctx* ctx, int64_t* solve_ids);
+/* Internal numbering of the solve space.  When both functions of every kept edge / face are kept (PEC elimination always
+ * does), the library orders the solve space by pairs (2j, 2j+1 = the two functions of kept entity j) so that A(f) is a
+ * block-CSR matrix of 2x2 blocks.  perm[s] = solve index of solve_ids[s].  Everything that crosses this ABI on the solve
+ * space - emb_get_csr(which=2), emb_spmv_host, the rows of top-level emb_aux_add* matrices, the device vectors of
+ * emb_recycle_export/import - is in SOLVE-INDEX order; full-space vectors (x_full, b_full) are unaffected. */
+int emb_get_solve_perm(emb_ctx* ctx, int64_t* perm);
+int emb_is_paired(const emb_ctx* ctx);
 /* A(f) = E - k0^2 B + sum_s gamma[s] S_s on the solve-space pattern (assembler.py:333,383) */
 int emb_form_A(emb_ctx* ctx, double k0, int nsurf, const int* sids, const emb_c128* gammas);
 
