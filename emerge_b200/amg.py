@@ -1,6 +1,6 @@
 """Smoothed-aggregation AMG setup for the nodal auxiliary problems of the multilevel preconditioner (host side, numpy /
 scipy, one-time per mesh).  Only the SETUP lives here (aggregates, prolongators, Galerkin products); the cycles run on
-the GPU (emerge_b200/csrc/multilevel.cu) from the level matrices this module produces.
+the GPU (emerge_b200/csrc/amg.cuh) from the level matrices this module produces.
 
 The reference has no counterpart: it solves every A(f) with a sparse direct solver (fem/solver.py:243-309).
 """
@@ -72,10 +72,12 @@ def _rho_DinvA(A, dinv, iters=12, seed=0):
     rng = np.random.default_rng(seed)
     x = rng.standard_normal(A.shape[0])
     lam = 1.0
+    nrm = lambda v: float(np.sqrt(np.sum(v * v)))      # not BLAS: a threaded dot costs milliseconds on these sizes
     for _ in range(iters):
         y = dinv * (A @ x)
-        lam = np.linalg.norm(y) / max(np.linalg.norm(x), 1e-300)
-        x = y / max(np.linalg.norm(y), 1e-300)
+        ny = nrm(y)
+        lam = ny / max(nrm(x), 1e-300)
+        x = y / max(ny, 1e-300)
     return lam
 
 

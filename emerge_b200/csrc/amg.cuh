@@ -12,12 +12,14 @@
 #include "krylov.cuh"
 
 // MODE 0: y = A x        MODE 1: y = b - A x        MODE 2: y = x + w d (b - A x)   (out of place)
-// MODE 3: y += A x
+// MODE 3: y += A x       MODE 4 (pre-smoothing from a zero guess fused with the residual): y2 = w d b, y = b - A y2,
+//                         called with x = b
 // KPR x NV lanes per row: lane (ks, v) walks nonzeros ks, ks + KPR, ... for column v (one gather wavefront per nonzero).
 template <int KPR, int MODE, int NV>
 __global__ void __launch_bounds__(256) k_rcsr(int64_t n, const int64_t* __restrict__ ptr, const int* __restrict__ col,
                                               const double* __restrict__ val, const cx* __restrict__ x, cx* __restrict__ y,
-                                              const cx* __restrict__ b, const double* __restrict__ d, double w) {
+                                              const cx* __restrict__ b, const double* __restrict__ d, double w,
+                                              cx* __restrict__ y2) {
     constexpr int LPR = KPR * NV;
     const int64_t gt = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int64_t r = gt / LPR;
@@ -26,8 +28,10 @@ __global__ void __launch_bounds__(256) k_rcsr(int64_t n, const int64_t* __restri
     double ar = 0.0, ai = 0.0;
     if (r < n)
         for (int64_t k = ptr[r] + ks; k < ptr[r + 1]; k += KPR) {
-            const double a = val[k];
-            const cx u = ldx(x + (int64_t)col[k] * NV + v);
+            const int cc = col[k];
+            double a = val[k];
+            if (MODE == 4) a *= w * d[cc];
+            const cx u = ldx(x + (int64_t)cc * NV + v);
             ar += a * u.re;
             ai += a * u.im;
         }
@@ -38,6 +42,12 @@ __global__ void __launch_bounds__(256) k_rcsr(int64_t n, const int64_t* __restri
     }
     if (r < n && ks == 0) {
         const int64_t o = r * NV + v;
+        if (MODE == 4) {
+            const cx bb = b[o];
+            const double sc = w * d[r];
+            y2[o] = cx{sc * bb.re, sc * bb.im};
+            y[o] = cx{bb.re - ar, bb.im - ai};
+        } else
         if (MODE == 0) y[o] = cx{ar, ai};
         else if (MODE == 1) { const cx bb = b[o]; y[o] = cx{bb.re - ar, bb.im - ai}; }
         else if (MODE == 2) {
@@ -94,11 +104,11 @@ static inline int pick_lpr(int64_t nnz, int64_t n) {
 }
 template <int MODE, int NV>
 static int rcsr_launch(emb_ctx* c, cudaStream_t s, int lpr, int64_t n, const int64_t* ptr, const int* col, const double* val,
-                       const cx* x, cx* y, const cx* b, const double* d, double w) {
+                       const cx* x, cx* y, const cx* b, const double* d, double w, cx* y2 = nullptr) {
     constexpr int KMAX = 32 / NV;          // KPR * NV lanes must fit a warp
-    if (lpr <= 4 || KMAX <= 4) k_rcsr<4, MODE, NV><<<blocks_for(n * 4 * NV, 256), 256, 0, s>>>(n, ptr, col, val, x, y, b, d, w);
-    else if (lpr == 8 || KMAX == 8) k_rcsr<8, MODE, NV><<<blocks_for(n * 8 * NV, 256), 256, 0, s>>>(n, ptr, col, val, x, y, b, d, w);
-    else k_rcsr<KMAX, MODE, NV><<<blocks_for(n * KMAX * NV, 256), 256, 0, s>>>(n, ptr, col, val, x, y, b, d, w);
+    if (lpr <= 4 || KMAX <= 4) k_rcsr<4, MODE, NV><<<blocks_for(n * 4 * NV, 256), 256, 0, s>>>(n, ptr, col, val, x, y, b, d, w, y2);
+    else if (lpr == 8 || KMAX == 8) k_rcsr<8, MODE, NV><<<blocks_for(n * 8 * NV, 256), 256, 0, s>>>(n, ptr, col, val, x, y, b, d, w, y2);
+    else k_rcsr<KMAX, MODE, NV><<<blocks_for(n * KMAX * NV, 256), 256, 0, s>>>(n, ptr, col, val, x, y, b, d, w, y2);
     EMB_LAUNCH_CHECK(c);
     return EMB_OK;
 }
@@ -115,8 +125,9 @@ static int amg_vcycle(emb_ctx* c, cudaStream_t s, AmgHierarchy& H, AmgWork& W, c
             xs[l] = W.xa[l].p;
             break;
         }
-        k_amg_smooth0<<<blocks_for(v.n * NV, 256), 256, 0, s>>>(v.n, NV, v.dinv.p, v.omega, W.b[l].p, W.xa[l].p); EMB_LAUNCH_CHECK(c);
-        EMB_TRY((rcsr_launch<1, NV>(c, s, v.lpr_a, v.n, v.aptr.p, v.acol.p, v.aval.p, W.xa[l].p, W.t[l].p, W.b[l].p, nullptr, 0.0)));
+        // xa = w D^-1 b and t = b - A xa in one kernel
+        EMB_TRY((rcsr_launch<4, NV>(c, s, v.lpr_a, v.n, v.aptr.p, v.acol.p, v.aval.p, W.b[l].p, W.t[l].p, W.b[l].p, v.dinv.p, v.omega,
+                                    W.xa[l].p)));
         EMB_TRY((rcsr_launch<0, NV>(c, s, v.lpr_t, v.nc, v.tptr.p, v.tcol.p, v.tval.p, W.t[l].p, W.b[l + 1].p, nullptr, nullptr, 0.0)));
         xs[l] = W.xa[l].p;
     }

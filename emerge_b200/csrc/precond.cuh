@@ -223,9 +223,49 @@ __global__ void __launch_bounds__(256) k_precond_final(int64_t ns, const cx* __r
     z[f] = acc;
 }
 
+// dst[i] += sum_s scale_s R_s t_s   (the children of one auxiliary space in a single pass over its vector)
+template <int NV>
+__global__ void __launch_bounds__(256) k_aux_prolong_multi(int64_t n, TopSpaces T, cx* __restrict__ dst) {
+    const int64_t f = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (f >= n * NV) return;
+    const int64_t i = f / NV;
+    const int v = (int)(f % NV);
+    cx acc = dst[f];
+    bool any = false;
+    for (int s = 0; s < T.n; ++s) {
+        const int64_t m0 = T.rptr[s][i], m1 = T.rptr[s][i + 1];
+        if (m0 == m1) continue;
+        double ar = 0.0, ai = 0.0;
+        for (int64_t q = m0; q < m1; ++q) {
+            const double w = __ldg(T.rval[s] + q);
+            const cx u = ldx(T.t[s] + (int64_t)__ldg(T.rcol[s] + q) * NV + v);
+            ar += w * u.re;
+            ai += w * u.im;
+        }
+        fma_c(acc, T.scale[s], cx{ar, ai});
+        any = true;
+    }
+    if (any) dst[f] = acc;
+}
+
+// Side streams, one per auxiliary space (modulo NSIDE).  The chain restrict -> V-cycle -> prolong of the nodal spaces is a
+// sequence of ~12 small latency-bound kernels; it gets the highest stream priority so that its blocks are scheduled ahead
+// of the bulk restrictions of the childless top-level spaces (tens of thousands of blocks), which fill the machine around it.
 static int precond_streams(emb_ctx* c) {
     if (c->side[0]) return EMB_OK;
-    for (int i = 0; i < emb_ctx::NSIDE; ++i) EMB_CUDA(c, cudaStreamCreateWithFlags(&c->side[i], cudaStreamNonBlocking));
+    int least = 0, greatest = 0;
+    cudaDeviceGetStreamPriorityRange(&least, &greatest);
+    for (int i = 0; i < emb_ctx::NSIDE; ++i) {
+        bool bulk = true;           // every space mapped to this stream is a childless diagonal top-level space
+        bool used = false;
+        for (size_t k = (size_t)i; k < c->aux.size(); k += emb_ctx::NSIDE) {
+            const AuxSpace& a = c->aux[k];
+            used = true;
+            if (a.parent >= 0 || a.has_children || a.solver != 0) bulk = false;
+        }
+        const int prio = (used && bulk) ? least : greatest;
+        EMB_CUDA(c, cudaStreamCreateWithPriority(&c->side[i], cudaStreamNonBlocking, prio));
+    }
     EMB_CUDA(c, cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     return EMB_OK;
 }
@@ -314,8 +354,20 @@ static int precond_apply(emb_ctx* c, int mode, const cx* r, cx* z) {
         k_precond_apply<<<blocks_for(c->Ns * NV, 256), 256, 0, main>>>(c->Ns, NV, c->dinv.p, mate, r, z);
         EMB_LAUNCH_CHECK(c);
     }
+    std::vector<TopSpaces> kids((size_t)na);
+    for (auto& k : kids) k.n = 0;
+    auto flush_kids = [&](int p) -> int {       // one pass over the parent's vector for up to 4 children
+        TopSpaces& K = kids[(size_t)p];
+        if (K.n == 0) return EMB_OK;
+        AuxSpace& pa = c->aux[p];
+        k_aux_prolong_multi<NV><<<blocks_for(pa.ncol * NV, 256), 256, 0, strm(p)>>>(pa.ncol, K, pa.tmp.p);
+        EMB_LAUNCH_CHECK(c);
+        K.n = 0;
+        return EMB_OK;
+    };
     for (int i = na - 1; i >= 0; --i) {
         AuxSpace& a = c->aux[i];
+        EMB_TRY(flush_kids(i));                  // every child of i has a larger index and was visited already
         cx scale = mk(1.0);
         if (a.solver == 1 && a.scale_mode == 1) scale = mk(-1.0 / (c->k0 * c->k0));
         cudaStream_t dst_s = a.parent < 0 ? main : strm(a.parent);
@@ -326,6 +378,13 @@ static int precond_apply(emb_ctx* c, int mode, const cx* r, cx* z) {
         if (a.parent < 0 && fuse) {
             const int q = T.n++;
             T.rptr[q] = a.rptr.p; T.rcol[q] = a.rcol.p; T.rval[q] = a.rval.p; T.t[q] = xres[i]; T.scale[q] = scale;
+            continue;
+        }
+        if (a.parent >= 0 && c->aux[a.parent].solver == 0) {
+            TopSpaces& K = kids[(size_t)a.parent];
+            const int q = K.n++;
+            K.rptr[q] = a.rptr.p; K.rcol[q] = a.rcol.p; K.rval[q] = a.rval.p; K.t[q] = xres[i]; K.scale[q] = scale;
+            if (K.n == 4) EMB_TRY(flush_kids(a.parent));
             continue;
         }
         cx* dst = a.parent < 0 ? z : c->aux[a.parent].tmp.p;

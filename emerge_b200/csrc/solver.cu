@@ -791,6 +791,9 @@ extern "C" int emb_aux_clear(emb_ctx* c) {
         amg_work_release(a.wk);
     }
     c->aux.clear();
+    for (auto& st : c->side)          // stream priorities follow the shape of the tree: recreated at the next setup
+        if (st) { cudaStreamDestroy(st); st = nullptr; }
+    if (c->ev_fork) { cudaEventDestroy(c->ev_fork); c->ev_fork = nullptr; }
     for (auto& h : c->amg) amg_release(h);
     c->amg.clear();
     c->have_As = false;

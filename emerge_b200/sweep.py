@@ -93,6 +93,7 @@ class FrequencySweep:
         self.f_ref = float(f_ref)           # frequency whose k0^2 shifts the nodal Helmholtz-type auxiliary operator
         self.recycle = int(recycle)        # directions kept from previous frequency points (0 = every point solved cold)
         self.lockstep = 4                   # ports solved together per lockstep group (1 = one port at a time)
+        self.amg_coarse_size = 2500         # the AMG level at or below this size is inverted densely (one launch, L2-resident)
         self.solver_opts = dict(method="cocr", precond="multilevel", rtol=1e-8, maxit=200000, restart=50)
 
     # ------------------------------------------------------------------ setup (once)
@@ -204,8 +205,8 @@ class FrequencySweep:
         Lm = Le if same else p1_stiffness_mass(self.t, w_mu)[0]
         kn = ~badN
         import scipy.sparse as sp
-        He = sa_hierarchy((Le[kn][:, kn] + 1e-3 * kmid2 * sp.diags(mass[kn] * np.mean(w_eps))).tocsr())
-        Hm = sa_hierarchy((Lm[kn][:, kn] + kmid2 * sp.diags(mass[kn] * np.mean(w_mu))).tocsr())
+        He = sa_hierarchy((Le[kn][:, kn] + 1e-3 * kmid2 * sp.diags(mass[kn] * np.mean(w_eps))).tocsr(), coarse_size=self.amg_coarse_size)
+        Hm = sa_hierarchy((Lm[kn][:, kn] + kmid2 * sp.diags(mass[kn] * np.mean(w_mu))).tocsr(), coarse_size=self.amg_coarse_size)
         he, hm = ctx.amg_upload(He), ctx.amg_upload(Hm)
         self.amg_levels = dict(eps=[l["A"].shape[0] for l in He], mu=[l["A"].shape[0] for l in Hm])
         ctx.aux_add_ex(G1s, parent=ip, solver="amg", hid=he, scale="minus_inv_k0sq")
