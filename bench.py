@@ -208,7 +208,9 @@ def run_gpu(args):
     if world > 1:
         import torch.distributed as dist
         torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        import datetime
+        # a short collective timeout: a mismatched collective must not hold the GPU box for the default 10 minutes
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=180))
     from emerge_b200.sweep import FrequencySweep, hierarchical_order
     from emerge_b200.distributed import ShardedSweep
     nx, ny, nz = args.cells
@@ -291,16 +293,27 @@ def run_gpu(args):
     S_mine = np.array([res.S[i] for i in order])
     if dist is not None:
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-        St = torch.view_as_real(torch.tensor(S_mine, device=f"cuda:{local}")).contiguous()
+        # NCCL all_gather needs equal shapes: blocks differ by one point when world does not divide the sweep
+        kmax = torch.tensor([len(order)], device=f"cuda:{local}")
+        dist.all_reduce(kmax, op=dist.ReduceOp.MAX)
+        pad = np.zeros((int(kmax.item()),) + S_mine.shape[1:], dtype=np.complex128)
+        pad[:len(order)] = S_mine
+        St = torch.view_as_real(torch.tensor(pad, device=f"cuda:{local}")).contiguous()
+        cnt = torch.tensor([len(order)], device=f"cuda:{local}")
+        cnts = [torch.empty_like(cnt) for _ in range(world)]
+        dist.all_gather(cnts, cnt)
+        total_points = int(sum(int(n.item()) for n in cnts))
         gath = [torch.empty_like(St) for _ in range(world)]
         dist.all_gather(gath, St)                      # NCCL: S-parameter blocks of every rank
-        S_all = np.concatenate([torch.view_as_complex(g).cpu().numpy() for g in gath])
+        S_all = np.concatenate([torch.view_as_complex(g).cpu().numpy()[:int(n.item())] for g, n in zip(gath, cnts)])
     else:
         S_all = S_mine
+        total_points = len(order)
     ms_max, ms_e2e_max = float(tm[0]), float(tm[1])
     if rank == 0:
-        value = world * K / (ms_max / 1e3)
-        e2e_val = world * e2e_K / (ms_e2e_max / 1e3) if e2e_K > 0 else None
+        value = total_points / (ms_max / 1e3)       # points solved by all ranks / slowest rank's device time
+        e2e_points = total_points if e2e_K == K else world * e2e_K
+        e2e_val = e2e_points / (ms_e2e_max / 1e3) if e2e_K > 0 else None
         peak, peak_src = peaks()
         # dominant kernel: the lockstep operator application of COCR, k_bspmv<NV, complex64 values> (2x2 block-CSR):
         # per nonzero 8 B value + 1 B (one 4 B column per 2x2 block), per row 4 B rowptr (8 B per block-row) +

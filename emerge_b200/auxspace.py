@@ -53,6 +53,31 @@ def _face_tables():
     return np.array(vert), np.array(edge), np.array(whit)
 
 
+def _rows_to_csr(rows, cols, vals, blocks, shape):
+    """CSR straight from per-row-block entry lists: every block of rows (edge-a, face-a, edge-b, face-b: contiguous,
+    ascending dof ranges that tile [0, N)) has a fixed number of entries per row, so no COO sort is needed.
+    rows/cols/vals: parallel lists of arrays, one entry per row of the block the row array belongs to."""
+    ip_parts, ix_parts, dv_parts = [], [], []
+    offset = 0
+    for blk in blocks:
+        sel = [k for k, r in enumerate(rows) if r is blk]
+        n, m = len(blk), len(sel)
+        ix = np.empty((n, m), dtype=np.int32)
+        dv = np.empty((n, m), dtype=np.float64)
+        for j, k in enumerate(sel):
+            ix[:, j] = cols[k]
+            dv[:, j] = vals[k]
+        ip_parts.append(offset + m * np.arange(n, dtype=np.int64))
+        ix_parts.append(ix.ravel())
+        dv_parts.append(dv.ravel())
+        offset += n * m
+    indptr = np.concatenate(ip_parts + [np.array([offset], dtype=np.int64)])
+    M = sp.csr_matrix((np.concatenate(dv_parts), np.concatenate(ix_parts), indptr), shape=shape)
+    M.eliminate_zeros()
+    M.sort_indices()
+    return M
+
+
 def build_aux_spaces(tables):
     """tables: MeshTables-like (nodes (3,nN), edges (2,nE), tris (3,nTri), tri_to_edge (3,nTri), edge_lengths).
     Returns (G, P, G1) as scipy CSR in the reference's dof numbering
@@ -86,11 +111,7 @@ def build_aux_spaces(tables):
         rows += [fa, fb]
         cols += [nN + t2e[k], nN + t2e[k]]
         vals += [et[k, 0] / lAE, et[k, 1] / lAB]
-    r = np.concatenate([np.broadcast_to(x, v.shape) for x, v in zip(rows, vals)])
-    c = np.concatenate([np.broadcast_to(x, v.shape) for x, v in zip(cols, vals)])
-    v = np.concatenate(vals)
-    keep = v != 0
-    G = sp.coo_matrix((v[keep], (r[keep], c[keep])), shape=(N, nN + nE)).tocsr()
+    G = _rows_to_csr(rows, cols, vals, (ea, fa, eb, fb), (N, nN + nE))
     # Whitney prolongation
     rows = [ea, eb]
     cols = [ea, ea]
@@ -99,11 +120,7 @@ def build_aux_spaces(tables):
         rows += [fa, fb]
         cols += [t2e[k], t2e[k]]
         vals += [wt[k, 0] / lAE, wt[k, 1] / lAB]
-    r = np.concatenate([np.broadcast_to(x, v.shape) for x, v in zip(rows, vals)])
-    c = np.concatenate([np.broadcast_to(x, v.shape) for x, v in zip(cols, vals)])
-    v = np.concatenate(vals)
-    keep = v != 0
-    P = sp.coo_matrix((v[keep], (r[keep], c[keep])), shape=(N, nE)).tocsr()
+    P = _rows_to_csr(rows, cols, vals, (ea, fa, eb, fb), (N, nE))
     # P1 gradient in the Whitney basis: grad(lam_v) = sum_e G1[e,v] w_e ; w_AB.t_AB = -1/l  =>  G1[e,A]=+1, G1[e,B]=-1
     G1 = sp.coo_matrix((np.concatenate([np.ones(nE), -np.ones(nE)]),
                         (np.concatenate([ea, ea]), np.concatenate([A, Bv]))), shape=(nE, nN)).tocsr()

@@ -40,12 +40,10 @@ extern "C" void emb_destroy(emb_ctx* c) {
     for (auto& w : c->work) w.release();
     c->dinv.release(); c->pairmate.release(); c->red.release(); c->As.release(); c->rc_x0.release();
     c->rcU.release(); c->rcQ.release(); c->rc_part.release(); c->rc_tmp.release(); c->bs.release(); c->As32.release();
-    for (auto& st : c->side) if (st) cudaStreamDestroy(st);
-    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     for (auto e : c->ev_restr) cudaEventDestroy(e);
     for (auto e : c->ev_done) cudaEventDestroy(e);
     if (c->evp0) { cudaEventDestroy(c->evp0); cudaEventDestroy(c->evp1); }
-    emb_aux_clear(c);
+    emb_aux_clear(c);          // also destroys the side streams and their fork event (once)
     cudaEventDestroy(c->evr0);
     cudaEventDestroy(c->evr1);
     cudaEventDestroy(c->evs0);
