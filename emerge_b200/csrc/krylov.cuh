@@ -92,8 +92,13 @@ __global__ void __launch_bounds__(256) k_spmv(int64_t n, const int64_t* __restri
 // contiguous 32*NV-byte piece of x, two contiguous value pairs - a quarter of the L1 wavefronts of the scalar kernel,
 // which is what bounds it (ncu: l1tex 68 %, DRAM 41 % on the scalar kernel at 1M tets, profiles/).
 // Algorithmic bytes: nnz * sizeof(VT) + nnz / 4 * 4 + n * (4 + 32 * NV).
-template <int NV, typename VT, int KPR, bool RESID>
-__global__ void __launch_bounds__(256) k_bspmv(int64_t nbr, const int64_t* __restrict__ rowptr, const int* __restrict__ blkcol,
+// BLK: the values are in BLOCK layout - block q of block-row j is the four consecutive entries rowptr[2j] + 4q + 2r + h =
+// A[2j+r][2c+h] (the inner operator As is stored this way, precond.cuh::k_sym_part), so the two entries a lane needs sit
+// in one 32-byte sector (complex64).  Fetching the block with one load per lane group and exchanging the entries by
+// shuffles was measured slower (0.98 vs 0.90 ms).  BLK = false: plain CSR order (A(f) itself, which other kernels
+// address by CSR position).
+template <int NV, typename VT, int KPR, bool RESID, bool BLK>
+__global__ void __launch_bounds__(256, 5) k_bspmv(int64_t nbr, const int64_t* __restrict__ rowptr, const int* __restrict__ blkcol,
                                                const VT* __restrict__ val, const cx* __restrict__ x, const cx* __restrict__ b,
                                                cx* __restrict__ y) {
     constexpr int LPB = 2 * NV;           // lanes per block
@@ -104,16 +109,16 @@ __global__ void __launch_bounds__(256) k_bspmv(int64_t nbr, const int64_t* __res
     const int u = s % LPB, ks = s / LPB;
     const int h = u / NV;
     double a0r = 0.0, a0i = 0.0, a1r = 0.0, a1i = 0.0;
-    if (j < nbr) {
-        const int64_t p0 = rowptr[2 * j], p1 = rowptr[2 * j + 1];
-        const int64_t nb = (p1 - p0) >> 1;
-        const int* bc = blkcol + (p0 >> 2);
+    int64_t p0 = 0, p1 = 0, nb = 0;
+    if (j < nbr) { p0 = rowptr[2 * j]; p1 = rowptr[2 * j + 1]; nb = (p1 - p0) >> 1; }
+    const int* bc = blkcol + (p0 >> 2);
+    {
 #pragma unroll 4
         for (int64_t q = ks; q < nb; q += KPR) {
             const int cb = __ldg(bc + q);
             const cx w = ldx(x + (int64_t)cb * LPB + u);
-            const cx e0 = ldval(val, p0 + 2 * q + h);
-            const cx e1 = ldval(val, p1 + 2 * q + h);
+            const cx e0 = ldval(val, BLK ? p0 + 4 * q + h : p0 + 2 * q + h);
+            const cx e1 = ldval(val, BLK ? p0 + 4 * q + 2 + h : p1 + 2 * q + h);
             a0r += e0.re * w.re - e0.im * w.im;
             a0i += e0.re * w.im + e0.im * w.re;
             a1r += e1.re * w.re - e1.im * w.im;
@@ -141,36 +146,44 @@ __global__ void __launch_bounds__(256) k_bspmv(int64_t nbr, const int64_t* __res
 }
 
 constexpr int SPMV_KPR = 8;      // ~43 nonzeros per row / ~21 blocks per block-row of the order-2 Nedelec operator
-template <int NV, typename VT, bool RESID>
-static int spmv_any(emb_ctx* c, const VT* val, const cx* x, const cx* b, cx* y) {
-    if (c->paired) {
-        // block slots per block-row (KPR x 2NV lanes): few lanes with several independent gathers each - the kernel is
-        // bound by memory-level parallelism per warp, not by bandwidth, when every warp owns a single short row
-        static const int kpr_env = getenv("EMB_SPMV_KPR") ? atoi(getenv("EMB_SPMV_KPR")) : 0;
-        const int64_t nbr = c->Ns / 2;
-        int kpr = kpr_env > 0 ? kpr_env : (NV == 1 ? 2 : 1);      // measured on B200 at 1M tets (profiles/r1_spmv_tuning.txt)
-        if (kpr * 2 * NV > 32) kpr = 32 / (2 * NV);
-        if (kpr >= 8)
-            k_bspmv<NV, VT, (NV == 4 ? 4 : 8), RESID><<<blocks_for(nbr * (NV == 4 ? 4 : 8) * 2 * NV, 256), 256, 0, c->stream>>>(
-                nbr, c->rowptr_s.p, c->blkcol.p, val, x, b, y);
-        else if (kpr >= 4)
-            k_bspmv<NV, VT, 4, RESID><<<blocks_for(nbr * 4 * 2 * NV, 256), 256, 0, c->stream>>>(nbr, c->rowptr_s.p, c->blkcol.p, val, x, b, y);
-        else if (kpr >= 2)
-            k_bspmv<NV, VT, 2, RESID><<<blocks_for(nbr * 2 * 2 * NV, 256), 256, 0, c->stream>>>(nbr, c->rowptr_s.p, c->blkcol.p, val, x, b, y);
-        else
-            k_bspmv<NV, VT, 1, RESID><<<blocks_for(nbr * 1 * 2 * NV, 256), 256, 0, c->stream>>>(nbr, c->rowptr_s.p, c->blkcol.p, val, x, b, y);
-    } else {
-        k_spmv<NV, VT, SPMV_KPR, RESID><<<blocks_for(c->Ns * SPMV_KPR * NV, 256), 256, 0, c->stream>>>(c->Ns, c->rowptr_s.p,
-                                                                                                       c->col_s.p, val, x, b, y);
-    }
+template <int NV, typename VT, bool RESID, bool BLK>
+static int bspmv_launch(emb_ctx* c, const VT* val, const cx* x, const cx* b, cx* y) {
+    // block slots per block-row (KPR x 2NV lanes): few lanes with several independent gathers each - the kernel is
+    // bound by memory-level parallelism per warp and L1 wavefronts, not by bandwidth, when every warp owns one short row
+    static const int kpr_env = getenv("EMB_SPMV_KPR") ? atoi(getenv("EMB_SPMV_KPR")) : 0;
+    const int64_t nbr = c->Ns / 2;
+    int kpr = kpr_env > 0 ? kpr_env : (NV == 1 ? 2 : 1);      // measured on B200 at 1M tets (profiles/r1_spmv_tuning.txt)
+    if (kpr * 2 * NV > 32) kpr = 32 / (2 * NV);
+    if (kpr >= 8)
+        k_bspmv<NV, VT, (NV == 4 ? 4 : 8), RESID, BLK><<<blocks_for(nbr * (NV == 4 ? 4 : 8) * 2 * NV, 256), 256, 0, c->stream>>>(
+            nbr, c->rowptr_s.p, c->blkcol.p, val, x, b, y);
+    else if (kpr >= 4)
+        k_bspmv<NV, VT, 4, RESID, BLK><<<blocks_for(nbr * 4 * 2 * NV, 256), 256, 0, c->stream>>>(nbr, c->rowptr_s.p, c->blkcol.p, val, x, b, y);
+    else if (kpr >= 2)
+        k_bspmv<NV, VT, 2, RESID, BLK><<<blocks_for(nbr * 2 * 2 * NV, 256), 256, 0, c->stream>>>(nbr, c->rowptr_s.p, c->blkcol.p, val, x, b, y);
+    else
+        k_bspmv<NV, VT, 1, RESID, BLK><<<blocks_for(nbr * 1 * 2 * NV, 256), 256, 0, c->stream>>>(nbr, c->rowptr_s.p, c->blkcol.p, val, x, b, y);
     EMB_LAUNCH_CHECK(c);
     return EMB_OK;
 }
+// inner: `val` is the inner operator As (block layout when the solve space is pair-ordered), else A(f) in CSR order
+template <int NV, typename VT, bool RESID>
+static int spmv_any(emb_ctx* c, const VT* val, const cx* x, const cx* b, cx* y, bool inner) {
+    if (c->paired) return inner ? bspmv_launch<NV, VT, RESID, true>(c, val, x, b, y) : bspmv_launch<NV, VT, RESID, false>(c, val, x, b, y);
+    k_spmv<NV, VT, SPMV_KPR, RESID><<<blocks_for(c->Ns * SPMV_KPR * NV, 256), 256, 0, c->stream>>>(c->Ns, c->rowptr_s.p, c->col_s.p,
+                                                                                                   val, x, b, y);
+    EMB_LAUNCH_CHECK(c);
+    return EMB_OK;
+}
+// y = A(f) x  (CSR-ordered values)
 template <int NV, typename VT>
-static int spmv(emb_ctx* c, const VT* val, const cx* x, cx* y) { return spmv_any<NV, VT, false>(c, val, x, nullptr, y); }
-// y = b - A x
+static int spmv(emb_ctx* c, const VT* val, const cx* x, cx* y) { return spmv_any<NV, VT, false>(c, val, x, nullptr, y, false); }
+// y = As x  (values as k_sym_part stores them)
 template <int NV, typename VT>
-static int spmv_resid(emb_ctx* c, const VT* val, const cx* x, const cx* b, cx* y) { return spmv_any<NV, VT, true>(c, val, x, b, y); }
+static int spmv_inner(emb_ctx* c, const VT* val, const cx* x, cx* y) { return spmv_any<NV, VT, false>(c, val, x, nullptr, y, true); }
+// y = b - A(f) x
+template <int NV, typename VT>
+static int spmv_resid(emb_ctx* c, const VT* val, const cx* x, const cx* b, cx* y) { return spmv_any<NV, VT, true>(c, val, x, b, y, false); }
 
 // ------------------------------------------------------------------------------------------------
 // deterministic per-column reductions over interleaved vectors (flat index: column = idx % NV; VBLOCK % NV == 0)

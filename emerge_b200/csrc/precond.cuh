@@ -10,14 +10,16 @@
 #pragma once
 #include "amg.cuh"
 
-// one warp per row: As[k] = (A[k] + A[k^T])/2; the pattern is structurally symmetric
+// one warp per row: As = (A + A^T)/2; the pattern is structurally symmetric.  blk: block layout of the pair-ordered solve
+// space (entry e of row r goes to rowptr[2 (r/2)] + 4 (e/2) + 2 (r%2) + e%2, krylov.cuh::k_bspmv), else CSR position.
 template <typename VT>
-__global__ void k_sym_part(int64_t n, const int64_t* __restrict__ rowptr, const int* __restrict__ col, const cx* __restrict__ A,
-                           VT* __restrict__ As) {
+__global__ void k_sym_part(int64_t n, int blk, const int64_t* __restrict__ rowptr, const int* __restrict__ col,
+                           const cx* __restrict__ A, VT* __restrict__ As) {
     const int lane = threadIdx.x & 31;
     const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     if (r >= n) return;
-    for (int64_t k = rowptr[r] + lane; k < rowptr[r + 1]; k += 32) {
+    const int64_t p0 = rowptr[r], pb = rowptr[r & ~(int64_t)1];
+    for (int64_t k = p0 + lane; k < rowptr[r + 1]; k += 32) {
         const int j = col[k];
         int64_t lo = rowptr[j], hi = rowptr[j + 1] - 1;
         while (lo < hi) {
@@ -26,7 +28,8 @@ __global__ void k_sym_part(int64_t n, const int64_t* __restrict__ rowptr, const 
         }
         cx a = A[k];
         if (col[lo] == (int)r) { const cx b = A[lo]; a = cx{0.5 * (a.re + b.re), 0.5 * (a.im + b.im)}; }
-        stval(As, k, a);
+        const int64_t e = k - p0;
+        stval(As, blk ? pb + 4 * (e >> 1) + 2 * (r & 1) + (e & 1) : k, a);
     }
 }
 
@@ -63,7 +66,9 @@ __global__ void k_precond_setup(int64_t ns, int mode, const int64_t* __restrict_
     const int m = (mode == 2) ? mate[i] : -1;
     if (mode == 0) { dinv[2 * i] = mk(1.0); dinv[2 * i + 1] = mk(0.0); return; }
     if (m < 0) { dinv[2 * i] = cdiv(mk(1.0), aii); dinv[2 * i + 1] = mk(0.0); return; }
-    const cx aim = csr_get(rowptr, col, val, (int)i, m), ami = csr_get(rowptr, col, val, m, (int)i);
+    // the block of the SYMMETRIC part (val may be A(f) itself)
+    const cx a1 = csr_get(rowptr, col, val, (int)i, m), a2 = csr_get(rowptr, col, val, m, (int)i);
+    const cx aim = cx{0.5 * (a1.re + a2.re), 0.5 * (a1.im + a2.im)}, ami = aim;
     const cx amm = csr_get(rowptr, col, val, m, m);
     const cx det = aii * amm - aim * ami;
     dinv[2 * i] = cdiv(amm, det);

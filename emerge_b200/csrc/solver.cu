@@ -89,7 +89,7 @@ struct CocrBody {
         k_dot<NV, false><<<NPART, VBLOCK, 0, c->stream>>>(n, Ap, MAp, partA); EMB_LAUNCH_CHECK(c);
         k_cocr_update<NV><<<NPART, VBLOCK, 0, c->stream>>>(n, partA, sc, p, Ap, MAp, d, r, z, partR); EMB_LAUNCH_CHECK(c);
         if (sample) cudaEventRecord(c->evs0, c->stream);
-        EMB_TRY((spmv<NV, VT>(c, As, z, Az)));
+        EMB_TRY((spmv_inner<NV, VT>(c, As, z, Az)));
         if (sample) cudaEventRecord(c->evs1, c->stream);
         k_dot<NV, false><<<NPART, VBLOCK, 0, c->stream>>>(n, z, Az, partZ); EMB_LAUNCH_CHECK(c);
         k_cocr_dir<NV><<<NPART, VBLOCK, 0, c->stream>>>(n, partZ, partR, sc, z, Az, p, Ap); EMB_LAUNCH_CHECK(c);
@@ -110,7 +110,7 @@ static int cocr(emb_ctx* c, int pmode, const VT* As, const cx* rhs, cx* d, const
     k_copy<<<vb, 256, 0, c->stream>>>(nn, rhs, B.r); EMB_LAUNCH_CHECK(c);
     EMB_TRY(precond_apply<NV>(c, pmode, B.r, B.z));
     k_copy<<<vb, 256, 0, c->stream>>>(nn, B.z, B.p); EMB_LAUNCH_CHECK(c);
-    EMB_TRY((spmv<NV, VT>(c, As, B.z, B.Az))); ++*spmvs;
+    EMB_TRY((spmv_inner<NV, VT>(c, As, B.z, B.Az))); ++*spmvs;
     k_copy<<<vb, 256, 0, c->stream>>>(nn, B.Az, B.Ap); EMB_LAUNCH_CHECK(c);
     k_dot<NV, false><<<NPART, VBLOCK, 0, c->stream>>>(n, B.z, B.Az, B.partZ); EMB_LAUNCH_CHECK(c);
     k_finish<NV><<<1, VBLOCK, 0, c->stream>>>(B.partZ, B.sc); EMB_LAUNCH_CHECK(c);
@@ -344,17 +344,19 @@ static int bicgstab(emb_ctx* c, int pmode, const cx* A, const cx* b, cx* x, doub
 // lockstep solve of NV right-hand sides: A xs = bs (device, solve space, interleaved); xs is in/out
 // (initial guess when use_x0)
 // ------------------------------------------------------------------------------------------------
+// As (inner operator, block layout on a pair-ordered solve space) and the preconditioner, whose diagonal blocks and
+// Galerkin diagonals are those of the symmetric part and are read straight from A(f): diag(R^T A R) = diag(R^T As R)
 template <typename VT>
 static int ensure_operator(emb_ctx* c, int precond, VT* As) {
     const int64_t n = c->Ns;
     if (!c->have_As) {
-        k_sym_part<VT><<<blocks_for(n * 32, 256), 256, 0, c->stream>>>(n, c->rowptr_s.p, c->col_s.p, c->A.p, As);
+        k_sym_part<VT><<<blocks_for(n * 32, 256), 256, 0, c->stream>>>(n, c->paired ? 1 : 0, c->rowptr_s.p, c->col_s.p, c->A.p, As);
         EMB_LAUNCH_CHECK(c);
-        EMB_TRY(precond_setup<VT>(c, precond, As));
+        EMB_TRY(precond_setup<cx>(c, precond, c->A.p));
         c->have_As = true;
         c->As_precond = precond;
     } else if (c->As_precond != precond) {
-        EMB_TRY(precond_setup<VT>(c, precond, As));
+        EMB_TRY(precond_setup<cx>(c, precond, c->A.p));
         c->As_precond = precond;
     }
     return EMB_OK;
@@ -663,15 +665,15 @@ extern "C" int emb_spmv_bench_ex(emb_ctx* c, int reps, int nv, int fp32, double*
     if (fp32) {
         EMB_TRY(dev_alloc(c, c->As32, (size_t)c->nnz_s * 2));
         A32 = reinterpret_cast<cf*>(c->As32.p);
-        k_sym_part<cf><<<blocks_for(c->Ns * 32, 256), 256, 0, c->stream>>>(c->Ns, c->rowptr_s.p, c->col_s.p, c->A.p, A32);
+        k_sym_part<cf><<<blocks_for(c->Ns * 32, 256), 256, 0, c->stream>>>(c->Ns, c->paired ? 1 : 0, c->rowptr_s.p, c->col_s.p, c->A.p, A32);
         EMB_LAUNCH_CHECK(c);
         c->have_As = false;
     }
     auto one = [&](const cx* x, cx* y) -> int {
         if (fp32) {
-            if (nv == 1) return spmv<1, cf>(c, A32, x, y);
-            if (nv == 2) return spmv<2, cf>(c, A32, x, y);
-            return spmv<4, cf>(c, A32, x, y);
+            if (nv == 1) return spmv_inner<1, cf>(c, A32, x, y);
+            if (nv == 2) return spmv_inner<2, cf>(c, A32, x, y);
+            return spmv_inner<4, cf>(c, A32, x, y);
         }
         if (nv == 1) return spmv<1, cx>(c, c->A.p, x, y);
         if (nv == 2) return spmv<2, cx>(c, c->A.p, x, y);
