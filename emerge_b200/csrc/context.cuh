@@ -147,6 +147,7 @@ struct emb_ctx {
     DevBuf<cx> As;
     DevBuf<float> As32;       // [nnz_s][2]
     bool as_fp32 = true;
+    bool block_krylov = true;  // the ports of a lockstep group share one Krylov space (block COCR)
     bool have_As = false;
     int As_precond = -1;
     // side streams of the additive preconditioner (independent auxiliary spaces run concurrently) and their events

@@ -302,60 +302,204 @@ __global__ void k_extract_col(int64_t n, const cx* __restrict__ a, const cx* __r
 }
 
 // ------------------------------------------------------------------------------------------------
-// fused COCR kernels.  Device scalars sc[q * NV + k]: q = 0 zAz, 1 alpha, 2 beta, 3 |r|^2, 4 zAz_new
+// Block COCR kernels.  The NV right-hand sides of a frequency point share ONE Krylov space (block conjugate-orthogonal
+// conjugate residual): the slowly converging propagating modes are found once for all ports, which shortens the plateau
+// every (re)started solve goes through (CPU prototype tools/: 544 -> 351 iterations for two ports at equal cost per
+// iteration).  With block = 0 the small matrices are reduced to their diagonals and the columns are independent
+// recurrences in lockstep (used for padded groups and as the fallback when the block recurrence breaks down).
+// Device scalars sc (NV x NV matrices, row-major, entry [i][j] at i * NV + j):
+//   RHO = sc + 0, ALPHA = sc + 16, BETA = sc + 32, RHO_NEW = sc + 48, RR (per column |r|^2) = sc + 64
 // ------------------------------------------------------------------------------------------------
-// alpha = zAz / sum(partA);  x += alpha p; r -= alpha Ap; z -= alpha MAp;  partial |r|^2
+constexpr int SC_RHO = 0, SC_ALPHA = 16, SC_BETA = 32, SC_RHONEW = 48, SC_RR = 64, SC_SIZE = 80;
+
+// all[i] = column i of this thread's row, gathered from the NV neighbouring lanes (flat interleaved index: the NV lanes
+// aligned at a multiple of NV hold one row).  Every lane of the warp must call it.
 template <int NV>
-__global__ void __launch_bounds__(VBLOCK) k_cocr_update(int64_t n, const cx* __restrict__ partA, cx* __restrict__ sc,
-                                                        const cx* __restrict__ p, const cx* __restrict__ Ap,
-                                                        const cx* __restrict__ MAp, cx* __restrict__ x, cx* __restrict__ r,
-                                                        cx* __restrict__ z, cx* __restrict__ partR) {
-    __shared__ cx s_den[NVMAX];
-    sum_partials<NV>(partA, s_den);
+__device__ __forceinline__ void row_gather(cx own, cx* all) {
+    const int base = (threadIdx.x & 31) & ~(NV - 1);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        all[i].re = __shfl_sync(0xffffffffu, own.re, base + i);
+        all[i].im = __shfl_sync(0xffffffffu, own.im, base + i);
+    }
+}
+// part[blockIdx][i][j] = partial of sum_rows a[row][i] * b[row][j]  (unconjugated Gram matrix).  Flat coalesced index:
+// thread (row, k) accumulates row k of the matrix, with the b entries of its row fetched by shuffles.
+template <int NV>
+__global__ void __launch_bounds__(VBLOCK) k_gram(int64_t n, const cx* __restrict__ a, const cx* __restrict__ b,
+                                                 cx* __restrict__ part) {
+    cx acc[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) acc[j] = mk(0.0);
+    int64_t lo, hi;
+    block_rows(n, lo, hi);
+    const int64_t end = hi * NV;
+    for (int64_t f0 = lo * NV + (threadIdx.x & ~31); f0 < end; f0 += VBLOCK) {
+        const int64_t f = f0 + (threadIdx.x & 31);
+        const bool live = f < end;
+        const cx u = live ? a[f] : mk(0.0);
+        const cx v = live ? b[f] : mk(0.0);
+        cx vb[NV];
+        row_gather<NV>(v, vb);
+#pragma unroll
+        for (int j = 0; j < NV; ++j) fma_c(acc[j], u, vb[j]);
+    }
     const int k = threadIdx.x % NV;
-    const cx alpha = sdiv(sc[k], s_den[k]);
-    if (blockIdx.x == 0 && threadIdx.x < NV) sc[NV + k] = alpha;
-    const cx na = -alpha;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        const cx t = block_sum_cols<NV>(acc[j]);      // per-k sums in threads 0..NV-1
+        if (threadIdx.x < NV) part[(int64_t)blockIdx.x * NV * NV + k * NV + j] = t;
+    }
+}
+// tot[q] = sum over the NPART partials of entry q (fixed order); result in shared memory s_m[0 .. NV*NV)
+template <int NV>
+__device__ __forceinline__ void sum_gram(const cx* __restrict__ part, cx* s_m) {
+    for (int q = 0; q < NV * NV; ++q) {
+        cx v = mk(0.0);
+        for (int i = threadIdx.x; i < NPART; i += VBLOCK) v += part[(int64_t)i * NV * NV + q];
+        const cx t = block_sum_cols<1>(v);
+        __syncthreads();
+        if (threadIdx.x == 0) s_m[q] = t;
+    }
+    __syncthreads();
+}
+// X = S^-1 B for NV x NV complex matrices (Gaussian elimination with partial pivoting, one thread); block = 0: diagonals
+template <int NV>
+__device__ void small_solve(const cx* S, const cx* B, int block, cx* X) {
+    if (!block) {
+        for (int q = 0; q < NV * NV; ++q) X[q] = mk(0.0);
+        for (int i = 0; i < NV; ++i) X[i * NV + i] = sdiv(B[i * NV + i], S[i * NV + i]);
+        return;
+    }
+    cx a[NV][NV], r[NV][NV];
+    for (int i = 0; i < NV; ++i)
+        for (int j = 0; j < NV; ++j) { a[i][j] = S[i * NV + j]; r[i][j] = B[i * NV + j]; }
+    for (int c = 0; c < NV; ++c) {
+        int pv = c;
+        double best = norm2(a[c][c]);
+        for (int i = c + 1; i < NV; ++i) { const double m = norm2(a[i][c]); if (m > best) { best = m; pv = i; } }
+        if (pv != c)
+            for (int j = 0; j < NV; ++j) { cx t = a[c][j]; a[c][j] = a[pv][j]; a[pv][j] = t; t = r[c][j]; r[c][j] = r[pv][j]; r[pv][j] = t; }
+        const cx inv = sdiv(mk(1.0), a[c][c]);
+        for (int i = c + 1; i < NV; ++i) {
+            const cx f = a[i][c] * inv;
+            for (int j = c; j < NV; ++j) a[i][j] -= f * a[c][j];
+            for (int j = 0; j < NV; ++j) r[i][j] -= f * r[c][j];
+        }
+    }
+    for (int j = 0; j < NV; ++j)
+        for (int i = NV - 1; i >= 0; --i) {
+            cx t = r[i][j];
+            for (int k = i + 1; k < NV; ++k) t -= a[i][k] * X[k * NV + j];
+            X[i * NV + j] = sdiv(t, a[i][i]);
+        }
+}
+
+// alpha = sigma^-1 rho with sigma = sum(partA);  X += P alpha; R -= AP alpha; Z -= MAP alpha;  partial |r_k|^2
+template <int NV>
+__global__ void __launch_bounds__(VBLOCK) k_bcocr_update(int64_t n, int block, const cx* __restrict__ partA, cx* __restrict__ sc,
+                                                         const cx* __restrict__ p, const cx* __restrict__ Ap,
+                                                         const cx* __restrict__ MAp, cx* __restrict__ x, cx* __restrict__ r,
+                                                         cx* __restrict__ z, cx* __restrict__ partR) {
+    __shared__ cx s_sig[NVMAX * NVMAX], s_al[NVMAX * NVMAX];
+    sum_gram<NV>(partA, s_sig);
+    if (threadIdx.x == 0) {
+        cx rho[NV * NV];
+        for (int q = 0; q < NV * NV; ++q) rho[q] = sc[SC_RHO + q];
+        small_solve<NV>(s_sig, rho, block, s_al);
+        if (blockIdx.x == 0)
+            for (int q = 0; q < NV * NV; ++q) sc[SC_ALPHA + q] = s_al[q];
+    }
+    __syncthreads();
+    // flat coalesced index: thread (row, k) updates column k and needs column k of alpha
+    const int k = threadIdx.x % NV;
+    cx al[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) al[i] = s_al[i * NV + k];
     cx acc = mk(0.0);
     int64_t lo, hi;
     block_rows(n, lo, hi);
-    for (int64_t i = lo * NV + threadIdx.x; i < hi * NV; i += VBLOCK) {
-        cx xi = x[i], ri = r[i], zi = z[i];
-        fma_c(xi, alpha, p[i]);
-        fma_c(ri, na, Ap[i]);
-        fma_c(zi, na, MAp[i]);
-        x[i] = xi; r[i] = ri; z[i] = zi;
-        acc.re += ri.re * ri.re + ri.im * ri.im;
+    const int64_t end = hi * NV;
+    for (int64_t f0 = lo * NV + (threadIdx.x & ~31); f0 < end; f0 += VBLOCK) {
+        const int64_t f = f0 + (threadIdx.x & 31);
+        const bool live = f < end;
+        cx pv[NV], apv[NV], mv[NV];
+        row_gather<NV>(live ? p[f] : mk(0.0), pv);
+        row_gather<NV>(live ? Ap[f] : mk(0.0), apv);
+        row_gather<NV>(live ? MAp[f] : mk(0.0), mv);
+        if (live) {
+            cx xi = x[f], ri = r[f], zi = z[f];
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                const cx na = -al[i];
+                fma_c(xi, al[i], pv[i]);
+                fma_c(ri, na, apv[i]);
+                fma_c(zi, na, mv[i]);
+            }
+            x[f] = xi; r[f] = ri; z[f] = zi;
+            acc.re += ri.re * ri.re + ri.im * ri.im;
+        }
     }
     const cx t = block_sum_cols<NV>(acc);
-    if (threadIdx.x < NV) partR[blockIdx.x * NV + threadIdx.x] = t;
+    if (threadIdx.x < NV) partR[(int64_t)blockIdx.x * NV + threadIdx.x] = t;
 }
-// beta = sum(partZ)/zAz; p = z + beta p; Ap = Az + beta Ap; also finishes |r|^2.  sc[0] (zAz) is read by every block,
-// so the new value goes to sc[4] and k_cocr_commit moves it afterwards.
+// beta = rho^-1 rho_new with rho_new = sum(partZ);  P = Z + P beta; AP = AZ + AP beta; also finishes |r_k|^2.
+// rho is read by every block, so rho_new goes to its own slot and k_bcocr_commit moves it afterwards.
 template <int NV>
-__global__ void __launch_bounds__(VBLOCK) k_cocr_dir(int64_t n, const cx* __restrict__ partZ, const cx* __restrict__ partR,
-                                                     cx* __restrict__ sc, const cx* __restrict__ z, const cx* __restrict__ Az,
-                                                     cx* __restrict__ p, cx* __restrict__ Ap) {
-    __shared__ cx s_z[NVMAX], s_r[NVMAX];
-    sum_partials<NV>(partZ, s_z);
-    sum_partials<NV>(partR, s_r);
+__global__ void __launch_bounds__(VBLOCK) k_bcocr_dir(int64_t n, int block, const cx* __restrict__ partZ,
+                                                      const cx* __restrict__ partR, cx* __restrict__ sc, const cx* __restrict__ z,
+                                                      const cx* __restrict__ Az, cx* __restrict__ p, cx* __restrict__ Ap) {
+    __shared__ cx s_new[NVMAX * NVMAX], s_be[NVMAX * NVMAX], s_rr[NVMAX];
+    sum_gram<NV>(partZ, s_new);
+    for (int k = 0; k < NV; ++k) {
+        cx v = mk(0.0);
+        for (int i = threadIdx.x; i < NPART; i += VBLOCK) v += partR[(int64_t)i * NV + k];
+        const cx t = block_sum_cols<1>(v);
+        __syncthreads();
+        if (threadIdx.x == 0) s_rr[k] = t;
+    }
+    if (threadIdx.x == 0) {
+        cx rho[NV * NV];
+        for (int q = 0; q < NV * NV; ++q) rho[q] = sc[SC_RHO + q];
+        small_solve<NV>(rho, s_new, block, s_be);
+    }
+    __syncthreads();
     const int k = threadIdx.x % NV;
-    const cx beta = sdiv(s_z[k], sc[k]);
+    cx be[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) be[i] = s_be[i * NV + k];
     int64_t lo, hi;
     block_rows(n, lo, hi);
-    for (int64_t i = lo * NV + threadIdx.x; i < hi * NV; i += VBLOCK) {
-        cx pi = z[i], api = Az[i];
-        fma_c(pi, beta, p[i]);
-        fma_c(api, beta, Ap[i]);
-        p[i] = pi; Ap[i] = api;
+    const int64_t end = hi * NV;
+    for (int64_t f0 = lo * NV + (threadIdx.x & ~31); f0 < end; f0 += VBLOCK) {
+        const int64_t f = f0 + (threadIdx.x & 31);
+        const bool live = f < end;
+        cx pv[NV], apv[NV];
+        row_gather<NV>(live ? p[f] : mk(0.0), pv);
+        row_gather<NV>(live ? Ap[f] : mk(0.0), apv);
+        if (live) {
+            cx pi = z[f], api = Az[f];
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                fma_c(pi, be[i], pv[i]);
+                fma_c(api, be[i], apv[i]);
+            }
+            p[f] = pi; Ap[f] = api;
+        }
     }
-    if (blockIdx.x == gridDim.x - 1 && threadIdx.x < NV) {
-        sc[2 * NV + k] = beta;
-        sc[3 * NV + k] = s_r[k];
-        sc[4 * NV + k] = s_z[k];
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
+        for (int q = 0; q < NV * NV; ++q) { sc[SC_BETA + q] = s_be[q]; sc[SC_RHONEW + q] = s_new[q]; }
+        for (int k = 0; k < NV; ++k) sc[SC_RR + k] = s_rr[k];
     }
 }
 template <int NV>
-__global__ void k_cocr_commit(cx* sc) {
-    if (threadIdx.x < NV) sc[threadIdx.x] = sc[4 * NV + threadIdx.x];
+__global__ void k_bcocr_commit(cx* sc) {
+    if (threadIdx.x < NV * NV) sc[SC_RHO + threadIdx.x] = sc[SC_RHONEW + threadIdx.x];
+}
+// rho = sum(partZ) at start-up
+template <int NV>
+__global__ void __launch_bounds__(VBLOCK) k_gram_finish(const cx* __restrict__ part, cx* __restrict__ out) {
+    __shared__ cx s_m[NVMAX * NVMAX];
+    sum_gram<NV>(part, s_m);
+    if (threadIdx.x < NV * NV) out[threadIdx.x] = s_m[threadIdx.x];
 }

@@ -29,14 +29,14 @@
 // workspace
 // ------------------------------------------------------------------------------------------------
 static inline cx* red_part(emb_ctx* c) { return reinterpret_cast<cx*>(c->red.p); }
-static inline cx* red_sc(emb_ctx* c) { return red_part(c) + (size_t)4 * NPART * NVMAX; }
+static inline cx* red_sc(emb_ctx* c) { return red_part(c) + (size_t)4 * NPART * NVMAX * NVMAX; }
 
 // `count` work vectors of Ns * nv entries
 static int ensure_work(emb_ctx* c, size_t count, int nv) {
     if (c->work.size() < count) c->work.resize(count);
     for (size_t i = 0; i < count; ++i)
         if (c->work[i].n < (size_t)c->Ns * nv) EMB_TRY(dev_alloc(c, c->work[i], (size_t)c->Ns * nv));
-    EMB_TRY(dev_alloc(c, c->red, ((size_t)4 * NPART * NVMAX + 8 * NVMAX + 16) * 2));
+    EMB_TRY(dev_alloc(c, c->red, ((size_t)4 * NPART * NVMAX * NVMAX + SC_SIZE + 8 * NVMAX + 16) * 2));
     return EMB_OK;
 }
 
@@ -44,7 +44,7 @@ static int spmv1(emb_ctx* c, const cx* val, const cx* x, cx* y) { return spmv<1,
 
 static int dot_host(emb_ctx* c, bool conj, const cx* a, const cx* b, cx* out) {
     cx* part = red_part(c);
-    cx* sc = red_sc(c) + 6 * NVMAX;
+    cx* sc = red_sc(c) + SC_SIZE;
     if (conj) k_dot<1, true><<<NPART, VBLOCK, 0, c->stream>>>(c->Ns, a, b, part);
     else k_dot<1, false><<<NPART, VBLOCK, 0, c->stream>>>(c->Ns, a, b, part);
     EMB_LAUNCH_CHECK(c);
@@ -58,7 +58,7 @@ static int dot_host(emb_ctx* c, bool conj, const cx* a, const cx* b, cx* out) {
 template <int NV>
 static int norms2_host(emb_ctx* c, const cx* a, double* out) {
     cx* part = red_part(c);
-    cx* sc = red_sc(c) + 6 * NVMAX;
+    cx* sc = red_sc(c) + SC_SIZE;
     k_dot<NV, true><<<NPART, VBLOCK, 0, c->stream>>>(c->Ns, a, a, part);
     EMB_LAUNCH_CHECK(c);
     k_finish<NV><<<1, VBLOCK, 0, c->stream>>>(part, sc);
@@ -77,7 +77,7 @@ static int norms2_host(emb_ctx* c, const cx* a, double* out) {
 template <int NV, typename VT>
 struct CocrBody {
     emb_ctx* c;
-    int pmode;
+    int pmode, block;
     const VT* As;
     cx *d, *r, *z, *p, *Az, *Ap, *MAp, *partA, *partR, *partZ, *sc;
     // one iteration; `sample`: CUDA events around the operator application and the preconditioner (plain launches only)
@@ -86,25 +86,25 @@ struct CocrBody {
         if (sample) cudaEventRecord(c->evp0, c->stream);
         EMB_TRY(precond_apply<NV>(c, pmode, Ap, MAp));
         if (sample) cudaEventRecord(c->evp1, c->stream);
-        k_dot<NV, false><<<NPART, VBLOCK, 0, c->stream>>>(n, Ap, MAp, partA); EMB_LAUNCH_CHECK(c);
-        k_cocr_update<NV><<<NPART, VBLOCK, 0, c->stream>>>(n, partA, sc, p, Ap, MAp, d, r, z, partR); EMB_LAUNCH_CHECK(c);
+        k_gram<NV><<<NPART, VBLOCK, 0, c->stream>>>(n, Ap, MAp, partA); EMB_LAUNCH_CHECK(c);
+        k_bcocr_update<NV><<<NPART, VBLOCK, 0, c->stream>>>(n, block, partA, sc, p, Ap, MAp, d, r, z, partR); EMB_LAUNCH_CHECK(c);
         if (sample) cudaEventRecord(c->evs0, c->stream);
         EMB_TRY((spmv_inner<NV, VT>(c, As, z, Az)));
         if (sample) cudaEventRecord(c->evs1, c->stream);
-        k_dot<NV, false><<<NPART, VBLOCK, 0, c->stream>>>(n, z, Az, partZ); EMB_LAUNCH_CHECK(c);
-        k_cocr_dir<NV><<<NPART, VBLOCK, 0, c->stream>>>(n, partZ, partR, sc, z, Az, p, Ap); EMB_LAUNCH_CHECK(c);
-        k_cocr_commit<NV><<<1, 32, 0, c->stream>>>(sc); EMB_LAUNCH_CHECK(c);
+        k_gram<NV><<<NPART, VBLOCK, 0, c->stream>>>(n, z, Az, partZ); EMB_LAUNCH_CHECK(c);
+        k_bcocr_dir<NV><<<NPART, VBLOCK, 0, c->stream>>>(n, block, partZ, partR, sc, z, Az, p, Ap); EMB_LAUNCH_CHECK(c);
+        k_bcocr_commit<NV><<<1, 32, 0, c->stream>>>(sc); EMB_LAUNCH_CHECK(c);
         return EMB_OK;
     }
 };
 
 template <int NV, typename VT>
-static int cocr(emb_ctx* c, int pmode, const VT* As, const cx* rhs, cx* d, const double* stop_abs, int maxit, int* its,
+static int cocr(emb_ctx* c, int pmode, int block, const VT* As, const cx* rhs, cx* d, const double* stop_abs, int maxit, int* its,
                 int* spmvs, double* rnorm_out) {
     const int64_t n = c->Ns, nn = c->Ns * NV;
     cx* part = red_part(c);
-    CocrBody<NV, VT> B{c, pmode, As, d, c->work[0].p, c->work[1].p, c->work[2].p, c->work[3].p, c->work[4].p, c->work[5].p,
-                       part, part + (size_t)NPART * NVMAX, part + (size_t)2 * NPART * NVMAX, red_sc(c)};
+    CocrBody<NV, VT> B{c, pmode, block, As, d, c->work[0].p, c->work[1].p, c->work[2].p, c->work[3].p, c->work[4].p, c->work[5].p,
+                       part, part + (size_t)NPART * NVMAX * NVMAX, part + (size_t)2 * NPART * NVMAX * NVMAX, red_sc(c)};
     const unsigned vb = blocks_for(nn, 256);
     k_zero<<<vb, 256, 0, c->stream>>>(nn, d); EMB_LAUNCH_CHECK(c);
     k_copy<<<vb, 256, 0, c->stream>>>(nn, rhs, B.r); EMB_LAUNCH_CHECK(c);
@@ -112,8 +112,8 @@ static int cocr(emb_ctx* c, int pmode, const VT* As, const cx* rhs, cx* d, const
     k_copy<<<vb, 256, 0, c->stream>>>(nn, B.z, B.p); EMB_LAUNCH_CHECK(c);
     EMB_TRY((spmv_inner<NV, VT>(c, As, B.z, B.Az))); ++*spmvs;
     k_copy<<<vb, 256, 0, c->stream>>>(nn, B.Az, B.Ap); EMB_LAUNCH_CHECK(c);
-    k_dot<NV, false><<<NPART, VBLOCK, 0, c->stream>>>(n, B.z, B.Az, B.partZ); EMB_LAUNCH_CHECK(c);
-    k_finish<NV><<<1, VBLOCK, 0, c->stream>>>(B.partZ, B.sc); EMB_LAUNCH_CHECK(c);
+    k_gram<NV><<<NPART, VBLOCK, 0, c->stream>>>(n, B.z, B.Az, B.partZ); EMB_LAUNCH_CHECK(c);
+    k_gram_finish<NV><<<1, VBLOCK, 0, c->stream>>>(B.partZ, B.sc + SC_RHO); EMB_LAUNCH_CHECK(c);
 
     // capture one iteration into a graph (side-stream branches of the preconditioner become parallel graph branches)
     static const bool use_graph = !(getenv("EMB_GRAPH") && atoi(getenv("EMB_GRAPH")) == 0);
@@ -157,7 +157,7 @@ static int cocr(emb_ctx* c, int pmode, const VT* As, const cx* rhs, cx* d, const
         ++it;
         if (it % check == 0 || it == maxit) {
             cx h[NVMAX];
-            if (cudaMemcpyAsync(h, B.sc + 3 * NV, NV * sizeof(cx), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+            if (cudaMemcpyAsync(h, B.sc + SC_RR, NV * sizeof(cx), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
                 cudaStreamSynchronize(c->stream) != cudaSuccess) { c->err = "COCR: read-back failed"; rc = EMB_ERR_CUDA; break; }
             if (it % check == 0) {
                 float sms = 0;
@@ -191,7 +191,7 @@ static int gmres(emb_ctx* c, int pmode, const cx* A, const cx* b, cx* x, double 
     auto V = [&](int j) { return c->work[6 + j].p; };
     const unsigned vb = blocks_for(n, 256);
     std::vector<cx> H((size_t)(m + 1) * m), cs(m), sn(m), g(m + 1), y(m);
-    cx* dsc = red_sc(c) + 6 * NVMAX + 2;
+    cx* dsc = red_sc(c) + SC_SIZE + NVMAX + 2;
     int it = 0;
     double res = 1.0;
     auto set_scalar = [&](cx v) { return cudaMemcpyAsync(dsc, &v, sizeof(cx), cudaMemcpyHostToDevice, c->stream); };
@@ -280,7 +280,7 @@ static int bicgstab(emb_ctx* c, int pmode, const cx* A, const cx* b, cx* x, doub
     cx *r = c->work[0].p, *r0 = c->work[1].p, *p = c->work[2].p, *v = c->work[3].p, *s = c->work[4].p, *t = c->work[5].p,
        *ph = c->work[6].p, *sh = c->work[7].p;
     const unsigned vb = blocks_for(n, 256);
-    cx* dsc = red_sc(c) + 6 * NVMAX + 2;
+    cx* dsc = red_sc(c) + SC_SIZE + NVMAX + 2;
     auto set_scalar = [&](cx val) { return cudaMemcpyAsync(dsc, &val, sizeof(cx), cudaMemcpyHostToDevice, c->stream); };
     auto axpy = [&](cx a, const cx* xx, double bfac, cx* yy) -> int {
         EMB_CUDA(c, set_scalar(a));
@@ -416,7 +416,7 @@ static int solve_device(emb_ctx* c, const emb_solve_opts* o, const cx* bs, cx* x
         const bool fp32 = c->as_fp32 && !as64;
         static const double inner_red = getenv("EMB_INNER") ? atof(getenv("EMB_INNER")) : 1e-2;
         static const bool verbose = getenv("EMB_VERBOSE") != nullptr;
-        bool iterated = false;
+        bool iterated = false, block_failed = false;
         for (int outer = 0; outer < 40 && its < o->maxit; ++outer) {
             double rn[NVMAX];
             if (outer > 0 || have_guess) {
@@ -449,15 +449,27 @@ static int solve_device(emb_ctx* c, const emb_solve_opts* o, const cx* bs, cx* x
             }
             int iit = 0;
             double irn[NVMAX];
+            // one Krylov space for all columns (block COCR) unless a column is empty / already exact, the group is
+            // padded, or the block recurrence broke down earlier in this solve
+            bool blk = NV > 1 && c->block_krylov && !block_failed;
+            for (int k = 0; k < NV; ++k)
+                if (!(bnorm[k] > 0) || !(rn[k] > 0)) blk = false;
             if (fp32) {
                 EMB_TRY(dev_alloc(c, c->As32, (size_t)c->nnz_s * 2));
                 cf* As = reinterpret_cast<cf*>(c->As32.p);
                 EMB_TRY(ensure_operator<cf>(c, o->precond, As));
-                rc = cocr<NV, cf>(c, o->precond, As, rr, dd, stop, o->maxit - its, &iit, &spmvs, irn);
+                rc = cocr<NV, cf>(c, o->precond, blk ? 1 : 0, As, rr, dd, stop, o->maxit - its, &iit, &spmvs, irn);
             } else {
                 EMB_TRY(dev_alloc(c, c->As, (size_t)c->nnz_s));
                 EMB_TRY(ensure_operator<cx>(c, o->precond, c->As.p));
-                rc = cocr<NV, cx>(c, o->precond, c->As.p, rr, dd, stop, o->maxit - its, &iit, &spmvs, irn);
+                rc = cocr<NV, cx>(c, o->precond, blk ? 1 : 0, c->As.p, rr, dd, stop, o->maxit - its, &iit, &spmvs, irn);
+            }
+            if (rc == EMB_NOT_CONVERGED && blk) {      // breakdown of the block recurrence: redo this step column by column
+                if (verbose) fprintf(stderr, "[emb] block COCR breakdown after %d iterations; lockstep recurrences from here\n", iit);
+                block_failed = true;
+                its += iit;
+                rc = EMB_OK;
+                continue;
             }
             its += iit;
             iterated = true;
@@ -916,6 +928,11 @@ extern "C" int emb_solver_config(emb_ctx* c, int inner_fp32, int side_streams) {
     c->as_fp32 = inner_fp32 != 0;
     c->use_side_streams = side_streams != 0;
     c->have_As = false;
+    return EMB_OK;
+}
+extern "C" int emb_solver_block(emb_ctx* c, int on) {
+    if (!c) return EMB_ERR_ARG;
+    c->block_krylov = on != 0;
     return EMB_OK;
 }
 extern "C" int64_t emb_graph_launch_count(const emb_ctx* c) { return c ? c->graph_launches : 0; }

@@ -75,6 +75,7 @@ _SIGS = {
     "emb_spmv_bench_ex": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "emb_solver_config": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "emb_graph_launch_count": (C.c_int64, [C.c_void_p]),
+    "emb_solver_block": (C.c_int, [C.c_void_p, C.c_int]),
     "emb_solve_rhs": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(SolveOpts), C.c_void_p, C.POINTER(SolveInfo)]),
     "emb_recycle_config": (C.c_int, [C.c_void_p, C.c_int, C.c_double]),
     "emb_recycle_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
@@ -321,8 +322,11 @@ class Context:
         self._check(self.lib.emb_spmv_bench_ex(self.h, reps, int(nv), int(bool(fp32)), C.byref(ms)))
         return ms.value
 
-    def solver_config(self, inner_fp32=True, side_streams=True):
+    def solver_config(self, inner_fp32=True, side_streams=True, block=True):
+        """inner_fp32: complex64 storage of the inner operator; side_streams: concurrent auxiliary spaces;
+        block: the ports of a lockstep group share one Krylov space (block COCR)"""
         self._check(self.lib.emb_solver_config(self.h, int(bool(inner_fp32)), int(bool(side_streams))))
+        self._check(self.lib.emb_solver_block(self.h, int(bool(block))))
 
     @property
     def graph_launches(self) -> int:

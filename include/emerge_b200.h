@@ -146,6 +146,9 @@ int emb_spmv_bench_ex(emb_ctx* ctx, int reps, int nv, int fp32, double* ms_per_s
 /* solver switches (no reference counterpart): complex64 storage of the inner operator (default 1), auxiliary spaces of
  * the preconditioner on concurrent streams (default 1).  Results of the second are bitwise independent of it. */
 int emb_solver_config(emb_ctx* ctx, int inner_fp32, int side_streams);
+/* 1 (default): the right-hand sides of an emb_solve_multi group share one Krylov space (block COCR); 0: independent
+ * recurrences in lockstep.  Padded groups, empty right-hand sides and a breakdown of the block recurrence use 0. */
+int emb_solver_block(emb_ctx* ctx, int on);
 /* iterations replayed from the captured CUDA graph so far (the kernels inside are counted by emb_launch_count) */
 int64_t emb_graph_launch_count(const emb_ctx* ctx);
 

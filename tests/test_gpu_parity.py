@@ -247,6 +247,22 @@ def test_lockstep_matches_port_by_port():
     lock.ctx.close()
 
 
+def test_block_krylov_shares_the_krylov_space():
+    """Block COCR (one Krylov space for both ports) and independent lockstep recurrences reach the same fields; the block
+    variant needs fewer iterations."""
+    res = {}
+    for name, block in (("block", True), ("lockstep", False)):
+        g, sw = _medium_sweep(recycle=0)
+        sw.ctx.solver_config(block=block)
+        r = sw.run(list(g["freqs"][:1]), keep_fields=True)
+        assert all(s["converged"] and s["relres"] <= 1e-10 for s in r.stats)
+        res[name] = r
+        sw.ctx.close()
+    for key, x in res["block"].fields.items():
+        assert np.linalg.norm(res["lockstep"].fields[key] - x) <= 1e-8 * np.linalg.norm(x)
+    assert res["block"].stats[0]["iters"] < res["lockstep"].stats[0]["iters"], (res["block"].stats[0], res["lockstep"].stats[0])
+
+
 def test_inner_precision_and_stream_schedule():
     """The complex64 inner operator only changes the path of the defect correction (the exit test is the FP64 residual
     of A(f)); running the auxiliary spaces on concurrent streams does not change a single bit."""
