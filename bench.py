@@ -191,9 +191,9 @@ def workload_config(args):
                         f"2 RectangularWaveguide ports + PEC walls, 201-point sweep 8-12 GHz (BASELINE config 4); "
                         f"step = one frequency point (A(f) + 2 port solves + S-parameters), K/M assembly once per job",
             "cells": [nx, ny, nz], "rtol": args.rtol,
-            "solver": "reduced-basis recycling across points (affine A(f)) + lockstep COCR over the ports on the complex64 "
-                      "symmetric part / FP64 defect correction, additive multilevel (Hiptmair-Xu + smoothed-aggregation AMG) "
-                      "preconditioner, iteration replayed from a CUDA graph",
+            "solver": "reduced-basis recycling across points (affine A(f)) + block COCR over the ports (one Krylov space) on the "
+                      "complex64 symmetric part (FP64 vectors and arithmetic) / FP64 defect correction on A(f), "
+                      "additive multilevel (Hiptmair-Xu + smoothed-aggregation AMG) preconditioner, iteration replayed from a CUDA graph",
             "recycle_vectors": args.recycle, "order": "hierarchical (bisection) within each rank's frequency block",
             "l2_policy": "inputs larger than L2 (A(f) alone is 5.3 GB at 1M tets)", "parallelism": f"freq-block x{args.gpus}"}
 
@@ -315,8 +315,8 @@ def run_gpu(args):
         e2e_points = total_points if e2e_K == K else world * e2e_K
         e2e_val = e2e_points / (ms_e2e_max / 1e3) if e2e_K > 0 else None
         peak, peak_src = peaks()
-        # dominant kernel: the lockstep operator application of COCR, k_bspmv<NV, complex64 values> (2x2 block-CSR):
-        # per nonzero 8 B value + 1 B (one 4 B column per 2x2 block), per row 4 B rowptr (8 B per block-row) +
+        # dominant kernel: the operator application of the block COCR iteration, k_bspmv<NV, complex64 values> (2x2
+        # block-CSR): per nonzero 8 B value + 1 B (one 4 B column per 2x2 block), per row 4 B rowptr (8 B per block-row) +
         # NV x (16 B x + 16 B y)   
         spmv_bytes = 9 * nnz_s + (4 + 32 * nv) * Ns + 8
         achieved = spmv_bytes / (spmv_ms * 1e-3) / 1e9 if spmv_ms > 0 else None
@@ -339,8 +339,8 @@ def run_gpu(args):
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "steps": e2e_K, "timed": "host wall clock around FrequencySweep() construction, setup() and the points"},
                 "gpu_launches": int(launches),
-                "roofline": {"kernel": f"k_bspmv<NV={nv}, complex64 values> (2x2 block-CSR operator application of the lockstep "
-                                       f"COCR iteration on {nv} interleaved right-hand sides)",
+                "roofline": {"kernel": f"k_bspmv<NV={nv}, complex64 values> (2x2 block-CSR operator application of the "
+                                       f"block COCR iteration on {nv} interleaved right-hand sides)",
                              "bound": "hbm", "achieved": achieved,
                              "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                              "frac": (achieved / peak) if achieved else None, "traffic": traffic,

@@ -15,11 +15,11 @@
 // MODE 3: y += A x       MODE 4 (pre-smoothing from a zero guess fused with the residual): y2 = w d b, y = b - A y2,
 //                         called with x = b
 // KPR x NV lanes per row: lane (ks, v) walks nonzeros ks, ks + KPR, ... for column v (one gather wavefront per nonzero).
-template <int KPR, int MODE, int NV>
+template <int KPR, int MODE, int NV, typename VX>
 __global__ void __launch_bounds__(256) k_rcsr(int64_t n, const int64_t* __restrict__ ptr, const int* __restrict__ col,
-                                              const double* __restrict__ val, const cx* __restrict__ x, cx* __restrict__ y,
-                                              const cx* __restrict__ b, const double* __restrict__ d, double w,
-                                              cx* __restrict__ y2) {
+                                              const double* __restrict__ val, const VX* __restrict__ x, VX* __restrict__ y,
+                                              const VX* __restrict__ b, const double* __restrict__ d, double w,
+                                              VX* __restrict__ y2) {
     constexpr int LPR = KPR * NV;
     const int64_t gt = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int64_t r = gt / LPR;
@@ -43,33 +43,27 @@ __global__ void __launch_bounds__(256) k_rcsr(int64_t n, const int64_t* __restri
     if (r < n && ks == 0) {
         const int64_t o = r * NV + v;
         if (MODE == 4) {
-            const cx bb = b[o];
+            const cx bb = ldv(b, o);
             const double sc = w * d[r];
-            y2[o] = cx{sc * bb.re, sc * bb.im};
-            y[o] = cx{bb.re - ar, bb.im - ai};
+            stv(y2, o, cx{sc * bb.re, sc * bb.im});
+            stv(y, o, cx{bb.re - ar, bb.im - ai});
         } else
-        if (MODE == 0) y[o] = cx{ar, ai};
-        else if (MODE == 1) { const cx bb = b[o]; y[o] = cx{bb.re - ar, bb.im - ai}; }
+        if (MODE == 0) stv(y, o, cx{ar, ai});
+        else if (MODE == 1) { const cx bb = ldv(b, o); stv(y, o, cx{bb.re - ar, bb.im - ai}); }
         else if (MODE == 2) {
-            const cx bb = b[o], xx = x[o];
+            const cx bb = ldv(b, o), xx = ldv(x, o);
             const double sc = w * d[r];
-            y[o] = cx{xx.re + sc * (bb.re - ar), xx.im + sc * (bb.im - ai)};
+            stv(y, o, cx{xx.re + sc * (bb.re - ar), xx.im + sc * (bb.im - ai)});
         } else {
-            const cx yy = y[o];
-            y[o] = cx{yy.re + ar, yy.im + ai};
+            const cx yy = ldv(y, o);
+            stv(y, o, cx{yy.re + ar, yy.im + ai});
         }
     }
 }
-// x = w d b   (flat over n * nv entries)
-__global__ void k_amg_smooth0(int64_t n, int nv, const double* __restrict__ d, double w, const cx* __restrict__ b,
-                              cx* __restrict__ x) {
-    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i < n * nv) { const double s = w * d[i / nv]; const cx v = b[i]; x[i] = cx{s * v.re, s * v.im}; }
-}
 // dense real matrix times NV interleaved complex vectors, one warp per row
-template <int NV>
-__global__ void __launch_bounds__(256) k_dense_mv(int64_t n, const double* __restrict__ M, const cx* __restrict__ b,
-                                                  cx* __restrict__ x) {
+template <int NV, typename VX>
+__global__ void __launch_bounds__(256) k_dense_mv(int64_t n, const double* __restrict__ M, const VX* __restrict__ b,
+                                                  VX* __restrict__ x) {
     const int lane = threadIdx.x & 31;
     const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     if (r >= n) return;
@@ -80,7 +74,7 @@ __global__ void __launch_bounds__(256) k_dense_mv(int64_t n, const double* __res
         const double a = M[r * n + k];
 #pragma unroll
         for (int v = 0; v < NV; ++v) {
-            const cx u = b[k * NV + v];
+            const cx u = ldv(b, k * NV + v);
             ar[v] += a * u.re;
             ai[v] += a * u.im;
         }
@@ -94,7 +88,7 @@ __global__ void __launch_bounds__(256) k_dense_mv(int64_t n, const double* __res
         }
     if (lane == 0)
 #pragma unroll
-        for (int v = 0; v < NV; ++v) x[r * NV + v] = cx{ar[v], ai[v]};
+        for (int v = 0; v < NV; ++v) stv(x, r * NV + v, cx{ar[v], ai[v]});
 }
 
 // lanes per row from the average row length (rows of P^T hold a whole aggregate neighbourhood: 50-200 entries)
@@ -102,40 +96,44 @@ static inline int pick_lpr(int64_t nnz, int64_t n) {
     const double avg = n > 0 ? (double)nnz / (double)n : 0.0;
     return avg <= 12.0 ? 4 : (avg <= 48.0 ? 8 : 32);
 }
-template <int MODE, int NV>
+template <int MODE, int NV, typename VX>
 static int rcsr_launch(emb_ctx* c, cudaStream_t s, int lpr, int64_t n, const int64_t* ptr, const int* col, const double* val,
-                       const cx* x, cx* y, const cx* b, const double* d, double w, cx* y2 = nullptr) {
+                       const VX* x, VX* y, const VX* b, const double* d, double w, VX* y2 = nullptr) {
     constexpr int KMAX = 32 / NV;          // KPR * NV lanes must fit a warp
-    if (lpr <= 4 || KMAX <= 4) k_rcsr<4, MODE, NV><<<blocks_for(n * 4 * NV, 256), 256, 0, s>>>(n, ptr, col, val, x, y, b, d, w, y2);
-    else if (lpr == 8 || KMAX == 8) k_rcsr<8, MODE, NV><<<blocks_for(n * 8 * NV, 256), 256, 0, s>>>(n, ptr, col, val, x, y, b, d, w, y2);
-    else k_rcsr<KMAX, MODE, NV><<<blocks_for(n * KMAX * NV, 256), 256, 0, s>>>(n, ptr, col, val, x, y, b, d, w, y2);
+    if (lpr <= 4 || KMAX <= 4) k_rcsr<4, MODE, NV, VX><<<blocks_for(n * 4 * NV, 256), 256, 0, s>>>(n, ptr, col, val, x, y, b, d, w, y2);
+    else if (lpr == 8 || KMAX == 8) k_rcsr<8, MODE, NV, VX><<<blocks_for(n * 8 * NV, 256), 256, 0, s>>>(n, ptr, col, val, x, y, b, d, w, y2);
+    else k_rcsr<KMAX, MODE, NV, VX><<<blocks_for(n * KMAX * NV, 256), 256, 0, s>>>(n, ptr, col, val, x, y, b, d, w, y2);
     EMB_LAUNCH_CHECK(c);
     return EMB_OK;
 }
 
-// V-cycle on stream s with right-hand side in W.b[0]; returns the device pointer holding the result (a level-0 buffer)
-template <int NV>
-static int amg_vcycle(emb_ctx* c, cudaStream_t s, AmgHierarchy& H, AmgWork& W, cx** result) {
+// V-cycle on stream s with right-hand side in W.b[0]; returns the device pointer holding the result (a level-0 buffer).
+// The level vectors are allocated as complex128 and used in the storage type VX of the inner iteration.
+template <int NV, typename VX>
+static int amg_vcycle(emb_ctx* c, cudaStream_t s, AmgHierarchy& H, AmgWork& W, VX** result) {
     const int L = (int)H.lev.size();
-    std::vector<cx*> xs(L, nullptr);
+    std::vector<VX*> xs(L, nullptr);
+    auto B = [&](int l) { return reinterpret_cast<VX*>(W.b[l].p); };
+    auto XA = [&](int l) { return reinterpret_cast<VX*>(W.xa[l].p); };
+    auto XB = [&](int l) { return reinterpret_cast<VX*>(W.xb[l].p); };
+    auto T = [&](int l) { return reinterpret_cast<VX*>(W.t[l].p); };
     for (int l = 0; l < L; ++l) {
         AmgLevel& v = H.lev[l];
         if (l == L - 1) {
-            k_dense_mv<NV><<<blocks_for(v.n * 32, 256), 256, 0, s>>>(v.n, H.cinv.p, W.b[l].p, W.xa[l].p); EMB_LAUNCH_CHECK(c);
-            xs[l] = W.xa[l].p;
+            k_dense_mv<NV, VX><<<blocks_for(v.n * 32, 256), 256, 0, s>>>(v.n, H.cinv.p, B(l), XA(l)); EMB_LAUNCH_CHECK(c);
+            xs[l] = XA(l);
             break;
         }
         // xa = w D^-1 b and t = b - A xa in one kernel
-        EMB_TRY((rcsr_launch<4, NV>(c, s, v.lpr_a, v.n, v.aptr.p, v.acol.p, v.aval.p, W.b[l].p, W.t[l].p, W.b[l].p, v.dinv.p, v.omega,
-                                    W.xa[l].p)));
-        EMB_TRY((rcsr_launch<0, NV>(c, s, v.lpr_t, v.nc, v.tptr.p, v.tcol.p, v.tval.p, W.t[l].p, W.b[l + 1].p, nullptr, nullptr, 0.0)));
-        xs[l] = W.xa[l].p;
+        EMB_TRY((rcsr_launch<4, NV, VX>(c, s, v.lpr_a, v.n, v.aptr.p, v.acol.p, v.aval.p, B(l), T(l), B(l), v.dinv.p, v.omega, XA(l))));
+        EMB_TRY((rcsr_launch<0, NV, VX>(c, s, v.lpr_t, v.nc, v.tptr.p, v.tcol.p, v.tval.p, T(l), B(l + 1), nullptr, nullptr, 0.0)));
+        xs[l] = XA(l);
     }
     for (int l = L - 2; l >= 0; --l) {
         AmgLevel& v = H.lev[l];
-        EMB_TRY((rcsr_launch<3, NV>(c, s, v.lpr_p, v.n, v.pptr.p, v.pcol.p, v.pval.p, xs[l + 1], W.xa[l].p, nullptr, nullptr, 0.0)));
-        EMB_TRY((rcsr_launch<2, NV>(c, s, v.lpr_a, v.n, v.aptr.p, v.acol.p, v.aval.p, W.xa[l].p, W.xb[l].p, W.b[l].p, v.dinv.p, v.omega)));
-        xs[l] = W.xb[l].p;
+        EMB_TRY((rcsr_launch<3, NV, VX>(c, s, v.lpr_p, v.n, v.pptr.p, v.pcol.p, v.pval.p, xs[l + 1], XA(l), nullptr, nullptr, 0.0)));
+        EMB_TRY((rcsr_launch<2, NV, VX>(c, s, v.lpr_a, v.n, v.aptr.p, v.acol.p, v.aval.p, XA(l), XB(l), B(l), v.dinv.p, v.omega)));
+        xs[l] = XB(l);
     }
     *result = xs[0];
     return EMB_OK;

@@ -36,6 +36,19 @@ __device__ __forceinline__ cx ldx(const cx* __restrict__ p) {
     const double2 a = __ldg(reinterpret_cast<const double2*>(p));
     return cx{a.x, a.y};
 }
+// The vector kernels are generic in the storage type VX of the inner-iteration vectors (cx = complex128, cf = complex64;
+// widen on load, FP64 arithmetic, narrow on store).  The solver instantiates VX = cx: with complex64 vectors the residual
+// gap of the recurrence grows like eps32 * cond(As) (~6e-8 * 1e6 at 1M tets), the inner solve stops reducing the true
+// residual and the defect correction stalls - measured on the B200 (round 1), although a 20k-tet CPU emulation had looked
+// harmless (+2 % iterations).  Only the operator VALUES are complex64.
+__device__ __forceinline__ cx ldx(const cf* __restrict__ p) {
+    const float2 a = __ldg(reinterpret_cast<const float2*>(p));
+    return cx{(double)a.x, (double)a.y};
+}
+__device__ __forceinline__ cx ldv(const cx* p, int64_t i) { return p[i]; }
+__device__ __forceinline__ cx ldv(const cf* p, int64_t i) { const float2 a = *reinterpret_cast<const float2*>(p + i); return cx{(double)a.x, (double)a.y}; }
+__device__ __forceinline__ void stv(cx* p, int64_t i, cx v) { *reinterpret_cast<double2*>(p + i) = make_double2(v.re, v.im); }
+__device__ __forceinline__ void stv(cf* p, int64_t i, cx v) { *reinterpret_cast<float2*>(p + i) = make_float2((float)v.re, (float)v.im); }
 // a / b, 0 when b == 0 (a frozen column: zero right-hand side or an exactly converged recurrence)
 __device__ __forceinline__ cx sdiv(cx a, cx b) {
     const double d = b.re * b.re + b.im * b.im;
@@ -51,10 +64,10 @@ __device__ __forceinline__ cx sdiv(cx a, cx b) {
 // Lane mapping: KPR x NV lanes per row; lane (ks, v) walks nonzeros ks, ks + KPR, ... of the row for column v, so the
 // NV lanes of one nonzero read ONE contiguous 16*NV-byte piece of x (one L1 wavefront per nonzero whatever NV is; the
 // gather wavefronts, not HBM, are what bounds this kernel once the values are complex64).
-template <int NV, typename VT, int KPR, bool RESID>
+template <int NV, typename VT, int KPR, bool RESID, typename VX>
 __global__ void __launch_bounds__(256) k_spmv(int64_t n, const int64_t* __restrict__ rowptr, const int* __restrict__ col,
-                                              const VT* __restrict__ val, const cx* __restrict__ x, const cx* __restrict__ b,
-                                              cx* __restrict__ y) {
+                                              const VT* __restrict__ val, const VX* __restrict__ x, const VX* __restrict__ b,
+                                              VX* __restrict__ y) {
     constexpr int LPR = KPR * NV;
     const int64_t gt = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int64_t r = gt / LPR;
@@ -77,12 +90,12 @@ __global__ void __launch_bounds__(256) k_spmv(int64_t n, const int64_t* __restri
         ai += __shfl_down_sync(0xffffffffu, ai, o, LPR);
     }
     if (r < n && ks == 0) {
-        double2 o2 = make_double2(ar, ai);
+        cx o2 = cx{ar, ai};
         if (RESID) {
-            const double2 bb = *reinterpret_cast<const double2*>(b + r * NV + v);
-            o2 = make_double2(bb.x - ar, bb.y - ai);
+            const cx bb = ldv(b, r * NV + v);
+            o2 = cx{bb.re - ar, bb.im - ai};
         }
-        *reinterpret_cast<double2*>(y + r * NV + v) = o2;
+        stv(y, r * NV + v, o2);
     }
 }
 
@@ -97,10 +110,10 @@ __global__ void __launch_bounds__(256) k_spmv(int64_t n, const int64_t* __restri
 // in one 32-byte sector (complex64).  Fetching the block with one load per lane group and exchanging the entries by
 // shuffles was measured slower (0.98 vs 0.90 ms).  BLK = false: plain CSR order (A(f) itself, which other kernels
 // address by CSR position).
-template <int NV, typename VT, int KPR, bool RESID, bool BLK>
+template <int NV, typename VT, int KPR, bool RESID, bool BLK, typename VX>
 __global__ void __launch_bounds__(256, 5) k_bspmv(int64_t nbr, const int64_t* __restrict__ rowptr, const int* __restrict__ blkcol,
-                                               const VT* __restrict__ val, const cx* __restrict__ x, const cx* __restrict__ b,
-                                               cx* __restrict__ y) {
+                                               const VT* __restrict__ val, const VX* __restrict__ x, const VX* __restrict__ b,
+                                               VX* __restrict__ y) {
     constexpr int LPB = 2 * NV;           // lanes per block
     constexpr int LPR = KPR * LPB;        // lanes per block-row (<= 32)
     const int64_t gt = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -133,21 +146,21 @@ __global__ void __launch_bounds__(256, 5) k_bspmv(int64_t nbr, const int64_t* __
         a1i += __shfl_down_sync(0xffffffffu, a1i, o, LPR);
     }
     if (j < nbr && s < NV) {
-        double2 o0 = make_double2(a0r, a0i), o1 = make_double2(a1r, a1i);
+        cx o0 = cx{a0r, a0i}, o1 = cx{a1r, a1i};
         const int64_t i0 = (2 * j) * NV + s, i1 = (2 * j + 1) * NV + s;
         if (RESID) {
-            const double2 b0 = *reinterpret_cast<const double2*>(b + i0), b1 = *reinterpret_cast<const double2*>(b + i1);
-            o0 = make_double2(b0.x - a0r, b0.y - a0i);
-            o1 = make_double2(b1.x - a1r, b1.y - a1i);
+            const cx b0 = ldv(b, i0), b1 = ldv(b, i1);
+            o0 = cx{b0.re - a0r, b0.im - a0i};
+            o1 = cx{b1.re - a1r, b1.im - a1i};
         }
-        *reinterpret_cast<double2*>(y + i0) = o0;
-        *reinterpret_cast<double2*>(y + i1) = o1;
+        stv(y, i0, o0);
+        stv(y, i1, o1);
     }
 }
 
 constexpr int SPMV_KPR = 8;      // ~43 nonzeros per row / ~21 blocks per block-row of the order-2 Nedelec operator
-template <int NV, typename VT, bool RESID, bool BLK>
-static int bspmv_launch(emb_ctx* c, const VT* val, const cx* x, const cx* b, cx* y) {
+template <int NV, typename VT, bool RESID, bool BLK, typename VX>
+static int bspmv_launch(emb_ctx* c, const VT* val, const VX* x, const VX* b, VX* y) {
     // block slots per block-row (KPR x 2NV lanes): few lanes with several independent gathers each - the kernel is
     // bound by memory-level parallelism per warp and L1 wavefronts, not by bandwidth, when every warp owns one short row
     static const int kpr_env = getenv("EMB_SPMV_KPR") ? atoi(getenv("EMB_SPMV_KPR")) : 0;
@@ -155,35 +168,35 @@ static int bspmv_launch(emb_ctx* c, const VT* val, const cx* x, const cx* b, cx*
     int kpr = kpr_env > 0 ? kpr_env : (NV == 1 ? 2 : 1);      // measured on B200 at 1M tets (profiles/r1_spmv_tuning.txt)
     if (kpr * 2 * NV > 32) kpr = 32 / (2 * NV);
     if (kpr >= 8)
-        k_bspmv<NV, VT, (NV == 4 ? 4 : 8), RESID, BLK><<<blocks_for(nbr * (NV == 4 ? 4 : 8) * 2 * NV, 256), 256, 0, c->stream>>>(
+        k_bspmv<NV, VT, (NV == 4 ? 4 : 8), RESID, BLK, VX><<<blocks_for(nbr * (NV == 4 ? 4 : 8) * 2 * NV, 256), 256, 0, c->stream>>>(
             nbr, c->rowptr_s.p, c->blkcol.p, val, x, b, y);
     else if (kpr >= 4)
-        k_bspmv<NV, VT, 4, RESID, BLK><<<blocks_for(nbr * 4 * 2 * NV, 256), 256, 0, c->stream>>>(nbr, c->rowptr_s.p, c->blkcol.p, val, x, b, y);
+        k_bspmv<NV, VT, 4, RESID, BLK, VX><<<blocks_for(nbr * 4 * 2 * NV, 256), 256, 0, c->stream>>>(nbr, c->rowptr_s.p, c->blkcol.p, val, x, b, y);
     else if (kpr >= 2)
-        k_bspmv<NV, VT, 2, RESID, BLK><<<blocks_for(nbr * 2 * 2 * NV, 256), 256, 0, c->stream>>>(nbr, c->rowptr_s.p, c->blkcol.p, val, x, b, y);
+        k_bspmv<NV, VT, 2, RESID, BLK, VX><<<blocks_for(nbr * 2 * 2 * NV, 256), 256, 0, c->stream>>>(nbr, c->rowptr_s.p, c->blkcol.p, val, x, b, y);
     else
-        k_bspmv<NV, VT, 1, RESID, BLK><<<blocks_for(nbr * 1 * 2 * NV, 256), 256, 0, c->stream>>>(nbr, c->rowptr_s.p, c->blkcol.p, val, x, b, y);
+        k_bspmv<NV, VT, 1, RESID, BLK, VX><<<blocks_for(nbr * 1 * 2 * NV, 256), 256, 0, c->stream>>>(nbr, c->rowptr_s.p, c->blkcol.p, val, x, b, y);
     EMB_LAUNCH_CHECK(c);
     return EMB_OK;
 }
 // inner: `val` is the inner operator As (block layout when the solve space is pair-ordered), else A(f) in CSR order
-template <int NV, typename VT, bool RESID>
-static int spmv_any(emb_ctx* c, const VT* val, const cx* x, const cx* b, cx* y, bool inner) {
-    if (c->paired) return inner ? bspmv_launch<NV, VT, RESID, true>(c, val, x, b, y) : bspmv_launch<NV, VT, RESID, false>(c, val, x, b, y);
-    k_spmv<NV, VT, SPMV_KPR, RESID><<<blocks_for(c->Ns * SPMV_KPR * NV, 256), 256, 0, c->stream>>>(c->Ns, c->rowptr_s.p, c->col_s.p,
+template <int NV, typename VT, bool RESID, typename VX>
+static int spmv_any(emb_ctx* c, const VT* val, const VX* x, const VX* b, VX* y, bool inner) {
+    if (c->paired) return inner ? bspmv_launch<NV, VT, RESID, true, VX>(c, val, x, b, y) : bspmv_launch<NV, VT, RESID, false, VX>(c, val, x, b, y);
+    k_spmv<NV, VT, SPMV_KPR, RESID, VX><<<blocks_for(c->Ns * SPMV_KPR * NV, 256), 256, 0, c->stream>>>(c->Ns, c->rowptr_s.p, c->col_s.p,
                                                                                                    val, x, b, y);
     EMB_LAUNCH_CHECK(c);
     return EMB_OK;
 }
 // y = A(f) x  (CSR-ordered values)
 template <int NV, typename VT>
-static int spmv(emb_ctx* c, const VT* val, const cx* x, cx* y) { return spmv_any<NV, VT, false>(c, val, x, nullptr, y, false); }
+static int spmv(emb_ctx* c, const VT* val, const cx* x, cx* y) { return spmv_any<NV, VT, false, cx>(c, val, x, nullptr, y, false); }
 // y = As x  (values as k_sym_part stores them)
-template <int NV, typename VT>
-static int spmv_inner(emb_ctx* c, const VT* val, const cx* x, cx* y) { return spmv_any<NV, VT, false>(c, val, x, nullptr, y, true); }
+template <int NV, typename VT, typename VX>
+static int spmv_inner(emb_ctx* c, const VT* val, const VX* x, VX* y) { return spmv_any<NV, VT, false, VX>(c, val, x, nullptr, y, true); }
 // y = b - A(f) x
 template <int NV, typename VT>
-static int spmv_resid(emb_ctx* c, const VT* val, const cx* x, const cx* b, cx* y) { return spmv_any<NV, VT, true>(c, val, x, b, y, false); }
+static int spmv_resid(emb_ctx* c, const VT* val, const cx* x, const cx* b, cx* y) { return spmv_any<NV, VT, true, cx>(c, val, x, b, y, false); }
 
 // ------------------------------------------------------------------------------------------------
 // deterministic per-column reductions over interleaved vectors (flat index: column = idx % NV; VBLOCK % NV == 0)
@@ -258,6 +271,22 @@ __global__ void k_zero(int64_t n, cx* __restrict__ a) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i < n) a[i] = cx{0, 0};
 }
+// b = a with a change of storage type; x += d (d in the inner storage type)
+template <typename VA, typename VB>
+__global__ void k_convert(int64_t n, const VA* __restrict__ a, VB* __restrict__ b) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) stv(b, i, ldv(a, i));
+}
+template <typename VX>
+__global__ void k_add_into(int64_t n, const VX* __restrict__ d, cx* __restrict__ x) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) { const cx v = ldv(d, i); cx xi = x[i]; xi.re += v.re; xi.im += v.im; x[i] = xi; }
+}
+template <typename VX>
+__global__ void k_zero_v(int64_t n, VX* __restrict__ a) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) stv(a, i, cx{0.0, 0.0});
+}
 // y = a*x + b*y with device scalars sa[0]*fa, sb[0]*fb (null => 1)
 __global__ void k_axpby(int64_t n, const cx* __restrict__ sa, double fa, const cx* __restrict__ x, const cx* __restrict__ sb,
                         double fb, cx* __restrict__ y) {
@@ -325,8 +354,8 @@ __device__ __forceinline__ void row_gather(cx own, cx* all) {
 }
 // part[blockIdx][i][j] = partial of sum_rows a[row][i] * b[row][j]  (unconjugated Gram matrix).  Flat coalesced index:
 // thread (row, k) accumulates row k of the matrix, with the b entries of its row fetched by shuffles.
-template <int NV>
-__global__ void __launch_bounds__(VBLOCK) k_gram(int64_t n, const cx* __restrict__ a, const cx* __restrict__ b,
+template <int NV, typename VX>
+__global__ void __launch_bounds__(VBLOCK) k_gram(int64_t n, const VX* __restrict__ a, const VX* __restrict__ b,
                                                  cx* __restrict__ part) {
     cx acc[NV];
 #pragma unroll
@@ -337,8 +366,8 @@ __global__ void __launch_bounds__(VBLOCK) k_gram(int64_t n, const cx* __restrict
     for (int64_t f0 = lo * NV + (threadIdx.x & ~31); f0 < end; f0 += VBLOCK) {
         const int64_t f = f0 + (threadIdx.x & 31);
         const bool live = f < end;
-        const cx u = live ? a[f] : mk(0.0);
-        const cx v = live ? b[f] : mk(0.0);
+        const cx u = live ? ldv(a, f) : mk(0.0);
+        const cx v = live ? ldv(b, f) : mk(0.0);
         cx vb[NV];
         row_gather<NV>(v, vb);
 #pragma unroll
@@ -396,11 +425,11 @@ __device__ void small_solve(const cx* S, const cx* B, int block, cx* X) {
 }
 
 // alpha = sigma^-1 rho with sigma = sum(partA);  X += P alpha; R -= AP alpha; Z -= MAP alpha;  partial |r_k|^2
-template <int NV>
+template <int NV, typename VX>
 __global__ void __launch_bounds__(VBLOCK) k_bcocr_update(int64_t n, int block, const cx* __restrict__ partA, cx* __restrict__ sc,
-                                                         const cx* __restrict__ p, const cx* __restrict__ Ap,
-                                                         const cx* __restrict__ MAp, cx* __restrict__ x, cx* __restrict__ r,
-                                                         cx* __restrict__ z, cx* __restrict__ partR) {
+                                                         const VX* __restrict__ p, const VX* __restrict__ Ap,
+                                                         const VX* __restrict__ MAp, VX* __restrict__ x, VX* __restrict__ r,
+                                                         VX* __restrict__ z, cx* __restrict__ partR) {
     __shared__ cx s_sig[NVMAX * NVMAX], s_al[NVMAX * NVMAX];
     sum_gram<NV>(partA, s_sig);
     if (threadIdx.x == 0) {
@@ -424,11 +453,11 @@ __global__ void __launch_bounds__(VBLOCK) k_bcocr_update(int64_t n, int block, c
         const int64_t f = f0 + (threadIdx.x & 31);
         const bool live = f < end;
         cx pv[NV], apv[NV], mv[NV];
-        row_gather<NV>(live ? p[f] : mk(0.0), pv);
-        row_gather<NV>(live ? Ap[f] : mk(0.0), apv);
-        row_gather<NV>(live ? MAp[f] : mk(0.0), mv);
+        row_gather<NV>(live ? ldv(p, f) : mk(0.0), pv);
+        row_gather<NV>(live ? ldv(Ap, f) : mk(0.0), apv);
+        row_gather<NV>(live ? ldv(MAp, f) : mk(0.0), mv);
         if (live) {
-            cx xi = x[f], ri = r[f], zi = z[f];
+            cx xi = ldv(x, f), ri = ldv(r, f), zi = ldv(z, f);
 #pragma unroll
             for (int i = 0; i < NV; ++i) {
                 const cx na = -al[i];
@@ -436,7 +465,7 @@ __global__ void __launch_bounds__(VBLOCK) k_bcocr_update(int64_t n, int block, c
                 fma_c(ri, na, apv[i]);
                 fma_c(zi, na, mv[i]);
             }
-            x[f] = xi; r[f] = ri; z[f] = zi;
+            stv(x, f, xi); stv(r, f, ri); stv(z, f, zi);
             acc.re += ri.re * ri.re + ri.im * ri.im;
         }
     }
@@ -445,10 +474,10 @@ __global__ void __launch_bounds__(VBLOCK) k_bcocr_update(int64_t n, int block, c
 }
 // beta = rho^-1 rho_new with rho_new = sum(partZ);  P = Z + P beta; AP = AZ + AP beta; also finishes |r_k|^2.
 // rho is read by every block, so rho_new goes to its own slot and k_bcocr_commit moves it afterwards.
-template <int NV>
+template <int NV, typename VX>
 __global__ void __launch_bounds__(VBLOCK) k_bcocr_dir(int64_t n, int block, const cx* __restrict__ partZ,
-                                                      const cx* __restrict__ partR, cx* __restrict__ sc, const cx* __restrict__ z,
-                                                      const cx* __restrict__ Az, cx* __restrict__ p, cx* __restrict__ Ap) {
+                                                      const cx* __restrict__ partR, cx* __restrict__ sc, const VX* __restrict__ z,
+                                                      const VX* __restrict__ Az, VX* __restrict__ p, VX* __restrict__ Ap) {
     __shared__ cx s_new[NVMAX * NVMAX], s_be[NVMAX * NVMAX], s_rr[NVMAX];
     sum_gram<NV>(partZ, s_new);
     for (int k = 0; k < NV; ++k) {
@@ -475,16 +504,16 @@ __global__ void __launch_bounds__(VBLOCK) k_bcocr_dir(int64_t n, int block, cons
         const int64_t f = f0 + (threadIdx.x & 31);
         const bool live = f < end;
         cx pv[NV], apv[NV];
-        row_gather<NV>(live ? p[f] : mk(0.0), pv);
-        row_gather<NV>(live ? Ap[f] : mk(0.0), apv);
+        row_gather<NV>(live ? ldv(p, f) : mk(0.0), pv);
+        row_gather<NV>(live ? ldv(Ap, f) : mk(0.0), apv);
         if (live) {
-            cx pi = z[f], api = Az[f];
+            cx pi = ldv(z, f), api = ldv(Az, f);
 #pragma unroll
             for (int i = 0; i < NV; ++i) {
                 fma_c(pi, be[i], pv[i]);
                 fma_c(api, be[i], apv[i]);
             }
-            p[f] = pi; Ap[f] = api;
+            stv(p, f, pi); stv(Ap, f, api);
         }
     }
     if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {

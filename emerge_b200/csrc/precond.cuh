@@ -75,16 +75,17 @@ __global__ void k_precond_setup(int64_t ns, int mode, const int64_t* __restrict_
     dinv[2 * i + 1] = cdiv(-aim, det);
 }
 // z = D_blk^-1 r   (flat over ns * nv entries)
+template <typename VX>
 __global__ void k_precond_apply(int64_t ns, int nv, const cx* __restrict__ dinv, const int* __restrict__ mate,
-                                const cx* __restrict__ r, cx* __restrict__ z) {
+                                const VX* __restrict__ r, VX* __restrict__ z) {
     int64_t f = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (f >= ns * nv) return;
     const int64_t i = f / nv;
     const int k = (int)(f % nv);
-    cx v = dinv[2 * i] * r[f];
+    cx v = dinv[2 * i] * ldv(r, f);
     const int m = mate ? mate[i] : -1;
-    if (m >= 0) fma_c(v, dinv[2 * i + 1], r[(int64_t)m * nv + k]);
-    z[f] = v;
+    if (m >= 0) fma_c(v, dinv[2 * i + 1], ldv(r, (int64_t)m * nv + k));
+    stv(z, f, v);
 }
 
 // one warp per aux column k: d_k = sum_{i,j in supp(k)} R_ik A_ij R_jk, supp(k) = row k of R^T (sorted by i)
@@ -127,10 +128,10 @@ __global__ void __launch_bounds__(256) k_aux_diag(int64_t ncol, const int64_t* _
 }
 // s = sum_i RT[k,i] r[i];  traw[k] = s (if traw);  t[k] = dinv ? dinv[k]*s : s     (KPR x NV lanes per aux column;
 // the rows of R^T are short (5-30 entries), so few lanes with several independent loads each beat many idle lanes)
-template <int NV, int KPR>
+template <int NV, int KPR, typename VX>
 __global__ void __launch_bounds__(256) k_aux_restrict(int64_t ncol, const int64_t* __restrict__ tptr, const int* __restrict__ tcol,
                                                       const double* __restrict__ tval, const cx* __restrict__ dinv,
-                                                      const cx* __restrict__ r, cx* __restrict__ t, cx* __restrict__ traw) {
+                                                      const VX* __restrict__ r, VX* __restrict__ t, VX* __restrict__ traw) {
     constexpr int LPR = KPR * NV;
     const int64_t gt = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int64_t k = gt / LPR;
@@ -154,27 +155,27 @@ __global__ void __launch_bounds__(256) k_aux_restrict(int64_t ncol, const int64_
     }
     if (k < ncol && ks == 0) {
         const cx sum = cx{ar, ai};
-        if (traw) traw[k * NV + v] = sum;
-        if (t) t[k * NV + v] = dinv ? dinv[k] * sum : sum;
+        if (traw) stv(traw, k * NV + v, sum);
+        if (t) stv(t, k * NV + v, dinv ? dinv[k] * sum : sum);
     }
 }
-template <int NV>
-static int aux_restrict_launch(emb_ctx* c, cudaStream_t s, const AuxSpace& a, const cx* dinv, const cx* src, cx* t, cx* traw) {
+template <int NV, typename VX>
+static int aux_restrict_launch(emb_ctx* c, cudaStream_t s, const AuxSpace& a, const cx* dinv, const VX* src, VX* t, VX* traw) {
     const double avg = a.ncol > 0 ? (double)a.nnz / (double)a.ncol : 0.0;
     if (avg <= 16.0)
-        k_aux_restrict<NV, 2><<<blocks_for(a.ncol * 2 * NV, 256), 256, 0, s>>>(a.ncol, a.tptr.p, a.tcol.p, a.tval.p, dinv, src, t, traw);
+        k_aux_restrict<NV, 2, VX><<<blocks_for(a.ncol * 2 * NV, 256), 256, 0, s>>>(a.ncol, a.tptr.p, a.tcol.p, a.tval.p, dinv, src, t, traw);
     else if (avg <= 48.0 || NV == 4)
-        k_aux_restrict<NV, 4><<<blocks_for(a.ncol * 4 * NV, 256), 256, 0, s>>>(a.ncol, a.tptr.p, a.tcol.p, a.tval.p, dinv, src, t, traw);
+        k_aux_restrict<NV, 4, VX><<<blocks_for(a.ncol * 4 * NV, 256), 256, 0, s>>>(a.ncol, a.tptr.p, a.tcol.p, a.tval.p, dinv, src, t, traw);
     else
-        k_aux_restrict<NV, 8><<<blocks_for(a.ncol * 8 * NV, 256), 256, 0, s>>>(a.ncol, a.tptr.p, a.tcol.p, a.tval.p, dinv, src, t, traw);
+        k_aux_restrict<NV, 8, VX><<<blocks_for(a.ncol * 8 * NV, 256), 256, 0, s>>>(a.ncol, a.tptr.p, a.tcol.p, a.tval.p, dinv, src, t, traw);
     EMB_LAUNCH_CHECK(c);
     return EMB_OK;
 }
 // z[i] += s * sum_k R[i,k] t[k]     (NV threads per row; rows of R are short)
-template <int NV>
+template <int NV, typename VX>
 __global__ void __launch_bounds__(256) k_aux_prolong(int64_t n, const int64_t* __restrict__ rptr, const int* __restrict__ rcol,
-                                                     const double* __restrict__ rval, const cx* __restrict__ t, cx s,
-                                                     cx* __restrict__ z) {
+                                                     const double* __restrict__ rval, const VX* __restrict__ t, cx s,
+                                                     VX* __restrict__ z) {
     const int64_t f = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (f >= n * NV) return;
     const int64_t i = f / NV;
@@ -188,9 +189,9 @@ __global__ void __launch_bounds__(256) k_aux_prolong(int64_t n, const int64_t* _
         ar += w * u.re;
         ai += w * u.im;
     }
-    cx zi = z[f];
+    cx zi = ldv(z, f);
     fma_c(zi, s, cx{ar, ai});
-    z[f] = zi;
+    stv(z, f, zi);
 }
 
 // Top-level spaces whose prolongations are fused with the block-Jacobi term into the single pass that writes z
@@ -199,58 +200,60 @@ struct TopSpaces {
     const int64_t* rptr[4];
     const int* rcol[4];
     const double* rval[4];
-    const cx* t[4];
+    const void* t[4];             // vectors in the storage type of the inner iteration
     cx scale[4];
 };
 // z = D_blk^-1 r + sum_s scale_s R_s t_s   (flat over ns * NV entries; terms added in the order of the list)
-template <int NV>
+template <int NV, typename VX>
 __global__ void __launch_bounds__(256) k_precond_final(int64_t ns, const cx* __restrict__ dinv, const int* __restrict__ mate,
-                                                       const cx* __restrict__ r, TopSpaces T, cx* __restrict__ z) {
+                                                       const VX* __restrict__ r, TopSpaces T, VX* __restrict__ z) {
     const int64_t f = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (f >= ns * NV) return;
     const int64_t i = f / NV;
     const int v = (int)(f % NV);
-    cx acc = dinv[2 * i] * r[f];
+    cx acc = dinv[2 * i] * ldv(r, f);
     const int m = mate ? mate[i] : -1;
-    if (m >= 0) fma_c(acc, dinv[2 * i + 1], r[(int64_t)m * NV + v]);
+    if (m >= 0) fma_c(acc, dinv[2 * i + 1], ldv(r, (int64_t)m * NV + v));
     for (int s = 0; s < T.n; ++s) {
         const int64_t m0 = T.rptr[s][i], m1 = T.rptr[s][i + 1];
         if (m0 == m1) continue;
+        const VX* ts = static_cast<const VX*>(T.t[s]);
         double ar = 0.0, ai = 0.0;
         for (int64_t q = m0; q < m1; ++q) {
             const double w = __ldg(T.rval[s] + q);
-            const cx u = ldx(T.t[s] + (int64_t)__ldg(T.rcol[s] + q) * NV + v);
+            const cx u = ldx(ts + (int64_t)__ldg(T.rcol[s] + q) * NV + v);
             ar += w * u.re;
             ai += w * u.im;
         }
         fma_c(acc, T.scale[s], cx{ar, ai});
     }
-    z[f] = acc;
+    stv(z, f, acc);
 }
 
 // dst[i] += sum_s scale_s R_s t_s   (the children of one auxiliary space in a single pass over its vector)
-template <int NV>
-__global__ void __launch_bounds__(256) k_aux_prolong_multi(int64_t n, TopSpaces T, cx* __restrict__ dst) {
+template <int NV, typename VX>
+__global__ void __launch_bounds__(256) k_aux_prolong_multi(int64_t n, TopSpaces T, VX* __restrict__ dst) {
     const int64_t f = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (f >= n * NV) return;
     const int64_t i = f / NV;
     const int v = (int)(f % NV);
-    cx acc = dst[f];
+    cx acc = ldv(dst, f);
     bool any = false;
     for (int s = 0; s < T.n; ++s) {
         const int64_t m0 = T.rptr[s][i], m1 = T.rptr[s][i + 1];
         if (m0 == m1) continue;
+        const VX* ts = static_cast<const VX*>(T.t[s]);
         double ar = 0.0, ai = 0.0;
         for (int64_t q = m0; q < m1; ++q) {
             const double w = __ldg(T.rval[s] + q);
-            const cx u = ldx(T.t[s] + (int64_t)__ldg(T.rcol[s] + q) * NV + v);
+            const cx u = ldx(ts + (int64_t)__ldg(T.rcol[s] + q) * NV + v);
             ar += w * u.re;
             ai += w * u.im;
         }
         fma_c(acc, T.scale[s], cx{ar, ai});
         any = true;
     }
-    if (any) dst[f] = acc;
+    if (any) stv(dst, f, acc);
 }
 
 // Side streams, one per auxiliary space (modulo NSIDE).  The chain restrict -> V-cycle -> prolong of the nodal spaces is a
@@ -315,38 +318,39 @@ static int precond_setup(emb_ctx* c, int mode_in, const VT* val) {
 // z = M^-1 r on NV interleaved columns.  mode 3: block-Jacobi on the solve space plus the tree of auxiliary spaces
 // (additive): restrict down the tree (parents before children), solve every space, prolong up; the prolongations of
 // the top-level spaces are fused with the block-Jacobi term into the one pass that writes z.
-template <int NV>
-static int precond_apply(emb_ctx* c, int mode, const cx* r, cx* z) {
+template <int NV, typename VX>
+static int precond_apply(emb_ctx* c, int mode, const VX* r, VX* z) {
     cudaStream_t main = c->stream;
     const int na = (mode == 3) ? (int)c->aux.size() : 0;
     const bool par = c->use_side_streams && na > 0;
     const int* mate = mode >= 2 ? c->pairmate.p : nullptr;
     if (na == 0) {
-        k_precond_apply<<<blocks_for(c->Ns * NV, 256), 256, 0, main>>>(c->Ns, NV, c->dinv.p, mate, r, z);
+        k_precond_apply<VX><<<blocks_for(c->Ns * NV, 256), 256, 0, main>>>(c->Ns, NV, c->dinv.p, mate, r, z);
         EMB_LAUNCH_CHECK(c);
         return EMB_OK;
     }
+    auto V = [](DevBuf<cx>& b) { return reinterpret_cast<VX*>(b.p); };      // complex128 allocations used as VX
     if (par) EMB_CUDA(c, cudaEventRecord(c->ev_fork, main));       // r is complete here
     auto strm = [&](int i) { return par ? c->side[i % emb_ctx::NSIDE] : main; };
-    std::vector<cx*> xres((size_t)na, nullptr);
+    std::vector<VX*> xres((size_t)na, nullptr);
     for (int i = 0; i < na; ++i) {
         AuxSpace& a = c->aux[i];
         cudaStream_t s = strm(i);
         if (par) EMB_CUDA(c, cudaStreamWaitEvent(s, a.parent < 0 ? c->ev_fork : c->ev_restr[a.parent], 0));
-        const cx* src = a.parent < 0 ? r : c->aux[a.parent].traw.p;
-        cx* traw = (a.has_children || a.solver == 1) ? a.traw.p : nullptr;
-        cx* t = a.solver == 0 ? a.tmp.p : nullptr;
+        const VX* src = a.parent < 0 ? r : V(c->aux[a.parent].traw);
+        VX* traw = (a.has_children || a.solver == 1) ? V(a.traw) : nullptr;
+        VX* t = a.solver == 0 ? V(a.tmp) : nullptr;
         // solver 1 restricts straight into the right-hand side of its V-cycle
-        if (a.solver == 1 && !a.has_children) traw = a.wk.b[0].p;
-        EMB_TRY(aux_restrict_launch<NV>(c, s, a, a.solver == 0 ? a.dinv.p : nullptr, src, t, traw));
+        if (a.solver == 1 && !a.has_children) traw = V(a.wk.b[0]);
+        EMB_TRY((aux_restrict_launch<NV, VX>(c, s, a, a.solver == 0 ? a.dinv.p : nullptr, src, t, traw)));
         if (par) EMB_CUDA(c, cudaEventRecord(c->ev_restr[i], s));
-        xres[i] = a.tmp.p;
+        xres[i] = V(a.tmp);
         if (a.solver == 1) {
             AmgHierarchy& H = c->amg[a.hid];
             if (a.has_children)
-                EMB_CUDA(c, cudaMemcpyAsync(a.wk.b[0].p, a.traw.p, (size_t)a.ncol * NV * sizeof(cx), cudaMemcpyDeviceToDevice, s));
-            cx* res = nullptr;
-            EMB_TRY(amg_vcycle<NV>(c, s, H, a.wk, &res));
+                EMB_CUDA(c, cudaMemcpyAsync(a.wk.b[0].p, a.traw.p, (size_t)a.ncol * NV * sizeof(VX), cudaMemcpyDeviceToDevice, s));
+            VX* res = nullptr;
+            EMB_TRY((amg_vcycle<NV, VX>(c, s, H, a.wk, &res)));
             xres[i] = res;
         }
     }
@@ -356,7 +360,7 @@ static int precond_apply(emb_ctx* c, int mode, const cx* r, cx* z) {
     for (int i = 0; i < na; ++i) ntop += c->aux[i].parent < 0;
     const bool fuse = ntop <= 4;
     if (!fuse) {
-        k_precond_apply<<<blocks_for(c->Ns * NV, 256), 256, 0, main>>>(c->Ns, NV, c->dinv.p, mate, r, z);
+        k_precond_apply<VX><<<blocks_for(c->Ns * NV, 256), 256, 0, main>>>(c->Ns, NV, c->dinv.p, mate, r, z);
         EMB_LAUNCH_CHECK(c);
     }
     std::vector<TopSpaces> kids((size_t)na);
@@ -365,7 +369,7 @@ static int precond_apply(emb_ctx* c, int mode, const cx* r, cx* z) {
         TopSpaces& K = kids[(size_t)p];
         if (K.n == 0) return EMB_OK;
         AuxSpace& pa = c->aux[p];
-        k_aux_prolong_multi<NV><<<blocks_for(pa.ncol * NV, 256), 256, 0, strm(p)>>>(pa.ncol, K, pa.tmp.p);
+        k_aux_prolong_multi<NV, VX><<<blocks_for(pa.ncol * NV, 256), 256, 0, strm(p)>>>(pa.ncol, K, V(pa.tmp));
         EMB_LAUNCH_CHECK(c);
         K.n = 0;
         return EMB_OK;
@@ -392,12 +396,12 @@ static int precond_apply(emb_ctx* c, int mode, const cx* r, cx* z) {
             if (K.n == 4) EMB_TRY(flush_kids(a.parent));
             continue;
         }
-        cx* dst = a.parent < 0 ? z : c->aux[a.parent].tmp.p;
-        k_aux_prolong<NV><<<blocks_for(a.nrow * NV, 256), 256, 0, dst_s>>>(a.nrow, a.rptr.p, a.rcol.p, a.rval.p, xres[i], scale, dst);
+        VX* dst = a.parent < 0 ? z : V(c->aux[a.parent].tmp);
+        k_aux_prolong<NV, VX><<<blocks_for(a.nrow * NV, 256), 256, 0, dst_s>>>(a.nrow, a.rptr.p, a.rcol.p, a.rval.p, xres[i], scale, dst);
         EMB_LAUNCH_CHECK(c);
     }
     if (fuse) {
-        k_precond_final<NV><<<blocks_for(c->Ns * NV, 256), 256, 0, main>>>(c->Ns, c->dinv.p, mate, r, T, z);
+        k_precond_final<NV, VX><<<blocks_for(c->Ns * NV, 256), 256, 0, main>>>(c->Ns, c->dinv.p, mate, r, T, z);
         EMB_LAUNCH_CHECK(c);
     }
     return EMB_OK;

@@ -74,45 +74,48 @@ static int norms2_host(emb_ctx* c, const cx* a, double* out) {
 // COCR on As D = RHS for NV columns in lockstep, D starts at 0.  Stops when every column has |r_k| <= stop_abs[k]
 // (or maxit).  Returns iterations in *its.
 // ------------------------------------------------------------------------------------------------
-template <int NV, typename VT>
+template <int NV, typename VT, typename VX>
 struct CocrBody {
     emb_ctx* c;
     int pmode, block;
     const VT* As;
-    cx *d, *r, *z, *p, *Az, *Ap, *MAp, *partA, *partR, *partZ, *sc;
+    VX *d, *r, *z, *p, *Az, *Ap, *MAp;
+    cx *partA, *partR, *partZ, *sc;
     // one iteration; `sample`: CUDA events around the operator application and the preconditioner (plain launches only)
     int run(bool sample) {
         const int64_t n = c->Ns;
         if (sample) cudaEventRecord(c->evp0, c->stream);
-        EMB_TRY(precond_apply<NV>(c, pmode, Ap, MAp));
+        EMB_TRY((precond_apply<NV, VX>(c, pmode, Ap, MAp)));
         if (sample) cudaEventRecord(c->evp1, c->stream);
-        k_gram<NV><<<NPART, VBLOCK, 0, c->stream>>>(n, Ap, MAp, partA); EMB_LAUNCH_CHECK(c);
-        k_bcocr_update<NV><<<NPART, VBLOCK, 0, c->stream>>>(n, block, partA, sc, p, Ap, MAp, d, r, z, partR); EMB_LAUNCH_CHECK(c);
+        k_gram<NV, VX><<<NPART, VBLOCK, 0, c->stream>>>(n, Ap, MAp, partA); EMB_LAUNCH_CHECK(c);
+        k_bcocr_update<NV, VX><<<NPART, VBLOCK, 0, c->stream>>>(n, block, partA, sc, p, Ap, MAp, d, r, z, partR); EMB_LAUNCH_CHECK(c);
         if (sample) cudaEventRecord(c->evs0, c->stream);
-        EMB_TRY((spmv_inner<NV, VT>(c, As, z, Az)));
+        EMB_TRY((spmv_inner<NV, VT, VX>(c, As, z, Az)));
         if (sample) cudaEventRecord(c->evs1, c->stream);
-        k_gram<NV><<<NPART, VBLOCK, 0, c->stream>>>(n, z, Az, partZ); EMB_LAUNCH_CHECK(c);
-        k_bcocr_dir<NV><<<NPART, VBLOCK, 0, c->stream>>>(n, block, partZ, partR, sc, z, Az, p, Ap); EMB_LAUNCH_CHECK(c);
+        k_gram<NV, VX><<<NPART, VBLOCK, 0, c->stream>>>(n, z, Az, partZ); EMB_LAUNCH_CHECK(c);
+        k_bcocr_dir<NV, VX><<<NPART, VBLOCK, 0, c->stream>>>(n, block, partZ, partR, sc, z, Az, p, Ap); EMB_LAUNCH_CHECK(c);
         k_bcocr_commit<NV><<<1, 32, 0, c->stream>>>(sc); EMB_LAUNCH_CHECK(c);
         return EMB_OK;
     }
 };
 
-template <int NV, typename VT>
-static int cocr(emb_ctx* c, int pmode, int block, const VT* As, const cx* rhs, cx* d, const double* stop_abs, int maxit, int* its,
+// rhs: FP64 residual of the outer loop; d: correction in the storage type VX of the inner iteration
+template <int NV, typename VT, typename VX>
+static int cocr(emb_ctx* c, int pmode, int block, const VT* As, const cx* rhs, VX* d, const double* stop_abs, int maxit, int* its,
                 int* spmvs, double* rnorm_out) {
     const int64_t n = c->Ns, nn = c->Ns * NV;
     cx* part = red_part(c);
-    CocrBody<NV, VT> B{c, pmode, block, As, d, c->work[0].p, c->work[1].p, c->work[2].p, c->work[3].p, c->work[4].p, c->work[5].p,
-                       part, part + (size_t)NPART * NVMAX * NVMAX, part + (size_t)2 * NPART * NVMAX * NVMAX, red_sc(c)};
+    auto W = [&](int i) { return reinterpret_cast<VX*>(c->work[i].p); };
+    CocrBody<NV, VT, VX> B{c, pmode, block, As, d, W(0), W(1), W(2), W(3), W(4), W(5),
+                           part, part + (size_t)NPART * NVMAX * NVMAX, part + (size_t)2 * NPART * NVMAX * NVMAX, red_sc(c)};
     const unsigned vb = blocks_for(nn, 256);
-    k_zero<<<vb, 256, 0, c->stream>>>(nn, d); EMB_LAUNCH_CHECK(c);
-    k_copy<<<vb, 256, 0, c->stream>>>(nn, rhs, B.r); EMB_LAUNCH_CHECK(c);
-    EMB_TRY(precond_apply<NV>(c, pmode, B.r, B.z));
-    k_copy<<<vb, 256, 0, c->stream>>>(nn, B.z, B.p); EMB_LAUNCH_CHECK(c);
-    EMB_TRY((spmv_inner<NV, VT>(c, As, B.z, B.Az))); ++*spmvs;
-    k_copy<<<vb, 256, 0, c->stream>>>(nn, B.Az, B.Ap); EMB_LAUNCH_CHECK(c);
-    k_gram<NV><<<NPART, VBLOCK, 0, c->stream>>>(n, B.z, B.Az, B.partZ); EMB_LAUNCH_CHECK(c);
+    k_zero_v<VX><<<vb, 256, 0, c->stream>>>(nn, d); EMB_LAUNCH_CHECK(c);
+    k_convert<cx, VX><<<vb, 256, 0, c->stream>>>(nn, rhs, B.r); EMB_LAUNCH_CHECK(c);
+    EMB_TRY((precond_apply<NV, VX>(c, pmode, B.r, B.z)));
+    k_convert<VX, VX><<<vb, 256, 0, c->stream>>>(nn, B.z, B.p); EMB_LAUNCH_CHECK(c);
+    EMB_TRY((spmv_inner<NV, VT, VX>(c, As, B.z, B.Az))); ++*spmvs;
+    k_convert<VX, VX><<<vb, 256, 0, c->stream>>>(nn, B.Az, B.Ap); EMB_LAUNCH_CHECK(c);
+    k_gram<NV, VX><<<NPART, VBLOCK, 0, c->stream>>>(n, B.z, B.Az, B.partZ); EMB_LAUNCH_CHECK(c);
     k_gram_finish<NV><<<1, VBLOCK, 0, c->stream>>>(B.partZ, B.sc + SC_RHO); EMB_LAUNCH_CHECK(c);
 
     // capture one iteration into a graph (side-stream branches of the preconditioner become parallel graph branches)
@@ -210,7 +213,7 @@ static int gmres(emb_ctx* c, int pmode, const cx* A, const cx* b, cx* x, double 
         g[0] = mk(beta);
         int j = 0;
         for (; j < m && it < o->maxit; ++j, ++it) {
-            EMB_TRY(precond_apply<1>(c, pmode, V(j), t));
+            EMB_TRY((precond_apply<1, cx>(c, pmode, V(j), t)));
             EMB_TRY(spmv1(c, A, t, w)); ++*spmvs;
             // classical Gram-Schmidt, two passes
             for (int i = 0; i <= j; ++i) H[(size_t)i * m + j] = mk(0.0);
@@ -266,7 +269,7 @@ static int gmres(emb_ctx* c, int pmode, const cx* A, const cx* b, cx* x, double 
             k_axpby<<<vb, 256, 0, c->stream>>>(n, dsc, 1.0, V(i), nullptr, 1.0, w); EMB_LAUNCH_CHECK(c);
             EMB_CUDA(c, cudaStreamSynchronize(c->stream));
         }
-        EMB_TRY(precond_apply<1>(c, pmode, w, t));
+        EMB_TRY((precond_apply<1, cx>(c, pmode, w, t)));
         k_axpby<<<vb, 256, 0, c->stream>>>(n, nullptr, 1.0, t, nullptr, 1.0, x); EMB_LAUNCH_CHECK(c);
     }
     *its = it;
@@ -310,14 +313,14 @@ static int bicgstab(emb_ctx* c, int pmode, const cx* A, const cx* b, cx* x, doub
         EMB_TRY(axpy(mk(1.0), r, 0.0, t));       // t = r (temp)
         EMB_TRY(axpy(beta, p, 1.0, t));          // t = r + beta p
         k_copy<<<vb, 256, 0, c->stream>>>(n, t, p); EMB_LAUNCH_CHECK(c);
-        EMB_TRY(precond_apply<1>(c, pmode, p, ph));
+        EMB_TRY((precond_apply<1, cx>(c, pmode, p, ph)));
         EMB_TRY(spmv1(c, A, ph, v)); ++*spmvs;
         cx r0v;
         EMB_TRY(dot_host(c, true, r0, v, &r0v));
         alpha = cdiv(rho1, r0v);
         k_copy<<<vb, 256, 0, c->stream>>>(n, r, s); EMB_LAUNCH_CHECK(c);
         EMB_TRY(axpy(-alpha, v, 1.0, s));
-        EMB_TRY(precond_apply<1>(c, pmode, s, sh));
+        EMB_TRY((precond_apply<1, cx>(c, pmode, s, sh)));
         EMB_TRY(spmv1(c, A, sh, t)); ++*spmvs;
         cx ts, tt;
         EMB_TRY(dot_host(c, true, t, s, &ts));
@@ -458,11 +461,11 @@ static int solve_device(emb_ctx* c, const emb_solve_opts* o, const cx* bs, cx* x
                 EMB_TRY(dev_alloc(c, c->As32, (size_t)c->nnz_s * 2));
                 cf* As = reinterpret_cast<cf*>(c->As32.p);
                 EMB_TRY(ensure_operator<cf>(c, o->precond, As));
-                rc = cocr<NV, cf>(c, o->precond, blk ? 1 : 0, As, rr, dd, stop, o->maxit - its, &iit, &spmvs, irn);
+                rc = cocr<NV, cf, cx>(c, o->precond, blk ? 1 : 0, As, rr, dd, stop, o->maxit - its, &iit, &spmvs, irn);
             } else {
                 EMB_TRY(dev_alloc(c, c->As, (size_t)c->nnz_s));
                 EMB_TRY(ensure_operator<cx>(c, o->precond, c->As.p));
-                rc = cocr<NV, cx>(c, o->precond, blk ? 1 : 0, c->As.p, rr, dd, stop, o->maxit - its, &iit, &spmvs, irn);
+                rc = cocr<NV, cx, cx>(c, o->precond, blk ? 1 : 0, c->As.p, rr, dd, stop, o->maxit - its, &iit, &spmvs, irn);
             }
             if (rc == EMB_NOT_CONVERGED && blk) {      // breakdown of the block recurrence: redo this step column by column
                 if (verbose) fprintf(stderr, "[emb] block COCR breakdown after %d iterations; lockstep recurrences from here\n", iit);
@@ -477,7 +480,7 @@ static int solve_device(emb_ctx* c, const emb_solve_opts* o, const cx* bs, cx* x
                 fprintf(stderr, "[emb] outer %d nv %d worst relres %.3e -> inner %d its, inner residual[0] %.3e\n", outer, NV, worst,
                         iit, irn[0] / (bnorm[0] > 0 ? bnorm[0] : 1.0));
             if (rc < 0) return rc;
-            k_axpby<<<vb, 256, 0, c->stream>>>(nn, nullptr, 1.0, dd, nullptr, 1.0, xs); EMB_LAUNCH_CHECK(c);
+            k_add_into<cx><<<vb, 256, 0, c->stream>>>(nn, dd, xs); EMB_LAUNCH_CHECK(c);
             if (rc == EMB_NOT_CONVERGED) break;
         }
         if (iterated) {
@@ -683,9 +686,9 @@ extern "C" int emb_spmv_bench_ex(emb_ctx* c, int reps, int nv, int fp32, double*
     }
     auto one = [&](const cx* x, cx* y) -> int {
         if (fp32) {
-            if (nv == 1) return spmv_inner<1, cf>(c, A32, x, y);
-            if (nv == 2) return spmv_inner<2, cf>(c, A32, x, y);
-            return spmv_inner<4, cf>(c, A32, x, y);
+            if (nv == 1) return spmv_inner<1, cf, cx>(c, A32, x, y);
+            if (nv == 2) return spmv_inner<2, cf, cx>(c, A32, x, y);
+            return spmv_inner<4, cf, cx>(c, A32, x, y);
         }
         if (nv == 1) return spmv<1, cx>(c, c->A.p, x, y);
         if (nv == 2) return spmv<2, cx>(c, c->A.p, x, y);

@@ -341,9 +341,12 @@ class Context:
         self._check(self.lib.emb_aux_clear(self.h))
         self._n_aux = 0
 
-    def aux_add(self, R):
-        """R: scipy sparse (n_solve x ncol) real transfer matrix of one auxiliary space."""
-        R = self._rows_to_internal(R.tocsr().astype(np.float64)).tocsr()
+    def aux_add(self, R, rows_internal=False):
+        """R: scipy sparse (n_solve x ncol) real transfer matrix of one auxiliary space, rows in the order of solve_ids()
+        (or already in the library's solve-index order when rows_internal)."""
+        R = R.tocsr().astype(np.float64)
+        if not rows_internal:
+            R = self._rows_to_internal(R).tocsr()
         R.sort_indices()
         T = R.T.tocsr()
         T.sort_indices()
@@ -360,9 +363,10 @@ class Context:
         M.sort_indices()
         return [_c(M.indptr, np.int64), _c(M.indices, np.int32), _c(M.data, np.float64)]
 
-    def aux_add_ex(self, R, parent=-1, solver="diag", hid=-1, scale="one"):
-        """R: scipy sparse (rows of the parent space x ncol) real transfer matrix; returns the index of the new space."""
-        if parent < 0:
+    def aux_add_ex(self, R, parent=-1, solver="diag", hid=-1, scale="one", rows_internal=False):
+        """R: scipy sparse (rows of the parent space x ncol) real transfer matrix; returns the index of the new space.
+        Top-level spaces (parent < 0): rows in the order of solve_ids(), or in solve-index order when rows_internal."""
+        if parent < 0 and not rows_internal:
             R = self._rows_to_internal(R.tocsr())
         a = self._csr_args(R) + self._csr_args(R.T)
         self._check(self.lib.emb_aux_add_ex(self.h, R.shape[0], R.shape[1], *[_p(x) for x in a], int(parent),

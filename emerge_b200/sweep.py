@@ -171,31 +171,37 @@ class FrequencySweep:
         keep[self.pec_ids] = False
         elim = ~keep
 
+        # rows straight into the library's solve-index order (one gather instead of mask + permutation)
+        ctx = self.ctx
+        perm = ctx.solve_perm()
+        inv = np.empty_like(perm)
+        inv[perm] = np.arange(len(perm))
+        rows_int = np.nonzero(keep)[0][inv]
+
         def restrict(R):
             bad = np.asarray(abs(R[elim]).sum(axis=0)).ravel() > 0
-            return R[keep][:, ~bad].tocsr(), bad
+            return R[rows_int][:, ~bad].tocsr(), bad
         Gs, _ = restrict(G)
         Ps, badP = restrict(P)
         G1r = G1[~badP]
         badN = np.asarray(abs(G1[badP]).sum(axis=0)).ravel() > 0
         G1s = G1r[:, ~badN].tocsr()
-        ctx = self.ctx
         ctx.aux_clear()
         self.aux_dims = []
         if Gs.shape[1] > 0:
-            ctx.aux_add(Gs)
+            ctx.aux_add(Gs, rows_internal=True)
             self.aux_dims.append(Gs.shape[1])
         if Ps.shape[1] == 0:
             return
         if not self.multilevel or G1s.shape[1] == 0:
-            ctx.aux_add(Ps)
+            ctx.aux_add(Ps, rows_internal=True)
             self.aux_dims.append(Ps.shape[1])
             if G1s.shape[1] > 0:
-                ctx.aux_add((Ps @ G1s).tocsr())
+                ctx.aux_add((Ps @ G1s).tocsr(), rows_internal=True)
                 self.aux_dims.append(G1s.shape[1])
             return
         from .amg import sa_hierarchy
-        ip = ctx.aux_add_ex(Ps, parent=-1, solver="diag")
+        ip = ctx.aux_add_ex(Ps, parent=-1, solver="diag", rows_internal=True)
         self.aux_dims.append(Ps.shape[1])
         tr = lambda T: np.real(T[0, 0] + T[1, 1] + T[2, 2]) / 3.0
         w_eps, w_mu = tr(self.er), 1.0 / tr(self.ur)

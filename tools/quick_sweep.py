@@ -28,7 +28,7 @@ for nv in (1, 2, 4):
     for fp32 in (False, True):
         ms = ctx.spmv_bench(20, nv=nv, fp32=fp32)
         nnz, Ns = int(ctx.lib.emb_csr_nnz(ctx.h, 2)), ctx.n_solve
-        b = (12 if fp32 else 20) * nnz + (8 + 32 * nv) * Ns
+        b = (9 if fp32 else 17) * nnz + (4 + 32 * nv) * Ns
         print(f"spmv nv={nv} fp32={fp32}: {ms:.3f} ms  {b / ms / 1e6:.0f} GB/s", flush=True)
 order = hierarchical_order(len(bench.FREQS))[:K]
 tot0 = time.perf_counter()
