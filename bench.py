@@ -194,7 +194,7 @@ def workload_config(args):
             "solver": "reduced-basis recycling across points (affine A(f)) + block COCR over the ports (one Krylov space) on the "
                       "complex64 symmetric part (FP64 vectors and arithmetic) / FP64 defect correction on A(f), "
                       "additive multilevel (Hiptmair-Xu + smoothed-aggregation AMG) preconditioner, iteration replayed from a CUDA graph",
-            "recycle_vectors": args.recycle, "order": "hierarchical (bisection) within each rank's frequency block",
+            "recycle_vectors": args.recycle, "snapshot_rtol_factor": args.snap, "order": "hierarchical (bisection) within each rank's frequency block",
             "l2_policy": "inputs larger than L2 (A(f) alone is 5.3 GB at 1M tets)", "parallelism": f"freq-block x{args.gpus}"}
 
 
@@ -217,7 +217,7 @@ def run_gpu(args):
     t0 = time.perf_counter()
     box, t, er, ur, bcs, L = make_waveguide(nx, ny, nz)
     host_mesh_s = time.perf_counter() - t0
-    sw = FrequencySweep(t, er, ur, bcs, device=local, recycle=args.recycle)
+    sw = FrequencySweep(t, er, ur, bcs, device=local, recycle=args.recycle, recycle_snap=args.snap)
     sw.solver_opts.update(rtol=args.rtol, precond=args.precond)
     sw.f_ref = float(np.median(FREQS))
     t0 = time.perf_counter()
@@ -240,7 +240,7 @@ def run_gpu(args):
         p.active = False
     for i in sh.order()[:args.warmup]:
         sw.solve_point(FREQS[i], raise_on_fail=False)
-    ctx.recycle_config(args.recycle)
+    ctx.recycle_config(args.recycle, args.snap)
     ctx.spmv_sampled()
     ctx.precond_sampled()
     barrier()
@@ -269,7 +269,7 @@ def run_gpu(args):
         ur_p = torch.from_numpy(ur).pin_memory().numpy()
         barrier()
         t0 = time.perf_counter()
-        sw2 = FrequencySweep(t, er_p, ur_p, bcs, device=local, recycle=args.recycle)
+        sw2 = FrequencySweep(t, er_p, ur_p, bcs, device=local, recycle=args.recycle, recycle_snap=args.snap)
         sw2.solver_opts.update(rtol=args.rtol, precond=args.precond)
         sw2.f_ref = float(np.median(FREQS))
         outs = {p.port_number: torch.empty(N, dtype=torch.complex128).pin_memory().numpy() for p in bcs[1:]}
@@ -378,7 +378,7 @@ def gpu_same_size(args, device):
         p.active = False
     for f in FREQS[:2]:
         sw.solve_point(f)
-    sw.ctx.recycle_config(args.recycle)
+    sw.ctx.recycle_config(args.recycle, args.snap)
     sw.ctx.timer_start()
     sw.ctx.assemble_KM()
     sw.run(FREQS)
@@ -432,6 +432,7 @@ def main():
     ap.add_argument("--precond", default="multilevel")
     ap.add_argument("--e2e-steps", type=int, default=0, help="points of the end-to-end pass; 0 = same as --steps, -1 = skip")
     ap.add_argument("--recycle", type=int, default=40)
+    ap.add_argument("--snap", type=float, default=0.3, help="points that iterate are solved to snap * rtol")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.ref_cells is None:

@@ -168,7 +168,7 @@ struct emb_ctx {
     std::vector<double> rc_uscale;      // x0 = sum_j y_j * uscale_j * U_j
     std::vector<std::complex<double>> aff_coef;            // coefficients of the last emb_form_A: 1, -k0^2, gamma_p...
     std::vector<int> aff_sids;
-    double rc_snap = 0.1;               // solves that feed the recycled space run to rc_snap * rtol
+    double rc_snap = 0.3;               // solves that feed the recycled space run to rc_snap * rtol
     DevBuf<cx> rc_x0;                   // start vectors of the current solve (new direction = x - x0)
     DevBuf<cx> rc_part;                 // dot partials + coefficients of the batched Gram-Schmidt / projection kernels
     DevBuf<cx> rc_tmp;                  // one contiguous vector

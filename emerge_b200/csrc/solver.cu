@@ -624,7 +624,7 @@ extern "C" int emb_recycle_config(emb_ctx* c, int max_vectors, double snapshot_r
         c->rc_terms.push_back(-1);        // never equal to a real term list => rc_prepare reallocates
     }
     c->rc_cap = max_vectors;
-    c->rc_snap = (snapshot_rtol_factor > 0 && snapshot_rtol_factor <= 1) ? snapshot_rtol_factor : 0.1;
+    c->rc_snap = (snapshot_rtol_factor > 0 && snapshot_rtol_factor <= 1) ? snapshot_rtol_factor : 0.3;
     rc_clear(c);
     return EMB_OK;
 }

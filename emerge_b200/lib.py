@@ -398,7 +398,7 @@ class Context:
         return ms.value, cnt.value
 
     # ---- subspace recycling across frequency points
-    def recycle_config(self, max_vectors: int, snapshot_rtol_factor: float = 0.1):
+    def recycle_config(self, max_vectors: int, snapshot_rtol_factor: float = 0.3):
         self._check(self.lib.emb_recycle_config(self.h, int(max_vectors), float(snapshot_rtol_factor)))
 
     def recycle_info(self):
