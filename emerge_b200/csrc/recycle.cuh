@@ -188,6 +188,16 @@ static int rc_prepare(emb_ctx* c) {
     if (same_terms) return EMB_OK;
     c->rc_terms = c->aff_sids;
     const int T = rc_T(c);
+    // the basis costs (1 + T) vectors per direction: never take more than half of the free HBM (5M tets: ~10 directions
+    // fewer than asked for rather than an allocation failure in the middle of a sweep)
+    c->rcU.release(); c->rcQ.release();
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+        const double per_dir = (double)(1 + T) * (double)c->Ns * sizeof(cx);
+        const int fit = (int)(0.5 * (double)free_b / per_dir);
+        if (fit < c->rc_cap) c->rc_cap = fit > 0 ? fit : 0;
+    }
+    if (c->rc_cap <= 0) { c->rc_cap = 0; return EMB_OK; }
     c->rc_qcap = T * c->rc_cap;
     EMB_TRY(dev_alloc(c, c->rcU, (size_t)c->rc_cap * c->Ns));
     EMB_TRY(dev_alloc(c, c->rcQ, (size_t)c->rc_qcap * c->Ns));
@@ -329,6 +339,7 @@ static int rc_compact(emb_ctx* c, int drop) {
 // add direction d (contiguous, solve space) as the NEWEST member; needs the A(f) it was computed with (aff_coef)
 static int rc_append(emb_ctx* c, const cx* d) {
     EMB_TRY(rc_prepare(c));
+    if (c->rc_cap <= 0) return EMB_OK;             // no room for a basis on this device
     const int T = rc_T(c);
     if (c->rc_n >= c->rc_cap || c->rc_nq + T > c->rc_qcap) {
         int drop = c->rc_cap / 4 > 0 ? c->rc_cap / 4 : 1;
