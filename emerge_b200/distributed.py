@@ -6,10 +6,12 @@ itself (cheaper than a broadcast at >70 Mtet/s) and only scalars cross the host/
 
 The ranks are independent except for two exchanges, both over torch.distributed (NCCL over NVLink on the GPU box, gloo in
 the CPU tests):
-  * seeding rounds: after each of its first `seed_rounds` points every rank contributes the directions that point added
-    to its recycled subspace (at most one per port); all ranks import all of them.  The expensive cold solves of a sweep
-    are the ones that build the recycled subspace (about a dozen points for the 8-12 GHz waveguide band) - shared this way
-    they are paid once per job instead of once per rank;
+  * exchange rounds: after each of its first points every rank contributes the directions that point added to its
+    reduced basis (at most one per port); all ranks import all of them.  The rounds go on while any rank still added a
+    direction (at least `seed_rounds`, at most `max_rounds`): in bisection order the points that have to iterate come
+    first on every rank, so the ranks are in step while they exchange and run free afterwards.  The expensive solves of a
+    sweep are the ones that build the basis (about a dozen points for the 8-12 GHz waveguide band) - shared this way they
+    are paid once per job instead of once per rank;
   * the S-parameter blocks are gathered to every rank at the end (all_gather, kilobytes).
 No collective runs inside a Krylov iteration.
 """
@@ -58,11 +60,13 @@ class GpuEngine:
 
 
 class ShardedSweep:
-    def __init__(self, sweep, freqs, rank=0, world=1, dist=None, device=0, seed_rounds=2, engine=None):
+    def __init__(self, sweep, freqs, rank=0, world=1, dist=None, device=0, seed_rounds=2, engine=None, max_rounds=16):
         self.freqs = np.asarray(freqs, dtype=float)
         self.rank, self.world, self.dist = rank, world, dist
         self.block = block_of(len(self.freqs), rank, world)
         self.seed_rounds = seed_rounds if (dist is not None and world > 1) else 0
+        self.max_rounds = max(max_rounds, self.seed_rounds) if self.seed_rounds > 0 else 0
+        self.rounds = 0
         self.engine = engine if engine is not None else GpuEngine(sweep, device)
         self.exchanged = 0
 
@@ -88,6 +92,7 @@ class ShardedSweep:
             for j in range(counts[r]):
                 eng.import_direction(bufs[r][j])
                 self.exchanged += 1
+        return int(sum(counts))
 
     # ------------------------------------------------------------------ the sweep
     def run(self, order=None, out_bufs=None, raise_on_fail=False) -> SweepResult:
@@ -97,8 +102,10 @@ class ShardedSweep:
         order = self.order() if order is None else list(order)
         S = None
         stats = {}
-        for step in range(max(len(order), self.seed_rounds)):
-            n_before = eng.recycle_count() if step < self.seed_rounds else 0
+        step = 0
+        exchanging = self.seed_rounds > 0
+        while step < len(order) or exchanging:
+            n_before = eng.recycle_count() if exchanging else 0
             if step < len(order):
                 i = order[step]
                 Si, st, _ = eng.solve_point(self.freqs[i], raise_on_fail=raise_on_fail, out_bufs=out_bufs)
@@ -106,8 +113,13 @@ class ShardedSweep:
                     S = np.zeros((len(self.freqs),) + Si.shape, dtype=np.complex128)
                 S[i] = Si
                 stats[i] = st
-            if step < self.seed_rounds:
-                self._exchange(eng.recycle_count() - n_before)
+            if exchanging:
+                # every rank sees the same total, so all ranks leave the exchange in the same round
+                total_new = self._exchange(eng.recycle_count() - n_before)
+                self.rounds += 1
+                if self.rounds >= self.max_rounds or (self.rounds >= self.seed_rounds and total_new == 0):
+                    exchanging = False
+            step += 1
         res = SweepResult(self.freqs, [], S if S is not None else np.zeros((len(self.freqs), 0, 0), dtype=np.complex128))
         for i in sorted(stats):
             res.stats.extend(stats[i])

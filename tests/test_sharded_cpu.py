@@ -33,13 +33,16 @@ def test_hierarchical_order_is_a_permutation_ends_first():
 class FakeEngine:
     """Every solved point adds one direction per port: the vector (f, port, rank-independent)."""
 
-    def __init__(self, n_ports=2, n=5):
+    def __init__(self, n_ports=2, n=5, iterating_points=10 ** 9):
         self.n_ports, self.n = n_ports, n
         self.vecs = []            # newest first
         self.imported = []
+        self.iterating_points = iterating_points      # only the first points leave directions (the others are "accepted")
+        self.solved = 0
 
     def solve_point(self, f, raise_on_fail=False, out_bufs=None):
-        for p in range(self.n_ports):
+        self.solved += 1
+        for p in range(self.n_ports if self.solved <= self.iterating_points else 0):
             self.vecs.insert(0, np.full(self.n, f * 1e-9 + 1j * p))
         S = np.full((self.n_ports, self.n_ports), f * 1e-9, dtype=complex)
         return S, [dict(freq=float(f), port=p, iters=1, relres=0.0) for p in range(self.n_ports)], {}
@@ -60,15 +63,19 @@ class FakeEngine:
         self.imported.append(v)
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, adaptive=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     freqs = np.linspace(8e9, 12e9, 21)
-    eng = FakeEngine()
-    sh = ShardedSweep(None, freqs, rank, world, dist=dist, seed_rounds=2, engine=eng)
+    if adaptive:       # rank 0 iterates at 4 points, rank 1 at 3: the exchange must go on for 4 rounds + 1 empty one
+        eng = FakeEngine(iterating_points=4 if rank == 0 else 3)
+        sh = ShardedSweep(None, freqs, rank, world, dist=dist, seed_rounds=2, engine=eng)
+    else:
+        eng = FakeEngine()
+        sh = ShardedSweep(None, freqs, rank, world, dist=dist, seed_rounds=2, max_rounds=2, engine=eng)
     res = sh.run()
     S = sh.gather_S(res)
-    q.put((rank, sh.order(), [v[0] for v in eng.imported], S[:, 0, 0].real.tolist(), sorted(res.solved)))
+    q.put((rank, sh.order(), [v[0] for v in eng.imported], S[:, 0, 0].real.tolist(), sorted(res.solved), sh.rounds))
     dist.destroy_process_group()
 
 
@@ -94,7 +101,8 @@ def test_two_rank_sweep_exchanges_seed_directions_and_gathers_S():
         p.join(timeout=30)
         assert p.exitcode == 0
     freqs = np.linspace(8e9, 12e9, 21)
-    (r0, o0, imp0, S0, solved0), (r1, o1, imp1, S1, solved1) = out
+    (r0, o0, imp0, S0, solved0, rounds0), (r1, o1, imp1, S1, solved1, rounds1) = out
+    assert rounds0 == rounds1 == 2
     # contiguous blocks, each processed ends-first
     assert solved0 == list(range(0, 11)) and solved1 == list(range(11, 21))
     assert o0[:2] == [0, 10] and o1[:2] == [11, 20]
@@ -103,4 +111,27 @@ def test_two_rank_sweep_exchanges_seed_directions_and_gathers_S():
     exp1 = sorted(freqs[i] * 1e-9 for i in o0[:2] for _ in range(2))
     assert np.allclose(sorted(np.real(imp0)), exp0) and np.allclose(sorted(np.real(imp1)), exp1)
     # every rank holds the S-parameters of the whole sweep
+    assert np.allclose(S0, freqs * 1e-9) and np.allclose(S1, freqs * 1e-9)
+
+
+@pytest.mark.timeout(120)
+def test_exchange_rounds_continue_while_any_rank_adds_directions():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, True)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = sorted(q.get(timeout=100) for _ in range(world))
+    for p in procs:
+        p.join(timeout=30)
+        assert p.exitcode == 0
+    freqs = np.linspace(8e9, 12e9, 21)
+    (r0, o0, imp0, S0, solved0, rounds0), (r1, o1, imp1, S1, solved1, rounds1) = out
+    assert rounds0 == rounds1 == 5                       # 4 rounds with new directions, then one empty round ends it
+    # rank 0 imported the directions of rank 1's first 3 points, rank 1 those of rank 0's first 4 points (2 ports each)
+    assert np.allclose(sorted(np.real(imp0)), sorted(freqs[i] * 1e-9 for i in o1[:3] for _ in range(2)))
+    assert np.allclose(sorted(np.real(imp1)), sorted(freqs[i] * 1e-9 for i in o0[:4] for _ in range(2)))
+    assert solved0 == list(range(0, 11)) and solved1 == list(range(11, 21))
     assert np.allclose(S0, freqs * 1e-9) and np.allclose(S1, freqs * 1e-9)
