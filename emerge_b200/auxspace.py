@@ -127,6 +127,82 @@ def build_aux_spaces(tables):
     return G, P, G1
 
 
+def build_aux_spaces_paired(tables, keep):
+    """G and P restricted to the kept dofs with rows already in the library's PAIR order of the solve space (row 2j / 2j+1 =
+    first / second function of kept entity j: kept edges in ascending order, then kept faces; csrc/operators.cu) and
+    columns touching an eliminated dof dropped - built directly, without the full matrices, row gathers or permutations
+    of build_aux_spaces + restriction (same entries; tests/test_auxspace_cpu.py).
+    keep: bool (n_field,), identical for the two functions of every entity.  Returns (Gs, Ps, badP, G1)."""
+    nodes = np.asarray(tables.nodes)
+    edges = np.asarray(tables.edges)
+    tris = np.asarray(tables.tris)
+    t2e = np.asarray(tables.tri_to_edge)
+    nN, nE, nTri = nodes.shape[1], edges.shape[1], tris.shape[1]
+    d = nodes[:, edges[1]] - nodes[:, edges[0]]
+    ell = np.sqrt((d ** 2).sum(axis=0))
+    il = 1.0 / ell
+    ke = np.asarray(keep[:nE], dtype=bool)
+    kf = np.asarray(keep[nE:nE + nTri], dtype=bool)
+    vt, et, wt = _face_tables()
+    lAE, lAB = ell[t2e[2]], ell[t2e[0]]
+
+    def edge_rows(sel, which):
+        """(cols, vals) of shape (n, 2, m): functions a and b of the selected edges"""
+        e = np.nonzero(sel)[0]
+        A, B, i = edges[0, e], edges[1, e], il[e]
+        if which == "G":
+            cols = np.stack([A, B, nN + e], axis=1)
+            va = np.stack([3 * i, i, -4 * i], axis=1)
+            vb = np.stack([-i, -3 * i, 4 * i], axis=1)
+        else:
+            cols = e[:, None]
+            va = vb = i[:, None]
+        return np.stack([cols, cols], axis=1), np.stack([va, vb], axis=1)
+
+    def face_rows(sel, which):
+        f = np.nonzero(sel)[0]
+        ia, ib = 1.0 / lAE[f], 1.0 / lAB[f]
+        if which == "G":
+            cols = np.concatenate([tris[:, f].T, nN + t2e[:, f].T], axis=1)                       # (n, 6)
+            ta = np.concatenate([vt[:, 0], et[:, 0]])
+            tb = np.concatenate([vt[:, 1], et[:, 1]])
+        else:
+            cols = t2e[:, f].T                                                                    # (n, 3)
+            ta, tb = wt[:, 0], wt[:, 1]
+        va = ta[None, :] * ia[:, None]
+        vb = tb[None, :] * ib[:, None]
+        return np.stack([cols, cols], axis=1), np.stack([va, vb], axis=1)
+
+    def assemble(which, ncol):
+        bad = np.zeros(ncol, dtype=bool)
+        for rows in (edge_rows(~ke, which), face_rows(~kf, which)):      # columns touched by eliminated rows
+            c, v = rows
+            bad[c[v != 0]] = True
+        newcol = np.cumsum(~bad) - 1
+        ip_parts, ix_parts, dv_parts, base = [], [], [], 0
+        for c, v in (edge_rows(ke, which), face_rows(kf, which)):
+            n, _, m = c.shape
+            c2, v2 = c.reshape(2 * n, m), v.reshape(2 * n, m)
+            ok = (v2 != 0) & ~bad[c2]
+            cnt = ok.sum(axis=1)
+            ip_parts.append(base + np.concatenate([[0], np.cumsum(cnt)[:-1]]) if 2 * n else np.zeros(0, dtype=np.int64))
+            base += int(cnt.sum())
+            ix_parts.append(newcol[c2[ok]].astype(np.int32))
+            dv_parts.append(v2[ok])
+        indptr = np.concatenate(ip_parts + [np.array([base])]).astype(np.int64)
+        M = sp.csr_matrix((np.concatenate(dv_parts), np.concatenate(ix_parts), indptr),
+                          shape=(len(indptr) - 1, int((~bad).sum())))
+        M.sort_indices()
+        return M, bad
+
+    Gs, _ = assemble("G", nN + nE)
+    Ps, badP = assemble("P", nE)
+    ea = np.arange(nE)
+    G1 = sp.coo_matrix((np.concatenate([np.ones(nE), -np.ones(nE)]),
+                        (np.concatenate([ea, ea]), np.concatenate([edges[0], edges[1]]))), shape=(nE, nN)).tocsr()
+    return Gs, Ps, badP, G1
+
+
 def nodal_interpolation(tables):
     """Pi_c (nE x nN), c = x, y, z: Whitney coefficients of the nodal vector field e_c * lam_v.  With the reference's sign
     convention w_AB.t_AB = -1/l on edge (A,B), the coefficient of a field E is -(E(v_A) + E(v_B))/2 . (v_B - v_A)."""

@@ -165,25 +165,28 @@ class FrequencySweep:
         smoothed-aggregation hierarchies of the P1 operators (grad, eps grad) and (grad, mu^-1 grad) + k^2 (lumped mass),
         set up once per mesh (emerge_b200/amg.py).  With multilevel=False the nodal problems are not solved and the
         P1 gradients only get a Jacobi scaling (the round-1 first version)."""
-        from .auxspace import build_aux_spaces, nodal_interpolation, p1_stiffness_mass
-        G, P, G1 = build_aux_spaces(self.t)
-        N = G.shape[0]
+        from .auxspace import build_aux_spaces, build_aux_spaces_paired, nodal_interpolation, p1_stiffness_mass
+        ctx = self.ctx
+        t = self.t
+        N = 2 * t.edges.shape[1] + 2 * t.tris.shape[1]
         keep = np.ones(N, dtype=bool)
         keep[self.pec_ids] = False
-        elim = ~keep
+        if ctx.paired:
+            # rows straight in the library's pair order of the solve space, no full matrices (auxspace.py)
+            Gs, Ps, badP, G1 = build_aux_spaces_paired(t, keep)
+        else:
+            G, P, G1 = build_aux_spaces(t)
+            elim = ~keep
+            perm = ctx.solve_perm()
+            inv = np.empty_like(perm)
+            inv[perm] = np.arange(len(perm))
+            rows_int = np.nonzero(keep)[0][inv]
 
-        # rows straight into the library's solve-index order (one gather instead of mask + permutation)
-        ctx = self.ctx
-        perm = ctx.solve_perm()
-        inv = np.empty_like(perm)
-        inv[perm] = np.arange(len(perm))
-        rows_int = np.nonzero(keep)[0][inv]
-
-        def restrict(R):
-            bad = np.asarray(abs(R[elim]).sum(axis=0)).ravel() > 0
-            return R[rows_int][:, ~bad].tocsr(), bad
-        Gs, _ = restrict(G)
-        Ps, badP = restrict(P)
+            def restrict(R):
+                bad = np.asarray(abs(R[elim]).sum(axis=0)).ravel() > 0
+                return R[rows_int][:, ~bad].tocsr(), bad
+            Gs, _ = restrict(G)
+            Ps, badP = restrict(P)
         G1r = G1[~badP]
         badN = np.asarray(abs(G1[badP]).sum(axis=0)).ravel() > 0
         G1s = G1r[:, ~badN].tocsr()
