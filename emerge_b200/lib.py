@@ -341,34 +341,34 @@ class Context:
         self._check(self.lib.emb_aux_clear(self.h))
         self._n_aux = 0
 
-    def aux_add(self, R, rows_internal=False):
-        """R: scipy sparse (n_solve x ncol) real transfer matrix of one auxiliary space, rows in the order of solve_ids()
-        (or already in the library's solve-index order when rows_internal)."""
-        R = R.tocsr().astype(np.float64)
-        if not rows_internal:
-            R = self._rows_to_internal(R).tocsr()
-        R.sort_indices()
-        T = R.T.tocsr()
-        T.sort_indices()
-        assert R.shape[0] == self.n_solve
-        a = [_c(R.indptr, np.int64), _c(R.indices, np.int32), _c(R.data, np.float64),
-             _c(T.indptr, np.int64), _c(T.indices, np.int32), _c(T.data, np.float64)]
-        self._check(self.lib.emb_aux_add(self.h, R.shape[1], *[_p(x) for x in a]))
-        self._n_aux = getattr(self, "_n_aux", 0) + 1
-        return self._n_aux - 1
-
     @staticmethod
     def _csr_args(M):
-        M = M.tocsr().astype(np.float64)
-        M.sort_indices()
+        M = M.tocsr()
+        if M.dtype != np.float64:
+            M = M.astype(np.float64)
+        if not M.has_sorted_indices:
+            M.sort_indices()
         return [_c(M.indptr, np.int64), _c(M.indices, np.int32), _c(M.data, np.float64)]
 
-    def aux_add_ex(self, R, parent=-1, solver="diag", hid=-1, scale="one", rows_internal=False):
+    @staticmethod
+    def csr_pair(R):
+        """(arguments of R, arguments of R^T) as the aux_add* calls take them; pure host work, safe to run in a worker
+        thread while the owner thread talks to the device"""
+        return Context._csr_args(R) + Context._csr_args(R.T)
+
+    def aux_add(self, R, rows_internal=False, prepared=None):
+        """R: scipy sparse (n_solve x ncol) real transfer matrix of one auxiliary space, rows in the order of solve_ids()
+        (or already in the library's solve-index order when rows_internal).  prepared: csr_pair(R) computed elsewhere."""
+        return self.aux_add_ex(R, parent=-1, solver="diag", rows_internal=rows_internal, prepared=prepared)
+
+    def aux_add_ex(self, R, parent=-1, solver="diag", hid=-1, scale="one", rows_internal=False, prepared=None):
         """R: scipy sparse (rows of the parent space x ncol) real transfer matrix; returns the index of the new space.
         Top-level spaces (parent < 0): rows in the order of solve_ids(), or in solve-index order when rows_internal."""
-        if parent < 0 and not rows_internal:
-            R = self._rows_to_internal(R.tocsr())
-        a = self._csr_args(R) + self._csr_args(R.T)
+        if prepared is None:
+            if parent < 0 and not rows_internal:
+                R = self._rows_to_internal(R.tocsr())
+            prepared = self.csr_pair(R)
+        a = prepared
         self._check(self.lib.emb_aux_add_ex(self.h, R.shape[0], R.shape[1], *[_p(x) for x in a], int(parent),
                                             {"diag": 0, "amg": 1}[solver], int(hid), {"one": 0, "minus_inv_k0sq": 1}[scale]))
         self._n_aux = getattr(self, "_n_aux", 0) + 1

@@ -165,19 +165,30 @@ class FrequencySweep:
         smoothed-aggregation hierarchies of the P1 operators (grad, eps grad) and (grad, mu^-1 grad) + k^2 (lumped mass),
         set up once per mesh (emerge_b200/amg.py).  With multilevel=False the nodal problems are not solved and the
         P1 gradients only get a Jacobi scaling (the round-1 first version)."""
+        from concurrent.futures import ThreadPoolExecutor
+        import scipy.sparse as sp
         from .auxspace import build_aux_spaces, build_aux_spaces_paired, nodal_interpolation, p1_stiffness_mass
+        from .amg import sa_hierarchy
         ctx = self.ctx
         t = self.t
         N = 2 * t.edges.shape[1] + 2 * t.tris.shape[1]
         keep = np.ones(N, dtype=bool)
         keep[self.pec_ids] = False
-        if ctx.paired:
-            # rows straight in the library's pair order of the solve space, no full matrices (auxspace.py)
-            Gs, Ps, badP, G1 = build_aux_spaces_paired(t, keep)
-        else:
+        multilevel = self.multilevel
+        tr = lambda T: np.real(T[0, 0] + T[1, 1] + T[2, 2]) / 3.0
+        w_eps, w_mu = tr(self.er), 1.0 / tr(self.ur)
+        same = np.allclose(w_eps, w_mu)
+        kmid2 = (2 * np.pi * self.f_ref / C0) ** 2
+
+        paired = ctx.paired                           # device queries from the owner thread only
+        perm = None if paired else ctx.solve_perm()
+
+        def top_level():
+            if paired:
+                # rows straight in the library's pair order of the solve space, no full matrices (auxspace.py)
+                return build_aux_spaces_paired(t, keep)
             G, P, G1 = build_aux_spaces(t)
             elim = ~keep
-            perm = ctx.solve_perm()
             inv = np.empty_like(perm)
             inv[perm] = np.arange(len(perm))
             rows_int = np.nonzero(keep)[0][inv]
@@ -187,42 +198,54 @@ class FrequencySweep:
                 return R[rows_int][:, ~bad].tocsr(), bad
             Gs, _ = restrict(G)
             Ps, badP = restrict(P)
-        G1r = G1[~badP]
-        badN = np.asarray(abs(G1[badP]).sum(axis=0)).ravel() > 0
-        G1s = G1r[:, ~badN].tocsr()
-        ctx.aux_clear()
-        self.aux_dims = []
-        if Gs.shape[1] > 0:
-            ctx.aux_add(Gs, rows_internal=True)
-            self.aux_dims.append(Gs.shape[1])
-        if Ps.shape[1] == 0:
-            return
-        if not self.multilevel or G1s.shape[1] == 0:
-            ctx.aux_add(Ps, rows_internal=True)
+            return Gs, Ps, badP, G1
+
+        # The host work is numpy / scipy kernels that release the GIL: independent pieces run in worker threads while
+        # this (owner) thread is the only one that talks to the device context.
+        with ThreadPoolExecutor(max_workers=4) as ex:
+            f_top = ex.submit(top_level)
+            f_le = ex.submit(p1_stiffness_mass, t, w_eps) if multilevel else None
+            f_lm = ex.submit(p1_stiffness_mass, t, w_mu) if (multilevel and not same) else None
+            f_pi = ex.submit(nodal_interpolation, t) if multilevel else None
+            Gs, Ps, badP, G1 = f_top.result()
+            f_g = ex.submit(ctx.csr_pair, Gs) if Gs.shape[1] > 0 else None
+            f_p = ex.submit(ctx.csr_pair, Ps) if Ps.shape[1] > 0 else None
+            badN = np.asarray(abs(G1[badP]).sum(axis=0)).ravel() > 0
+            kn = ~badN
+            G1s = G1[~badP][:, kn].tocsr()
+            f_he = f_hm = None
+            if multilevel and Ps.shape[1] > 0 and G1s.shape[1] > 0:
+                Le, mass = f_le.result()
+                Lm = Le if same else f_lm.result()[0]
+                f_he = ex.submit(lambda: sa_hierarchy((Le[kn][:, kn] + 1e-3 * kmid2 * sp.diags(mass[kn] * np.mean(w_eps))).tocsr(),
+                                                      coarse_size=self.amg_coarse_size))
+                f_hm = ex.submit(lambda: sa_hierarchy((Lm[kn][:, kn] + kmid2 * sp.diags(mass[kn] * np.mean(w_mu))).tocsr(),
+                                                      coarse_size=self.amg_coarse_size))
+                f_kids = [ex.submit(lambda M: ctx.csr_pair(M), G1s)]
+                f_pcs = ex.submit(lambda: [Pc[~badP][:, kn].tocsr() for Pc in f_pi.result()])
+            ctx.aux_clear()
+            self.aux_dims = []
+            if f_g is not None:
+                ctx.aux_add(Gs, rows_internal=True, prepared=f_g.result())
+                self.aux_dims.append(Gs.shape[1])
+            if f_p is None:
+                return
+            if f_he is None:
+                ctx.aux_add(Ps, rows_internal=True, prepared=f_p.result())
+                self.aux_dims.append(Ps.shape[1])
+                if G1s.shape[1] > 0:
+                    ctx.aux_add((Ps @ G1s).tocsr(), rows_internal=True)
+                    self.aux_dims.append(G1s.shape[1])
+                return
+            ip = ctx.aux_add_ex(Ps, parent=-1, solver="diag", rows_internal=True, prepared=f_p.result())
             self.aux_dims.append(Ps.shape[1])
-            if G1s.shape[1] > 0:
-                ctx.aux_add((Ps @ G1s).tocsr(), rows_internal=True)
-                self.aux_dims.append(G1s.shape[1])
-            return
-        from .amg import sa_hierarchy
-        ip = ctx.aux_add_ex(Ps, parent=-1, solver="diag", rows_internal=True)
-        self.aux_dims.append(Ps.shape[1])
-        tr = lambda T: np.real(T[0, 0] + T[1, 1] + T[2, 2]) / 3.0
-        w_eps, w_mu = tr(self.er), 1.0 / tr(self.ur)
-        kmid2 = (2 * np.pi * self.f_ref / C0) ** 2
-        Le, mass = p1_stiffness_mass(self.t, w_eps)
-        same = np.allclose(w_eps, w_mu)
-        Lm = Le if same else p1_stiffness_mass(self.t, w_mu)[0]
-        kn = ~badN
-        import scipy.sparse as sp
-        He = sa_hierarchy((Le[kn][:, kn] + 1e-3 * kmid2 * sp.diags(mass[kn] * np.mean(w_eps))).tocsr(), coarse_size=self.amg_coarse_size)
-        Hm = sa_hierarchy((Lm[kn][:, kn] + kmid2 * sp.diags(mass[kn] * np.mean(w_mu))).tocsr(), coarse_size=self.amg_coarse_size)
-        he, hm = ctx.amg_upload(He), ctx.amg_upload(Hm)
-        self.amg_levels = dict(eps=[l["A"].shape[0] for l in He], mu=[l["A"].shape[0] for l in Hm])
-        ctx.aux_add_ex(G1s, parent=ip, solver="amg", hid=he, scale="minus_inv_k0sq")
-        for Pc in nodal_interpolation(self.t):
-            ctx.aux_add_ex(Pc[~badP][:, kn].tocsr(), parent=ip, solver="amg", hid=hm, scale="one")
-        self.aux_dims += [G1s.shape[1]] * 4
+            He, Hm = f_he.result(), f_hm.result()
+            he, hm = ctx.amg_upload(He), ctx.amg_upload(Hm)
+            self.amg_levels = dict(eps=[l["A"].shape[0] for l in He], mu=[l["A"].shape[0] for l in Hm])
+            ctx.aux_add_ex(G1s, parent=ip, solver="amg", hid=he, scale="minus_inv_k0sq", prepared=f_kids[0].result())
+            for Pc in f_pcs.result():
+                ctx.aux_add_ex(Pc, parent=ip, solver="amg", hid=hm, scale="one")
+            self.aux_dims += [G1s.shape[1]] * 4
 
     def _setup_vline(self, b, ids):
         """define_lumped_port_integration_points (emfreq3d.py:366-389) + point location for the 10 midpoints."""
