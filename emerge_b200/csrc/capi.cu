@@ -43,6 +43,7 @@ extern "C" void emb_destroy(emb_ctx* c) {
     for (auto e : c->ev_restr) cudaEventDestroy(e);
     for (auto e : c->ev_done) cudaEventDestroy(e);
     if (c->evp0) { cudaEventDestroy(c->evp0); cudaEventDestroy(c->evp1); }
+    if (c->evt0) { cudaEventDestroy(c->evt0); cudaEventDestroy(c->evt1); }
     emb_aux_clear(c);          // also destroys the side streams and their fork event (once)
     cudaEventDestroy(c->evr0);
     cudaEventDestroy(c->evr1);
