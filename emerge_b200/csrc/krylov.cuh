@@ -401,12 +401,25 @@ __device__ void small_solve(const cx* S, const cx* B, int block, cx* X) {
         return;
     }
     cx a[NV][NV], r[NV][NV];
+    double amax = 0.0;
     for (int i = 0; i < NV; ++i)
-        for (int j = 0; j < NV; ++j) { a[i][j] = S[i * NV + j]; r[i][j] = B[i * NV + j]; }
+        for (int j = 0; j < NV; ++j) {
+            a[i][j] = S[i * NV + j];
+            r[i][j] = B[i * NV + j];
+            const double m = norm2(a[i][j]);
+            if (m > amax) amax = m;
+        }
     for (int c = 0; c < NV; ++c) {
         int pv = c;
         double best = norm2(a[c][c]);
         for (int i = c + 1; i < NV; ++i) { const double m = norm2(a[i][c]); if (m > best) { best = m; pv = i; } }
+        // (numerically) dependent block columns: the block recurrence has broken down.  Poison the result so that the
+        // host sees NaN residuals at its next check and restarts this step with independent recurrences.
+        if (!(best > 1e-24 * amax)) {
+            const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+            for (int q = 0; q < NV * NV; ++q) X[q] = cx{qnan, qnan};
+            return;
+        }
         if (pv != c)
             for (int j = 0; j < NV; ++j) { cx t = a[c][j]; a[c][j] = a[pv][j]; a[pv][j] = t; t = r[c][j]; r[c][j] = r[pv][j]; r[pv][j] = t; }
         const cx inv = sdiv(mk(1.0), a[c][c]);

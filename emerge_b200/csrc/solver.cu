@@ -144,8 +144,8 @@ static int cocr(emb_ctx* c, int pmode, int block, const VT* As, const cx* rhs, V
         }
     }
     int it = 0, rc = EMB_OK;
-    double rn[NVMAX];
-    for (int k = 0; k < NV; ++k) rn[k] = 1e300;
+    double rn[NVMAX], rbest[NVMAX];
+    for (int k = 0; k < NV; ++k) rn[k] = rbest[k] = 1e300;
     const int check = 10;
     while (it < maxit) {
         const bool sample = ((it + 1) % check == 0) || !gexec;
@@ -172,8 +172,11 @@ static int cocr(emb_ctx* c, int pmode, int block, const VT* As, const cx* rhs, V
                 rn[k] = sqrt(fabs(h[k].re));
                 if (!(rn[k] == rn[k])) nan = true;
                 if (!(rn[k] <= stop_abs[k])) all = false;
+                // a residual that has grown a million times above its smallest value is a breakdown, not slow convergence
+                if (rn[k] < rbest[k]) rbest[k] = rn[k];
+                if (rn[k] > 1e6 * rbest[k] && rbest[k] > 0) nan = true;
             }
-            if (nan) { c->err = "COCR breakdown (NaN)"; rc = EMB_NOT_CONVERGED; break; }
+            if (nan) { c->err = "COCR breakdown (NaN or diverging residual)"; rc = EMB_NOT_CONVERGED; break; }
             if (all) break;
         }
     }

@@ -295,3 +295,38 @@ def test_chunked_numeric_phase_is_bitwise_identical(gpu_ctx):
         assert np.array_equal(E.view(np.float64), E2.view(np.float64))
         assert np.array_equal(B.view(np.float64), B2.view(np.float64))
     gpu_ctx.assemble_config(0, True)
+
+
+def test_four_right_hand_sides_block_and_breakdown_fallback():
+    """A group of four DISTINCT right-hand sides runs as one block Krylov solve; a group with repeated right-hand sides
+    makes the block recurrence singular and must fall back to independent recurrences - both meet rtol on A(f)."""
+    g, sw = _medium_sweep(recycle=0)
+    sw.setup()
+    ctx = sw.ctx
+    f0 = float(g["freqs"][0])
+    ref = {}
+    sw.lockstep = 1
+    r1 = sw.run([f0], keep_fields=True)
+    for p in sw.ports:
+        ref[p.port_number] = r1.fields[(0, p.port_number)]
+    # two more surfaces on the port triangles, carrying other (random) incident fields: right-hand sides 2 and 3
+    rng = np.random.default_rng(11)
+    from emerge_b200.sweep import _tri_ids
+    for extra, p in zip((2, 3), sw.ports):
+        ids = _tri_ids(p, sw.get_triangles)
+        n = ctx.surface_define(extra, ids, 0, np.asarray(p.get_inv_basis(), dtype=float), np.asarray(p.cs.origin, dtype=float))
+        ctx.surface_set_U(extra, rng.standard_normal((3, 6, n)) + 1j * rng.standard_normal((3, 6, n)))
+    k0 = sw.assemble_frequency(f0)
+    sids = [sw.sid[id(p)] for p in sw.ports]
+    xs, infos = ctx.solve_multi(sids + [2, 3], **sw.solver_opts)
+    assert all(i["converged"] and i["relres"] <= 1e-10 for i in infos), infos
+    for k, p in enumerate(sw.ports):
+        assert np.linalg.norm(xs[k] - ref[p.port_number]) <= 1e-8 * np.linalg.norm(ref[p.port_number])
+    assert np.linalg.norm(xs[2]) > 0 and np.linalg.norm(xs[2] - xs[0]) > 1e-3 * np.linalg.norm(xs[0])
+    # repeated right-hand sides: singular block recurrence -> lockstep fallback, still converged
+    xs2, infos2 = ctx.solve_multi(sids + sids, **sw.solver_opts)
+    assert all(i["converged"] and i["relres"] <= 1e-10 for i in infos2), infos2
+    for k, p in enumerate(sw.ports):
+        assert np.linalg.norm(xs2[k] - ref[p.port_number]) <= 1e-8 * np.linalg.norm(ref[p.port_number])
+        assert np.linalg.norm(xs2[k + 2] - xs2[k]) <= 1e-8 * np.linalg.norm(xs2[k])
+    ctx.close()
