@@ -108,7 +108,6 @@ def peaks():
 # ------------------------------------------------------------------------------------------------ CPU port
 def cpu_port_setup(nx, ny, nz):
     """Reference CPU path on a bounded sample (oracle port): returns a closure running one frequency point."""
-    import scipy.sparse as sp
     import scipy.sparse.linalg as spla
     from scipy.sparse.csgraph import reverse_cuthill_mckee
     from oracle import ned2_oracle as O
@@ -247,7 +246,7 @@ def run_gpu(args):
         import datetime
         # a short collective timeout: a mismatched collective must not hold the GPU box for the default 10 minutes
         dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=180))
-    from emerge_b200.sweep import FrequencySweep, hierarchical_order
+    from emerge_b200.sweep import FrequencySweep
     from emerge_b200.distributed import ShardedSweep
     nx, ny, nz = args.cells
     t0 = time.perf_counter()

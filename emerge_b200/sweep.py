@@ -15,8 +15,7 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
-from .lib import Context, NotConverged
-from . import bc as _bc
+from .lib import Context
 
 C0 = 299792458.0
 
