@@ -1,11 +1,11 @@
 // Multi-right-hand-side building blocks of the frequency-domain solve (sm_100a, FP64 arithmetic).
 //
-// All ports of one frequency point are solved in lockstep: NV (1, 2 or 4) vectors are stored INTERLEAVED,
+// All ports of one frequency point are solved together: NV (1, 2 or 4) vectors are stored INTERLEAVED,
 // v[i * NV + k] = entry i of right-hand side k.  The operator is then read ONCE per iteration for all ports
 // (the matrix is 93 % of the SpMV traffic), every gather of x is a full 32-byte sector or more, and the
-// latency-bound multilevel kernels are shared.  Every reduction is per column, in a fixed order (block partials
-// summed by the consumer kernel), so results are bitwise reproducible and column k does not depend on what the
-// other columns hold.
+// latency-bound multilevel kernels are shared.  Every reduction runs in a fixed order (block partials summed by the
+// consumer kernel), so results are bitwise reproducible; in lockstep mode (independent recurrences) column k does not
+// depend on what the other columns hold, in block mode the columns share one Krylov space.
 //
 // Reference path replaced: the per-port loop around SolveRoutine.solve (fem/physics/edm/emfreq3d.py:683-694,
 // fem/solver.py:405-469), which factorises once and back-substitutes per port.

@@ -7,15 +7,17 @@
 // ALL ports of the frequency point at once:
 //   1. start vectors from the reduced basis of earlier solves (recycle.cuh); accepted as they are when the FP64
 //      residual of A(f) already meets rtol;
-//   2. otherwise COCR (conjugate-orthogonal conjugate-residual, one operator application per iteration) in
-//      lockstep over the ports (krylov.cuh: interleaved vectors, the operator is read once per iteration) on the
-//      complex-symmetric part As = (A + A^T)/2 stored in complex64, with the additive multilevel preconditioner
-//      (precond.cuh), wrapped in defect correction on the true FP64 operator:  X += As^-1 (B - A X).
-//      A(f) is not exactly symmetric because the reference's mass matrix is not (fem/mth/tet.py:1036, SURVEY App. A.1;
-//      relative asymmetry ~5e-5); that and the complex64 rounding of As are both removed by the outer correction,
-//      which gains 2-3 digits per step.  The exit test is always ||b - A(f) x|| / ||b|| <= rtol in FP64 on A(f).
+//   2. otherwise block COCR (conjugate-orthogonal conjugate-residual, one operator application per iteration; the
+//      ports share ONE Krylov space, krylov.cuh: interleaved vectors, the operator is read once per iteration, NV x NV
+//      small solves on the device) on the complex-symmetric part As = (A + A^T)/2 stored in complex64, with the
+//      additive multilevel preconditioner (precond.cuh), wrapped in defect correction on the true FP64 operator:
+//      X += As^-1 (B - A X).  A(f) is not exactly symmetric because the reference's mass matrix is not
+//      (fem/mth/tet.py:1036; relative asymmetry ~5e-5); that and the complex64 rounding of As are both
+//      removed by the outer correction, which gains two digits per step.  Padded groups, empty right-hand sides and
+//      a breakdown of the block recurrence (dependent columns, diverging residual) use independent recurrences in
+//      lockstep.  The exit test is always ||b - A(f) x|| / ||b|| <= rtol in FP64 on A(f).
 //   method 0: restarted GMRES(m) on A, method 1: BiCGStab on A (single right-hand side; cross-checks).
-// An iteration is ~90 kernel launches (the multilevel cycle is latency-bound), so the loop body is captured once per
+// An iteration is ~60 kernel launches (the multilevel cycle is latency-bound), so the loop body is captured once per
 // solve into a CUDA graph whose independent auxiliary-space branches run concurrently; every 10th iteration is issued
 // as plain launches instead, with CUDA events around the operator application (roofline sampling) and the
 // convergence read-back.  No host synchronisation otherwise: all scalars live on the device.
