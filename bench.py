@@ -212,7 +212,7 @@ def run_e2e(args, torch, dist, rank, world, local, t, er, ur, bcs, K, barrier):
     outs = {p.port_number: torch.empty(N, dtype=torch.complex128).pin_memory().numpy() for p in bcs[1:]}
     barrier()
     t0 = time.perf_counter()
-    sw2 = FrequencySweep(t, er_p, ur_p, bcs, device=local, recycle=args.recycle, recycle_snap=args.snap)
+    sw2 = FrequencySweep(t, er_p, ur_p, bcs, device=local, recycle=args.recycle, recycle_snap=args.snap, coarse_basis=args.coarse_basis)
     sw2.solver_opts.update(rtol=args.rtol, precond=args.precond)
     sw2.f_ref = float(np.median(FREQS))
     sw2.setup()
@@ -264,13 +264,13 @@ def run_gpu(args):
     # FIRST: it has to see the process as a user's script would (a device heap that just released tens of GB makes
     # cudaMalloc ten times slower, which is what the e2e leg measured when it ran after the resident leg)
     wbox, wt, wer, wur, wbcs, _ = make_waveguide(8, 4, 12)
-    wsw = FrequencySweep(wt, wer, wur, wbcs, device=local, recycle=args.recycle, recycle_snap=args.snap)
+    wsw = FrequencySweep(wt, wer, wur, wbcs, device=local, recycle=args.recycle, recycle_snap=args.snap, coarse_basis=args.coarse_basis)
     wsw.solver_opts.update(rtol=args.rtol, precond=args.precond)
     wsw.run(list(FREQS[:: max(1, len(FREQS) // max(1, args.warmup))][:max(3, args.warmup)]), raise_on_fail=False)
     wsw.ctx.close()
     del wsw
     e2e_K, ms_e2e, h2d, d2h, e2e_timings = run_e2e(args, torch, dist, rank, world, local, t, er, ur, bcs, K, barrier)
-    sw = FrequencySweep(t, er, ur, bcs, device=local, recycle=args.recycle, recycle_snap=args.snap)
+    sw = FrequencySweep(t, er, ur, bcs, device=local, recycle=args.recycle, recycle_snap=args.snap, coarse_basis=args.coarse_basis)
     sw.solver_opts.update(rtol=args.rtol, precond=args.precond)
     sw.f_ref = float(np.median(FREQS))
     t0 = time.perf_counter()
@@ -453,6 +453,8 @@ def main():
     ap.add_argument("--recycle", type=int, default=40)
     ap.add_argument("--snap", type=float, default=0.3, help="points that iterate are solved to snap * rtol")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--coarse-basis", action="store_true",
+                    help="EXPERIMENTAL: reduced basis as an extra coarse space of the preconditioner (default off)")
     args = ap.parse_args()
     if args.ref_cells is None:
         args.ref_cells = pick_ref_cells(max(args.steps, 1) + args.warmup) if args.impl == "reference" else pick_ref_cells(3, 60.0)

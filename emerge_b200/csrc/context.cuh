@@ -176,6 +176,16 @@ struct emb_ctx {
     int64_t rc_rebuilds = 0;
     double rc_last_proj_relres = -1;    // relative residual left by the projection in the last solve
     int nsol = 0;                       // columns of the last lockstep solve held in xs
+    // EXPERIMENTAL (off by default, not yet measured on the GPU): the reduced basis as an extra coarse space of the
+    // preconditioner, M^-1 += U Ceff U^T with Ceff = T (T^T U^T As U T)^-1 T^T and T a truncated orthonormalisation of U
+    // (recycle.cuh::rc_coarse_update; CPU prototype tools/proto_coarse_basis.py: 326 -> 211 iterations with 4 vectors)
+    bool coarse_basis = false;
+    std::vector<std::complex<double>> rc_UtQ;      // [rc_cap][rc_qcap]  u_j^T q_i (unconjugated)
+    std::vector<std::complex<double>> rc_UhU;      // [rc_cap][rc_cap]   u_i^H u_j
+    DevBuf<cx> rc_ceff, rc_ct;                     // [rc_cap][rc_cap] coefficient map; [2][rc_cap][NVMAX] small vectors
+    int coarse_m = 0;                              // directions in the coarse space of the current operator (0 = none)
+    int rc_version = 0, coarse_version = -1;       // basis change counter / the one the coefficient map was built for
+    double coarse_k0 = -1;
     double spmv_ms_sum = 0;   // sampled SpMV timings inside solves (CUDA events)
     int64_t spmv_ms_cnt = 0;
     double prec_ms_sum = 0;   // sampled preconditioner applications

@@ -58,3 +58,48 @@ static void ls_solve(int nq, int m, std::vector<zc>& G, int nv, std::vector<zc>&
     }
 }
 
+
+// Eigen-decomposition of a small complex Hermitian matrix H (n x n, row-major; destroyed) by cyclic Jacobi rotations:
+// H = V diag(lam) V^H, V row-major with eigenvectors in its COLUMNS.  n <= a few dozen (Gram matrices of the reduced basis).
+static void herm_eig_jacobi(int n, std::vector<zc>& H, std::vector<zc>& V, std::vector<double>& lam) {
+    V.assign((size_t)n * n, zc(0.0, 0.0));
+    for (int i = 0; i < n; ++i) V[(size_t)i * n + i] = zc(1.0, 0.0);
+    auto off2 = [&]() {
+        double s = 0;
+        for (int i = 0; i < n; ++i)
+            for (int j = 0; j < n; ++j)
+                if (i != j) s += std::norm(H[(size_t)i * n + j]);
+        return s;
+    };
+    double diag2 = 0;
+    for (int i = 0; i < n; ++i) diag2 += std::norm(H[(size_t)i * n + i]);
+    const double tiny = 1e-30 * (diag2 + off2()) + 1e-300;
+    for (int sweep = 0; sweep < 60 && off2() > tiny; ++sweep)
+        for (int p = 0; p < n - 1; ++p)
+            for (int q = p + 1; q < n; ++q) {
+                const zc hpq = H[(size_t)p * n + q];
+                const double a = std::abs(hpq);
+                if (a == 0.0) continue;
+                const double hpp = H[(size_t)p * n + p].real(), hqq = H[(size_t)q * n + q].real();
+                const zc ph = hpq / a;                                   // H_pq = a * ph
+                const double tau = (hqq - hpp) / (2.0 * a);
+                const double t = (tau >= 0 ? 1.0 : -1.0) / (std::fabs(tau) + std::sqrt(1.0 + tau * tau));
+                const double cs = 1.0 / std::sqrt(1.0 + t * t), sn = t * cs;
+                // unitary rotation J: columns p, q of H and V;  J = [[cs, sn*ph], [-sn*conj(ph), cs]] acting on (p, q)
+                for (int k = 0; k < n; ++k) {                           // H <- H J
+                    const zc hkp = H[(size_t)k * n + p], hkq = H[(size_t)k * n + q];
+                    H[(size_t)k * n + p] = cs * hkp - sn * std::conj(ph) * hkq;
+                    H[(size_t)k * n + q] = sn * ph * hkp + cs * hkq;
+                    const zc vkp = V[(size_t)k * n + p], vkq = V[(size_t)k * n + q];
+                    V[(size_t)k * n + p] = cs * vkp - sn * std::conj(ph) * vkq;
+                    V[(size_t)k * n + q] = sn * ph * vkp + cs * vkq;
+                }
+                for (int k = 0; k < n; ++k) {                           // H <- J^H H
+                    const zc hpk = H[(size_t)p * n + k], hqk = H[(size_t)q * n + k];
+                    H[(size_t)p * n + k] = cs * hpk - sn * ph * hqk;
+                    H[(size_t)q * n + k] = sn * std::conj(ph) * hpk + cs * hqk;
+                }
+            }
+    lam.resize((size_t)n);
+    for (int i = 0; i < n; ++i) lam[(size_t)i] = H[(size_t)i * n + i].real();
+}

@@ -100,7 +100,8 @@ __device__ __forceinline__ cx block_sum1(cx v) {
 }
 // part[(j * RC_NP + blockIdx.x) * NV + v] = partial of <q_j, r_v> over this block's rows;  j = blockIdx.y;
 // Q: contiguous columns of length n, r: NV interleaved columns
-template <int NV>
+// CONJ = false: unconjugated products q_j^T r_v
+template <int NV, bool CONJ = true>
 __global__ void __launch_bounds__(VBLOCK) k_rc_dots(int64_t n, const cx* __restrict__ Q, const cx* __restrict__ r,
                                                     cx* __restrict__ part) {
     const cx* q = Q + (int64_t)blockIdx.y * n;
@@ -114,8 +115,12 @@ __global__ void __launch_bounds__(VBLOCK) k_rc_dots(int64_t n, const cx* __restr
 #pragma unroll
         for (int v = 0; v < NV; ++v) {
             const cx w = r[i * NV + v];
-            acc[v].re += u.re * w.re + u.im * w.im;
-            acc[v].im += u.re * w.im - u.im * w.re;
+            if (CONJ) {
+                acc[v].re += u.re * w.re + u.im * w.im;
+                acc[v].im += u.re * w.im - u.im * w.re;
+            } else {
+                fma_c(acc[v], u, w);
+            }
         }
     }
 #pragma unroll
@@ -178,6 +183,8 @@ static inline cx* rc_Q(emb_ctx* c, int j) { return c->rcQ.p + (int64_t)j * c->Ns
 static void rc_clear(emb_ctx* c) {
     c->rc_n = 0;
     c->rc_nq = 0;
+    c->rc_version++;
+    c->coarse_m = 0;
     for (auto& R : c->rc_R) std::fill(R.begin(), R.end(), zc(0.0, 0.0));
 }
 
@@ -205,6 +212,12 @@ static int rc_prepare(emb_ctx* c) {
     EMB_TRY(dev_alloc(c, c->rc_tmp, (size_t)c->Ns));
     c->rc_R.assign((size_t)T, std::vector<zc>((size_t)c->rc_qcap * c->rc_cap, zc(0.0, 0.0)));
     c->rc_uscale.assign((size_t)c->rc_cap, 1.0);
+    if (c->coarse_basis) {
+        c->rc_UtQ.assign((size_t)c->rc_cap * c->rc_qcap, zc(0.0, 0.0));
+        c->rc_UhU.assign((size_t)c->rc_cap * c->rc_cap, zc(0.0, 0.0));
+        EMB_TRY(dev_alloc(c, c->rc_ceff, (size_t)c->rc_cap * c->rc_cap));
+        EMB_TRY(dev_alloc(c, c->rc_ct, (size_t)2 * c->rc_cap * NVMAX));
+    }
     rc_clear(c);
     return EMB_OK;
 }
@@ -260,6 +273,7 @@ static int rc_insert(emb_ctx* c, int slot, bool accept_test, bool* accepted) {
     cx* coef = rc_coef_area(c);                 // h1 [qcap], h2 [qcap], norms [2]
     const int qc = c->rc_qcap;
     std::vector<cx> host((size_t)2 * qc + 2);
+    const int nq_before = c->rc_nq;
     for (int t = 0; t < T; ++t) {
         const int nq = c->rc_nq;
         if (nq >= qc) { c->err = "recycling: orthonormal basis is full"; return EMB_ERR_LIMIT; }
@@ -315,6 +329,38 @@ static int rc_insert(emb_ctx* c, int slot, bool accept_test, bool* accepted) {
         for (int t = 0; t < T; ++t)
             for (int i = 0; i < qc; ++i) c->rc_R[(size_t)t][(size_t)slot * qc + i] = zc(0.0, 0.0);
     }
+    if (ok && c->coarse_basis && !c->rc_UtQ.empty()) {
+        // bookkeeping of the experimental coarse space: u^T q for the new direction against every basis column, for the
+        // new basis columns against every older direction, and the Hermitian Gram row of the new direction
+        const int nq1 = c->rc_nq;
+        auto fetch = [&](int cnt, std::vector<cx>& out) -> int {
+            out.resize((size_t)cnt);
+            EMB_CUDA(c, cudaMemcpyAsync(out.data(), coef, (size_t)cnt * sizeof(cx), cudaMemcpyDeviceToHost, c->stream));
+            EMB_CUDA(c, cudaStreamSynchronize(c->stream));
+            return EMB_OK;
+        };
+        std::vector<cx> hb;
+        k_rc_dots<1, false><<<dim3(RC_NP, nq1), VBLOCK, 0, c->stream>>>(n, c->rcQ.p, rc_U(c, slot), part); EMB_LAUNCH_CHECK(c);
+        k_rc_coef<1><<<nq1, VBLOCK, 0, c->stream>>>(part, coef); EMB_LAUNCH_CHECK(c);
+        EMB_TRY(fetch(nq1, hb));
+        for (int i = 0; i < qc; ++i) c->rc_UtQ[(size_t)slot * qc + i] = i < nq1 ? zc(hb[(size_t)i].re, hb[(size_t)i].im) : zc(0.0, 0.0);
+        if (slot > 0)
+            for (int i = nq_before; i < nq1; ++i) {
+                k_rc_dots<1, false><<<dim3(RC_NP, slot), VBLOCK, 0, c->stream>>>(n, c->rcU.p, rc_Q(c, i), part); EMB_LAUNCH_CHECK(c);
+                k_rc_coef<1><<<slot, VBLOCK, 0, c->stream>>>(part, coef); EMB_LAUNCH_CHECK(c);
+                EMB_TRY(fetch(slot, hb));
+                for (int j = 0; j < slot; ++j) c->rc_UtQ[(size_t)j * qc + i] = zc(hb[(size_t)j].re, hb[(size_t)j].im);
+            }
+        k_rc_dots<1, true><<<dim3(RC_NP, slot + 1), VBLOCK, 0, c->stream>>>(n, c->rcU.p, rc_U(c, slot), part); EMB_LAUNCH_CHECK(c);
+        k_rc_coef<1><<<slot + 1, VBLOCK, 0, c->stream>>>(part, coef); EMB_LAUNCH_CHECK(c);
+        EMB_TRY(fetch(slot + 1, hb));
+        const int cap = c->rc_cap;
+        for (int j = 0; j <= slot; ++j) {                 // hb[j] = u_j^H u_slot
+            c->rc_UhU[(size_t)j * cap + slot] = zc(hb[(size_t)j].re, hb[(size_t)j].im);
+            c->rc_UhU[(size_t)slot * cap + j] = zc(hb[(size_t)j].re, -hb[(size_t)j].im);
+        }
+    }
+    if (ok) c->rc_version++;
     if (accepted) *accepted = ok;
     return EMB_OK;
 }
@@ -388,5 +434,97 @@ static int rc_project(emb_ctx* c, const cx* r0, cx* xs) {
     EMB_CUDA(c, cudaStreamSynchronize(c->stream));      // yd is a stack-lifetime host buffer
     k_rc_combine<NV><<<blocks_for(n, 256), 256, (size_t)m * NV * sizeof(cx), c->stream>>>(n, m, ydev, c->rcU.p, xs);
     EMB_LAUNCH_CHECK(c);
+    return EMB_OK;
+}
+
+// ---- EXPERIMENTAL: the reduced basis as a coarse space of the preconditioner -----------------------------------------
+// c[i * nv + v] = sum_j C[i * m + j] t[j * nv + v]   (one block)
+__global__ void k_small_mm(int m, int nv, const cx* __restrict__ C, const cx* __restrict__ t, cx* __restrict__ out) {
+    for (int e = threadIdx.x; e < m * nv; e += blockDim.x) {
+        const int i = e / nv, v = e % nv;
+        cx acc = mk(0.0);
+        for (int j = 0; j < m; ++j) fma_c(acc, C[i * m + j], t[j * nv + v]);
+        out[e] = acc;
+    }
+}
+
+// Coefficient map of the coarse correction for the current A(f) and the current basis (host side, small matrices):
+//   Gs  = sym( D UtQ G(f) ),  D = diag(uscale)            = (U D)^T As (U D)   from the stored products, no SpMV
+//   H   = D UhU D = V L V^H  (Jacobi),  T = V_k L_k^-1/2 for the eigenvalues above 1e-10 of the largest
+//   Ceff = D T (T^T Gs T)^-1 T^T D                          so that  z += U Ceff (U^T r)
+static int rc_coarse_update(emb_ctx* c) {
+    c->coarse_m = 0;
+    if (!c->coarse_basis || c->rc_n <= 0 || c->rc_UtQ.empty() || c->rc_terms != c->aff_sids) return EMB_OK;
+    const int m = c->rc_n, nq = c->rc_nq, qc = c->rc_qcap, cap = c->rc_cap;
+    std::vector<zc> G;
+    rc_build_G(c, m, G);                                   // nq x m, columns already scaled by uscale
+    std::vector<zc> Gs((size_t)m * m);
+    for (int i = 0; i < m; ++i)
+        for (int j = 0; j < m; ++j) {
+            zc s(0.0, 0.0);
+            for (int k = 0; k < nq; ++k) s += c->rc_UtQ[(size_t)i * qc + k] * G[(size_t)j * nq + k];
+            Gs[(size_t)i * m + j] = s * c->rc_uscale[(size_t)i];
+        }
+    for (int i = 0; i < m; ++i)
+        for (int j = i + 1; j < m; ++j) {
+            const zc a = 0.5 * (Gs[(size_t)i * m + j] + Gs[(size_t)j * m + i]);
+            Gs[(size_t)i * m + j] = Gs[(size_t)j * m + i] = a;
+        }
+    std::vector<zc> H((size_t)m * m), V;
+    std::vector<double> lam;
+    for (int i = 0; i < m; ++i)
+        for (int j = 0; j < m; ++j) H[(size_t)i * m + j] = c->rc_uscale[(size_t)i] * c->rc_uscale[(size_t)j] * c->rc_UhU[(size_t)i * cap + j];
+    herm_eig_jacobi(m, H, V, lam);
+    double lmax = 0;
+    for (double l : lam) if (l > lmax) lmax = l;
+    std::vector<int> keep;
+    for (int k = 0; k < m; ++k) if (lam[(size_t)k] > 1e-10 * lmax) keep.push_back(k);
+    const int r = (int)keep.size();
+    if (r == 0) return EMB_OK;
+    std::vector<zc> T((size_t)m * r);                      // row-major m x r
+    for (int i = 0; i < m; ++i)
+        for (int k = 0; k < r; ++k) T[(size_t)i * r + k] = V[(size_t)i * m + keep[(size_t)k]] / std::sqrt(lam[(size_t)keep[(size_t)k]]);
+    // Gc = T^T Gs T (r x r, column-major for ls_solve), right-hand sides T^T (r x m)
+    std::vector<zc> GsT((size_t)m * r, zc(0.0, 0.0));
+    for (int i = 0; i < m; ++i)
+        for (int k = 0; k < r; ++k)
+            for (int j = 0; j < m; ++j) GsT[(size_t)i * r + k] += Gs[(size_t)i * m + j] * T[(size_t)j * r + k];
+    std::vector<zc> Gc((size_t)r * r, zc(0.0, 0.0)), rhs((size_t)r * m), Y;
+    for (int a = 0; a < r; ++a)
+        for (int b = 0; b < r; ++b)
+            for (int i = 0; i < m; ++i) Gc[(size_t)b * r + a] += T[(size_t)i * r + a] * GsT[(size_t)i * r + b];
+    for (int j = 0; j < m; ++j)
+        for (int a = 0; a < r; ++a) rhs[(size_t)j * r + a] = T[(size_t)j * r + a];
+    std::vector<double> res;
+    ls_solve(r, r, Gc, m, rhs, Y, res);                    // Y[a * m + j] = (Gc^-1 T^T)[a][j]
+    std::vector<cx> Ceff((size_t)m * m);
+    for (int i = 0; i < m; ++i)
+        for (int j = 0; j < m; ++j) {
+            zc s(0.0, 0.0);
+            for (int a = 0; a < r; ++a) s += T[(size_t)i * r + a] * Y[(size_t)a * m + j];
+            s *= c->rc_uscale[(size_t)i] * c->rc_uscale[(size_t)j];
+            if (!(s == s)) return EMB_OK;                   // NaN: leave the coarse space off for this operator
+            Ceff[(size_t)i * m + j] = cx{s.real(), s.imag()};
+        }
+    EMB_CUDA(c, cudaMemcpyAsync(c->rc_ceff.p, Ceff.data(), Ceff.size() * sizeof(cx), cudaMemcpyHostToDevice, c->stream));
+    EMB_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->coarse_m = m;
+    c->coarse_version = c->rc_version;
+    c->coarse_k0 = c->k0;
+    return EMB_OK;
+}
+
+// z += U Ceff (U^T r) for NV interleaved columns (three launches on the context stream; capturable)
+template <int NV>
+static int rc_coarse_apply(emb_ctx* c, const cx* r, cx* z) {
+    const int m = c->coarse_m;
+    if (m <= 0) return EMB_OK;
+    const int64_t n = c->Ns;
+    cx* t = c->rc_ct.p;
+    cx* cc = c->rc_ct.p + (size_t)c->rc_cap * NVMAX;
+    k_rc_dots<NV, false><<<dim3(RC_NP, m), VBLOCK, 0, c->stream>>>(n, c->rcU.p, r, c->rc_part.p); EMB_LAUNCH_CHECK(c);
+    k_rc_coef<NV><<<m, VBLOCK, 0, c->stream>>>(c->rc_part.p, t); EMB_LAUNCH_CHECK(c);
+    k_small_mm<<<1, 256, 0, c->stream>>>(m, NV, c->rc_ceff.p, t, cc); EMB_LAUNCH_CHECK(c);
+    k_rc_combine<NV><<<blocks_for(n, 256), 256, (size_t)m * NV * sizeof(cx), c->stream>>>(n, m, cc, c->rcU.p, z); EMB_LAUNCH_CHECK(c);
     return EMB_OK;
 }

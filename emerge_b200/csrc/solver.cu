@@ -25,6 +25,7 @@
 #include "krylov.cuh"
 #include "precond.cuh"
 #include "recycle.cuh"
+#include <type_traits>
 #include <vector>
 
 // ------------------------------------------------------------------------------------------------
@@ -76,6 +77,16 @@ static int norms2_host(emb_ctx* c, const cx* a, double* out) {
 // COCR on As D = RHS for NV columns in lockstep, D starts at 0.  Stops when every column has |r_k| <= stop_abs[k]
 // (or maxit).  Returns iterations in *its.
 // ------------------------------------------------------------------------------------------------
+// preconditioner of the inner iteration: the multilevel cycle, plus (experimental, off by default) the reduced basis as a
+// coarse space
+template <int NV, typename VX>
+static int precond_inner(emb_ctx* c, int pmode, const VX* r, VX* z) {
+    EMB_TRY((precond_apply<NV, VX>(c, pmode, r, z)));
+    if constexpr (std::is_same<VX, cx>::value)
+        if (c->coarse_basis && c->coarse_m > 0) EMB_TRY(rc_coarse_apply<NV>(c, r, z));
+    return EMB_OK;
+}
+
 template <int NV, typename VT, typename VX>
 struct CocrBody {
     emb_ctx* c;
@@ -87,7 +98,7 @@ struct CocrBody {
     int run(bool sample) {
         const int64_t n = c->Ns;
         if (sample) cudaEventRecord(c->evp0, c->stream);
-        EMB_TRY((precond_apply<NV, VX>(c, pmode, Ap, MAp)));
+        EMB_TRY((precond_inner<NV, VX>(c, pmode, Ap, MAp)));
         if (sample) cudaEventRecord(c->evp1, c->stream);
         k_gram<NV, VX><<<NPART, VBLOCK, 0, c->stream>>>(n, Ap, MAp, partA); EMB_LAUNCH_CHECK(c);
         k_bcocr_update<NV, VX><<<NPART, VBLOCK, 0, c->stream>>>(n, block, partA, sc, p, Ap, MAp, d, r, z, partR); EMB_LAUNCH_CHECK(c);
@@ -113,7 +124,7 @@ static int cocr(emb_ctx* c, int pmode, int block, const VT* As, const cx* rhs, V
     const unsigned vb = blocks_for(nn, 256);
     k_zero_v<VX><<<vb, 256, 0, c->stream>>>(nn, d); EMB_LAUNCH_CHECK(c);
     k_convert<cx, VX><<<vb, 256, 0, c->stream>>>(nn, rhs, B.r); EMB_LAUNCH_CHECK(c);
-    EMB_TRY((precond_apply<NV, VX>(c, pmode, B.r, B.z)));
+    EMB_TRY((precond_inner<NV, VX>(c, pmode, B.r, B.z)));
     k_convert<VX, VX><<<vb, 256, 0, c->stream>>>(nn, B.z, B.p); EMB_LAUNCH_CHECK(c);
     EMB_TRY((spmv_inner<NV, VT, VX>(c, As, B.z, B.Az))); ++*spmvs;
     k_convert<VX, VX><<<vb, 256, 0, c->stream>>>(nn, B.Az, B.Ap); EMB_LAUNCH_CHECK(c);
@@ -462,6 +473,8 @@ static int solve_device(emb_ctx* c, const emb_solve_opts* o, const cx* bs, cx* x
             bool blk = NV > 1 && c->block_krylov && !block_failed;
             for (int k = 0; k < NV; ++k)
                 if (!(bnorm[k] > 0) || !(rn[k] > 0)) blk = false;
+            if (c->coarse_basis && (c->coarse_version != c->rc_version || c->coarse_k0 != c->k0))
+                EMB_TRY(rc_coarse_update(c));          // experimental: coefficient map of the coarse space for this A(f)
             if (fp32) {
                 EMB_TRY(dev_alloc(c, c->As32, (size_t)c->nnz_s * 2));
                 cf* As = reinterpret_cast<cf*>(c->As32.p);
@@ -941,6 +954,18 @@ extern "C" int emb_solver_config(emb_ctx* c, int inner_fp32, int side_streams) {
 extern "C" int emb_solver_block(emb_ctx* c, int on) {
     if (!c) return EMB_ERR_ARG;
     c->block_krylov = on != 0;
+    return EMB_OK;
+}
+// EXPERIMENTAL: the reduced basis as an extra coarse space of the preconditioner (default off).  Takes effect for the
+// directions added after the call (emb_recycle_config clears the basis).
+extern "C" int emb_solver_coarse_basis(emb_ctx* c, int on) {
+    if (!c) return EMB_ERR_ARG;
+    c->coarse_basis = on != 0;
+    c->coarse_m = 0;
+    c->coarse_version = -1;
+    c->rc_terms.clear();
+    c->rc_terms.push_back(-1);          // forces rc_prepare to (re)allocate with the bookkeeping matrices
+    rc_clear(c);
     return EMB_OK;
 }
 extern "C" int64_t emb_graph_launch_count(const emb_ctx* c) { return c ? c->graph_launches : 0; }

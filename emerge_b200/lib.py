@@ -76,6 +76,7 @@ _SIGS = {
     "emb_solver_config": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "emb_graph_launch_count": (C.c_int64, [C.c_void_p]),
     "emb_solver_block": (C.c_int, [C.c_void_p, C.c_int]),
+    "emb_solver_coarse_basis": (C.c_int, [C.c_void_p, C.c_int]),
     "emb_solve_rhs": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(SolveOpts), C.c_void_p, C.POINTER(SolveInfo)]),
     "emb_recycle_config": (C.c_int, [C.c_void_p, C.c_int, C.c_double]),
     "emb_recycle_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
@@ -327,6 +328,10 @@ class Context:
         block: the ports of a lockstep group share one Krylov space (block COCR)"""
         self._check(self.lib.emb_solver_config(self.h, int(bool(inner_fp32)), int(bool(side_streams))))
         self._check(self.lib.emb_solver_block(self.h, int(bool(block))))
+
+    def solver_coarse_basis(self, on: bool):
+        """EXPERIMENTAL (default off): the reduced basis as an extra coarse space of the preconditioner; clears the basis."""
+        self._check(self.lib.emb_solver_coarse_basis(self.h, int(bool(on))))
 
     @property
     def graph_launches(self) -> int:

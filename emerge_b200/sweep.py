@@ -79,7 +79,8 @@ class FrequencySweep:
     nodes, tets, tris, edges, tri_to_tet, tet_to_field, tri_to_field).  bcs: PEC / RobinBC objects (ours or fem's)."""
 
     def __init__(self, tables, er, ur, bcs, device: int = 0, get_triangles=None, ctx: Context | None = None,
-                 recycle: int = 40, multilevel: bool = True, f_ref: float = 10e9, recycle_snap: float = 0.3):
+                 recycle: int = 40, multilevel: bool = True, f_ref: float = 10e9, recycle_snap: float = 0.3,
+                 coarse_basis: bool = False):
         self.t = tables
         self.er = np.ascontiguousarray(er, dtype=np.complex128)
         self.ur = np.ascontiguousarray(ur, dtype=np.complex128)
@@ -92,6 +93,9 @@ class FrequencySweep:
         self.f_ref = float(f_ref)           # frequency whose k0^2 shifts the nodal Helmholtz-type auxiliary operator
         self.recycle = int(recycle)        # directions kept from previous frequency points (0 = every point solved cold)
         self.recycle_snap = float(recycle_snap)   # points that iterate are solved to recycle_snap * rtol (they feed the basis)
+        import os
+        # EXPERIMENTAL: reduced basis as a coarse space of the preconditioner (also EMB_COARSE_BASIS=1)
+        self.coarse_basis = bool(coarse_basis) or os.environ.get("EMB_COARSE_BASIS", "0") == "1"
         self.lockstep = 4                   # ports solved together per lockstep group (1 = one port at a time)
         self.amg_coarse_size = 2500         # the AMG level at or below this size is inverted densely (one launch, L2-resident)
         self.solver_opts = dict(method="cocr", precond="multilevel", rtol=1e-8, maxit=200000, restart=50)
@@ -129,6 +133,8 @@ class FrequencySweep:
         ctx.set_dirichlet(pec)
         self.pec_ids = pec
         ctx.recycle_config(self.recycle, self.recycle_snap)
+        if self.coarse_basis and self.recycle:
+            ctx.solver_coarse_basis(True)
         if self.solver_opts.get("precond") == "multilevel":
             t1 = time.perf_counter()
             self._setup_aux_spaces()

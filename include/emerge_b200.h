@@ -149,6 +149,9 @@ int emb_solver_config(emb_ctx* ctx, int inner_fp32, int side_streams);
 /* 1 (default): the right-hand sides of an emb_solve_multi group share one Krylov space (block COCR); 0: independent
  * recurrences in lockstep.  Padded groups, empty right-hand sides and a breakdown of the block recurrence use 0. */
 int emb_solver_block(emb_ctx* ctx, int on);
+/* EXPERIMENTAL, default 0, not yet measured on the GPU: the reduced basis as an extra coarse space of the preconditioner,
+ * M^-1 += U Ceff U^T (csrc/recycle.cuh::rc_coarse_update).  Clears the basis. */
+int emb_solver_coarse_basis(emb_ctx* ctx, int on);
 /* iterations replayed from the captured CUDA graph so far (the kernels inside are counted by emb_launch_count) */
 int64_t emb_graph_launch_count(const emb_ctx* ctx);
 

@@ -19,6 +19,8 @@ def lsq():
     lib = C.CDLL(SO)
     lib.lsq_solve.argtypes = [C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 4
     lib.lsq_solve.restype = None
+    lib.herm_eig.argtypes = [C.c_int] + [C.c_void_p] * 3
+    lib.herm_eig.restype = None
 
     def solve(G, g):
         nq, m = G.shape
@@ -30,6 +32,7 @@ def lsq():
         res = np.zeros(nv)
         lib.lsq_solve(nq, m, nv, Gc.ctypes.data, gc.ctypes.data, y.ctypes.data, res.ctypes.data)
         return y, res
+    solve.lib = lib
     return solve
 
 
@@ -55,3 +58,20 @@ def test_rank_deficient_basis_is_harmless(lsq):
     assert np.all(np.isfinite(y))
     assert np.linalg.norm(g - G @ y) <= 1e-10 * np.linalg.norm(g)
     assert np.all(res <= 1e-10 * np.linalg.norm(g))
+
+
+@pytest.mark.parametrize("n", [1, 2, 7, 40])
+def test_hermitian_jacobi_eigensolver(lsq, n):
+    """Gram matrices of the reduced basis are Hermitian and nearly singular: eigenvalues over 16 decades."""
+    rng = np.random.default_rng(n)
+    Q, _ = np.linalg.qr(rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n)))
+    lam_true = np.logspace(0, -16, n) if n > 1 else np.array([2.5])
+    H = (Q * lam_true) @ Q.conj().T
+    H = 0.5 * (H + H.conj().T)
+    Hc = np.ascontiguousarray(H, dtype=np.complex128)
+    V = np.zeros((n, n), dtype=np.complex128)
+    lam = np.zeros(n)
+    lsq.lib.herm_eig(n, Hc.ctypes.data, V.ctypes.data, lam.ctypes.data)
+    assert np.allclose(V.conj().T @ V, np.eye(n), atol=1e-12)                       # unitary
+    assert np.allclose((V * lam) @ V.conj().T, H, atol=1e-13 * np.abs(H).max())     # reconstructs H
+    assert np.allclose(np.sort(lam)[::-1][: max(1, n // 2)], np.sort(lam_true)[::-1][: max(1, n // 2)], rtol=1e-8)
