@@ -330,3 +330,29 @@ def test_four_right_hand_sides_block_and_breakdown_fallback():
         assert np.linalg.norm(xs2[k] - ref[p.port_number]) <= 1e-8 * np.linalg.norm(ref[p.port_number])
         assert np.linalg.norm(xs2[k + 2] - xs2[k]) <= 1e-8 * np.linalg.norm(xs2[k])
     ctx.close()
+
+
+def test_coarse_basis_option_reduces_iterations():
+    """EXPERIMENTAL option (off by default): the reduced basis as an extra coarse space of the preconditioner.  Same
+    accuracy contract (FP64 residual on A(f)), fewer block iterations once the basis holds a few directions
+    (profiles/r1_coarse_basis_small_mesh.txt: 1,360 -> 1,000 on this mesh)."""
+    import bench
+    from emerge_b200.sweep import FrequencySweep, hierarchical_order
+    box, t, er, ur, bcs, L = bench.make_waveguide(12, 6, 24)
+    freqs = [bench.FREQS[i] for i in hierarchical_order(len(bench.FREQS))[:9]]
+    total, S = {}, {}
+    for on in (False, True):
+        sw = FrequencySweep(t, er, ur, bcs, coarse_basis=on)
+        sw.solver_opts.update(rtol=1e-8)
+        sw.f_ref = float(np.median(bench.FREQS))
+        sw.setup()
+        its, Ss = 0, []
+        for f in freqs:
+            Sf, st, _ = sw.solve_point(f)
+            assert all(s["converged"] and s["relres"] <= 1e-8 for s in st), st
+            its += st[0]["iters"]
+            Ss.append(Sf)
+        total[on], S[on] = its, np.array(Ss)
+        sw.ctx.close()
+    assert db_deg_close(S[True], S[False])
+    assert total[True] < 0.85 * total[False], total
