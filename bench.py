@@ -353,7 +353,7 @@ def run_gpu(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
                 "ms_per_step": ms_max / K, "higher_is_better": True,
                 "scaling": "strong" if K * world >= len(FREQS) - world else "weak", "vs_baseline": None,
-                "dtype": "f64/c128", "data": "synthetic", "config": workload_config(args),
+                "dtype": "f64/c128 (all arithmetic, vectors, A(f), residuals; the VALUES of the inner operator As are stored c64)", "data": "synthetic", "config": workload_config(args),
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "steps": e2e_K, "timed": "host wall clock around FrequencySweep() construction, setup() and the points"},
                 "gpu_launches": int(launches),
