@@ -178,7 +178,7 @@ def run_reference(args):
               f"SuperLU is serial); assembly ({setup_s:.1f}s) outside the steps as the reference caches E,B")
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64/c128", "data": "synthetic",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args),
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "host_cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -194,6 +194,7 @@ def workload_config(args):
             "solver": "reduced-basis recycling across points (affine A(f)) + block COCR over the ports (one Krylov space) on the "
                       "complex64 symmetric part (FP64 vectors and arithmetic) / FP64 defect correction on A(f), "
                       "additive multilevel (Hiptmair-Xu + smoothed-aggregation AMG) preconditioner, iteration replayed from a CUDA graph",
+            "precision": "complex128 arithmetic, vectors, A(f) and residuals; only the VALUES of the inner (preconditioned) operator As are stored complex64",
             "recycle_vectors": args.recycle, "snapshot_rtol_factor": args.snap, "order": "hierarchical (bisection) within each rank's frequency block",
             "l2_policy": "inputs larger than L2 (A(f) alone is 5.3 GB at 1M tets)", "parallelism": f"freq-block x{args.gpus}"}
 
@@ -353,7 +354,7 @@ def run_gpu(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
                 "ms_per_step": ms_max / K, "higher_is_better": True,
                 "scaling": "strong" if K * world >= len(FREQS) - world else "weak", "vs_baseline": None,
-                "dtype": "f64/c128 (all arithmetic, vectors, A(f), residuals; the VALUES of the inner operator As are stored c64)", "data": "synthetic", "config": workload_config(args),
+                "dtype": "f64", "data": "synthetic", "config": workload_config(args),
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "steps": e2e_K, "timed": "host wall clock around FrequencySweep() construction, setup() and the points"},
                 "gpu_launches": int(launches),
