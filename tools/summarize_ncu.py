@@ -17,7 +17,7 @@ FULL = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
 
 
 def short(name):
-    return re.sub(r"\(.*", "", name).replace("void ", "")
+    return re.sub(r"\(.*", "", name).replace("void ", "").replace(", ", ";")
 
 
 def launches(src, dst, title=""):
