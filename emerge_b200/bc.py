@@ -166,6 +166,28 @@ class LumpedPort(PortBC):
         return np.array([px * o, py * o, pz * o])
 
 
+class SampledField:
+    """Vector field known at a fixed set of points (3, n): the port-mode field of a boundary-mode analysis sampled at the
+    Dunavant points of the port triangles - the only points the hot path ever evaluates it at (assembler.py:63-98,
+    mth/sparam.py:72-139).  Lookup is by nearest stored point, so the local->global round trip of ModalPort.port_mode_3d
+    (fem/bc.py:469-480) lands on the same sample."""
+
+    def __init__(self, pts, values):
+        from scipy.spatial import cKDTree
+        self.pts = np.ascontiguousarray(np.asarray(pts, dtype=float).T)
+        self.values = np.asarray(values, dtype=np.complex128)
+        self.tree = cKDTree(self.pts)
+        span = np.ptp(self.pts, axis=0).max()
+        self.tol = 1e-6 * (span if span > 0 else 1.0)
+
+    def __call__(self, x, y, z):
+        q = np.stack([np.ravel(x), np.ravel(y), np.ravel(z)], axis=1)
+        d, i = self.tree.query(q)
+        if d.size and d.max() > self.tol:
+            raise ValueError("SampledField: evaluation point is not one of the stored sample points")
+        return self.values[:, i]
+
+
 class ModalPort(PortBC):
     """Port whose mode field comes from a boundary-mode analysis done upstream (fem/bc.py:329-494).
     `E_function(xg,yg,zg) -> (3,n)` is the mode field in global coordinates (already normalised)."""

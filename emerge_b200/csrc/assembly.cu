@@ -8,7 +8,15 @@
 //   er/ur  [9][nT] c128 (component-major: a warp of tets reads 32 consecutive values per component)
 //   cooK/cooM [nT_chunk][20][20] c128 scratch: row (t,i) is 320 contiguous bytes = 10 full sectors
 //   adj    dof -> ascending list of (tet*20+i)   rowptr/col canonical CSR   K,M [nnz] c128
-// Kernels
+// Kernels (default numeric phase, "fused": K and M values are written exactly once, no COO intermediate)
+//   k_tet_records: one thread per tetrahedron -> 896-B record (ned2_fused.cuh): everything an element-matrix row needs.
+//   k_asm_rows   : one warp per ENTITY (edge / face = rows e and e + nE + nTri, which share adjacency and column list);
+//                  walks the entity's tetrahedra in ascending order, lanes 0..19 = the 20 columns of the element-matrix
+//                  rows, evaluates the 2 x 20 K and M entries from the record (staged in shared memory, next record
+//                  prefetched into registers), accumulates into the row held in shared memory (fixed order => bitwise
+//                  reproducible), then streams the four finished rows to HBM.  Persistent grid, entities ordered by
+//                  their first tetrahedron so that records are re-read from L2.
+// Kernels (alternative numeric phase, emb_assemble_mode(1): element kernel -> COO scratch -> row reduction)
 //   tet_kernel   : one thread per tetrahedron, FP64, all indices compile-time (ned2_tet.cuh); algorithmic
 //                  traffic 16+96+288 B in, 12.8 KB out per tet.  Store-bound.
 //   reduce_rows  : one warp per CSR row; walks the row's adjacency in ascending tet order (fixed summation
@@ -16,6 +24,7 @@
 //                  locate the column by binary search in the row's sorted column list held in shared memory.
 #include "context.cuh"
 #include "ned2_tet.cuh"
+#include "ned2_fused.cuh"
 #include <cub/cub.cuh>
 
 // ------------------------------------------------------------------------------------------------
@@ -123,6 +132,13 @@ __global__ void k_segptr(const int* __restrict__ keys, int64_t n, int64_t N, int
     if (i == n - 1)
         for (int64_t d = (int64_t)k + 1; d <= N; ++d) ptr[d] = n;
 }
+
+__global__ void k_key_class(int n, const unsigned* __restrict__ key, int* __restrict__ cls) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) cls[i] = (int)(key[i] >> 28);
+}
+
+static int build_entity_order(emb_ctx* c);   // work list of the fused numeric phase (below)
 
 constexpr int CANDCAP = 2048;   // candidates per row held in shared memory: up to 102 tets around a dof
 constexpr int PWARPS = 4;
@@ -242,6 +258,10 @@ extern "C" int emb_symbolic(emb_ctx* c) {
     c->have_KM = c->have_dirichlet = c->have_A = false;
     c->asm_items.release();
     c->asm_chunk = 0;
+    {
+        PhaseTimer pt2(c, "symbolic_entities");
+        EMB_TRY(build_entity_order(c));
+    }
     return EMB_OK;
 }
 
@@ -488,6 +508,295 @@ __global__ void __launch_bounds__(RWARPS * 32) k_reduce_rows(int64_t N, int64_t 
         }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// numeric phase, fused: per-tet records + one warp per entity
+// ------------------------------------------------------------------------------------------------
+__device__ const ned2f::Tables d_ftab{};
+
+__global__ void __launch_bounds__(128) k_tet_records(int64_t nT, const int* __restrict__ tetc, const double* __restrict__ nodes,
+                                                     const cx* __restrict__ er, const cx* __restrict__ ur,
+                                                     ned2f::TetRec* __restrict__ recs) {
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= nT) return;
+    const int4 v = __ldg(reinterpret_cast<const int4*>(tetc) + t);
+    const int vi[4] = {v.x, v.y, v.z, v.w};
+    double p[4][3];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const double* q = nodes + (int64_t)vi[k] * 3;
+        p[k][0] = __ldg(q); p[k][1] = __ldg(q + 1); p[k][2] = __ldg(q + 2);
+    }
+    cx mu[3][3], Ms[3][3], Mm[3][3];
+    load_tensor(ur, nT, t, mu);
+    ned2::matinv_ref(mu, Ms);
+    load_tensor(er, nT, t, Mm);
+    ned2f::TetRec r;
+    ned2f::make_record(p, Ms, Mm, r);
+    cx* out = reinterpret_cast<cx*>(recs + t);
+    const cx* in = reinterpret_cast<const cx*>(&r);
+#pragma unroll
+    for (int k = 0; k < (int)(sizeof(ned2f::TetRec) / 32); ++k) st32(out + 2 * k, in[2 * k], in[2 * k + 1]);
+}
+
+// the mesh tables have the structure the fused kernel relies on: gid[t][c+10] = gid[t][c] + nE + nTri
+__global__ void k_check_pairs(int64_t nT, int nEF, const int* __restrict__ gid, int* __restrict__ bad) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= nT * 10) return;
+    const int64_t t = i / 10;
+    const int c = (int)(i % 10);
+    const int a = gid[t * 20 + c], b = gid[t * 20 + c + 10];
+    if (a >= nEF || b != a + nEF) atomicExch(bad, 1);
+}
+
+// processing class of an entity and its sort key (class << 28 | first tet)
+constexpr int ACLS0 = 32, ACLS1 = 80, ACLS2 = 160;   // row-length caps of the shared-memory classes; class 3 = global accumulators
+__global__ void k_entity_keys(int nEF, const int64_t* __restrict__ adjptr, const int* __restrict__ adj,
+                              const int64_t* __restrict__ rowptr, unsigned* __restrict__ key, int* __restrict__ val,
+                              int* __restrict__ bad) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nEF) return;
+    const int64_t a0 = adjptr[e];
+    const int deg = (int)(adjptr[e + 1] - a0);
+    const int len = (int)(rowptr[e + 1] - rowptr[e]);
+    const int len2 = (int)(rowptr[e + nEF + 1] - rowptr[e + nEF]);
+    const int deg2 = (int)(adjptr[e + nEF + 1] - adjptr[e + nEF]);
+    if (len2 != len || deg2 != deg) atomicExch(bad, 1);
+    int cls = len <= ACLS0 ? 0 : len <= ACLS1 ? 1 : len <= ACLS2 ? 2 : 3;
+    if (deg > 32) cls = 3;
+    const unsigned t0 = deg > 0 ? (unsigned)(adj[a0] / 20) : 0u;
+    key[e] = ((unsigned)cls << 28) | t0;
+    val[e] = e;
+}
+
+struct AsmWarpBufHdr {};
+template <int ROWCAP>
+struct AsmWarpBuf {
+    double2 acc[4][ROWCAP];      // K row a, K row b, M row a, M row b
+    double2 rec[56];             // the current tetrahedron's record
+    int cols[ROWCAP];
+};
+
+template <int ROWCAP, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) k_asm_rows(int64_t nitems, const int* __restrict__ items, int nEF,
+                                                         const int64_t* __restrict__ adjptr, const int* __restrict__ adj,
+                                                         const int* __restrict__ gid, const int64_t* __restrict__ rowptr,
+                                                         const int* __restrict__ col,
+                                                         const ned2f::TetRec* __restrict__ recs, cx* __restrict__ K,
+                                                         cx* __restrict__ M) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    ned2f::Tables* T = reinterpret_cast<ned2f::Tables*>(smem_raw);
+    {
+        const double* src = reinterpret_cast<const double*>(&d_ftab);
+        double* dst = reinterpret_cast<double*>(T);
+        for (int i = threadIdx.x; i < (int)(sizeof(ned2f::Tables) / sizeof(double)); i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    constexpr size_t TOFF = (sizeof(ned2f::Tables) + 15) / 16 * 16;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    AsmWarpBuf<ROWCAP>& wb = reinterpret_cast<AsmWarpBuf<ROWCAP>*>(smem_raw + TOFF)[warp];
+    const bool colLane = lane < 20;
+    const ned2f::FnTab fj = T->f[colLane ? lane : 0];      // this lane's column function (registers)
+    const cx* recD = reinterpret_cast<const cx*>(wb.rec);
+    const cx* recG = recD + 36;
+    const double* recLen = reinterpret_cast<const double*>(recD + 52);
+
+    for (int64_t w = blockIdx.x * (int64_t)WARPS + warp; w < nitems; w += (int64_t)gridDim.x * WARPS) {
+        const int e = __ldg(items + w);
+        const int64_t a0 = adjptr[e];
+        const int deg = (int)(adjptr[e + 1] - a0);
+        const int64_t p0 = rowptr[e], p1 = rowptr[e + nEF];
+        const int len = (int)(rowptr[e + 1] - p0);
+        for (int k = lane; k < len; k += 32) {
+            wb.cols[k] = __ldg(col + p0 + k);
+            const double2 z = make_double2(0.0, 0.0);
+            wb.acc[0][k] = z; wb.acc[1][k] = z; wb.acc[2][k] = z; wb.acc[3][k] = z;
+        }
+        const int myadj = lane < deg ? __ldg(adj + a0 + lane) : 0;
+        // prefetch the first record (56 x 16 B: every lane one piece, lanes 0..23 a second one) and the tet's dof ids
+        double2 r0 = make_double2(0, 0), r1 = r0;
+        int cj = 0;
+        if (deg > 0) {
+            const int t = __shfl_sync(0xffffffffu, myadj, 0) / 20;
+            const double2* rp = reinterpret_cast<const double2*>(recs + t);
+            r0 = __ldg(rp + lane);
+            if (lane < 24) r1 = __ldg(rp + 32 + lane);
+            if (colLane) cj = __ldg(gid + (int64_t)t * 20 + lane);
+        }
+        for (int n = 0; n < deg; ++n) {
+            const int ic = __shfl_sync(0xffffffffu, myadj, n) % 20;      // canonical local row of the entity's first function
+            wb.rec[lane] = r0;
+            if (lane < 24) wb.rec[32 + lane] = r1;
+            const int c = cj;
+            __syncwarp();
+            if (n + 1 < deg) {
+                const int t = __shfl_sync(0xffffffffu, myadj, n + 1) / 20;
+                const double2* rp = reinterpret_cast<const double2*>(recs + t);
+                r0 = __ldg(rp + lane);
+                if (lane < 24) r1 = __ldg(rp + 32 + lane);
+                if (colLane) cj = __ldg(gid + (int64_t)t * 20 + lane);
+            }
+            if (colLane) {
+                // position of column c in the row's sorted column list (present by construction)
+                int lo = 0, m = len;
+                while (m > 1) {
+                    const int half = m >> 1;
+                    lo = (wb.cols[lo + half] <= c) ? lo + half : lo;
+                    m -= half;
+                }
+                cx Ka, Kb, Ma, Mb;
+                ned2f::row_pair_entry(T->pt[ic], T->f[ic], T->f[ic + 10], fj, T->mc[ic][lane], T->mc[ic + 10][lane], recD, recG,
+                                      recLen, Ka, Kb, Ma, Mb);
+                double2 v;
+                v = wb.acc[0][lo]; v.x += Ka.re; v.y += Ka.im; wb.acc[0][lo] = v;
+                v = wb.acc[1][lo]; v.x += Kb.re; v.y += Kb.im; wb.acc[1][lo] = v;
+                v = wb.acc[2][lo]; v.x += Ma.re; v.y += Ma.im; wb.acc[2][lo] = v;
+                v = wb.acc[3][lo]; v.x += Mb.re; v.y += Mb.im; wb.acc[3][lo] = v;
+            }
+            __syncwarp();
+        }
+        double2* Ka = reinterpret_cast<double2*>(K + p0);
+        double2* Kb = reinterpret_cast<double2*>(K + p1);
+        double2* Ma = reinterpret_cast<double2*>(M + p0);
+        double2* Mb = reinterpret_cast<double2*>(M + p1);
+        for (int k = lane; k < len; k += 32) {
+            Ka[k] = wb.acc[0][k]; Kb[k] = wb.acc[1][k]; Ma[k] = wb.acc[2][k]; Mb[k] = wb.acc[3][k];
+        }
+        __syncwarp();
+    }
+}
+
+// entities whose rows do not fit the shared-memory classes (or with more than 32 tetrahedra): accumulators in K / M
+// themselves, column search in global memory.  Same summation order.
+__global__ void __launch_bounds__(128) k_asm_rows_big(int64_t nitems, const int* __restrict__ items, int nEF,
+                                                      const int64_t* __restrict__ adjptr, const int* __restrict__ adj,
+                                                      const int* __restrict__ gid, const int64_t* __restrict__ rowptr,
+                                                      const int* __restrict__ col, const ned2f::TetRec* __restrict__ recs,
+                                                      cx* __restrict__ K, cx* __restrict__ M) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t w = blockIdx.x * (int64_t)4 + warp;
+    if (w >= nitems) return;
+    const ned2f::Tables& T = d_ftab;
+    const int e = items[w];
+    const int64_t a0 = adjptr[e], a1 = adjptr[e + 1];
+    const int64_t p0 = rowptr[e], p1 = rowptr[e + nEF];
+    const int len = (int)(rowptr[e + 1] - p0);
+    for (int k = lane; k < len; k += 32) {
+        st16(K + p0 + k, cx{0, 0}); st16(K + p1 + k, cx{0, 0});
+        st16(M + p0 + k, cx{0, 0}); st16(M + p1 + k, cx{0, 0});
+    }
+    __syncwarp();
+    for (int64_t ai = a0; ai < a1; ++ai) {
+        const int a = adj[ai];
+        const int t = a / 20, ic = a % 20;
+        if (lane < 20) {
+            const int c = gid[(int64_t)t * 20 + lane];
+            int lo = 0, m = len;
+            while (m > 1) {
+                const int half = m >> 1;
+                lo = (col[p0 + lo + half] <= c) ? lo + half : lo;
+                m -= half;
+            }
+            const cx* D = reinterpret_cast<const cx*>(recs + t);
+            cx Ka, Kb, Ma, Mb;
+            ned2f::row_pair_entry(T.pt[ic], T.f[ic], T.f[ic + 10], T.f[lane], T.mc[ic][lane], T.mc[ic + 10][lane], D, D + 36,
+                                  reinterpret_cast<const double*>(D + 52), Ka, Kb, Ma, Mb);
+            st16(K + p0 + lo, K[p0 + lo] + Ka); st16(K + p1 + lo, K[p1 + lo] + Kb);
+            st16(M + p0 + lo, M[p0 + lo] + Ma); st16(M + p1 + lo, M[p1 + lo] + Mb);
+        }
+        __syncwarp();
+    }
+}
+
+template <int ROWCAP, int WARPS>
+static int launch_asm_rows(emb_ctx* c, int64_t i0, int64_t i1, const ned2f::TetRec* recs) {
+    if (i1 <= i0) return EMB_OK;
+    constexpr size_t TOFF = (sizeof(ned2f::Tables) + 15) / 16 * 16;
+    const size_t smem = TOFF + (size_t)WARPS * sizeof(AsmWarpBuf<ROWCAP>);
+    auto kern = k_asm_rows<ROWCAP, WARPS>;
+    EMB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0, nsm = 0;
+    EMB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem));
+    EMB_CUDA(c, cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->device));
+    if (per_sm < 1) per_sm = 1;
+    int64_t grid = (int64_t)nsm * per_sm;
+    const int64_t need = (i1 - i0 + WARPS - 1) / WARPS;
+    if (grid > need) grid = need;
+    kern<<<(unsigned)grid, WARPS * 32, smem, c->stream>>>(i1 - i0, c->asm_ent.p + i0, (int)(c->nE + c->nTri), c->adjptr.p,
+                                                        c->adj.p, c->gid.p, c->rowptr.p, c->col.p, recs, c->K.p, c->M.p);
+    EMB_LAUNCH_CHECK(c);
+    return EMB_OK;
+}
+
+// one-time (per pattern) work list of the fused numeric phase
+static int build_entity_order(emb_ctx* c) {
+    const int nEF = (int)(c->nE + c->nTri);
+    c->asm_pairs_ok = false;
+    DevBuf<int> bad, val;
+    DevBuf<unsigned> key, key2;
+    DevBuf<char> tmp;
+    EMB_TRY(dev_alloc(c, bad, 1));
+    EMB_CUDA(c, cudaMemsetAsync(bad.p, 0, sizeof(int), c->stream));
+    k_check_pairs<<<blocks_for(c->nT * 10, 256), 256, 0, c->stream>>>(c->nT, nEF, c->gid.p, bad.p);
+    EMB_LAUNCH_CHECK(c);
+    EMB_TRY(dev_alloc(c, key, (size_t)nEF));
+    EMB_TRY(dev_alloc(c, key2, (size_t)nEF));
+    EMB_TRY(dev_alloc(c, val, (size_t)nEF));
+    EMB_TRY(dev_alloc(c, c->asm_ent, (size_t)nEF));
+    k_entity_keys<<<blocks_for(nEF, 256), 256, 0, c->stream>>>(nEF, c->adjptr.p, c->adj.p, c->rowptr.p, key.p, val.p, bad.p);
+    EMB_LAUNCH_CHECK(c);
+    size_t tb = 0;
+    EMB_CUDA(c, cub::DeviceRadixSort::SortPairs(nullptr, tb, key.p, key2.p, val.p, c->asm_ent.p, nEF, 0, 30, c->stream));
+    EMB_TRY(dev_alloc(c, tmp, tb));
+    EMB_CUDA(c, cub::DeviceRadixSort::SortPairs(tmp.p, tb, key.p, key2.p, val.p, c->asm_ent.p, nEF, 0, 30, c->stream));
+    c->launches += 4;
+    // class boundaries: first position whose key is >= cls << 28
+    DevBuf<int64_t> ptr;
+    DevBuf<int> cls;
+    EMB_TRY(dev_alloc(c, ptr, 5));
+    EMB_TRY(dev_alloc(c, cls, (size_t)nEF));
+    k_key_class<<<blocks_for(nEF, 256), 256, 0, c->stream>>>(nEF, key2.p, cls.p);
+    EMB_LAUNCH_CHECK(c);
+    k_segptr<<<blocks_for(nEF, 256), 256, 0, c->stream>>>(cls.p, nEF, 4, ptr.p);
+    EMB_LAUNCH_CHECK(c);
+    int hbad = 0;
+    EMB_CUDA(c, cudaMemcpyAsync(&hbad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    EMB_CUDA(c, cudaMemcpyAsync(c->asm_cls_ptr, ptr.p, 5 * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+    EMB_CUDA(c, cudaStreamSynchronize(c->stream));
+    bad.release(); val.release(); key.release(); key2.release(); tmp.release(); ptr.release(); cls.release();
+    c->asm_pairs_ok = hbad == 0;
+    return EMB_OK;
+}
+
+static int assemble_fused(emb_ctx* c) {
+    DevBuf<ned2f::TetRec> recs;
+    EMB_TRY(dev_alloc(c, recs, (size_t)c->nT));
+    {
+        PhaseTimer pt(c, "tet_kernel");
+        k_tet_records<<<blocks_for(c->nT, 128), 128, 0, c->stream>>>(c->nT, c->tetc.p, c->nodes.p, c->er.p, c->ur.p, recs.p);
+        EMB_LAUNCH_CHECK(c);
+    }
+    const double ms_rec = c->ms["tet_kernel"];
+    {
+        PhaseTimer pt(c, "reduce");
+        const int64_t* cp = c->asm_cls_ptr;
+        EMB_TRY((launch_asm_rows<ACLS0, 8>(c, cp[0], cp[1], recs.p)));
+        EMB_TRY((launch_asm_rows<ACLS1, 8>(c, cp[1], cp[2], recs.p)));
+        EMB_TRY((launch_asm_rows<ACLS2, 8>(c, cp[2], cp[3], recs.p)));
+        if (cp[4] > cp[3]) {
+            k_asm_rows_big<<<blocks_for(cp[4] - cp[3], 4), 128, 0, c->stream>>>(cp[4] - cp[3], c->asm_ent.p + cp[3],
+                                                                              (int)(c->nE + c->nTri), c->adjptr.p, c->adj.p,
+                                                                              c->gid.p, c->rowptr.p, c->col.p, recs.p, c->K.p,
+                                                                              c->M.p);
+            EMB_LAUNCH_CHECK(c);
+        }
+    }
+    c->ms["assemble"] = ms_rec + c->ms["reduce"];
+    EMB_CUDA(c, cudaStreamSynchronize(c->stream));
+    recs.release();
+    return EMB_OK;
+}
+
 // ---- chunk work lists ------------------------------------------------------------------------------------
 // The numeric phase runs chunk by chunk over the tetrahedra so that the COO scratch of one chunk (12.8 KB per tet)
 // stays resident in the 126 MB L2 between the element kernel that writes it and the reduction that reads it: HBM then
@@ -568,6 +877,12 @@ static int build_chunk_items(emb_ctx* c, int64_t CT) {
     return EMB_OK;
 }
 
+extern "C" int emb_assemble_mode(emb_ctx* c, int mode) {
+    if (!c || mode < 0 || mode > 1) return EMB_ERR_ARG;
+    c->asm_mode = mode;
+    return EMB_OK;
+}
+
 extern "C" int emb_assemble_config(emb_ctx* c, int64_t chunk_tets, int persist_l2) {
     if (!c || chunk_tets < 0) return EMB_ERR_ARG;
     c->asm_chunk_req = chunk_tets;
@@ -582,6 +897,14 @@ extern "C" int emb_assemble_KM(emb_ctx* c) {
     }
     EMB_TRY(dev_alloc(c, c->K, (size_t)c->nnz));
     EMB_TRY(dev_alloc(c, c->M, (size_t)c->nnz));
+    int mode = c->asm_mode;
+    if (const char* e = getenv("EMB_ASM_MODE")) mode = atoi(e);
+    if (mode == 0 && c->asm_pairs_ok) {
+        EMB_TRY(assemble_fused(c));
+        c->have_KM = true;
+        c->have_A = false;
+        return EMB_OK;
+    }
     // chunk size in tets: 0 (default) = single pass, the COO scratch makes one round trip through HBM.  Chunks of one
     // wave of element-kernel blocks (32 tets x 148 SMs = 60 MB of COO, pinned in L2) were measured on a B200 and LOSE
     // (1M tets: 16.6 ms vs 14.4 ms, profiles/r1_asm_chunk_sweep.json): one block per SM leaves the element kernel

@@ -111,6 +111,12 @@ struct emb_ctx {
     bool asm_persist = true;
     DevBuf<unsigned long long> asm_items;
     std::vector<int64_t> asm_chunk_ptr;
+    // fused numeric phase (assembly.cu, k_asm_rows): entities (edge / face = the pair of rows e, e + nE + nTri) grouped
+    // by row-length class and, inside a class, ordered by their first tetrahedron (L2 locality of the per-tet records)
+    int asm_mode = 0;                   // 0: fused (default), 1: element kernel -> COO scratch -> row reduction
+    bool asm_pairs_ok = false;          // the mesh tables have the pair structure the fused kernel relies on
+    DevBuf<int> asm_ent;                // [nE + nTri] entity ids in processing order
+    int64_t asm_cls_ptr[5] = {0, 0, 0, 0, 0};
 
     // solve space
     int64_t Ns = 0, nnz_s = 0;

@@ -210,6 +210,9 @@ static int rc_prepare(emb_ctx* c) {
     EMB_TRY(dev_alloc(c, c->rcQ, (size_t)c->rc_qcap * c->Ns));
     EMB_TRY(dev_alloc(c, c->rc_part, (size_t)c->rc_qcap * RC_NP * NVMAX + (size_t)(3 * c->rc_qcap + c->rc_cap + 8) * NVMAX));
     EMB_TRY(dev_alloc(c, c->rc_tmp, (size_t)c->Ns));
+    // the coefficient area is copied to the host as a whole (rc_insert) while only the first nq entries are written:
+    // defined contents keep compute-sanitizer --tool initcheck clean
+    EMB_CUDA(c, cudaMemsetAsync(c->rc_part.p, 0, c->rc_part.n * sizeof(cx), c->stream));
     c->rc_R.assign((size_t)T, std::vector<zc>((size_t)c->rc_qcap * c->rc_cap, zc(0.0, 0.0)));
     c->rc_uscale.assign((size_t)c->rc_cap, 1.0);
     if (c->coarse_basis) {

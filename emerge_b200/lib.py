@@ -43,6 +43,7 @@ _SIGS = {
     "emb_symbolic": (C.c_int, [C.c_void_p]),
     "emb_assemble_KM": (C.c_int, [C.c_void_p]),
     "emb_assemble_config": (C.c_int, [C.c_void_p, C.c_int64, C.c_int]),
+    "emb_assemble_mode": (C.c_int, [C.c_void_p, C.c_int]),
     "emb_n_field": (C.c_int64, [C.c_void_p]),
     "emb_nnz": (C.c_int64, [C.c_void_p]),
     "emb_get_csr": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -215,6 +216,11 @@ class Context:
 
     def assemble_KM(self):
         self._check(self.lib.emb_assemble_KM(self.h))
+
+    def assemble_mode(self, mode: str = "fused"):
+        """numeric-phase algorithm: "fused" (default: per-tet records + one warp per edge / face, rows written once) or
+        "coo" (element kernel -> COO scratch -> deterministic row reduction)."""
+        self._check(self.lib.emb_assemble_mode(self.h, {"fused": 0, "coo": 1}[mode]))
 
     def assemble_config(self, chunk_tets: int = 0, persist_l2: bool = True):
         """tets per chunk of the numeric phase (0: default = single pass) and L2 pinning of a chunk's COO scratch."""

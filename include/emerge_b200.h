@@ -57,7 +57,14 @@ int emb_symbolic(emb_ctx* ctx);
 /* Numeric phase: element kernel + deterministic reduction -> E (curl-curl) and B (mass) values.
  * Replaces tet_mass_stiffness_matrices(field, er, ur) (optimized_assembly.py:43-64). */
 int emb_assemble_KM(emb_ctx* ctx);
-/* Numeric-phase tuning (no reference counterpart): tets per chunk of the element kernel -> reduction pipeline
+/* Numeric-phase algorithm (no reference counterpart; results agree to rounding, each is bitwise reproducible):
+ *   0 (default) fused: per-tetrahedron records + one warp per edge / face that evaluates its element-matrix rows and
+ *     writes the finished CSR rows once (no COO intermediate); needs the Nedelec2 table structure
+ *     tet_to_field[c+10] = tet_to_field[c] + nE + nTri (fem/elements/nedelec2.py:46-50), else mode 1 is used;
+ *   1 element kernel -> COO scratch [nT][20][20] -> deterministic row reduction (the reference's own two-step shape,
+ *     optimized_assembly.py:76-116 + coo.tocsr()). */
+int emb_assemble_mode(emb_ctx* ctx, int mode);
+/* Mode-1 tuning: tets per chunk of the element kernel -> reduction pipeline
  * (0 = default = single pass through HBM; e.g. 32 x SM count keeps the COO scratch of a chunk resident in L2)
  * and whether the scratch is pinned in L2 with a persisting access-policy window.  Results are bitwise independent
  * of both settings. */

@@ -1,8 +1,10 @@
-"""Drives the UNMODIFIED reference (/root/reference) on synthetic meshes.  TEST INFRASTRUCTURE.
+"""Drives the UNMODIFIED reference on synthetic meshes.  TEST INFRASTRUCTURE.
 
-Used only in the build container (the reference does not exist on the GPU box) to (a) generate
-the golden fixtures under tests/golden/ (tests/golden/make_golden.py) and (b) validate the numpy
-restatement in oracle/.  Recipe: SURVEY.md Appendix C.  Nothing in emerge_b200/ imports this.
+Used (a) in the build container to generate the golden fixtures under tests/golden/ (tests/golden/make_golden.py) and
+to validate the numpy restatement in oracle/, and (b) on the GPU box by the `-m gpu` drop-in tests, which run the
+reference's own frequency_domain() with and without emerge_b200.dropin.install().  The reference package is taken from
+oracle/_ref (verbatim copy made by oracle/make_ref.py, git-ignored, travels to the GPU box) or, in the build container
+only, from /root/reference.  Recipe: SURVEY.md Appendix C.  Nothing in emerge_b200/ imports this.
 """
 from __future__ import annotations
 
@@ -11,11 +13,14 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REPO = os.path.dirname(os.path.dirname(HERE))
-REFERENCE = "/root/reference"
+_REF_LOCAL = os.path.join(os.path.dirname(HERE), "_ref")
+REFERENCE = _REF_LOCAL if os.path.isdir(os.path.join(_REF_LOCAL, "fem")) else "/root/reference"
 
 
 def setup_paths():
-    os.environ.setdefault("NUMBA_CACHE_DIR", "/tmp/numba_cache")
+    # the numba cache travels with oracle/_ref so that the GPU box does not have to JIT the whole package again
+    cache = os.path.join(_REF_LOCAL, "numba_cache") if REFERENCE == _REF_LOCAL else "/tmp/numba_cache"
+    os.environ.setdefault("NUMBA_CACHE_DIR", cache)
     for p in (REFERENCE, os.path.join(HERE, "stubs"), REPO):
         if p not in sys.path:
             sys.path.insert(0, p)

@@ -49,7 +49,7 @@ def _csr_dict(prefix, M):
             prefix + "_data": M.data.copy()}
 
 
-def _sweep(fem, phys, mesh, freqs, full, out):
+def _sweep(fem, phys, mesh, freqs, full, out, keep_x=()):
     """Run frequency_domain() and collect outputs; `full` stores matrices/fields, else only checks."""
     from fem.elements.nedelec2 import Nedelec2
     phys.frequencies = list(freqs)
@@ -88,7 +88,7 @@ def _sweep(fem, phys, mesh, freqs, full, out):
             x = ds._fields[p.port_number]
             r = K[np.ix_(solve_ids, solve_ids)] @ x[solve_ids] - pv[p.port_number][solve_ids]
             out[f"xres_{i}_p{p.port_number}"] = np.linalg.norm(r) / np.linalg.norm(pv[p.port_number][solve_ids])
-            if full:
+            if full or i in keep_x:
                 out[f"x_{i}_p{p.port_number}"] = x
         if full and i == 0:
             K.eliminate_zeros()
@@ -204,8 +204,96 @@ def case_abc_lumped():
     return out
 
 
+def microstrip_box(nx=12, ny=6, nz=8):
+    """Shielded microstrip look-alike of demo1_stepped_imp_filter.py (SURVEY App. C.7 ii): 12 x 6 x 20 mm PEC box, lossy
+    substrate (2 cells high), PEC strip 4 mm wide on the substrate top over the whole length, ports on z=0 / z=L."""
+    a, b, L = 12e-3, 6e-3, 20e-3
+    hy = b / ny
+    ysub = -b / 2 + 2 * hy
+
+    def vol(x, y, z):
+        return np.where(y < ysub, 1, 2)
+
+    def strip(x, y, z):
+        return (np.abs(y - ysub) < 1e-9) & (np.abs(x) < 2e-3)
+
+    return box_mesh(nx, ny, nz, a, b, L, jitter=0.0, seed=0, vol_fn=vol, internal_faces=[(7, (0, 1, 0), strip)])
+
+
+def modal_physics(box, tand=0.01):
+    H.setup_paths()
+    import fem
+    fem, phys, mesh = H.build_physics(box, {1: fem.Material(er=2.2, tand=tand), 2: fem.AIR}, pec_extra_tags=(7,))
+    a, b, L = box.dims
+    ports = []
+    for num, (tag, z) in enumerate([(5, 0.0), (6, L)], start=1):
+        cs = fem.CoordinateSystem(fem.XAX, fem.YAX, fem.ZAX, origin=np.array([0.0, 0.0, z]))
+        ports.append(fem.bc.ModalPort(fem.FaceSelection([tag]), num, cs=cs))
+    phys.assign(*ports)
+    # ParallelRoutine (the reference's SuperLU routine) carries no eigen-solver; the reference's default routine uses
+    # SolverLAPACK for modal_analysis(direct=True) (fem/solver.py:578-583)
+    from fem.solver import SolverLAPACK
+    phys.solveroutine.direct_eig_solver = SolverLAPACK()
+    return fem, phys, mesh, ports
+
+
+def case_modal_microstrip():
+    """Two TEM ModalPorts whose mode comes from the reference's own modal_analysis (emfreq3d.py:201-364,
+    bc.py:329-494): BASELINE configs 1-2 (demo1 / demo2 use ModalPort).  The mode field is stored sampled at the
+    Dunavant-4 points of the port triangles (the only points the hot path evaluates it at)."""
+    from emerge_b200.sweep import dunavant4
+    box = microstrip_box()
+    fem, phys, mesh, ports = modal_physics(box)
+    freqs = [1e9, 2e9, 3e9]
+    phys.frequencies = list(freqs)
+    for p in ports:
+        phys.modal_analysis(p, 1, direct=True, TEM=True, freq=freqs[0])
+    out = dict(kind="modal_microstrip", dims=np.array(box.dims), face_tris=box.face_tris.astype(np.int32),
+               face_tag=box.face_tag)
+    _sweep(fem, phys, mesh, freqs, False, out, keep_x=(0,))     # matrices as checksums; fields of the first point
+    for k in [k for k in out if k.startswith("K_dot_v_") and k != "K_dot_v_0"]:
+        del out[k]
+    DP = dunavant4()
+    for p in ports:
+        ids = mesh.get_triangles(p.tags)
+        P = mesh.nodes[:, mesh.tris[:, ids]]                        # (3 xyz, 3 vert, ntri)
+        pts = np.einsum("kq,xkt->xqt", DP[1:4], P).reshape(3, -1)
+        n = p.port_number
+        mode = p.get_mode()
+        out[f"mode_pts_p{n}"] = pts
+        out[f"mode_E_p{n}"] = np.asarray(p.port_mode_3d_global(pts[0], pts[1], pts[2], 1.0), dtype=np.complex128)
+        out[f"mode_scalars_p{n}"] = np.array([mode.beta, mode.k0, float(bool(mode.TEM)), mode.freq, mode.norm_factor,
+                                              complex(mode.Z0).real, complex(mode.Z0).imag], dtype=np.float64)
+        out[f"mode_type_p{n}"] = str(mode.modetype)
+    return out
+
+
+def case_lossy_slabs():
+    """Dielectric-loaded waveguide (look-alike of BASELINE config 5 at fixture size): eps_r = 9.8(1 - 1e-4j) slabs periodic
+    in z, vacuum elsewhere, RectangularWaveguide ports.  Pins the solver on a complex (lossy) mass matrix."""
+    a, b = WR90
+    L = 36e-3
+    nz = 18
+    hz = L / nz
+
+    def vol(x, y, z):
+        return np.where((np.floor(z / hz).astype(int) % 6) >= 4, 2, 1)      # 2 of every 6 cell layers are ceramic
+
+    box = box_mesh(6, 3, nz, a, b, L, jitter=0.08, seed=5, vol_fn=vol)
+    H.setup_paths()
+    import fem
+    cer = fem.Material(_fer=_mat_fn([9.8 * (1 - 1e-4j)] * 3))
+    fem, phys, mesh = H.build_physics(box, {1: fem.VACUUM, 2: cer})
+    H.rect_waveguide_ports(fem, phys, box)
+    out = dict(kind="rectwg", dims=np.array(box.dims), face_tris=box.face_tris.astype(np.int32), face_tag=box.face_tag)
+    _sweep(fem, phys, mesh, [8e9, 9.3e9, 10.1e9, 12e9], False, out)
+    for k in [k for k in out if k.startswith(("K_dot_v_", "bvec_")) and not k.startswith(("K_dot_v_0", "bvec_0"))]:
+        del out[k]
+    return out
+
+
 CASES = dict(wg_tiny=case_wg_tiny, wg_materials=case_wg_materials, wg_medium=case_wg_medium,
-             abc_lumped=case_abc_lumped)
+             abc_lumped=case_abc_lumped, modal_microstrip=case_modal_microstrip, lossy_slabs=case_lossy_slabs)
 
 if __name__ == "__main__":
     names = sys.argv[1:] or list(CASES)

@@ -114,6 +114,53 @@ def test_Af_rhs_solution_sparams(name):
     ctx.close()
 
 
+@pytest.mark.parametrize("name", ["modal_microstrip", "lossy_slabs"])
+def test_modal_port_and_lossy_dielectric_fixtures(name):
+    """BASELINE configs 1-2 use ModalPort (mode field from the reference's modal_analysis, bc.py:329-494), config 5 lossy
+    ceramic slabs: right-hand sides, fields of the first point and S-parameters of every point against the reference."""
+    from emerge_b200.sweep import FrequencySweep
+    g, t = load_golden(name)
+    sw = FrequencySweep(t, g["er"], g["ur"], golden_bcs(g, t))
+    sw.solver_opts.update(rtol=1e-10)
+    sw.setup()
+    assert np.array_equal(sw.ctx.solve_ids(), g["solve_ids"])
+    k0 = 2 * np.pi * g["freqs"][0] / 299792458
+    for p in sw.ports:
+        xy = sw.points[id(p)]
+        U = p.get_Uinc(xy[0].ravel(), xy[1].ravel(), k0).reshape(3, 6, -1)
+        b = sw.ctx.surface_set_U(sw.sid[id(p)], U, want_full=True)
+        ref = g[f"bvec_0_p{p.port_number}"]
+        assert np.abs(b - ref).max() <= 1e-11 * np.abs(ref).max()
+    res = sw.run(list(g["freqs"]), keep_fields=True)
+    assert all(st["converged"] and st["relres"] <= 1e-10 for st in res.stats)
+    for p in sw.ports:
+        key = f"x_0_p{p.port_number}"
+        if key in g:
+            x = res.fields[(0, p.port_number)]
+            assert np.linalg.norm(x - g[key]) <= 1e-7 * np.linalg.norm(g[key])
+    assert db_deg_close(res.S, g["S"]), (res.S, g["S"])
+    sw.ctx.close()
+
+
+@pytest.mark.parametrize("name", ["wg_tiny", "wg_materials", "abc_lumped", "wg_medium", "modal_microstrip", "lossy_slabs"])
+def test_sparams_at_shipped_tolerance(name):
+    """Every S-parity check at the SHIPPED defaults (rtol 1e-8, reduced-basis recycling on, bisection order): points the
+    reduced basis accepts without iterating are accepted at exactly this tolerance and must still meet 1e-3 dB / 0.1 deg.
+    The sweep is refined to 9 points between the fixture's end points so that accepted points occur; the fixture's own
+    frequencies are a subset."""
+    from emerge_b200.sweep import FrequencySweep
+    g, t = load_golden(name)
+    sw = FrequencySweep(t, g["er"], g["ur"], golden_bcs(g, t))
+    assert sw.solver_opts["rtol"] == 1e-8 and sw.recycle == 40
+    fx = np.asarray(g["freqs"], dtype=float)
+    dense = np.unique(np.concatenate([fx, np.linspace(fx.min(), fx.max(), 9)]))
+    res = sw.run(list(dense))
+    assert all(st["converged"] and st["relres"] <= 1e-8 for st in res.stats)
+    idx = [int(np.argmin(np.abs(dense - f))) for f in fx]
+    assert db_deg_close(res.S[idx], g["S"]), (res.S[idx], g["S"])
+    sw.ctx.close()
+
+
 @pytest.mark.parametrize("method,precond", [("gmres", "jacobi"), ("bicgstab", "block"), ("cocr", "jacobi"),
                                             ("cocr", "block"), ("gmres", "multilevel")])
 def test_other_solvers_agree(method, precond):
@@ -281,8 +328,63 @@ def test_inner_precision_and_stream_schedule():
         assert np.array_equal(out["serial"].fields[key].view(np.float64), x.view(np.float64))
 
 
+@pytest.mark.parametrize("name", ["wg_tiny", "wg_materials", "abc_lumped", "wg_medium"])
+def test_fused_and_coo_numeric_phases_agree(gpu_ctx, name):
+    """The default fused numeric phase (records + one warp per edge / face) against the element-kernel -> COO -> row
+    reduction path: same pattern, values equal to rounding, each path bitwise reproducible."""
+    g, t = load_golden(name)
+    gpu_ctx.assemble_mode("fused")
+    _assembled(gpu_ctx, g, t)
+    _, _, E = gpu_ctx.get_csr(0, pattern=False)
+    _, _, B = gpu_ctx.get_csr(1, pattern=False)
+    gpu_ctx.assemble_KM()
+    _, _, E1 = gpu_ctx.get_csr(0, pattern=False)
+    _, _, B1 = gpu_ctx.get_csr(1, pattern=False)
+    assert np.array_equal(E.view(np.float64), E1.view(np.float64))
+    assert np.array_equal(B.view(np.float64), B1.view(np.float64))
+    gpu_ctx.assemble_mode("coo")
+    gpu_ctx.assemble_KM()
+    _, _, E2 = gpu_ctx.get_csr(0, pattern=False)
+    _, _, B2 = gpu_ctx.get_csr(1, pattern=False)
+    gpu_ctx.assemble_mode("fused")
+    assert np.abs(E - E2).max() <= 1e-13 * np.abs(E2).max()
+    assert np.abs(B - B2).max() <= 1e-13 * np.abs(B2).max()
+
+
+def test_fused_numeric_phase_long_rows_and_high_degree(gpu_ctx):
+    """A fan of 40 tetrahedra around one edge: that edge's rows (482 entries, 40 tetrahedra) take the global-accumulator
+    path of the fused numeric phase, rows of 80..160 entries the large shared-memory class.  Checked against the COO path."""
+    from emerge_b200.synthmesh import mesh_tables
+    n = 40
+    ang = 2 * np.pi * np.arange(n) / n
+    nodes = np.concatenate([[[0, 0, 0], [0, 0, 1.0]], np.stack([np.cos(ang), np.sin(ang), 0.5 + 0.1 * np.cos(3 * ang)], axis=1)])
+    tets = np.array([[0, 1, 2 + k, 2 + (k + 1) % n] for k in range(n)], dtype=np.int64)
+    p = nodes[tets]
+    det = np.einsum("ij,ij->i", np.cross(p[:, 1] - p[:, 0], p[:, 2] - p[:, 0]), p[:, 3] - p[:, 0])
+    tets[det < 0] = tets[det < 0][:, [0, 2, 1, 3]]
+    t = mesh_tables(nodes * 1e-2, tets)
+    rng = np.random.default_rng(11)
+    er = np.repeat(np.eye(3, dtype=complex)[:, :, None], n, axis=2) * (2 + rng.random(n)) * (1 - 0.01j)
+    ur = np.repeat(np.eye(3, dtype=complex)[:, :, None], n, axis=2)
+    ctx = gpu_ctx
+    ctx.upload_mesh(t.nodes, t.tets, t.tris, t.tet_to_field, t.tri_to_field, t.edges.shape[1])
+    ctx.upload_materials(er, ur)
+    ctx.symbolic()
+    out = {}
+    for mode in ("fused", "coo"):
+        ctx.assemble_mode(mode)
+        ctx.assemble_KM()
+        out[mode] = (ctx.get_csr(0, pattern=False)[2], ctx.get_csr(1, pattern=False)[2])
+    ctx.assemble_mode("fused")
+    indptr = ctx.get_csr(0, values=False)[0]
+    assert np.diff(indptr).max() > 160
+    for a, b in zip(out["fused"], out["coo"]):
+        assert np.abs(a - b).max() <= 1e-13 * np.abs(b).max()
+
+
 def test_chunked_numeric_phase_is_bitwise_identical(gpu_ctx):
     g, t = load_golden("wg_medium")
+    gpu_ctx.assemble_mode("coo")
     gpu_ctx.assemble_config(0, True)
     _assembled(gpu_ctx, g, t)
     _, _, E = gpu_ctx.get_csr(0, pattern=False)
@@ -295,6 +397,7 @@ def test_chunked_numeric_phase_is_bitwise_identical(gpu_ctx):
         assert np.array_equal(E.view(np.float64), E2.view(np.float64))
         assert np.array_equal(B.view(np.float64), B2.view(np.float64))
     gpu_ctx.assemble_config(0, True)
+    gpu_ctx.assemble_mode("fused")
 
 
 def test_four_right_hand_sides_block_and_breakdown_fallback():

@@ -16,18 +16,18 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 def hostlib():
     src = os.path.join(HERE, "hostcheck", "ned2_host.cpp")
     so = os.path.join(HERE, "hostcheck", "ned2_host.so")
-    hdr = os.path.join(HERE, "..", "emerge_b200", "csrc", "ned2_tet.cuh")
-    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+    hdrs = [os.path.join(HERE, "..", "emerge_b200", "csrc", h) for h in ("ned2_tet.cuh", "ned2_fused.cuh")]
+    if not os.path.exists(so) or os.path.getmtime(so) < max([os.path.getmtime(src)] + [os.path.getmtime(h) for h in hdrs]):
         subprocess.check_call(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-o", so, src])
     return ctypes.CDLL(so)
 
 
-def _run(lib, p, vid, ur, er):
+def _run(lib, p, vid, ur, er, fn="ned2_host_element"):
     K = np.zeros((20, 20), complex)
     M = np.zeros((20, 20), complex)
     arrs = [np.ascontiguousarray(p, dtype=float), np.ascontiguousarray(vid, dtype=np.int64),
             np.ascontiguousarray(ur, dtype=complex), np.ascontiguousarray(er, dtype=complex), K, M]
-    lib.ned2_host_element(*[a.ctypes.data_as(ctypes.c_void_p) for a in arrs])
+    getattr(lib, fn)(*[a.ctypes.data_as(ctypes.c_void_p) for a in arrs])
     return K, M
 
 
@@ -53,3 +53,26 @@ def test_invariance_under_vertex_relabelling(hostlib):
     assert np.abs(K0 - K0.T).max() < 1e-13 * np.abs(K0).max()
     # rank 11 = 20 - 9 gradients
     assert np.linalg.matrix_rank(K0, tol=1e-9 * np.abs(K0).max()) == 11
+
+
+def test_fused_row_form_matches_templates_and_reference(hostlib):
+    """ned2_fused.cuh (table-driven rows of the fused assembly kernel) against the compile-time templates and against the
+    reference's element matrices, including full non-symmetric tensors (mirror rule, index typo, matinv quirk)."""
+    g, t = load_golden("wg_tiny")
+    rng = np.random.default_rng(5)
+    cases = [(t.nodes[:, t.tets[:, it]].T, t.tets[:, it], g["ur"][:, :, it], g["er"][:, :, it], g["elemE"][it], g["elemB"][it])
+             for it in range(6)]
+    cases += [(t.nodes[:, t.tets[:, it]].T, t.tets[:, it], g["full_ur"][it], g["full_er"][it], g["full_elemE"][it],
+               g["full_elemB"][it]) for it in range(4)]
+    for p, vid, ur, er, Eref, Bref in cases:
+        for perm in (np.arange(4), rng.permutation(4), rng.permutation(4)):
+            # relabelled global ids exercise every canonical ordering; the reference-order result must not change
+            ids = np.array([10, 20, 30, 40])[perm] if perm is not None else vid
+            K0, M0 = _run(hostlib, p, ids, ur, er)
+            for fn in ("ned2_host_fused", "ned2_host_fused_pairs"):
+                K1, M1 = _run(hostlib, p, ids, ur, er, fn=fn)
+                assert np.abs(K1 - K0).max() <= 1e-14 * np.abs(K0).max()
+                assert np.abs(M1 - M0).max() <= 1e-14 * np.abs(M0).max()
+        K1, M1 = _run(hostlib, p, vid, ur, er, fn="ned2_host_fused_pairs")
+        assert np.abs(K1 - Eref).max() <= 1e-12 * np.abs(Eref).max()
+        assert np.abs(M1 - Bref).max() <= 1e-12 * np.abs(Bref).max()

@@ -37,6 +37,16 @@ def golden_bcs(g, t):
         lp = B.LumpedPort(tag_tris(g, t, 8), 1, cs, w, h, (0, 0, 1), Z0=z0)
         abc = B.AbsorbingBoundary(np.concatenate([tag_tris(g, t, k) for k in (1, 2, 3, 4, 6)]))
         return [pec, lp, abc]
+    if kind == "modal_microstrip":
+        a, b, L = g["dims"]
+        pec = B.PEC(np.concatenate([tag_tris(g, t, k) for k in (1, 2, 3, 4, 7)]))
+        ports = []
+        for n, (tag, z) in enumerate([(5, 0.0), (6, L)], start=1):
+            beta, k0m, tem, fm = g[f"mode_scalars_p{n}"][:4]
+            ports.append(B.ModalPort(tag_tris(g, t, tag), n, B.CoordSys(origin=(0, 0, z)),
+                                     B.SampledField(g[f"mode_pts_p{n}"], g[f"mode_E_p{n}"]), beta, k0m, TEM=bool(tem),
+                                     freq_mode=fm, modetype=str(g[f"mode_type_p{n}"])))
+        return [pec] + ports
     raise ValueError(kind)
 
 
