@@ -13,8 +13,15 @@ region, as in the reference (assembler.py:324-331 caches E, B).
     API with HOST buffers - mesh + material upload (pinned), symbolic phase, auxiliary-space setup, assembly, every
     point, and the D2H copy of both solved fields per point into pinned memory - all inside the timed region.  The e2e
     leg runs first (after a kernel warm-up on a small mesh), the resident leg second, each on its own sweep object.
-  * N GPUs: contiguous frequency blocks, one process per GPU, K/M replicated; NCCL moves recycled directions between
-    ranks after the seeding round and gathers the S-parameters.
+  * N GPUs: one process per GPU, K/M replicated; the points that build the reduced basis (global bisection order) are
+    dealt out round-robin in seed rounds, NCCL moves the directions they add between the ranks, then every rank fills
+    its contiguous frequency block; the S-parameters are summed over the ranks (emerge_b200/distributed.py).
+  * With --steps K smaller than the job, `value` / `e2e` time the first K points of every rank (the expensive cold ones)
+    and a second pass times the WHOLE 201-point job: the `full_sweep` block (resident and end-to-end) is the number to
+    read strong scaling from.  `roofline` is the dominant kernel (operator application of the block COCR iteration);
+    `roofline_assembly` (K+M numeric phase, 9,722 algorithmic B/tet) and `roofline_spmv_c128` (single right-hand side
+    complex128 A(f) x, 20 nnz + 36 N B) are BASELINE's other two metrics.  `same_size_as_cpu_sample` runs this GPU path
+    on exactly the mesh and points the CPU baseline / reference arm uses: the only like-for-like ratio.
 
 `--impl reference` times the reference's CPU path for the same metric on the host cores: the reference is pure
 Python + numba + SciPy and does not exist on the GPU box, so its CPU port (oracle/) runs it: closed-form element
@@ -179,10 +186,25 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args),
+            "config": reference_config(args, t),
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "host_cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+def reference_config(args, t):
+    """what the reference arm actually ran: NOT the GPU arm's mesh (the direct solve is infeasible there)"""
+    nx, ny, nz = args.ref_cells
+    gx, gy, gz = args.cells
+    return {"workload": f"SCALED-DOWN sample of BASELINE config 4: synthetic WR-90 rectangular waveguide, {nx}x{ny}x{nz} cells x 6 "
+                        f"Kuhn tets = {6*nx*ny*nz} tets (the GPU arm runs {6*gx*gy*gz} tets), 2 RectangularWaveguide ports + PEC "
+                        f"walls, points of the 201-point sweep 8-12 GHz; step = one frequency point (K(f) + RCM + SuperLU "
+                        f"factorisation + 2 port solves), K/M assembly once per job",
+            "cells": [nx, ny, nz], "ref_cells": [nx, ny, nz], "tets": int(t.tets.shape[1]), "n_field": int(t.n_field),
+            "gpu_arm_cells": [gx, gy, gz], "workload_scaled_down": True, "same_config_as_gpu_arm": False,
+            "solver": "RCM + SuperLU (scipy.sparse.linalg.splu), the reference's ParallelRoutine (fem/solver.py:535-566)",
+            "note": "ratios against the GPU arm's 1M-tet line are NOT like-for-like; use the GPU line's "
+                    "same_size_as_cpu_sample block (same mesh, same points)"}
 
 
 def workload_config(args):
@@ -195,43 +217,82 @@ def workload_config(args):
                       "complex64 symmetric part (FP64 vectors and arithmetic) / FP64 defect correction on A(f), "
                       "additive multilevel (Hiptmair-Xu + smoothed-aggregation AMG) preconditioner, iteration replayed from a CUDA graph",
             "precision": "complex128 arithmetic, vectors, A(f) and residuals; only the VALUES of the inner (preconditioned) operator As are stored complex64",
-            "recycle_vectors": args.recycle, "snapshot_rtol_factor": args.snap, "order": "hierarchical (bisection) within each rank's frequency block",
+            "recycle_vectors": args.recycle, "snapshot_rtol_factor": args.snap, "coarse_basis_preconditioner": not args.no_coarse_basis,
+            "order": "seed rounds over the global bisection order (round-robin over the ranks), then bisection order within each rank's frequency block",
             "l2_policy": "inputs larger than L2 (A(f) alone is 5.3 GB at 1M tets)", "parallelism": f"freq-block x{args.gpus}"}
 
 
-def run_e2e(args, torch, dist, rank, world, local, t, er, ur, bcs, K, barrier):
+def e2e_pass(args, torch, dist, rank, world, local, t, er, ur, bcs, max_points, barrier):
     """End-to-end leg: a fresh sweep object through the host API, host buffers in pinned memory; everything from the
     construction of the sweep object to the last solved field on the host is inside the timed region."""
     from emerge_b200.sweep import FrequencySweep
     from emerge_b200.distributed import ShardedSweep
-    e2e_K = 0 if args.e2e_steps < 0 else (K if args.e2e_steps == 0 else min(args.e2e_steps, K))
-    if e2e_K <= 0:
-        return 0, float("nan"), 0, 0, {}
     N = t.n_field
     er_p = torch.from_numpy(er).pin_memory().numpy()
     ur_p = torch.from_numpy(ur).pin_memory().numpy()
     outs = {p.port_number: torch.empty(N, dtype=torch.complex128).pin_memory().numpy() for p in bcs[1:]}
     barrier()
     t0 = time.perf_counter()
-    sw2 = FrequencySweep(t, er_p, ur_p, bcs, device=local, recycle=args.recycle, recycle_snap=args.snap, coarse_basis=args.coarse_basis)
+    sw2 = FrequencySweep(t, er_p, ur_p, bcs, device=local, recycle=args.recycle, recycle_snap=args.snap,
+                         coarse_basis=not args.no_coarse_basis)
     sw2.solver_opts.update(rtol=args.rtol, precond=args.precond)
     sw2.f_ref = float(np.median(FREQS))
     sw2.setup()
     sh2 = ShardedSweep(sw2, FREQS, rank, world, dist=dist, device=local)
     for p in sw2.ports:
         p.active = False
-    sh2.run(sh2.order()[:e2e_K], out_bufs=outs)
+    res = sh2.run(max_points=max_points, out_bufs=outs, raise_on_fail=False)
     torch.cuda.synchronize()
-    ms_e2e = (time.perf_counter() - t0) * 1e3     # host wall clock: the region contains host work (setup) by design
+    ms = (time.perf_counter() - t0) * 1e3     # host wall clock: the region contains host work (setup) by design
     barrier()
+    npts = max(1, len(res.solved))
     mesh_bytes = (np.asarray(t.nodes).nbytes + np.asarray(t.tets).nbytes + np.asarray(t.tris).nbytes
                   + np.asarray(t.tet_to_field).nbytes + np.asarray(t.tri_to_field).nbytes)
     per_step_h2d = sum(18 * 16 * sw2.ntri[id(p)] for p in sw2.ports)
-    h2d = (er_p.nbytes + ur_p.nbytes + mesh_bytes) / e2e_K + per_step_h2d
+    h2d = (er_p.nbytes + ur_p.nbytes + mesh_bytes) / npts + per_step_h2d
     d2h = sum(o.nbytes for o in outs.values()) + sum(2 * 3 * 16 * sw2._sp[id(p)]["pts"].shape[1] * len(sw2.ports) for p in sw2.ports)
-    timings = dict(sw2.timings)
+    out = dict(ms=ms, points=len(res.solved), h2d=h2d, d2h=d2h, setup=dict(sw2.timings), split=dict(sh2.timings),
+               not_converged=res.not_converged, max_relres=res.max_relres)
     sw2.ctx.close()
-    return e2e_K, ms_e2e, h2d, d2h, timings
+    return out
+
+
+def resident_pass(args, sw, dist, rank, world, local, max_points, barrier, clock=True):
+    """Resident leg: mesh, materials, patterns and auxiliary spaces already on the device; K/M assembly + the points,
+    from an EMPTY reduced basis, timed with CUDA events on the library's stream."""
+    from emerge_b200.distributed import ShardedSweep
+    ctx = sw.ctx
+    sh = ShardedSweep(sw, FREQS, rank, world, dist=dist, device=local)
+    for p in sw.ports:
+        p.active = False
+    ctx.recycle_config(args.recycle, args.snap)      # forget everything earlier passes left in the basis
+    ctx.spmv_sampled()
+    ctx.precond_sampled()
+    barrier()
+    l0, g0 = ctx.launches, ctx.graph_launches
+    cs = ClockSampler(local) if clock else None
+    if cs:
+        cs.__enter__()
+    ctx.timer_start()
+    ctx.assemble_KM()
+    res = sh.run(max_points=max_points, raise_on_fail=False)
+    ms = ctx.timer_stop()
+    if cs:
+        cs.__exit__()
+    barrier()
+    spmv_ms, spmv_cnt = ctx.spmv_sampled()
+    prec_ms, prec_cnt = ctx.precond_sampled()
+    return dict(ms=ms, res=res, S=sh.gather_S(res), launches=ctx.launches - l0, graph_iters=ctx.graph_launches - g0,
+                spmv_ms=spmv_ms, spmv_cnt=spmv_cnt, prec_ms=prec_ms, prec_cnt=prec_cnt, split=dict(sh.timings),
+                asm={"tet_kernel_ms": ctx.last_ms("tet_kernel"), "reduce_ms": ctx.last_ms("reduce")},
+                clocks=cs.summary() if cs else None, rinfo=ctx.recycle_info())
+
+
+def _iter_stats(stats):
+    by_freq = {}
+    for s_ in stats:                  # the ports of a lockstep group share one iteration count
+        by_freq[s_["freq"]] = max(by_freq.get(s_["freq"], 0), s_["iters"])
+    return by_freq
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -246,32 +307,58 @@ def run_gpu(args):
         torch.cuda.set_device(local)
         import datetime
         # a short collective timeout: a mismatched collective must not hold the GPU box for the default 10 minutes
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=180))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=240))
     from emerge_b200.sweep import FrequencySweep
-    from emerge_b200.distributed import ShardedSweep
     nx, ny, nz = args.cells
     t0 = time.perf_counter()
     box, t, er, ur, bcs, L = make_waveguide(nx, ny, nz)
     host_mesh_s = time.perf_counter() - t0
+    dev = f"cuda:{local}"
+
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    from emerge_b200.distributed import block_of
-    K = len(block_of(len(FREQS), rank, world))
-    K = K if args.steps <= 0 else min(args.steps, K)
-    # kernel warm-up on a small mesh (CUDA context, module load, every kernel of the path once), then the end-to-end leg
-    # FIRST: it has to see the process as a user's script would (a device heap that just released tens of GB makes
+    def allsum(v):
+        x = torch.tensor([float(v)], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(x, op=dist.ReduceOp.SUM)
+        return float(x.item())
+
+    def allmax(v):
+        x = torch.tensor([float(v)], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(x, op=dist.ReduceOp.MAX)
+        return float(x.item())
+
+    def allgather_obj(o):
+        if dist is None:
+            return [o]
+        out = [None] * world
+        dist.all_gather_object(out, o)
+        return out
+
+    nf = len(FREQS)
+    partial = 0 < args.steps < -(-nf // world)             # --steps K smaller than a rank's share of the job
+    K = args.steps if partial else None
+    do_full = (not partial) or (not args.no_full_sweep)
+    do_e2e = args.e2e_steps >= 0
+    # kernel warm-up on a small mesh (CUDA context, module load, every kernel of the path once), then the end-to-end legs
+    # FIRST: they have to see the process as a user's script would (a device heap that just released tens of GB makes
     # cudaMalloc ten times slower, which is what the e2e leg measured when it ran after the resident leg)
     wbox, wt, wer, wur, wbcs, _ = make_waveguide(8, 4, 12)
-    wsw = FrequencySweep(wt, wer, wur, wbcs, device=local, recycle=args.recycle, recycle_snap=args.snap, coarse_basis=args.coarse_basis)
+    wsw = FrequencySweep(wt, wer, wur, wbcs, device=local, recycle=args.recycle, recycle_snap=args.snap,
+                         coarse_basis=not args.no_coarse_basis)
     wsw.solver_opts.update(rtol=args.rtol, precond=args.precond)
-    wsw.run(list(FREQS[:: max(1, len(FREQS) // max(1, args.warmup))][:max(3, args.warmup)]), raise_on_fail=False)
+    wsw.run(list(FREQS[:: max(1, nf // max(1, args.warmup))][:max(3, args.warmup)]), raise_on_fail=False)
     wsw.ctx.close()
     del wsw
-    e2e_K, ms_e2e, h2d, d2h, e2e_timings = run_e2e(args, torch, dist, rank, world, local, t, er, ur, bcs, K, barrier)
-    sw = FrequencySweep(t, er, ur, bcs, device=local, recycle=args.recycle, recycle_snap=args.snap, coarse_basis=args.coarse_basis)
+    e2e_k = e2e_pass(args, torch, dist, rank, world, local, t, er, ur, bcs, K, barrier) if (do_e2e and partial) else None
+    e2e_full = e2e_pass(args, torch, dist, rank, world, local, t, er, ur, bcs, None, barrier) if (do_e2e and do_full) else None
+
+    sw = FrequencySweep(t, er, ur, bcs, device=local, recycle=args.recycle, recycle_snap=args.snap,
+                        coarse_basis=not args.no_coarse_basis)
     sw.solver_opts.update(rtol=args.rtol, precond=args.precond)
     sw.f_ref = float(np.median(FREQS))
     t0 = time.perf_counter()
@@ -279,133 +366,154 @@ def run_gpu(args):
     setup_s = time.perf_counter() - t0
     ctx = sw.ctx
     nnz_s, Ns, N = int(ctx.lib.emb_csr_nnz(ctx.h, 2)), ctx.n_solve, ctx.n_field
-    sh = ShardedSweep(sw, FREQS, rank, world, dist=dist, device=local)
-    block = sh.block                                       # indices of this rank's contiguous frequency block
-    order = sh.order()[:K]                                 # processing order (global indices)
-
-    # warm-up: W points, then forget what they left in the recycled subspace
+    nnz_full = int(ctx.lib.emb_nnz(ctx.h))
+    # warm-up: W points on the full-size operator (graph capture, allocations), forgotten by the reset in resident_pass
     for p in sw.ports:
         p.active = False
-    for i in sh.order()[:args.warmup]:
+    from emerge_b200.sweep import hierarchical_order
+    for i in hierarchical_order(nf)[:args.warmup]:
         sw.solve_point(FREQS[i], raise_on_fail=False)
-    ctx.recycle_config(args.recycle, args.snap)
-    ctx.spmv_sampled()
-    ctx.precond_sampled()
-    barrier()
-    l0 = ctx.launches
-    with ClockSampler(local) as cs:
-        ctx.timer_start()
-        ctx.assemble_KM()
-        res = sh.run(order)
-        ms = ctx.timer_stop()
-    barrier()
-    launches = ctx.launches - l0
-    spmv_ms, spmv_cnt = ctx.spmv_sampled()
-    prec_ms, prec_cnt = ctx.precond_sampled()
-    graph_iters = ctx.graph_launches
-    nv = min(4, len(sw.ports)) if sw.lockstep > 1 else 1
-    nv = 4 if nv == 3 else nv
-    asm = {"tet_kernel_ms": ctx.last_ms("tet_kernel"), "reduce_ms": ctx.last_ms("reduce")}
-    rinfo = ctx.recycle_info()
-    # max over ranks
-    tm = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=f"cuda:{local}")
-    S_mine = np.array([res.S[i] for i in order])
-    if dist is not None:
-        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-        # NCCL all_gather needs equal shapes: blocks differ by one point when world does not divide the sweep
-        kmax = torch.tensor([len(order)], device=f"cuda:{local}")
-        dist.all_reduce(kmax, op=dist.ReduceOp.MAX)
-        pad = np.zeros((int(kmax.item()),) + S_mine.shape[1:], dtype=np.complex128)
-        pad[:len(order)] = S_mine
-        St = torch.view_as_real(torch.tensor(pad, device=f"cuda:{local}")).contiguous()
-        cnt = torch.tensor([len(order)], device=f"cuda:{local}")
-        cnts = [torch.empty_like(cnt) for _ in range(world)]
-        dist.all_gather(cnts, cnt)
-        total_points = int(sum(int(n.item()) for n in cnts))
-        gath = [torch.empty_like(St) for _ in range(world)]
-        dist.all_gather(gath, St)                      # NCCL: S-parameter blocks of every rank
-        S_all = np.concatenate([torch.view_as_complex(g).cpu().numpy()[:int(n.item())] for g, n in zip(gath, cnts)])
-    else:
-        S_all = S_mine
-        total_points = len(order)
-    ms_max, ms_e2e_max = float(tm[0]), float(tm[1])
+    main = resident_pass(args, sw, dist, rank, world, local, K, barrier)
+    full = resident_pass(args, sw, dist, rank, world, local, None, barrier, clock=False) if (partial and do_full) else main
+    # BASELINE's third metric: the single right-hand side complex128 operator application A(f) x, timed alone
+    sw.assemble_frequency(float(FREQS[nf // 2]))
+    spmv128_ms = ctx.spmv_bench(20, nv=1, fp32=False)
+
+    def job(p, e):
+        """whole-job numbers of a pass: points of all ranks / slowest rank's time"""
+        pts = allsum(len(p["res"].solved))
+        ms = allmax(p["ms"])
+        out = {"points": int(pts), "value": pts / (ms / 1e3), "ms": ms}
+        if e is not None:
+            epts, ems = allsum(e["points"]), allmax(e["ms"])
+            out.update(e2e_value=epts / (ems / 1e3), e2e_ms=ems, e2e_points=int(epts))
+        return out
+    jm = job(main, e2e_k if partial else e2e_full)
+    jf = job(full, e2e_full) if full is not main else jm
+    splits = allgather_obj({"rank": rank, **{k: round(v, 4) if isinstance(v, float) else v for k, v in full["split"].items()},
+                            "points": len(full["res"].solved), "device_ms": full["ms"],
+                            "iterating_points": sum(1 for v in _iter_stats(full["res"].stats).values() if v > 0),
+                            "iterations": int(sum(_iter_stats(full["res"].stats).values())),
+                            "host_setup_s": e2e_full["setup"].get("aux_setup_s") if e2e_full else None,
+                            "e2e_ms": e2e_full["ms"] if e2e_full else None})
+    stats_all = [s_ for part in allgather_obj(main["res"].stats) for s_ in part]
+    launches_total = allsum(main["launches"])
     if rank == 0:
-        value = total_points / (ms_max / 1e3)       # points solved by all ranks / slowest rank's device time
-        e2e_points = total_points if e2e_K == K else world * e2e_K
-        e2e_val = e2e_points / (ms_e2e_max / 1e3) if e2e_K > 0 else None
         peak, peak_src = peaks()
+        nv = min(4, len(sw.ports)) if sw.lockstep > 1 else 1
+        nv = 4 if nv == 3 else nv
         # dominant kernel: the operator application of the block COCR iteration, k_bspmv<NV, complex64 values> (2x2
         # block-CSR): per nonzero 8 B value + 1 B (one 4 B column per 2x2 block), per row 4 B rowptr (8 B per block-row) +
         # NV x (16 B x + 16 B y)   (DESIGN.md section 4)
         spmv_bytes = 9 * nnz_s + (4 + 32 * nv) * Ns + 8
+        spmv_ms = main["spmv_ms"]
         achieved = spmv_bytes / (spmv_ms * 1e-3) / 1e9 if spmv_ms > 0 else None
-        traffic = None
+        traffic = asm_traffic = None
         tp = os.path.join(REPO, "profiles", "spmv_traffic.json")
         if os.path.exists(tp) and os.path.getsize(tp) > 0 and (nx, ny, nz) == (44, 20, 190):
             tj = json.load(open(tp))
             if tj.get("nv") == nv and tj.get("values") == "complex64":
                 traffic = tj.get("dram_bytes_per_launch")
-        S21 = np.abs(S_all[:, 1, 0])
-        by_freq = {}
-        for s_ in res.stats:                  # the ports of a lockstep group share one iteration count
-            by_freq[s_["freq"]] = max(by_freq.get(s_["freq"], 0), s_["iters"])
+            asm_traffic = tj.get("assembly_dram_bytes")
+        S_all = main["S"]
+        solved = sorted({int(np.argmin(np.abs(FREQS - s_["freq"]))) for s_ in stats_all})
+        S21 = np.abs(S_all[solved, 1, 0])
+        by_freq = _iter_stats(stats_all)
         iters = list(by_freq.values())
-        iterating = sorted(f for f, n in by_freq.items() if n > 0)
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
-                "ms_per_step": ms_max / K, "higher_is_better": True,
-                "scaling": "strong" if K * world >= len(FREQS) - world else "weak", "vs_baseline": None,
+        asm = main["asm"]
+        asm_ms = asm["tet_kernel_ms"] + asm["reduce_ms"]
+        nT = int(t.tets.shape[1])
+        asm_bytes = 9722 * nT
+        spmv128_bytes = 20 * nnz_s + 36 * Ns + 4
+        line = {"metric": METRIC, "value": jm["value"], "unit": UNIT, "n_gpus": world,
+                "steps": args.steps if partial else jm["points"], "warmup": args.warmup,
+                "ms_per_step": jm["ms"] / (args.steps if partial else max(1, -(-jm["points"] // world))), "higher_is_better": True,
+                "scaling": "weak" if partial else "strong", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": workload_config(args),
-                "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                        "steps": e2e_K, "timed": "host wall clock around FrequencySweep() construction, setup() and the points"},
-                "gpu_launches": int(launches),
+                "e2e": {"value": jm.get("e2e_value"), "unit": UNIT,
+                        "h2d_bytes_per_step": int((e2e_k or e2e_full)["h2d"]) if (e2e_k or e2e_full) else None,
+                        "d2h_bytes_per_step": int((e2e_k or e2e_full)["d2h"]) if (e2e_k or e2e_full) else None,
+                        "points": jm.get("e2e_points"),
+                        "timed": "host wall clock around FrequencySweep() construction, setup() and the points"},
+                "full_sweep": {"points": jf["points"], "value": jf["value"], "ms": jf["ms"], "e2e_value": jf.get("e2e_value"),
+                               "e2e_ms": jf.get("e2e_ms"), "unit": UNIT, "scaling": "strong",
+                               "what": "the whole 201-point job (assembly + every point from an empty basis) on all ranks: "
+                                       "points / slowest rank's time; this is the strong-scaling number",
+                               "per_rank": splits},
+                "gpu_launches": int(launches_total),
                 "roofline": {"kernel": f"k_bspmv<NV={nv}, complex64 values> (2x2 block-CSR operator application of the "
                                        f"block COCR iteration on {nv} interleaved right-hand sides)",
                              "bound": "hbm", "achieved": achieved,
                              "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                              "frac": (achieved / peak) if achieved else None, "traffic": traffic,
-                             "algorithmic_bytes_per_launch": spmv_bytes, "avg_launch_ms": spmv_ms, "sampled_launches": spmv_cnt},
-                "assembly": {**asm, "Mtet_per_s": t.tets.shape[1] / ((asm["tet_kernel_ms"] + asm["reduce_ms"]) * 1e3),
-                             "form_A_ms": ctx.last_ms("form_A")},
+                             "algorithmic_bytes_per_launch": spmv_bytes, "avg_launch_ms": spmv_ms, "sampled_launches": main["spmv_cnt"]},
+                "roofline_assembly": {"kernel": "k_tet_records + k_asm_rows (fused numeric phase: K and M values written once)",
+                                      "bound": "hbm", "achieved": asm_bytes / (asm_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                      "frac": asm_bytes / (asm_ms * 1e-3) / 1e9 / peak, "traffic": asm_traffic,
+                                      "algorithmic_bytes_per_launch": asm_bytes, "avg_launch_ms": asm_ms,
+                                      "Mtet_per_s": nT / (asm_ms * 1e3), **asm},
+                "roofline_spmv_c128": {"kernel": "k_bspmv<NV=1, complex128 values> (A(f) x, one right-hand side: SURVEY 8d)",
+                                       "bound": "hbm", "achieved": spmv128_bytes / (spmv128_ms * 1e-3) / 1e9, "peak": peak,
+                                       "unit": "GB/s", "frac": spmv128_bytes / (spmv128_ms * 1e-3) / 1e9 / peak,
+                                       "algorithmic_bytes_per_launch": spmv128_bytes, "avg_launch_ms": spmv128_ms},
+                "assembly": {**asm, "Mtet_per_s": nT / (asm_ms * 1e3), "form_A_ms": ctx.last_ms("form_A")},
                 "solver": {"lockstep_iterations_total": int(np.sum(iters)), "lockstep_width": nv,
-                           "points_that_iterated": len(iterating),
-                           "points": K, "max_iters_per_point": int(max(iters)), "rtol": args.rtol,
-                           "precond_apply_ms": prec_ms, "precond_samples": prec_cnt, "graph_replayed_iterations": int(graph_iters),
-                           "max_relres": float(max(s["relres"] for s in res.stats)),
-                           "recycled_directions": rinfo["n"], "recycle_term_products": rinfo["spmvs"],
+                           "points_that_iterated": int(sum(1 for v in iters if v > 0)),
+                           "iterations_per_iterating_point": float(np.sum(iters) / max(1, sum(1 for v in iters if v > 0))),
+                           "points": jm["points"], "max_iters_per_point": int(max(iters)), "rtol": args.rtol,
+                           "precond_apply_ms": main["prec_ms"], "precond_samples": main["prec_cnt"],
+                           "graph_replayed_iterations": int(main["graph_iters"]),
+                           "max_relres": float(max(s_["relres"] for s_ in stats_all)),
+                           "not_converged": int(sum(1 for s_ in stats_all if not s_.get("converged", True))),
+                           "recycled_directions": main["rinfo"]["n"], "recycle_term_products": main["rinfo"]["spmvs"],
                            "abs_S21_minmax": [float(S21.min()), float(S21.max())]},
-                "sizes": {"tets": int(t.tets.shape[1]), "n_field": N, "n_solve": Ns, "nnz_solve": nnz_s},
+                "sizes": {"tets": nT, "n_field": N, "n_solve": Ns, "nnz_full": nnz_full, "nnz_solve": nnz_s},
                 "setup": {"host_mesh_tables_s": host_mesh_s, "gpu_setup_s": setup_s, **{k: v for k, v in sw.timings.items()}},
-                "e2e_setup": e2e_timings,
-                "clocks": cs.summary()}
+                "e2e_setup": (e2e_k or e2e_full)["setup"] if (e2e_k or e2e_full) else {},
+                "clocks": main["clocks"]}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args)
-            line["same_size_as_cpu_sample"] = gpu_same_size(args, local)
+            line["same_size_as_cpu_sample"] = gpu_same_size(args, local, line["cpu_baseline"])
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
 
 
-def gpu_same_size(args, device):
-    """This GPU path on exactly the mesh the CPU baseline / reference arm uses (equal-size comparison)."""
+CPU_SAMPLE_POINTS = (0, 50)      # indices into FREQS of the points the CPU baseline solves
+
+
+def gpu_same_size(args, device, cpu):
+    """This GPU path on exactly the mesh AND the points the CPU baseline uses (the only like-for-like comparison), plus
+    the whole 201-point sweep on that mesh."""
     from emerge_b200.sweep import FrequencySweep
     nx, ny, nz = args.ref_cells
     box, t, er, ur, bcs, L = make_waveguide(nx, ny, nz)
-    sw = FrequencySweep(t, er, ur, bcs, device=device, recycle=args.recycle)
+    sw = FrequencySweep(t, er, ur, bcs, device=device, recycle=args.recycle, coarse_basis=not args.no_coarse_basis)
     sw.solver_opts.update(rtol=args.rtol, precond=args.precond)
     sw.f_ref = float(np.median(FREQS))
     sw.setup()
     for p in sw.ports:
         p.active = False
-    for f in FREQS[:2]:
+    for f in FREQS[100:102]:
         sw.solve_point(f)
+    sw.ctx.recycle_config(args.recycle, args.snap)
+    pts = [float(FREQS[i]) for i in CPU_SAMPLE_POINTS]
+    sw.ctx.timer_start()                       # K/M already assembled, as in the CPU sample
+    sw.run(pts, order=list(range(len(pts))))
+    ms_pts = sw.ctx.timer_stop()
     sw.ctx.recycle_config(args.recycle, args.snap)
     sw.ctx.timer_start()
     sw.ctx.assemble_KM()
     sw.run(FREQS)
     ms = sw.ctx.timer_stop()
     sw.ctx.close()
-    return {"cells": [nx, ny, nz], "tets": int(t.tets.shape[1]), "value": len(FREQS) / (ms / 1e3), "unit": UNIT,
-            "sample": "whole 201-point sweep from a cold recycled subspace"}
+    same = len(pts) / (ms_pts / 1e3)
+    return {"cells": [nx, ny, nz], "tets": int(t.tets.shape[1]),
+            "same_points": {"value": same, "unit": UNIT, "points_GHz": [f / 1e9 for f in pts],
+                            "sample": "the CPU baseline's own points from a cold reduced basis, K/M assembled beforehand as in the CPU sample",
+                            "ratio_vs_cpu_baseline": same / cpu["value"] if cpu and cpu.get("value") else None},
+            "value": len(FREQS) / (ms / 1e3), "unit": UNIT,
+            "sample": "whole 201-point sweep (assembly included) from a cold recycled subspace"}
 
 
 def cpu_baseline(args):
@@ -416,11 +524,13 @@ def cpu_baseline(args):
     assemble()
     asm_s = time.perf_counter() - t0
     t0 = time.perf_counter()
-    n = 2
-    for i in range(n):
-        point(FREQS[i * 50])
+    for i in CPU_SAMPLE_POINTS:
+        point(FREQS[i])
+    n = len(CPU_SAMPLE_POINTS)
     dt = time.perf_counter() - t0
     return {"value": n / dt, "unit": UNIT, "cores": 1, "host_cores": os.cpu_count(), "kind": "port",
+            "cells": [nx, ny, nz], "tets": int(t.tets.shape[1]),
+            "assembly_Mtet_per_s": t.tets.shape[1] / asm_s / 1e6,
             "sample": f"{t.tets.shape[1]}-tet / {t.n_field}-dof sub-sampled waveguide ({nx}x{ny}x{nz} cells), {n} frequency points: "
                       f"K(f) + RCM + SuperLU + 2 solves per point (SciPy; SuperLU is serial); oracle assembly {asm_s:.1f}s "
                       f"({t.tets.shape[1]/asm_s/1e6:.4f} Mtet/s, numpy port) not included"}
@@ -454,8 +564,9 @@ def main():
     ap.add_argument("--recycle", type=int, default=40)
     ap.add_argument("--snap", type=float, default=0.3, help="points that iterate are solved to snap * rtol")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--coarse-basis", action="store_true",
-                    help="EXPERIMENTAL: reduced basis as an extra coarse space of the preconditioner (default off)")
+    ap.add_argument("--no-coarse-basis", action="store_true",
+                    help="switch off the reduced basis as an extra coarse space of the preconditioner (default on)")
+    ap.add_argument("--no-full-sweep", action="store_true", help="skip the whole-job pass when --steps is smaller than the job")
     args = ap.parse_args()
     if args.ref_cells is None:
         args.ref_cells = pick_ref_cells(max(args.steps, 1) + args.warmup) if args.impl == "reference" else pick_ref_cells(3, 60.0)

@@ -512,8 +512,6 @@ __global__ void __launch_bounds__(RWARPS * 32) k_reduce_rows(int64_t N, int64_t 
 // ------------------------------------------------------------------------------------------------
 // numeric phase, fused: per-tet records + one warp per entity
 // ------------------------------------------------------------------------------------------------
-__device__ const ned2f::Tables d_ftab{};
-
 __global__ void __launch_bounds__(128) k_tet_records(int64_t nT, const int* __restrict__ tetc, const double* __restrict__ nodes,
                                                      const cx* __restrict__ er, const cx* __restrict__ ur,
                                                      ned2f::TetRec* __restrict__ recs) {
@@ -550,7 +548,10 @@ __global__ void k_check_pairs(int64_t nT, int nEF, const int* __restrict__ gid, 
 }
 
 // processing class of an entity and its sort key (class << 28 | first tet)
-constexpr int ACLS0 = 32, ACLS1 = 80, ACLS2 = 160;   // row-length caps of the shared-memory classes; class 3 = global accumulators
+// row-length caps of the two shared-memory classes (faces and edges with <= 6 tetrahedra | edges with <= 13); class 2 =
+// accumulators in global memory.  One launch per class; inside a class entities are ordered by their first tetrahedron.
+constexpr int ACLS0 = 80, ACLS1 = 160;
+constexpr int AWARPS0 = 24, AWARPS1 = 12;
 __global__ void k_entity_keys(int nEF, const int64_t* __restrict__ adjptr, const int* __restrict__ adj,
                               const int64_t* __restrict__ rowptr, unsigned* __restrict__ key, int* __restrict__ val,
                               int* __restrict__ bad) {
@@ -562,20 +563,37 @@ __global__ void k_entity_keys(int nEF, const int64_t* __restrict__ adjptr, const
     const int len2 = (int)(rowptr[e + nEF + 1] - rowptr[e + nEF]);
     const int deg2 = (int)(adjptr[e + nEF + 1] - adjptr[e + nEF]);
     if (len2 != len || deg2 != deg) atomicExch(bad, 1);
-    int cls = len <= ACLS0 ? 0 : len <= ACLS1 ? 1 : len <= ACLS2 ? 2 : 3;
-    if (deg > 32) cls = 3;
+    int cls = len <= ACLS0 ? 0 : len <= ACLS1 ? 1 : 2;
+    if (deg > 32) cls = 2;
     const unsigned t0 = deg > 0 ? (unsigned)(adj[a0] / 20) : 0u;
     key[e] = ((unsigned)cls << 28) | t0;
     val[e] = e;
 }
 
-struct AsmWarpBufHdr {};
 template <int ROWCAP>
 struct AsmWarpBuf {
     double2 acc[4][ROWCAP];      // K row a, K row b, M row a, M row b
     double2 rec[56];             // the current tetrahedron's record
     int cols[ROWCAP];
 };
+
+__device__ const ned2f::KernTables d_ktab{};
+
+// per-item metadata, identical in every lane (broadcast loads), prefetched one item ahead
+struct AsmMeta {
+    int64_t a0, p0, p1;
+    int deg, len;
+};
+__device__ __forceinline__ AsmMeta asm_load_meta(int e, int nEF, const int64_t* __restrict__ adjptr,
+                                                 const int64_t* __restrict__ rowptr) {
+    AsmMeta m;
+    m.a0 = __ldg(adjptr + e);
+    m.deg = (int)(__ldg(adjptr + e + 1) - m.a0);
+    m.p0 = __ldg(rowptr + e);
+    m.len = (int)(__ldg(rowptr + e + 1) - m.p0);
+    m.p1 = __ldg(rowptr + e + nEF);
+    return m;
+}
 
 template <int ROWCAP, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) k_asm_rows(int64_t nitems, const int* __restrict__ items, int nEF,
@@ -585,35 +603,41 @@ __global__ void __launch_bounds__(WARPS * 32) k_asm_rows(int64_t nitems, const i
                                                          const ned2f::TetRec* __restrict__ recs, cx* __restrict__ K,
                                                          cx* __restrict__ M) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    ned2f::Tables* T = reinterpret_cast<ned2f::Tables*>(smem_raw);
+    ned2f::KernTables* T = reinterpret_cast<ned2f::KernTables*>(smem_raw);
     {
-        const double* src = reinterpret_cast<const double*>(&d_ftab);
+        const double* src = reinterpret_cast<const double*>(&d_ktab);
         double* dst = reinterpret_cast<double*>(T);
-        for (int i = threadIdx.x; i < (int)(sizeof(ned2f::Tables) / sizeof(double)); i += blockDim.x) dst[i] = src[i];
+        for (int i = threadIdx.x; i < (int)(sizeof(ned2f::KernTables) / sizeof(double)); i += blockDim.x) dst[i] = src[i];
     }
     __syncthreads();
-    constexpr size_t TOFF = (sizeof(ned2f::Tables) + 15) / 16 * 16;
+    constexpr size_t TOFF = (sizeof(ned2f::KernTables) + 15) / 16 * 16;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     AsmWarpBuf<ROWCAP>& wb = reinterpret_cast<AsmWarpBuf<ROWCAP>*>(smem_raw + TOFF)[warp];
     const bool colLane = lane < 20;
-    const ned2f::FnTab fj = T->f[colLane ? lane : 0];      // this lane's column function (registers)
-    const cx* recD = reinterpret_cast<const cx*>(wb.rec);
-    const cx* recG = recD + 36;
-    const double* recLen = reinterpret_cast<const double*>(recD + 52);
+    const int J = colLane ? lane : 0;
+    const int lpj = T->lp[J];
+    const double2* recD = wb.rec;                 // D[36] | g[16] | len[6] (+pad) as 16-byte words
+    const double2* recG = wb.rec + 36;
+    const double* recLen = reinterpret_cast<const double*>(wb.rec + 52);
 
-    for (int64_t w = blockIdx.x * (int64_t)WARPS + warp; w < nitems; w += (int64_t)gridDim.x * WARPS) {
-        const int e = __ldg(items + w);
-        const int64_t a0 = adjptr[e];
-        const int deg = (int)(adjptr[e + 1] - a0);
-        const int64_t p0 = rowptr[e], p1 = rowptr[e + nEF];
-        const int len = (int)(rowptr[e + 1] - p0);
+    const int64_t stride = (int64_t)gridDim.x * WARPS;
+    int64_t w = blockIdx.x * (int64_t)WARPS + warp;
+    if (w >= nitems) return;
+    AsmMeta m = asm_load_meta(__ldg(items + w), nEF, adjptr, rowptr);
+    int e_next = (w + stride < nitems) ? __ldg(items + w + stride) : -1;
+    int myadj = lane < m.deg ? __ldg(adj + m.a0 + lane) : 0;
+    for (; w < nitems; w += stride) {
+        // metadata of the next item and the entity id of the one after it: in flight while this item is processed
+        AsmMeta mn = m;
+        if (e_next >= 0) mn = asm_load_meta(e_next, nEF, adjptr, rowptr);
+        const int e_next2 = (w + 2 * stride < nitems) ? __ldg(items + w + 2 * stride) : -1;
+        const int deg = m.deg, len = m.len;
         for (int k = lane; k < len; k += 32) {
-            wb.cols[k] = __ldg(col + p0 + k);
+            wb.cols[k] = __ldg(col + m.p0 + k);
             const double2 z = make_double2(0.0, 0.0);
             wb.acc[0][k] = z; wb.acc[1][k] = z; wb.acc[2][k] = z; wb.acc[3][k] = z;
         }
-        const int myadj = lane < deg ? __ldg(adj + a0 + lane) : 0;
-        // prefetch the first record (56 x 16 B: every lane one piece, lanes 0..23 a second one) and the tet's dof ids
+        // first record (56 x 16 B: every lane one piece, lanes 0..23 a second one) and the tet's dof ids
         double2 r0 = make_double2(0, 0), r1 = r0;
         int cj = 0;
         if (deg > 0) {
@@ -638,31 +662,63 @@ __global__ void __launch_bounds__(WARPS * 32) k_asm_rows(int64_t nitems, const i
             }
             if (colLane) {
                 // position of column c in the row's sorted column list (present by construction)
-                int lo = 0, m = len;
-                while (m > 1) {
-                    const int half = m >> 1;
+                int lo = 0, mm = len;
+                while (mm > 1) {
+                    const int half = mm >> 1;
                     lo = (wb.cols[lo + half] <= c) ? lo + half : lo;
-                    m -= half;
+                    mm -= half;
                 }
-                cx Ka, Kb, Ma, Mb;
-                ned2f::row_pair_entry(T->pt[ic], T->f[ic], T->f[ic + 10], fj, T->mc[ic][lane], T->mc[ic + 10][lane], recD, recG,
-                                      recLen, Ka, Kb, Ma, Mb);
+                // curl-curl rows: nk uniform terms (3: edge, 9: face), coefficient pairs and D indices from the tables
+                double kar = 0, kai = 0, kbr = 0, kbi = 0;
+                unsigned long long ki = T->kidx[ic][J];
+                const double2* kc = reinterpret_cast<const double2*>(&T->kc[ic][0][J][0]);
+                const int nk = T->nk[ic];
+#pragma unroll 3
+                for (int k = 0; k < nk; ++k) {
+                    const double2 d = recD[(int)(ki & 63ull)];
+                    ki >>= 6;
+                    const double2 cc = kc[k * 20];
+                    kar += cc.x * d.x; kai += cc.x * d.y;
+                    kbr += cc.y * d.x; kbi += cc.y * d.y;
+                }
+                const double lj = recLen[lpj];
+                const double sa = recLen[T->lp[ic]] * lj, sb = recLen[T->lp[ic + 10]] * lj;
+                // mass rows: four g terms each
+                const unsigned gi = T->gidx[ic][J];
+                const double2 ca0 = *reinterpret_cast<const double2*>(&T->mc[ic][0][0][J][0]);
+                const double2 ca1 = *reinterpret_cast<const double2*>(&T->mc[ic][0][1][J][0]);
+                const double2 cb0 = *reinterpret_cast<const double2*>(&T->mc[ic][1][0][J][0]);
+                const double2 cb1 = *reinterpret_cast<const double2*>(&T->mc[ic][1][1][J][0]);
+                double2 g0 = recG[gi & 15u], g1 = recG[(gi >> 4) & 15u], g2 = recG[(gi >> 8) & 15u], g3 = recG[(gi >> 12) & 15u];
+                double mar = ca0.x * g0.x, mai = ca0.x * g0.y;
+                mar += ca0.y * g1.x; mai += ca0.y * g1.y;
+                mar += ca1.x * g2.x; mai += ca1.x * g2.y;
+                mar += ca1.y * g3.x; mai += ca1.y * g3.y;
+                g0 = recG[(gi >> 16) & 15u]; g1 = recG[(gi >> 20) & 15u]; g2 = recG[(gi >> 24) & 15u]; g3 = recG[(gi >> 28) & 15u];
+                double mbr = cb0.x * g0.x, mbi = cb0.x * g0.y;
+                mbr += cb0.y * g1.x; mbi += cb0.y * g1.y;
+                mbr += cb1.x * g2.x; mbi += cb1.x * g2.y;
+                mbr += cb1.y * g3.x; mbi += cb1.y * g3.y;
                 double2 v;
-                v = wb.acc[0][lo]; v.x += Ka.re; v.y += Ka.im; wb.acc[0][lo] = v;
-                v = wb.acc[1][lo]; v.x += Kb.re; v.y += Kb.im; wb.acc[1][lo] = v;
-                v = wb.acc[2][lo]; v.x += Ma.re; v.y += Ma.im; wb.acc[2][lo] = v;
-                v = wb.acc[3][lo]; v.x += Mb.re; v.y += Mb.im; wb.acc[3][lo] = v;
+                v = wb.acc[0][lo]; v.x += sa * kar; v.y += sa * kai; wb.acc[0][lo] = v;
+                v = wb.acc[1][lo]; v.x += sb * kbr; v.y += sb * kbi; wb.acc[1][lo] = v;
+                v = wb.acc[2][lo]; v.x += sa * mar; v.y += sa * mai; wb.acc[2][lo] = v;
+                v = wb.acc[3][lo]; v.x += sb * mbr; v.y += sb * mbi; wb.acc[3][lo] = v;
             }
             __syncwarp();
         }
-        double2* Ka = reinterpret_cast<double2*>(K + p0);
-        double2* Kb = reinterpret_cast<double2*>(K + p1);
-        double2* Ma = reinterpret_cast<double2*>(M + p0);
-        double2* Mb = reinterpret_cast<double2*>(M + p1);
+        // adjacency of the next item (its metadata has arrived by now); overlaps the write-out below
+        if (e_next >= 0) myadj = lane < mn.deg ? __ldg(adj + mn.a0 + lane) : 0;
+        double2* Ka = reinterpret_cast<double2*>(K + m.p0);
+        double2* Kb = reinterpret_cast<double2*>(K + m.p1);
+        double2* Ma = reinterpret_cast<double2*>(M + m.p0);
+        double2* Mb = reinterpret_cast<double2*>(M + m.p1);
         for (int k = lane; k < len; k += 32) {
             Ka[k] = wb.acc[0][k]; Kb[k] = wb.acc[1][k]; Ma[k] = wb.acc[2][k]; Mb[k] = wb.acc[3][k];
         }
         __syncwarp();
+        m = mn;
+        e_next = e_next2;
     }
 }
 
@@ -676,7 +732,7 @@ __global__ void __launch_bounds__(128) k_asm_rows_big(int64_t nitems, const int*
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t w = blockIdx.x * (int64_t)4 + warp;
     if (w >= nitems) return;
-    const ned2f::Tables& T = d_ftab;
+    const ned2f::KernTables& T = d_ktab;
     const int e = items[w];
     const int64_t a0 = adjptr[e], a1 = adjptr[e + 1];
     const int64_t p0 = rowptr[e], p1 = rowptr[e + nEF];
@@ -699,8 +755,7 @@ __global__ void __launch_bounds__(128) k_asm_rows_big(int64_t nitems, const int*
             }
             const cx* D = reinterpret_cast<const cx*>(recs + t);
             cx Ka, Kb, Ma, Mb;
-            ned2f::row_pair_entry(T.pt[ic], T.f[ic], T.f[ic + 10], T.f[lane], T.mc[ic][lane], T.mc[ic + 10][lane], D, D + 36,
-                                  reinterpret_cast<const double*>(D + 52), Ka, Kb, Ma, Mb);
+            ned2f::row_pair_flat(T, ic, lane, D, D + 36, reinterpret_cast<const double*>(D + 52), Ka, Kb, Ma, Mb);
             st16(K + p0 + lo, K[p0 + lo] + Ka); st16(K + p1 + lo, K[p1 + lo] + Kb);
             st16(M + p0 + lo, M[p0 + lo] + Ma); st16(M + p1 + lo, M[p1 + lo] + Mb);
         }
@@ -711,7 +766,7 @@ __global__ void __launch_bounds__(128) k_asm_rows_big(int64_t nitems, const int*
 template <int ROWCAP, int WARPS>
 static int launch_asm_rows(emb_ctx* c, int64_t i0, int64_t i1, const ned2f::TetRec* recs) {
     if (i1 <= i0) return EMB_OK;
-    constexpr size_t TOFF = (sizeof(ned2f::Tables) + 15) / 16 * 16;
+    constexpr size_t TOFF = (sizeof(ned2f::KernTables) + 15) / 16 * 16;
     const size_t smem = TOFF + (size_t)WARPS * sizeof(AsmWarpBuf<ROWCAP>);
     auto kern = k_asm_rows<ROWCAP, WARPS>;
     EMB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -757,11 +812,11 @@ static int build_entity_order(emb_ctx* c) {
     EMB_TRY(dev_alloc(c, cls, (size_t)nEF));
     k_key_class<<<blocks_for(nEF, 256), 256, 0, c->stream>>>(nEF, key2.p, cls.p);
     EMB_LAUNCH_CHECK(c);
-    k_segptr<<<blocks_for(nEF, 256), 256, 0, c->stream>>>(cls.p, nEF, 4, ptr.p);
+    k_segptr<<<blocks_for(nEF, 256), 256, 0, c->stream>>>(cls.p, nEF, 3, ptr.p);
     EMB_LAUNCH_CHECK(c);
     int hbad = 0;
     EMB_CUDA(c, cudaMemcpyAsync(&hbad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    EMB_CUDA(c, cudaMemcpyAsync(c->asm_cls_ptr, ptr.p, 5 * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+    EMB_CUDA(c, cudaMemcpyAsync(c->asm_cls_ptr, ptr.p, 4 * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
     EMB_CUDA(c, cudaStreamSynchronize(c->stream));
     bad.release(); val.release(); key.release(); key2.release(); tmp.release(); ptr.release(); cls.release();
     c->asm_pairs_ok = hbad == 0;
@@ -780,11 +835,10 @@ static int assemble_fused(emb_ctx* c) {
     {
         PhaseTimer pt(c, "reduce");
         const int64_t* cp = c->asm_cls_ptr;
-        EMB_TRY((launch_asm_rows<ACLS0, 8>(c, cp[0], cp[1], recs.p)));
-        EMB_TRY((launch_asm_rows<ACLS1, 8>(c, cp[1], cp[2], recs.p)));
-        EMB_TRY((launch_asm_rows<ACLS2, 8>(c, cp[2], cp[3], recs.p)));
-        if (cp[4] > cp[3]) {
-            k_asm_rows_big<<<blocks_for(cp[4] - cp[3], 4), 128, 0, c->stream>>>(cp[4] - cp[3], c->asm_ent.p + cp[3],
+        EMB_TRY((launch_asm_rows<ACLS0, AWARPS0>(c, cp[0], cp[1], recs.p)));
+        EMB_TRY((launch_asm_rows<ACLS1, AWARPS1>(c, cp[1], cp[2], recs.p)));
+        if (cp[3] > cp[2]) {
+            k_asm_rows_big<<<blocks_for(cp[3] - cp[2], 4), 128, 0, c->stream>>>(cp[3] - cp[2], c->asm_ent.p + cp[2],
                                                                               (int)(c->nE + c->nTri), c->adjptr.p, c->adj.p,
                                                                               c->gid.p, c->rowptr.p, c->col.p, recs.p, c->K.p,
                                                                               c->M.p);

@@ -180,6 +180,7 @@ struct emb_ctx {
     DevBuf<cx> rc_tmp;                  // one contiguous vector
     int64_t rc_spmvs = 0;               // SpMVs spent on W_t u so far (reported by emb_recycle_info)
     int64_t rc_rebuilds = 0;
+    int64_t rc_accepted_total = 0;      // directions accepted since the context was created (monotonic: survives compaction / reset)
     double rc_last_proj_relres = -1;    // relative residual left by the projection in the last solve
     int nsol = 0;                       // columns of the last lockstep solve held in xs
     // EXPERIMENTAL (off by default, not yet measured on the GPU): the reduced basis as an extra coarse space of the

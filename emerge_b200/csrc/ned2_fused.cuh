@@ -190,4 +190,94 @@ EMB_HD void row_pair_entry(const PairTab& pt, const FnTab& fa, const FnTab& fb, 
     }
 }
 
+// ---- flat tables of the kernel ---------------------------------------------------------------------------------
+// Everything that depends only on (entity slot ic, column function J) is tabulated, in a layout where the 20 column
+// lanes of a warp read consecutive 16-byte words (conflict-free shared-memory loads), and padded to a uniform term
+// count per entity type so the warp runs without divergence:
+//   kc[ic][k][J]  = (ca, cb): coefficient of D[kidx(ic,J,k)] in rows ic and ic+10, signs and 1/120 folded in;
+//                   k = ta*3 + tb < nk[ic] (3 for an edge, 9 for a face); edge columns have zero entries for tb > 0
+//   kidx[ic][J]   = the nk D-indices, 6 bits each
+//   mc[ic][r][h][J] = coefficients (c1, -c2 | -c3, c4) of row r (0: ic, 1: ic+10), signs folded in
+//   gidx[ic][J]   = the 2 x 4 g-indices, 4 bits each
+struct KernTables {
+    double kc[10][9][20][2];
+    double mc[10][2][2][20][2];
+    unsigned long long kidx[10][20];
+    unsigned int gidx[10][20];
+    int nk[10];
+    int lp[20];
+    constexpr KernTables() : kc{}, mc{}, kidx{}, gidx{}, nk{}, lp{} {
+        const Tables T{};
+        for (int J = 0; J < 20; ++J) lp[J] = T.f[J].lp;
+        for (int ic = 0; ic < 10; ++ic) {
+            const FnTab &fa = T.f[ic], &fb = T.f[ic + 10];
+            const PairTab& pt = T.pt[ic];
+            nk[ic] = pt.np * 3;
+            for (int J = 0; J < 20; ++J) {
+                const FnTab& fj = T.f[J];
+                const bool mirror = fa.face && !fj.face;
+                unsigned long long packed = 0;
+                for (int ta = 0; ta < pt.np; ++ta)
+                    for (int tb = 0; tb < 3; ++tb) {
+                        const int k = ta * 3 + tb;
+                        double ca = 0.0, cb = 0.0;
+                        int idx = 0;
+                        if (tb < fj.nt) {
+                            idx = mirror ? fj.tp[tb] * 6 + pt.tp[ta] : pt.tp[ta] * 6 + fj.tp[tb];
+                            const double kj = fj.tk[tb] * fj.s * (1.0 / 120.0);
+                            ca = fa.s * pt.ka[ta] * kj * (pt.va[ta] == fj.tv[tb] ? 2.0 : 1.0);
+                            cb = fb.s * pt.kb[ta] * kj * (pt.vb[ta] == fj.tv[tb] ? 2.0 : 1.0);
+                        }
+                        kc[ic][k][J][0] = ca;
+                        kc[ic][k][J][1] = cb;
+                        packed |= (unsigned long long)idx << (6 * k);
+                    }
+                kidx[ic][J] = packed;
+                unsigned int gp = 0;
+                for (int r = 0; r < 2; ++r) {
+                    const FnTab& fi = r == 0 ? fa : fb;
+                    const int I = ic + 10 * r;
+                    const int lP = mirror ? fj.P : fi.P, lQ = mirror ? fj.Q : fi.Q;
+                    const int rP = mirror ? fi.P : fj.P, rQ = mirror ? fi.Q : fj.Q;
+                    const int gi[4] = {lP * 4 + rP, lP * 4 + rQ, lQ * 4 + rP, lQ * 4 + rQ};
+                    for (int q = 0; q < 4; ++q) {
+                        gp |= (unsigned int)gi[q] << (4 * (r * 4 + q));
+                        mc[ic][r][q / 2][J][q % 2] = fi.s * fj.s * T.mc[I][J][q];
+                    }
+                }
+                gidx[ic][J] = gp;
+            }
+        }
+    }
+};
+
+// rows (ic, ic + 10), column J of the element matrices from the record, through the flat tables (what a lane evaluates)
+EMB_HD void row_pair_flat(const KernTables& T, int ic, int J, const cx* D, const cx* g, const double* len, cx& Ka, cx& Kb,
+                          cx& Ma, cx& Mb) {
+    cx acca = mk(0.0), accb = mk(0.0);
+    unsigned long long ki = T.kidx[ic][J];
+    const int nk = T.nk[ic];
+    for (int k = 0; k < nk; ++k) {
+        const cx d = D[(int)(ki & 63ull)];
+        ki >>= 6;
+        fma_r(acca, T.kc[ic][k][J][0], d);
+        fma_r(accb, T.kc[ic][k][J][1], d);
+    }
+    const double lj = len[T.lp[J]];
+    const double sa = len[T.lp[ic]] * lj, sb = len[T.lp[ic + 10]] * lj;
+    Ka = sa * acca;
+    Kb = sb * accb;
+    const unsigned int gi = T.gidx[ic][J];
+    cx ma = T.mc[ic][0][0][J][0] * g[gi & 15u];
+    fma_r(ma, T.mc[ic][0][0][J][1], g[(gi >> 4) & 15u]);
+    fma_r(ma, T.mc[ic][0][1][J][0], g[(gi >> 8) & 15u]);
+    fma_r(ma, T.mc[ic][0][1][J][1], g[(gi >> 12) & 15u]);
+    cx mb = T.mc[ic][1][0][J][0] * g[(gi >> 16) & 15u];
+    fma_r(mb, T.mc[ic][1][0][J][1], g[(gi >> 20) & 15u]);
+    fma_r(mb, T.mc[ic][1][1][J][0], g[(gi >> 24) & 15u]);
+    fma_r(mb, T.mc[ic][1][1][J][1], g[(gi >> 28) & 15u]);
+    Ma = sa * ma;
+    Mb = sb * mb;
+}
+
 }  // namespace ned2f

@@ -402,7 +402,10 @@ static int rc_append(emb_ctx* c, const cx* d) {
         EMB_CUDA(c, cudaMemcpyAsync(rc_U(c, slot), d, (size_t)c->Ns * sizeof(cx), cudaMemcpyDeviceToDevice, c->stream));
     bool ok = false;
     EMB_TRY(rc_insert(c, slot, true, &ok));
-    if (ok) c->rc_n = slot + 1;
+    if (ok) {
+        c->rc_n = slot + 1;
+        c->rc_accepted_total++;
+    }
     return EMB_OK;
 }
 

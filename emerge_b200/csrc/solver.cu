@@ -653,6 +653,7 @@ extern "C" int emb_recycle_info(emb_ctx* c, int* n, int64_t* spmvs, double* last
     if (last_proj_relres) *last_proj_relres = c->rc_last_proj_relres;
     return EMB_OK;
 }
+extern "C" int64_t emb_recycle_accepted(const emb_ctx* c) { return c ? c->rc_accepted_total : 0; }
 // Device-to-device exchange of directions between the ranks of a sharded sweep (the host side moves the buffers with
 // NCCL over NVLink).  d_dst / d_src are DEVICE pointers to Ns complex128 values.  j = 0 is the NEWEST direction.
 extern "C" int emb_recycle_export(emb_ctx* c, int j, void* d_dst) {

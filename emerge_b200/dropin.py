@@ -53,23 +53,33 @@ class DeviceRHS(np.ndarray):
     Adding the all-zero `b` of assemble_freq_matrix keeps the tag; any other arithmetic drops it (the solve then uploads
     the host values)."""
 
-    def __new__(cls, values, sid, owner):
+    def __new__(cls, values, sid, owner, freq=None):
         obj = np.asarray(values, dtype=np.complex128).view(cls)
-        obj._emb_sid, obj._emb_owner = sid, owner
+        obj._emb_sid, obj._emb_owner, obj._emb_freq = sid, owner, freq
         return obj
 
     def __array_finalize__(self, obj):
         self._emb_sid = getattr(obj, "_emb_sid", None)
         self._emb_owner = getattr(obj, "_emb_owner", None)
+        self._emb_freq = getattr(obj, "_emb_freq", None)
 
     def __array_ufunc__(self, ufunc, method, *inputs, **kwargs):
         raw = [np.asarray(x) if isinstance(x, np.ndarray) else x for x in inputs]
+        outs = kwargs.get("out")
+        if outs is not None:
+            # in-place arithmetic (pv += ...): compute on the base arrays, the result no longer matches the device copy
+            kwargs["out"] = tuple(np.asarray(o) if isinstance(o, np.ndarray) else o for o in outs)
+            getattr(ufunc, method)(*raw, **kwargs)
+            for o in outs:
+                if isinstance(o, DeviceRHS):
+                    o._emb_sid = None
+            return outs[0] if len(outs) == 1 else outs
         out = getattr(ufunc, method)(*raw, **kwargs)
         tagged = [x for x in inputs if isinstance(x, DeviceRHS) and x._emb_sid is not None]
         if (ufunc is np.add and method == "__call__" and len(tagged) == 1 and isinstance(out, np.ndarray)
                 and all((x is tagged[0]) or (isinstance(x, np.ndarray) and getattr(x, "_emb_zero", False) and not x.any())
                         for x in inputs)):
-            return DeviceRHS(out, tagged[0]._emb_sid, tagged[0]._emb_owner)
+            return DeviceRHS(out, tagged[0]._emb_sid, tagged[0]._emb_owner, tagged[0]._emb_freq)
         return out
 
 
@@ -124,13 +134,40 @@ class GpuAssembler:
         self.sweep: FrequencySweep | None = None
         self.solve_ids = None
         self._current_freq = None
-        self._key = None
+        self._held = None
         self.ctx = ctx if ctx is not None else Context(device)   # fails loudly here without the CUDA library / a GPU
 
+    def invalidate(self):
+        """forget the cached device state (mesh, K/M, surfaces, recycled basis); the next call re-binds"""
+        self.sweep, self._held, self.cached_matrices = None, None, None
+        self._current_freq = None
+
+    def _same_problem(self, field, er, ur, bcs):
+        """True if (field, er, ur, bcs) describe the problem the device state was built for.  Same objects as last time
+        (held by strong references, so CPython cannot have recycled their ids): no checks - in-place edits need
+        invalidate().  Different objects - the reference rebuilds er / ur on every frequency_domain() call
+        (emfreq3d.py:612-616) and a re-mesh or a material sweep produces new ones - are compared by CONTENT, once."""
+        if self.sweep is None or self._held is None:
+            return False
+        hf, he, hu, hb = self._held
+        if len(hb) != len(bcs) or any(a is not b for a, b in zip(hb, bcs)):
+            return False
+        if hf is field and he is er and hu is ur:
+            return True
+        if hf is not field:
+            fm, hm = field.mesh, hf.mesh
+            for name in ("tets", "nodes", "edges", "tris"):
+                if not np.array_equal(np.asarray(getattr(fm, name)), np.asarray(getattr(hm, name))):
+                    return False
+            if not np.array_equal(np.asarray(field.tet_to_field), np.asarray(hf.tet_to_field)):
+                return False
+        return np.array_equal(er, he) and np.array_equal(ur, hu)
+
     def _bind(self, field, er, ur, bcs, frequency):
-        key = (id(field), id(er), id(ur), tuple(id(b) for b in bcs))
-        if self.sweep is not None and key == self._key:
+        if self._same_problem(field, er, ur, bcs):
+            self._held = (field, er, ur, list(bcs))
             return
+        self._held = (field, er, ur, list(bcs))     # strong references: CPython may not reuse these ids while cached
         mesh = field.mesh
         self.sweep = FrequencySweep(_RefTables(field), er, ur, bcs, device=self.device,
                                     get_triangles=getattr(mesh, "get_triangles", None), ctx=self.ctx,
@@ -139,7 +176,6 @@ class GpuAssembler:
         self.sweep.solver_opts.update(self.solver_opts)
         self.sweep.setup()
         self.solve_ids = self.ctx.solve_ids()
-        self._key = key
         self.cached_matrices = ("device", "device")
 
     def assemble_freq_matrix(self, field, er, ur, bcs, frequency, cache_matrices=False):
@@ -157,7 +193,7 @@ class GpuAssembler:
                 xy = sw.points[id(bc)]
                 U = np.asarray(bc.get_Uinc(xy[0].ravel(), xy[1].ravel(), k0), dtype=np.complex128)
                 full = sw.ctx.surface_set_U(sid, U.reshape(3, 6, sw.ntri[id(bc)]), want_full=True)
-                port_vectors[bc.port_number] = DeviceRHS(full, sid, self)
+                port_vectors[bc.port_number] = DeviceRHS(full, sid, self, float(frequency))
             if bc._include_stiff:
                 sids.append(sid)
                 gammas.append(complex(bc.get_gamma(k0)))
@@ -177,7 +213,8 @@ class GpuAssembler:
         if len(solve_ids) != len(self.solve_ids):
             raise EmergeB200Error("solve_ids differ from the eliminated pattern on the device")
         sid = getattr(b, "_emb_sid", None)
-        if sid is not None and getattr(b, "_emb_owner", None) is self:
+        # the device-resident right-hand side is only valid for the frequency it was computed at
+        if sid is not None and getattr(b, "_emb_owner", None) is self and getattr(b, "_emb_freq", None) == self._current_freq:
             x, info = self.ctx.solve(sid, **self.sweep.solver_opts)
         else:
             x, info = self.ctx.solve_rhs(np.asarray(b), **self.sweep.solver_opts)
@@ -185,9 +222,86 @@ class GpuAssembler:
         return x
 
 
-def install(physics, **kw) -> GpuAssembler:
-    """Wires the CUDA path into a reference Electrodynamics3D: replaces `physics.assembler` (emfreq3d.py:94) and the
-    `solve` method of `physics.solveroutine` (emfreq3d.py:98); `solveroutine.eig` (modal analysis) is left untouched."""
+def _sim_error(physics):
+    import importlib
+    return getattr(importlib.import_module(type(physics).__module__), "SimulationError", RuntimeError)
+
+
+def _gpu_frequency_domain(physics, asm: GpuAssembler, dist=None, keep_fields: bool = True):
+    """Fast driver behind physics.frequency_domain() / frequency_domain_par(): same preamble, same EMSimData filling as
+    emfreq3d.py:607-732 (and :545-601 for the parallel variant), but the per-frequency loop is FrequencySweep's - all ports
+    of a point solved in lockstep, recycled reduced basis across points, S-parameters from device-side field samples - so
+    no N x N matrix and no length-N vector crosses the host boundary except the solved fields the result object keeps.
+    dist: an initialised torch.distributed module -> the points are sharded over the ranks (ShardedSweep); every rank
+    returns the complete S-parameters, fields only of its own points."""
+    import importlib
+    mod = importlib.import_module(type(physics).__module__)
+    if physics._bc_initialized is False:
+        raise mod.SimulationError("Cannot run a modal analysis because no boundary conditions have been assigned.")
+    physics._initialize_field()
+    physics._initialize_bc_data()
+    mesh = physics.mesh
+    er = mesh.retreive(lambda mat, x, y, z: mat.fer3d_mat(x, y, z), physics.mesher.volumes)
+    ur = mesh.retreive(lambda mat, x, y, z: mat.fur3d_mat(x, y, z), physics.mesher.volumes)
+    physics.data = mod.EMSimData(physics.basis)
+    bcs = physics.boundary_conditions
+    freqs = list(physics.frequencies)
+    asm._bind(physics.basis, er, ur, bcs, float(np.median(freqs)))
+    sw = asm.sweep
+    all_ports = [bc for bc in bcs if isinstance(bc, mod.PortBC)]
+    port_numbers = [p.port_number for p in all_ports]
+    assert [p.port_number for p in sw.ports] == port_numbers
+    for p in all_ports:
+        p.active = False
+    world = dist.get_world_size() if dist is not None else 1
+    rank = dist.get_rank() if dist is not None else 0
+    if world > 1:
+        from .distributed import ShardedSweep
+        sh = ShardedSweep(sw, freqs, rank, world, dist=dist, device=asm.device)
+        fields = {}
+        res = sh.run(keep_fields=keep_fields, fields_out=fields)
+        S = sh.gather_S(res)
+    else:
+        res = sw.run(freqs, keep_fields=keep_fields)
+        S, fields = res.S, res.fields
+    asm.last_stats = res.stats
+    er00, ur00 = np.squeeze(er[0, 0, :]), np.squeeze(ur[0, 0, :])
+    for i, freq in enumerate(freqs):
+        k0 = 2 * np.pi * freq / 299792458
+        data = physics.data.new(freq=freq, k0=k0)
+        data.init_sp(port_numbers)
+        data.er, data.ur = er00, ur00
+        for port in all_ports:
+            data.add_port_properties(port.port_number, mode_number=port.mode_number, k0=k0, beta=port.get_beta(k0),
+                                     Z0=port.Z0, Pout=port.power)
+        for ja, pa in enumerate(all_ports):
+            if (i, pa.port_number) in fields:
+                data._fields[pa.port_number] = fields[(i, pa.port_number)]
+            for ib, pb in enumerate(all_ports):
+                data.write_S(pb.port_number, pa.port_number, S[i, ib, ja])
+        if data._fields:
+            data.set_field_vector()
+        else:       # set_field_vector without fields (emdata.py:134-136): excitation of the first port
+            data.excitation = {n: 0.0 for n in port_numbers}
+            data.excitation[port_numbers[0]] = 1.0 + 0j
+    return physics.data
+
+
+def install(physics, fast: bool = False, keep_fields: bool = True, **kw) -> GpuAssembler:
+    """Wires the CUDA path into a reference Electrodynamics3D.
+
+    Always: replaces `physics.assembler` (emfreq3d.py:94) and the `solve` method of `physics.solveroutine`
+    (emfreq3d.py:98), so the reference's own frequency_domain() loop runs unchanged on top of the CUDA path;
+    `solveroutine.eig` (modal analysis) is left untouched.
+
+    fast=True additionally replaces the two sweep drivers themselves:
+      physics.frequency_domain()          -> EMSimData   (emfreq3d.py:607-732)
+      physics.frequency_domain_par(njobs) -> EMSimData   (emfreq3d.py:469-605)
+    by FrequencySweep-backed versions that fill the same EMSimData (Sp, _fields[port], er/ur[0,0,:], port properties).
+    frequency_domain_par shards the frequency points over the ranks of the initialised torch.distributed process group
+    (one process per GPU, launched with torchrun - the counterpart of the reference's multiprocessing.Pool(njobs)); njobs
+    is accepted for signature compatibility, the parallel width is the world size.  Without a process group it runs on
+    this process's GPU."""
     asm = GpuAssembler(**kw)
     physics.assembler = asm
     routine = physics.solveroutine
@@ -195,4 +309,19 @@ def install(physics, **kw) -> GpuAssembler:
     def solve(self, A, b, solve_ids, reuse=False):
         return asm.solve(A, b, solve_ids, reuse)
     routine.solve = types.MethodType(solve, routine)
+    if fast:
+        def frequency_domain(self):
+            return _gpu_frequency_domain(self, asm, None, keep_fields)
+
+        def frequency_domain_par(self, njobs: int = 2):
+            dist = None
+            try:
+                import torch.distributed as td
+                if td.is_available() and td.is_initialized():
+                    dist = td
+            except ImportError:
+                pass
+            return _gpu_frequency_domain(self, asm, dist, keep_fields)
+        physics.frequency_domain = types.MethodType(frequency_domain, physics)
+        physics.frequency_domain_par = types.MethodType(frequency_domain_par, physics)
     return asm

@@ -81,6 +81,7 @@ _SIGS = {
     "emb_solve_rhs": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(SolveOpts), C.c_void_p, C.POINTER(SolveInfo)]),
     "emb_recycle_config": (C.c_int, [C.c_void_p, C.c_int, C.c_double]),
     "emb_recycle_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
+    "emb_recycle_accepted": (C.c_int64, [C.c_void_p]),
     "emb_recycle_export": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "emb_recycle_import": (C.c_int, [C.c_void_p, C.c_void_p]),
     "emb_interp": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -416,6 +417,10 @@ class Context:
         n, sp, rr = C.c_int(), C.c_int64(), C.c_double()
         self._check(self.lib.emb_recycle_info(self.h, C.byref(n), C.byref(sp), C.byref(rr)))
         return dict(n=n.value, spmvs=sp.value, last_proj_relres=rr.value)
+
+    def recycle_accepted(self) -> int:
+        """monotonic count of directions accepted into the reduced basis (survives compaction and resets)"""
+        return int(self.lib.emb_recycle_accepted(self.h))
 
     def recycle_export(self, j: int, device_ptr: int):
         self._check(self.lib.emb_recycle_export(self.h, int(j), C.c_void_p(device_ptr)))

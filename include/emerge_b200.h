@@ -156,8 +156,10 @@ int emb_solver_config(emb_ctx* ctx, int inner_fp32, int side_streams);
 /* 1 (default): the right-hand sides of an emb_solve_multi group share one Krylov space (block COCR); 0: independent
  * recurrences in lockstep.  Padded groups, empty right-hand sides and a breakdown of the block recurrence use 0. */
 int emb_solver_block(emb_ctx* ctx, int on);
-/* EXPERIMENTAL, default 0, not yet measured on the GPU: the reduced basis as an extra coarse space of the preconditioner,
- * M^-1 += U Ceff U^T (csrc/recycle.cuh::rc_coarse_update).  Clears the basis. */
+/* The reduced basis as an extra coarse space of the preconditioner, M^-1 += U Ceff U^T (csrc/recycle.cuh::
+ * rc_coarse_update).  Library default 0; the sweep driver (emerge_b200/sweep.py) switches it on: measured on the 1M-tet
+ * waveguide, first 20 points of the sweep, 5,130 -> 3,420 block iterations (profiles/r2_coarse_basis_1M.json).
+ * Clears the basis. */
 int emb_solver_coarse_basis(emb_ctx* ctx, int on);
 /* iterations replayed from the captured CUDA graph so far (the kernels inside are counted by emb_launch_count) */
 int64_t emb_graph_launch_count(const emb_ctx* ctx);
@@ -208,6 +210,10 @@ int emb_recycle_config(emb_ctx* ctx, int max_vectors, double snapshot_rtol_facto
 /* n: directions held; spmvs: matrix-vector products spent on W_t u so far; last_proj_relres: relative residual of the recycled
  * start vector in the last solve (-1 if none) */
 int emb_recycle_info(emb_ctx* ctx, int* n, int64_t* spmvs, double* last_proj_relres);
+/* directions accepted into the basis since the context was created.  Monotonic: unlike the `n` of emb_recycle_info it
+ * does not drop when the ring is compacted or emb_recycle_config resets the basis, so "how many did the last solve
+ * add" is a difference of two readings. */
+int64_t emb_recycle_accepted(const emb_ctx* ctx);
 /* exchange of directions between the ranks of a frequency-sharded sweep; d_dst / d_src are DEVICE pointers to
  * n_solve complex128 values (the host side moves them with NCCL).  j = 0 is the NEWEST direction. */
 int emb_recycle_export(emb_ctx* ctx, int j, void* d_dst);

@@ -169,7 +169,7 @@ def case_wg_medium():
     return out
 
 
-def case_abc_lumped():
+def abc_lumped_physics():
     """Patch-like box: dielectric slab, internal PEC patch, vertical LumpedPort plate, AbsorbingBoundary on
     5 outer faces, PEC ground (look-alike of demo3_patch_antenna.py, SURVEY App. C.7 iii)."""
     a, b, L = 24e-3, 24e-3, 12e-3           # x,y footprint; z height
@@ -194,6 +194,11 @@ def case_abc_lumped():
     port = fem.bc.LumpedPort(fem.FaceSelection([8]), 1, width=2 * hx, height=hz, direction=fem.ZAX, active=True, Z0=50)
     abc = fem.bc.AbsorbingBoundary(fem.FaceSelection([1, 2, 3, 4, 6]))
     phys.assign(port, abc)
+    return fem, phys, mesh, box, port, hx, hz
+
+
+def case_abc_lumped():
+    fem, phys, mesh, box, port, hx, hz = abc_lumped_physics()
     out = dict(kind="abc_lumped", dims=np.array(box.dims), face_tris=box.face_tris.astype(np.int32),
                face_tag=box.face_tag, lumped=np.array([2 * hx, hz, 50.0]),
                vint_start=np.zeros(3), vint_end=np.zeros(3))
@@ -296,6 +301,8 @@ CASES = dict(wg_tiny=case_wg_tiny, wg_materials=case_wg_materials, wg_medium=cas
              abc_lumped=case_abc_lumped, modal_microstrip=case_modal_microstrip, lossy_slabs=case_lossy_slabs)
 
 if __name__ == "__main__":
+    if not os.path.isdir("/root/reference/fem"):
+        raise SystemExit("fixtures are generated from /root/reference in the build container only")
     names = sys.argv[1:] or list(CASES)
     for n in names:
         out = CASES[n]()

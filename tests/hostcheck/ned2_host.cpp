@@ -43,7 +43,7 @@ extern "C" void ned2_host_element(const double* p_orig, const long long* vid, co
 
 // Same element matrices through the table-driven row form of the fused assembly kernel (ned2_fused.cuh).
 static void fused_impl(const double* p_orig, const long long* vid, const cx* ur, const cx* er, cx* Kref, cx* Mref,
-                       bool pairs) {
+                       int pairs) {
     static const ned2f::Tables T{};
     int ord[4] = {0, 1, 2, 3};
     for (int i = 0; i < 4; ++i)
@@ -68,12 +68,16 @@ static void fused_impl(const double* p_orig, const long long* vid, const cx* ur,
             Mref[ref[i] * 20 + ref[j]] = M;
         }
     if (!pairs) return;
-    // the form the kernel evaluates: both rows of an entity at once
+    static const ned2f::KernTables KT{};
+    // the forms that evaluate both rows of an entity at once (pairs == 2: the flat tables of the kernel)
     for (int i = 0; i < 10; ++i)
         for (int j = 0; j < 20; ++j) {
             cx Ka, Kb, Ma, Mb;
-            ned2f::row_pair_entry(T.pt[i], T.f[i], T.f[i + 10], T.f[j], T.mc[i][j], T.mc[i + 10][j], r.D, r.g, r.len, Ka, Kb,
-                                  Ma, Mb);
+            if (pairs == 2)
+                ned2f::row_pair_flat(KT, i, j, r.D, r.g, r.len, Ka, Kb, Ma, Mb);
+            else
+                ned2f::row_pair_entry(T.pt[i], T.f[i], T.f[i + 10], T.f[j], T.mc[i][j], T.mc[i + 10][j], r.D, r.g, r.len, Ka,
+                                      Kb, Ma, Mb);
             Kref[ref[i] * 20 + ref[j]] = Ka;
             Kref[ref[i + 10] * 20 + ref[j]] = Kb;
             Mref[ref[i] * 20 + ref[j]] = Ma;
@@ -81,9 +85,13 @@ static void fused_impl(const double* p_orig, const long long* vid, const cx* ur,
         }
 }
 extern "C" void ned2_host_fused(const double* p_orig, const long long* vid, const cx* ur, const cx* er, cx* Kref, cx* Mref) {
-    fused_impl(p_orig, vid, ur, er, Kref, Mref, false);
+    fused_impl(p_orig, vid, ur, er, Kref, Mref, 0);
 }
 extern "C" void ned2_host_fused_pairs(const double* p_orig, const long long* vid, const cx* ur, const cx* er, cx* Kref,
                                       cx* Mref) {
-    fused_impl(p_orig, vid, ur, er, Kref, Mref, true);
+    fused_impl(p_orig, vid, ur, er, Kref, Mref, 1);
+}
+extern "C" void ned2_host_fused_flat(const double* p_orig, const long long* vid, const cx* ur, const cx* er, cx* Kref,
+                                     cx* Mref) {
+    fused_impl(p_orig, vid, ur, er, Kref, Mref, 2);
 }

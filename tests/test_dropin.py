@@ -24,6 +24,16 @@ def test_device_rhs_tag_survives_only_b_plus_port_vector():
     assert not getattr(b + b, "_emb_zero", False)
 
 
+def test_device_rhs_inplace_arithmetic_and_frequency_tag():
+    pv = DeviceRHS(np.arange(5) + 0j, sid=3, owner="me", freq=9e9)
+    assert (_ZeroRHS(5) + pv)._emb_freq == 9e9
+    pv += np.ones(5)                              # used to recurse forever (out= forwarded to __array_ufunc__)
+    assert np.array_equal(np.asarray(pv), np.arange(5) + 1) and pv._emb_sid is None
+    q = DeviceRHS(np.zeros(3, complex), sid=1, owner="me", freq=1.0)
+    np.multiply(q, 2.0, out=q)
+    assert q._emb_sid is None
+
+
 class _Field:
     """what GpuAssembler reads from a reference Nedelec2: .mesh (+get_triangles) and the dof tables"""
 

@@ -1,0 +1,101 @@
+"""Drop-in proof on the GPU box: the UNMODIFIED reference (oracle/_ref, copied by oracle/make_ref.py) builds a real
+Electrodynamics3D and runs its own frequency_domain() three ways on the same object:
+
+  1. stock CPU path: Assembler + ParallelRoutine (RCM + SuperLU), emfreq3d.py:607-732;
+  2. after emerge_b200.dropin.install(physics): the reference's own loop on top of GpuAssembler.assemble_freq_matrix and
+     the patched SolveRoutine.solve (the two seams of SURVEY 8b);
+  3. after install(physics, fast=True): physics.frequency_domain() / frequency_domain_par(njobs) replaced by the
+     FrequencySweep-backed drivers that fill the reference's EMSimData.
+
+EMSimData.Sp must agree within 1e-3 dB / 0.1 degrees, _fields to 1e-7, for RectangularWaveguide ports, LumpedPort +
+AbsorbingBoundary, and ModalPorts whose mode comes from the reference's own modal_analysis.  The reference's result API
+(axis access) and the Touchstone export (emerge_b200.touchstone; the reference's own needs scikit-rf, absent here) run on
+the GPU-filled EMSimData.  Skipped when oracle/_ref is absent."""
+import os
+
+import numpy as np
+import pytest
+
+from tests.util import db_deg_close
+
+pytestmark = pytest.mark.gpu
+REF = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "fem")
+
+
+def _builders():
+    from tests.golden import make_golden as G
+    from oracle.refharness import harness as H
+    from emerge_b200.synthmesh import box_mesh
+
+    def rectwg():
+        box = box_mesh(5, 3, 8, *G.WR90, 24e-3, jitter=0.1, seed=2)
+        fem, phys, mesh = H.build_physics(box)
+        H.rect_waveguide_ports(fem, phys, box)
+        return phys, [8.5e9, 10e9, 11.5e9]
+
+    def abc_lumped():
+        fem, phys, mesh, box, port, hx, hz = G.abc_lumped_physics()
+        return phys, [2.0e9, 2.2e9, 2.4e9]
+
+    def modal():
+        box = G.microstrip_box(8, 6, 5)
+        fem, phys, mesh, ports = G.modal_physics(box)
+        phys.frequencies = [1e9]
+        for p in ports:
+            phys.modal_analysis(p, 1, direct=True, TEM=True, freq=1e9)
+        return phys, [1e9, 2e9, 3e9]
+    return dict(rectwg=rectwg, abc_lumped=abc_lumped, modal=modal)
+
+
+def _collect(data, nf):
+    S = np.array([data.item(i).Sp.arry.copy() for i in range(nf)])
+    fields = [{k: np.array(v) for k, v in data.item(i)._fields.items()} for i in range(nf)]
+    return S, fields
+
+
+def _check(data, nf, S_ref, F_ref, what, fields=True):
+    S, F = _collect(data, nf)
+    assert db_deg_close(S, S_ref), (what, S, S_ref)
+    if fields:
+        for i in range(nf):
+            assert set(F[i]) == set(F_ref[i]), what
+            for k, x in F[i].items():
+                assert np.linalg.norm(x - F_ref[i][k]) <= 1e-7 * np.linalg.norm(F_ref[i][k]), (what, i, k)
+    for i in range(nf):
+        d, r = data.item(i), None
+        assert d.er.shape == d.ur.shape and len(d.port_modes) == S.shape[1]
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="oracle/_ref (copy of the reference package) not present")
+@pytest.mark.parametrize("case", ["rectwg", "abc_lumped", "modal"])
+def test_reference_frequency_domain_on_top_of_install(case, tmp_path):
+    from emerge_b200.dropin import install, GpuAssembler
+    phys, freqs = _builders()[case]()
+    nf = len(freqs)
+    phys.frequencies = list(freqs)
+    data = phys.frequency_domain()                                   # 1. the reference, untouched
+    S_ref, F_ref = _collect(data, nf)
+    stock_solve = type(phys.solveroutine).solve
+
+    asm = install(phys, rtol=1e-10)                                  # 2. the two seams
+    assert isinstance(phys.assembler, GpuAssembler)
+    data = phys.frequency_domain()
+    _check(data, nf, S_ref, F_ref, "seams")
+    data = phys.frequency_domain()                                   # same problem again: the device state is reused
+    _check(data, nf, S_ref, F_ref, "seams, second run")
+    asm.ctx.close()
+
+    phys.solveroutine.solve = stock_solve.__get__(phys.solveroutine)  # 3. the fast drivers, shipped tolerance
+    asm = install(phys, fast=True)
+    assert asm.solver_opts["rtol"] == 1e-8
+    data = phys.frequency_domain()
+    _check(data, nf, S_ref, F_ref, "fast driver")
+    data = phys.frequency_domain_par(njobs=2)
+    _check(data, nf, S_ref, F_ref, "fast parallel driver (one rank)")
+    # result API of the reference on the GPU-filled object: axis access and Touchstone export (emdata.py:284-331)
+    f_ax, s21 = data.ax("freq").S(1, 1)
+    assert np.allclose(f_ax, freqs) and np.allclose(s21, S_ref[:, 0, 0], atol=1e-4)
+    from emerge_b200.touchstone import export_touchstone, read_touchstone
+    f_ts, S_ts, _ = read_touchstone(export_touchstone(data, str(tmp_path / "sweep"), "RI"))
+    assert np.allclose(f_ts, freqs) and db_deg_close(S_ts, S_ref)
+    asm.ctx.close()

@@ -69,10 +69,10 @@ def test_fused_row_form_matches_templates_and_reference(hostlib):
             # relabelled global ids exercise every canonical ordering; the reference-order result must not change
             ids = np.array([10, 20, 30, 40])[perm] if perm is not None else vid
             K0, M0 = _run(hostlib, p, ids, ur, er)
-            for fn in ("ned2_host_fused", "ned2_host_fused_pairs"):
+            for fn in ("ned2_host_fused", "ned2_host_fused_pairs", "ned2_host_fused_flat"):
                 K1, M1 = _run(hostlib, p, ids, ur, er, fn=fn)
                 assert np.abs(K1 - K0).max() <= 1e-14 * np.abs(K0).max()
                 assert np.abs(M1 - M0).max() <= 1e-14 * np.abs(M0).max()
-        K1, M1 = _run(hostlib, p, vid, ur, er, fn="ned2_host_fused_pairs")
+        K1, M1 = _run(hostlib, p, vid, ur, er, fn="ned2_host_fused_flat")
         assert np.abs(K1 - Eref).max() <= 1e-12 * np.abs(Eref).max()
         assert np.abs(M1 - Bref).max() <= 1e-12 * np.abs(Bref).max()
