@@ -551,7 +551,7 @@ __global__ void k_check_pairs(int64_t nT, int nEF, const int* __restrict__ gid, 
 // row-length caps of the two shared-memory classes (faces and edges with <= 6 tetrahedra | edges with <= 13); class 2 =
 // accumulators in global memory.  One launch per class; inside a class entities are ordered by their first tetrahedron.
 constexpr int ACLS0 = 80, ACLS1 = 160;
-constexpr int AWARPS0 = 24, AWARPS1 = 12;
+constexpr int AWARPS0 = 20, AWARPS1 = 12;
 __global__ void k_entity_keys(int nEF, const int64_t* __restrict__ adjptr, const int* __restrict__ adj,
                               const int64_t* __restrict__ rowptr, unsigned* __restrict__ key, int* __restrict__ val,
                               int* __restrict__ bad) {
@@ -620,45 +620,69 @@ __global__ void __launch_bounds__(WARPS * 32) k_asm_rows(int64_t nitems, const i
     const double2* recG = wb.rec + 36;
     const double* recLen = reinterpret_cast<const double*>(wb.rec + 52);
 
+    // Software pipeline over the items of this warp (every stage is a dependent global load of the previous one):
+    //   item w+3: entity id          item w+2: metadata (row / adjacency offsets)
+    //   item w+1: adjacency list and column list (registers)          item w: records, tet by tet, one ahead
+    // so that no item starts with an exposed chain of DRAM round trips.
+    constexpr int CREG = (ROWCAP + 31) / 32;
     const int64_t stride = (int64_t)gridDim.x * WARPS;
     int64_t w = blockIdx.x * (int64_t)WARPS + warp;
     if (w >= nitems) return;
+    auto item_at = [&](int64_t i) { return i < nitems ? __ldg(items + i) : -1; };
+    auto load_adj = [&](const AsmMeta& mm) { return lane < mm.deg ? __ldg(adj + mm.a0 + lane) : 0; };
+    int e1 = item_at(w + stride), e2 = item_at(w + 2 * stride);
     AsmMeta m = asm_load_meta(__ldg(items + w), nEF, adjptr, rowptr);
-    int e_next = (w + stride < nitems) ? __ldg(items + w + stride) : -1;
-    int myadj = lane < m.deg ? __ldg(adj + m.a0 + lane) : 0;
+    AsmMeta m1 = m;
+    if (e1 >= 0) m1 = asm_load_meta(e1, nEF, adjptr, rowptr);
+    int myadj = load_adj(m);
+    int colr[CREG];
+#pragma unroll
+    for (int i = 0; i < CREG; ++i) colr[i] = (lane + 32 * i < m.len) ? __ldg(col + m.p0 + lane + 32 * i) : 0;
+    double2 r0 = make_double2(0, 0), r1 = r0;
+    int cj = 0;
+    auto fetch_rec = [&](int t) {
+        const double2* rp = reinterpret_cast<const double2*>(recs + t);
+        r0 = __ldg(rp + lane);
+        if (lane < 24) r1 = __ldg(rp + 32 + lane);
+        if (colLane) cj = __ldg(gid + (int64_t)t * 20 + lane);
+    };
+    if (m.deg > 0) fetch_rec(__shfl_sync(0xffffffffu, myadj, 0) / 20);
     for (; w < nitems; w += stride) {
-        // metadata of the next item and the entity id of the one after it: in flight while this item is processed
-        AsmMeta mn = m;
-        if (e_next >= 0) mn = asm_load_meta(e_next, nEF, adjptr, rowptr);
-        const int e_next2 = (w + 2 * stride < nitems) ? __ldg(items + w + 2 * stride) : -1;
+        // stage loads of the following items
+        int adj1 = 0, colr1[CREG];
+#pragma unroll
+        for (int i = 0; i < CREG; ++i) colr1[i] = 0;
+        if (e1 >= 0) {
+            adj1 = load_adj(m1);
+#pragma unroll
+            for (int i = 0; i < CREG; ++i) colr1[i] = (lane + 32 * i < m1.len) ? __ldg(col + m1.p0 + lane + 32 * i) : 0;
+        }
+        AsmMeta m2 = m1;
+        if (e2 >= 0) m2 = asm_load_meta(e2, nEF, adjptr, rowptr);
+        const int e3 = item_at(w + 3 * stride);
         const int deg = m.deg, len = m.len;
-        for (int k = lane; k < len; k += 32) {
-            wb.cols[k] = __ldg(col + m.p0 + k);
-            const double2 z = make_double2(0.0, 0.0);
-            wb.acc[0][k] = z; wb.acc[1][k] = z; wb.acc[2][k] = z; wb.acc[3][k] = z;
+#pragma unroll
+        for (int i = 0; i < CREG; ++i) {
+            const int k = lane + 32 * i;
+            if (k < len) {
+                wb.cols[k] = colr[i];
+                const double2 z = make_double2(0.0, 0.0);
+                wb.acc[0][k] = z; wb.acc[1][k] = z; wb.acc[2][k] = z; wb.acc[3][k] = z;
+            }
         }
-        // first record (56 x 16 B: every lane one piece, lanes 0..23 a second one) and the tet's dof ids
-        double2 r0 = make_double2(0, 0), r1 = r0;
-        int cj = 0;
-        if (deg > 0) {
-            const int t = __shfl_sync(0xffffffffu, myadj, 0) / 20;
-            const double2* rp = reinterpret_cast<const double2*>(recs + t);
-            r0 = __ldg(rp + lane);
-            if (lane < 24) r1 = __ldg(rp + 32 + lane);
-            if (colLane) cj = __ldg(gid + (int64_t)t * 20 + lane);
-        }
+        bool next_fetched = false;
         for (int n = 0; n < deg; ++n) {
             const int ic = __shfl_sync(0xffffffffu, myadj, n) % 20;      // canonical local row of the entity's first function
             wb.rec[lane] = r0;
             if (lane < 24) wb.rec[32 + lane] = r1;
             const int c = cj;
             __syncwarp();
+            // next record: of this entity, or the first one of the next entity
             if (n + 1 < deg) {
-                const int t = __shfl_sync(0xffffffffu, myadj, n + 1) / 20;
-                const double2* rp = reinterpret_cast<const double2*>(recs + t);
-                r0 = __ldg(rp + lane);
-                if (lane < 24) r1 = __ldg(rp + 32 + lane);
-                if (colLane) cj = __ldg(gid + (int64_t)t * 20 + lane);
+                fetch_rec(__shfl_sync(0xffffffffu, myadj, n + 1) / 20);
+            } else if (e1 >= 0 && m1.deg > 0) {
+                fetch_rec(__shfl_sync(0xffffffffu, adj1, 0) / 20);
+                next_fetched = true;
             }
             if (colLane) {
                 // position of column c in the row's sorted column list (present by construction)
@@ -707,18 +731,20 @@ __global__ void __launch_bounds__(WARPS * 32) k_asm_rows(int64_t nitems, const i
             }
             __syncwarp();
         }
-        // adjacency of the next item (its metadata has arrived by now); overlaps the write-out below
-        if (e_next >= 0) myadj = lane < mn.deg ? __ldg(adj + mn.a0 + lane) : 0;
+        if (!next_fetched && e1 >= 0 && m1.deg > 0) fetch_rec(__shfl_sync(0xffffffffu, adj1, 0) / 20);
         double2* Ka = reinterpret_cast<double2*>(K + m.p0);
         double2* Kb = reinterpret_cast<double2*>(K + m.p1);
         double2* Ma = reinterpret_cast<double2*>(M + m.p0);
         double2* Mb = reinterpret_cast<double2*>(M + m.p1);
-        for (int k = lane; k < len; k += 32) {
-            Ka[k] = wb.acc[0][k]; Kb[k] = wb.acc[1][k]; Ma[k] = wb.acc[2][k]; Mb[k] = wb.acc[3][k];
+#pragma unroll
+        for (int i = 0; i < CREG; ++i) {
+            const int k = lane + 32 * i;
+            if (k < len) { Ka[k] = wb.acc[0][k]; Kb[k] = wb.acc[1][k]; Ma[k] = wb.acc[2][k]; Mb[k] = wb.acc[3][k]; }
         }
         __syncwarp();
-        m = mn;
-        e_next = e_next2;
+        m = m1; m1 = m2; e1 = e2; e2 = e3; myadj = adj1;
+#pragma unroll
+        for (int i = 0; i < CREG; ++i) colr[i] = colr1[i];
     }
 }
 
@@ -835,7 +861,10 @@ static int assemble_fused(emb_ctx* c) {
     {
         PhaseTimer pt(c, "reduce");
         const int64_t* cp = c->asm_cls_ptr;
-        EMB_TRY((launch_asm_rows<ACLS0, AWARPS0>(c, cp[0], cp[1], recs.p)));
+        static const int warps_env = getenv("EMB_ASM_WARPS") ? atoi(getenv("EMB_ASM_WARPS")) : 0;     // tuning probe
+        if (warps_env == 16) EMB_TRY((launch_asm_rows<ACLS0, 16>(c, cp[0], cp[1], recs.p)));
+        else if (warps_env == 24) EMB_TRY((launch_asm_rows<ACLS0, 24>(c, cp[0], cp[1], recs.p)));
+        else EMB_TRY((launch_asm_rows<ACLS0, AWARPS0>(c, cp[0], cp[1], recs.p)));
         EMB_TRY((launch_asm_rows<ACLS1, AWARPS1>(c, cp[1], cp[2], recs.p)));
         if (cp[3] > cp[2]) {
             k_asm_rows_big<<<blocks_for(cp[3] - cp[2], 4), 128, 0, c->stream>>>(cp[3] - cp[2], c->asm_ent.p + cp[2],

@@ -132,6 +132,13 @@ struct emb_ctx {
     bool paired = false;
     DevBuf<int> sperm;        // [Ns] ascending-dof position -> solve index (identity when not paired)
     DevBuf<int> blkcol;       // [nnz_s / 4] entity column of each 2x2 block (paired only)
+    // SELL-8-sigma layout of the inner operator As (complex64), sell.cuh: slice-row -> block-row, block-row -> slice-row,
+    // slice offsets (in blocks), column of every padded block slot
+    bool sell_ready = false, sell_active = false, sell_tried = false;
+    const void* sell_zeroed = nullptr;        // As32 buffer whose padding slots are known to be zero
+    int64_t sell_nslices = 0, sell_blocks = 0;
+    DevBuf<int> sell_rows, sell_pos, sell_bcol;
+    DevBuf<int64_t> sell_sptr;
     DevBuf<cx> A;             // [nnz_s]
     bool have_dirichlet = false, have_A = false;
     double k0 = 0;

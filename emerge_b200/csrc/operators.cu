@@ -532,6 +532,9 @@ extern "C" int emb_set_dirichlet(emb_ctx* c, int64_t npec, const int64_t* pec_id
         paired = false;
     }
     c->paired = paired;
+    c->sell_ready = c->sell_active = c->sell_tried = false;      // the SELL layout of the inner operator follows the pattern
+    c->sell_zeroed = nullptr;
+    c->sell_rows.release(); c->sell_pos.release(); c->sell_bcol.release(); c->sell_sptr.release();
     flag.release();
     EMB_CUDA(c, cudaStreamSynchronize(c->stream));
     keep.release(); scan.release(); dids.release(); rowlen.release(); tmp.release();

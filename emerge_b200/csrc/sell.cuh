@@ -1,0 +1,201 @@
+// Inner operator As (complex64, 2x2 blocks) in a sliced-ELL layout: SELL-8-sigma over BLOCK-ROWS.
+//
+// Why: in block-CSR (krylov.cuh::k_bspmv) every lane group walks its own block-row, so one warp-wide load of values or
+// column indices touches 8 different cache lines and uses 16 of each 32-byte sector; ncu (profiles/r1_*): l1tex 80 %,
+// 86 % long-scoreboard stalls, 50 % of the HBM roofline although DRAM traffic is only 1.08 x the algorithmic bytes.  Here
+// the block-rows are grouped in slices of 8 with the blocks of a slice interleaved (slot = sptr[s] + 8 q + r for block q
+// of slice-row r), so the same warp-wide load reads 8 consecutive 32-byte blocks (two full lines) and 8 consecutive
+// column indices (one sector); what is left for the load/store unit are the x gathers.  Slices are padded to their
+// longest block-row; block-rows are sorted by length inside windows of SIGMA rows first (padding < 1 % on the waveguide
+// meshes instead of ~25 % - edge rows alternate between 25 and 37 blocks), which only permutes which rows a warp owns:
+// the numbering of x and y is untouched.
+// Block storage is column-major, [h][r]: the two values a lane needs (rows 2j, 2j+1 of column 2c+h) are one 16-byte load.
+// The reference has no counterpart (it factorises, fem/solver.py:243-309).
+#pragma once
+#include "krylov.cuh"
+#include <cub/cub.cuh>
+
+constexpr int SELL_C = 8;
+constexpr int SELL_SIGMA = 1024;
+constexpr int SELL_LENBITS = 12;
+
+__global__ void k_sell_keys(int nbr, const int64_t* __restrict__ rowptr_s, unsigned* __restrict__ key, int* __restrict__ val,
+                            int* __restrict__ flag) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nbr) return;
+    const int64_t len = (rowptr_s[2 * j + 1] - rowptr_s[2 * j]) >> 1;
+    if (len >= (1 << SELL_LENBITS)) atomicExch(flag, 1);
+    key[j] = ((unsigned)(j / SELL_SIGMA) << SELL_LENBITS) | (unsigned)(len & ((1 << SELL_LENBITS) - 1));
+    val[j] = j;
+}
+// rows[R] = block-row of slice-row R (or -1), pos[j] = R, slen[s] = 8 * (longest block-row of slice s)
+__global__ void k_sell_slices(int nbr, int nslices, const int* __restrict__ sorted, const int64_t* __restrict__ rowptr_s,
+                              int* __restrict__ rows, int* __restrict__ pos, int64_t* __restrict__ slen) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s > nslices) return;
+    if (s == nslices) { slen[s] = 0; return; }
+    int64_t mx = 0;
+    for (int r = 0; r < SELL_C; ++r) {
+        const int R = s * SELL_C + r;
+        int j = -1;
+        if (R < nbr) {
+            j = sorted[R];
+            pos[j] = R;
+            const int64_t len = (rowptr_s[2 * j + 1] - rowptr_s[2 * j]) >> 1;
+            mx = len > mx ? len : mx;
+        }
+        rows[R] = j;
+    }
+    slen[s] = mx * SELL_C;
+}
+__global__ void k_sell_bcol(int nslices, const int* __restrict__ rows, const int64_t* __restrict__ sptr,
+                            const int64_t* __restrict__ rowptr_s, const int* __restrict__ blkcol, int* __restrict__ bcol) {
+    const int lane = threadIdx.x & 31;
+    const int64_t R = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (R >= (int64_t)nslices * SELL_C) return;
+    const int s = (int)(R / SELL_C), r = (int)(R % SELL_C);
+    const int64_t base = sptr[s];
+    const int nb = (int)((sptr[s + 1] - base) / SELL_C);
+    const int j = rows[R];
+    int64_t p0 = 0;
+    int len = 0;
+    if (j >= 0) { p0 = rowptr_s[2 * j]; len = (int)((rowptr_s[2 * j + 1] - p0) >> 1); }
+    const int padcol = len > 0 ? blkcol[p0 >> 2] : 0;        // padding blocks carry zero values: any valid column will do
+    for (int q = lane; q < nb; q += 32) bcol[base + (int64_t)q * SELL_C + r] = q < len ? blkcol[(p0 >> 2) + q] : padcol;
+}
+
+static int sell_build(emb_ctx* c) {
+    c->sell_ready = false;
+    if (!c->paired) return EMB_OK;
+    const int nbr = (int)(c->Ns / 2);
+    const int nslices = (nbr + SELL_C - 1) / SELL_C;
+    DevBuf<unsigned> key, key2;
+    DevBuf<int> val, sorted, flag;
+    DevBuf<int64_t> slen;
+    DevBuf<char> tmp;
+    EMB_TRY(dev_alloc(c, key, (size_t)nbr));
+    EMB_TRY(dev_alloc(c, key2, (size_t)nbr));
+    EMB_TRY(dev_alloc(c, val, (size_t)nbr));
+    EMB_TRY(dev_alloc(c, sorted, (size_t)nbr));
+    EMB_TRY(dev_alloc(c, flag, 1));
+    EMB_CUDA(c, cudaMemsetAsync(flag.p, 0, sizeof(int), c->stream));
+    k_sell_keys<<<blocks_for(nbr, 256), 256, 0, c->stream>>>(nbr, c->rowptr_s.p, key.p, val.p, flag.p);
+    EMB_LAUNCH_CHECK(c);
+    int wbits = 1;
+    while (((int64_t)1 << wbits) < (nbr + SELL_SIGMA - 1) / SELL_SIGMA + 1) ++wbits;
+    size_t tb = 0;
+    EMB_CUDA(c, cub::DeviceRadixSort::SortPairs(nullptr, tb, key.p, key2.p, val.p, sorted.p, nbr, 0, SELL_LENBITS + wbits, c->stream));
+    EMB_TRY(dev_alloc(c, tmp, tb));
+    EMB_CUDA(c, cub::DeviceRadixSort::SortPairs(tmp.p, tb, key.p, key2.p, val.p, sorted.p, nbr, 0, SELL_LENBITS + wbits, c->stream));
+    EMB_TRY(dev_alloc(c, c->sell_rows, (size_t)nslices * SELL_C));
+    EMB_TRY(dev_alloc(c, c->sell_pos, (size_t)nbr));
+    EMB_TRY(dev_alloc(c, slen, (size_t)nslices + 1));
+    EMB_TRY(dev_alloc(c, c->sell_sptr, (size_t)nslices + 1));
+    k_sell_slices<<<blocks_for(nslices + 1, 256), 256, 0, c->stream>>>(nbr, nslices, sorted.p, c->rowptr_s.p, c->sell_rows.p,
+                                                                      c->sell_pos.p, slen.p);
+    EMB_LAUNCH_CHECK(c);
+    size_t tb2 = 0;
+    EMB_CUDA(c, cub::DeviceScan::ExclusiveSum(nullptr, tb2, slen.p, c->sell_sptr.p, nslices + 1, c->stream));
+    if (tb2 > tmp.n) EMB_TRY(dev_alloc(c, tmp, tb2));
+    EMB_CUDA(c, cub::DeviceScan::ExclusiveSum(tmp.p, tb2, slen.p, c->sell_sptr.p, nslices + 1, c->stream));
+    c->launches += 4;
+    int hflag = 0;
+    int64_t total = 0;
+    EMB_CUDA(c, cudaMemcpyAsync(&hflag, flag.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    EMB_CUDA(c, cudaMemcpyAsync(&total, c->sell_sptr.p + nslices, sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+    EMB_CUDA(c, cudaStreamSynchronize(c->stream));
+    key.release(); key2.release(); val.release(); sorted.release(); flag.release(); slen.release(); tmp.release();
+    if (hflag || total >= ((int64_t)1 << 31)) {           // a block-row of >= 4096 blocks / int32 slots: keep block-CSR
+        c->sell_rows.release(); c->sell_pos.release(); c->sell_sptr.release();
+        return EMB_OK;
+    }
+    c->sell_nslices = nslices;
+    c->sell_blocks = total;
+    EMB_TRY(dev_alloc(c, c->sell_bcol, (size_t)total));
+    k_sell_bcol<<<blocks_for((int64_t)nslices * SELL_C * 32, 256), 256, 0, c->stream>>>(nslices, c->sell_rows.p, c->sell_sptr.p,
+                                                                                       c->rowptr_s.p, c->blkcol.p, c->sell_bcol.p);
+    EMB_LAUNCH_CHECK(c);
+    c->sell_ready = true;
+    return EMB_OK;
+}
+
+// As = (A + A^T) / 2 in complex64, written straight into the SELL layout.  One warp per block-row; the transposed
+// entry is found by binary search in the column list of the other row (the pattern is structurally symmetric).
+__global__ void k_sym_part_sell(int64_t nbr, const int64_t* __restrict__ rowptr, const int* __restrict__ col,
+                                const cx* __restrict__ A, const int* __restrict__ pos, const int64_t* __restrict__ sptr,
+                                cf* __restrict__ As) {
+    const int lane = threadIdx.x & 31;
+    const int64_t j = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (j >= nbr) return;
+    const int R = pos[j];
+    const int64_t base = sptr[R / SELL_C];
+    const int r = R % SELL_C;
+    const int64_t p0 = rowptr[2 * j], p1 = rowptr[2 * j + 1];
+    const int n2 = (int)(p1 - p0);                      // entries per row = 2 x blocks
+    for (int e2 = lane; e2 < 2 * n2; e2 += 32) {
+        const int rr = e2 >= n2 ? 1 : 0, e = e2 - rr * n2;
+        const int64_t k = (rr ? p1 : p0) + e;
+        const int row = (int)(2 * j + rr);
+        const int cj = col[k];
+        int64_t lo = rowptr[cj], hi = rowptr[cj + 1] - 1;
+        while (lo < hi) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (col[mid] < row) lo = mid + 1; else hi = mid;
+        }
+        cx a = A[k];
+        if (col[lo] == row) { const cx b = A[lo]; a = cx{0.5 * (a.re + b.re), 0.5 * (a.im + b.im)}; }
+        const int q = e >> 1, h = e & 1;
+        stval(As, (base + (int64_t)q * SELL_C + r) * 4 + h * 2 + rr, a);
+    }
+}
+
+// y = As x on NV interleaved right-hand sides.  Thread (R, u): slice-row R = block-row rows[R], u = (h, k) = column half
+// and right-hand side; per block one column index (broadcast over the 2 NV lanes of the row), one 16-byte piece of x, one
+// 16-byte pair of values.  NV = 2: a warp is exactly one slice.
+template <int NV>
+__global__ void __launch_bounds__(256) k_bsell(int64_t nR, const int* __restrict__ rows, const int64_t* __restrict__ sptr,
+                                               const int* __restrict__ bcol, const float4* __restrict__ val,
+                                               const cx* __restrict__ x, cx* __restrict__ y) {
+    constexpr int LPB = 2 * NV;
+    const int64_t gt = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    int64_t R = gt / LPB;
+    const int u = (int)(gt % LPB);
+    const int h = u / NV;
+    const bool live = R < nR;
+    if (!live) R = nR - 1;
+    const int64_t s = R / SELL_C;
+    const int r = (int)(R % SELL_C);
+    const int64_t base = __ldg(sptr + s);
+    const int nb = live ? (int)((__ldg(sptr + s + 1) - base) / SELL_C) : 0;
+    const int* bc = bcol + base + r;
+    const float4* vv = val + (base + r) * 2 + h;
+    double a0r = 0.0, a0i = 0.0, a1r = 0.0, a1i = 0.0;
+#pragma unroll 4
+    for (int q = 0; q < nb; ++q) {
+        const int cb = __ldg(bc + q * SELL_C);
+        const float4 e = __ldg(vv + q * (SELL_C * 2));
+        const cx w = ldx(x + (int64_t)cb * LPB + u);
+        a0r += (double)e.x * w.re - (double)e.y * w.im;
+        a0i += (double)e.x * w.im + (double)e.y * w.re;
+        a1r += (double)e.z * w.re - (double)e.w * w.im;
+        a1i += (double)e.z * w.im + (double)e.w * w.re;
+    }
+    a0r += __shfl_xor_sync(0xffffffffu, a0r, NV);
+    a0i += __shfl_xor_sync(0xffffffffu, a0i, NV);
+    a1r += __shfl_xor_sync(0xffffffffu, a1r, NV);
+    a1i += __shfl_xor_sync(0xffffffffu, a1i, NV);
+    const int j = live ? __ldg(rows + R) : -1;
+    if (j >= 0 && h == 0) {
+        stv(y, (int64_t)(2 * j) * NV + u, cx{a0r, a0i});
+        stv(y, (int64_t)(2 * j + 1) * NV + u, cx{a1r, a1i});
+    }
+}
+
+template <int NV>
+static int bsell_launch(emb_ctx* c, const cf* val, const cx* x, cx* y) {
+    const int64_t nR = (int64_t)c->sell_nslices * SELL_C;
+    k_bsell<NV><<<blocks_for(nR * 2 * NV, 256), 256, 0, c->stream>>>(nR, c->sell_rows.p, c->sell_sptr.p, c->sell_bcol.p,
+                                                                    reinterpret_cast<const float4*>(val), x, y);
+    EMB_LAUNCH_CHECK(c);
+    return EMB_OK;
+}

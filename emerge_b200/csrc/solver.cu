@@ -25,8 +25,56 @@
 #include "krylov.cuh"
 #include "precond.cuh"
 #include "recycle.cuh"
+#include "sell.cuh"
 #include <type_traits>
 #include <vector>
+
+// inner operator application: SELL layout (sell.cuh) when As was built that way, else block-CSR / CSR (krylov.cuh)
+template <int NV, typename VT, typename VX>
+static int apply_inner(emb_ctx* c, const VT* As, const VX* x, VX* y) {
+    if constexpr (std::is_same<VT, cf>::value && std::is_same<VX, cx>::value) {
+        if (c->sell_active) return bsell_launch<NV>(c, As, x, y);
+    }
+    return spmv_inner<NV, VT, VX>(c, As, x, y);
+}
+// complex64 storage of the inner operator in the layout of this pattern: SELL-8-sigma on a pair-ordered solve space
+// (EMB_SPMV_SELL=0: block layout), with the padding slots zeroed once per buffer
+static int alloc_As32(emb_ctx* c, cf** out) {
+    static const bool want_sell = !(getenv("EMB_SPMV_SELL") && atoi(getenv("EMB_SPMV_SELL")) == 0);
+    if (want_sell && c->paired && !c->sell_tried) {
+        c->sell_tried = true;
+        EMB_TRY(sell_build(c));
+    }
+    if (want_sell && c->paired && c->sell_ready) {
+        EMB_TRY(dev_alloc(c, c->As32, (size_t)c->sell_blocks * 8));
+        if (c->sell_zeroed != c->As32.p || !c->sell_active) {
+            EMB_CUDA(c, cudaMemsetAsync(c->As32.p, 0, c->As32.n * sizeof(float), c->stream));
+            c->sell_zeroed = c->As32.p;
+            c->have_As = false;
+        }
+        c->sell_active = true;
+    } else {
+        EMB_TRY(dev_alloc(c, c->As32, (size_t)c->nnz_s * 2));
+        if (c->sell_active) c->have_As = false;
+        c->sell_active = false;
+    }
+    *out = reinterpret_cast<cf*>(c->As32.p);
+    return EMB_OK;
+}
+template <typename VT>
+static int fill_As(emb_ctx* c, VT* As) {
+    if constexpr (std::is_same<VT, cf>::value) {
+        if (c->sell_active) {
+            k_sym_part_sell<<<blocks_for((c->Ns / 2) * 32, 256), 256, 0, c->stream>>>(c->Ns / 2, c->rowptr_s.p, c->col_s.p, c->A.p,
+                                                                                   c->sell_pos.p, c->sell_sptr.p, As);
+            EMB_LAUNCH_CHECK(c);
+            return EMB_OK;
+        }
+    }
+    k_sym_part<VT><<<blocks_for(c->Ns * 32, 256), 256, 0, c->stream>>>(c->Ns, c->paired ? 1 : 0, c->rowptr_s.p, c->col_s.p, c->A.p, As);
+    EMB_LAUNCH_CHECK(c);
+    return EMB_OK;
+}
 
 // ------------------------------------------------------------------------------------------------
 // workspace
@@ -103,7 +151,7 @@ struct CocrBody {
         k_gram<NV, VX><<<NPART, VBLOCK, 0, c->stream>>>(n, Ap, MAp, partA); EMB_LAUNCH_CHECK(c);
         k_bcocr_update<NV, VX><<<NPART, VBLOCK, 0, c->stream>>>(n, block, partA, sc, p, Ap, MAp, d, r, z, partR); EMB_LAUNCH_CHECK(c);
         if (sample) cudaEventRecord(c->evs0, c->stream);
-        EMB_TRY((spmv_inner<NV, VT, VX>(c, As, z, Az)));
+        EMB_TRY((apply_inner<NV, VT, VX>(c, As, z, Az)));
         if (sample) cudaEventRecord(c->evs1, c->stream);
         k_gram<NV, VX><<<NPART, VBLOCK, 0, c->stream>>>(n, z, Az, partZ); EMB_LAUNCH_CHECK(c);
         k_bcocr_dir<NV, VX><<<NPART, VBLOCK, 0, c->stream>>>(n, block, partZ, partR, sc, z, Az, p, Ap); EMB_LAUNCH_CHECK(c);
@@ -126,7 +174,7 @@ static int cocr(emb_ctx* c, int pmode, int block, const VT* As, const cx* rhs, V
     k_convert<cx, VX><<<vb, 256, 0, c->stream>>>(nn, rhs, B.r); EMB_LAUNCH_CHECK(c);
     EMB_TRY((precond_inner<NV, VX>(c, pmode, B.r, B.z)));
     k_convert<VX, VX><<<vb, 256, 0, c->stream>>>(nn, B.z, B.p); EMB_LAUNCH_CHECK(c);
-    EMB_TRY((spmv_inner<NV, VT, VX>(c, As, B.z, B.Az))); ++*spmvs;
+    EMB_TRY((apply_inner<NV, VT, VX>(c, As, B.z, B.Az))); ++*spmvs;
     k_convert<VX, VX><<<vb, 256, 0, c->stream>>>(nn, B.Az, B.Ap); EMB_LAUNCH_CHECK(c);
     k_gram<NV, VX><<<NPART, VBLOCK, 0, c->stream>>>(n, B.z, B.Az, B.partZ); EMB_LAUNCH_CHECK(c);
     k_gram_finish<NV><<<1, VBLOCK, 0, c->stream>>>(B.partZ, B.sc + SC_RHO); EMB_LAUNCH_CHECK(c);
@@ -369,8 +417,7 @@ template <typename VT>
 static int ensure_operator(emb_ctx* c, int precond, VT* As) {
     const int64_t n = c->Ns;
     if (!c->have_As) {
-        k_sym_part<VT><<<blocks_for(n * 32, 256), 256, 0, c->stream>>>(n, c->paired ? 1 : 0, c->rowptr_s.p, c->col_s.p, c->A.p, As);
-        EMB_LAUNCH_CHECK(c);
+        EMB_TRY(fill_As<VT>(c, As));
         EMB_TRY(precond_setup<cx>(c, precond, c->A.p));
         c->have_As = true;
         c->As_precond = precond;
@@ -476,8 +523,8 @@ static int solve_device(emb_ctx* c, const emb_solve_opts* o, const cx* bs, cx* x
             if (c->coarse_basis && (c->coarse_version != c->rc_version || c->coarse_k0 != c->k0))
                 EMB_TRY(rc_coarse_update(c));          // experimental: coefficient map of the coarse space for this A(f)
             if (fp32) {
-                EMB_TRY(dev_alloc(c, c->As32, (size_t)c->nnz_s * 2));
-                cf* As = reinterpret_cast<cf*>(c->As32.p);
+                cf* As = nullptr;
+                EMB_TRY(alloc_As32(c, &As));
                 EMB_TRY(ensure_operator<cf>(c, o->precond, As));
                 rc = cocr<NV, cf, cx>(c, o->precond, blk ? 1 : 0, As, rr, dd, stop, o->maxit - its, &iit, &spmvs, irn);
             } else {
@@ -697,17 +744,15 @@ extern "C" int emb_spmv_bench_ex(emb_ctx* c, int reps, int nv, int fp32, double*
     EMB_CUDA(c, cudaMemsetAsync(dy.p, 0, (size_t)c->Ns * nv * sizeof(cx), c->stream));
     cf* A32 = nullptr;
     if (fp32) {
-        EMB_TRY(dev_alloc(c, c->As32, (size_t)c->nnz_s * 2));
-        A32 = reinterpret_cast<cf*>(c->As32.p);
-        k_sym_part<cf><<<blocks_for(c->Ns * 32, 256), 256, 0, c->stream>>>(c->Ns, c->paired ? 1 : 0, c->rowptr_s.p, c->col_s.p, c->A.p, A32);
-        EMB_LAUNCH_CHECK(c);
+        EMB_TRY(alloc_As32(c, &A32));
+        EMB_TRY(fill_As<cf>(c, A32));
         c->have_As = false;
     }
     auto one = [&](const cx* x, cx* y) -> int {
         if (fp32) {
-            if (nv == 1) return spmv_inner<1, cf, cx>(c, A32, x, y);
-            if (nv == 2) return spmv_inner<2, cf, cx>(c, A32, x, y);
-            return spmv_inner<4, cf, cx>(c, A32, x, y);
+            if (nv == 1) return apply_inner<1, cf, cx>(c, A32, x, y);
+            if (nv == 2) return apply_inner<2, cf, cx>(c, A32, x, y);
+            return apply_inner<4, cf, cx>(c, A32, x, y);
         }
         if (nv == 1) return spmv<1, cx>(c, c->A.p, x, y);
         if (nv == 2) return spmv<2, cx>(c, c->A.p, x, y);

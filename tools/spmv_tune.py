@@ -20,4 +20,5 @@ for nv in (1, 2, 4):
     for fp32 in (False, True):
         ms = ctx.spmv_bench(20, nv=nv, fp32=fp32)
         b = (8 if fp32 else 16) * nnz + nnz + (4 + 32 * nv) * Ns
-        print(f"KPR={os.environ.get('EMB_SPMV_KPR')} paired={ctx.paired} nv={nv} fp32={fp32}: {ms:.3f} ms  {b / ms / 1e6:.0f} GB/s", flush=True)
+        print(f"KPR={os.environ.get('EMB_SPMV_KPR')} SELL={os.environ.get('EMB_SPMV_SELL', '1')} paired={ctx.paired} nv={nv} fp32={fp32}: "
+              f"{ms:.3f} ms  {b / ms / 1e6:.0f} GB/s", flush=True)
