@@ -134,7 +134,7 @@ struct emb_ctx {
     DevBuf<int> blkcol;       // [nnz_s / 4] entity column of each 2x2 block (paired only)
     // SELL-8-sigma layout of the inner operator As (complex64), sell.cuh: slice-row -> block-row, block-row -> slice-row,
     // slice offsets (in blocks), column of every padded block slot
-    bool sell_ready = false, sell_active = false, sell_tried = false;
+    bool sell_ready = false, sell_active = false, sell_tried = false, sell_has_empty = false;
     const void* sell_zeroed = nullptr;        // As32 buffer whose padding slots are known to be zero
     int64_t sell_nslices = 0, sell_blocks = 0;
     DevBuf<int> sell_rows, sell_pos, sell_bcol;

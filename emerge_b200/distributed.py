@@ -34,15 +34,19 @@ def block_of(n: int, rank: int, world: int) -> np.ndarray:
 
 
 class GpuEngine:
-    """What ShardedSweep needs from a FrequencySweep + its device context (the CPU tests substitute a fake)."""
+    """What ShardedSweep needs from a FrequencySweep + its device context (the CPU tests substitute a fake).
+    host_staged: the exchange buffers live in (pinned) host memory and are staged through one device vector - for
+    process groups that cannot move CUDA tensors (gloo's all_gather), e.g. two ranks sharing one GPU in the tests."""
 
-    def __init__(self, sweep, device):
+    def __init__(self, sweep, device, host_staged=False):
         import torch
         self.torch = torch
         self.sweep = sweep
         self.device = torch.device("cuda", device)
         self.n_ports = len(sweep.ports)
         self.n = sweep.ctx.n_solve
+        self.host_staged = bool(host_staged)
+        self._stage = torch.zeros(self.n, dtype=torch.complex128, device=self.device) if self.host_staged else None
 
     def solve_point(self, f, **kw):
         return self.sweep.solve_point(f, **kw)
@@ -52,34 +56,51 @@ class GpuEngine:
         return self.sweep.ctx.recycle_accepted()
 
     def new_buffer(self, k):
+        if self.host_staged:
+            return self.torch.zeros((k, self.n), dtype=self.torch.complex128).pin_memory()
         return self.torch.zeros((k, self.n), dtype=self.torch.complex128, device=self.device)
 
     def tensor(self, values, dtype=None):
-        return self.torch.as_tensor(np.asarray(values), dtype=dtype, device=self.device)
+        return self.torch.as_tensor(np.asarray(values), dtype=dtype, device="cpu" if self.host_staged else self.device)
 
     def export_newest(self, k, buf):
-        """copy the k newest recycled directions into rows 0..k-1 of buf (device tensor); synchronises the library stream"""
+        """copy the k newest recycled directions into rows 0..k-1 of buf; synchronises the library stream"""
         for j in range(k):
-            self.sweep.ctx.recycle_export(j, buf[j].data_ptr())
+            if self.host_staged:
+                self.sweep.ctx.recycle_export(j, self._stage.data_ptr())
+                buf[j].copy_(self._stage)
+            else:
+                self.sweep.ctx.recycle_export(j, buf[j].data_ptr())
+        if self.host_staged:
+            self.torch.cuda.synchronize(self.device)
 
     def sync(self):
         """the collectives run on torch's stream, the library on its own: one device synchronisation per exchange"""
         self.torch.cuda.synchronize(self.device)
 
     def import_direction(self, row):
-        self.sweep.ctx.recycle_import(row.data_ptr())
+        if self.host_staged:
+            self._stage.copy_(row)
+            self.torch.cuda.synchronize(self.device)
+            self.sweep.ctx.recycle_import(self._stage.data_ptr())
+        else:
+            self.sweep.ctx.recycle_import(row.data_ptr())
 
 
 class ShardedSweep:
     def __init__(self, sweep, freqs, rank=0, world=1, dist=None, device=0, engine=None, max_seed_rounds=6,
-                 min_seed_rounds=1):
+                 min_seed_rounds=1, host_staged=None):
         self.freqs = np.asarray(freqs, dtype=float)
         self.rank, self.world, self.dist = rank, world, dist
         self.block = block_of(len(self.freqs), rank, world)
         self.parallel = dist is not None and world > 1
         self.max_seed_rounds = max_seed_rounds if self.parallel else 0
         self.min_seed_rounds = min(min_seed_rounds, self.max_seed_rounds)
-        self.engine = engine if engine is not None else GpuEngine(sweep, device)
+        if engine is None:
+            if host_staged is None:       # gloo cannot all_gather CUDA tensors
+                host_staged = bool(self.parallel and dist.get_backend() == "gloo")
+            engine = GpuEngine(sweep, device, host_staged=host_staged)
+        self.engine = engine
         self.global_order = hierarchical_order(len(self.freqs))
         self.rounds = 0
         self.exchanged = 0

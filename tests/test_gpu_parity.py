@@ -161,6 +161,46 @@ def test_sparams_at_shipped_tolerance(name):
     sw.ctx.close()
 
 
+@pytest.mark.parametrize("kappa", [0.05, 0.6])
+def test_nonsymmetric_material_tensor_converges_or_fails_loudly(kappa):
+    """A genuinely non-symmetric (gyrotropic) eps_r = [[e, j k, 0], [-j k, e, 0], [0, 0, e]]: the inner iteration works on
+    the complex-symmetric part of A(f) and the asymmetry is left to the FP64 defect correction.  Either the solve meets
+    rtol on the TRUE operator - then the field must match a sparse direct solve of the oracle's K(f) - or it raises
+    NotConverged; it must never return an unconverged field silently (SURVEY 8b error convention)."""
+    import scipy.sparse.linalg as spla
+    from oracle import ned2_oracle as O
+    from emerge_b200.lib import NotConverged
+    from emerge_b200.sweep import FrequencySweep
+    from tests.util import oracle_system
+    g, t = load_golden("wg_tiny")
+    nT = t.tets.shape[1]
+    er = np.zeros((3, 3, nT), complex)
+    er[0, 0] = er[1, 1] = er[2, 2] = 2.0
+    er[0, 1], er[1, 0] = 1j * kappa * 2.0, -1j * kappa * 2.0
+    ur = g["ur"]
+    f = float(g["freqs"][0])
+    k0 = 2 * np.pi * f / 299792458
+    E, Bm = O.assemble_EB(t.nodes, t.tets, t.edges, t.tris, t.edge_lengths, t.tet_to_field, t.tet_to_edge, ur, er)
+    assert abs(Bm - Bm.T).max() > 1e-2 * abs(Bm).max()               # the mass matrix really is non-symmetric
+    K, bvecs = oracle_system(g, t, k0, E, Bm)
+    sid = g["solve_ids"]
+    lu = spla.splu(K[sid][:, sid].tocsc())
+    sw = FrequencySweep(t, er, ur, golden_bcs(g, t), recycle=0)
+    sw.solver_opts.update(rtol=1e-9, maxit=4000)
+    try:
+        res = sw.run([f], keep_fields=True)
+    except NotConverged:
+        sw.ctx.close()
+        return                                                      # failed loudly: acceptable
+    assert all(st["converged"] and st["relres"] <= 1e-9 for st in res.stats)
+    for p in sw.ports:
+        xr = np.zeros(t.n_field, complex)
+        xr[sid] = lu.solve(bvecs[p.port_number][sid])
+        x = res.fields[(0, p.port_number)]
+        assert np.linalg.norm(x - xr) <= 1e-6 * np.linalg.norm(xr)
+    sw.ctx.close()
+
+
 @pytest.mark.parametrize("method,precond", [("gmres", "jacobi"), ("bicgstab", "block"), ("cocr", "jacobi"),
                                             ("cocr", "block"), ("gmres", "multilevel")])
 def test_other_solvers_agree(method, precond):

@@ -4,7 +4,7 @@ import pytest
 import scipy.sparse as sp
 
 from oracle import ned2_oracle as O
-from tests.util import load_golden, golden_bcs, csr, tag_tris
+from tests.util import load_golden, golden_bcs, csr, tag_tris, oracle_system
 from emerge_b200.sweep import dunavant4
 
 RTOL = 1e-12      # relative to the largest entry (north_star: K/M to 1e-12 in FP64; reference is fastmath)
@@ -46,35 +46,13 @@ def test_csr_pattern_and_values(name):
 def _surface_terms(g, t, k0):
     N = t.n_field
     if "E_indptr" in g:
-        K = csr(g, "E", N) - csr(g, "E", N, "B_data") * k0 ** 2
+        E, Bm = csr(g, "E", N), csr(g, "E", N, "B_data")
     else:       # checksum-only fixture: E, B from the oracle (pinned by the E_dot_v / B_dot_v checks below)
         E, Bm = O.assemble_EB(t.nodes, t.tets, t.edges, t.tris, t.edge_lengths, t.tet_to_field, t.tet_to_edge, g["ur"], g["er"])
         v = g["probe_v"]
         assert np.abs(E @ v - g["E_dot_v"]).max() <= 1e-11 * np.abs(g["E_dot_v"]).max()
         assert np.abs(Bm @ v - g["B_dot_v"]).max() <= 1e-11 * np.abs(g["B_dot_v"]).max()
-        K = E - Bm * k0 ** 2
-    DP = dunavant4()
-    bvecs = {}
-    for bc in golden_bcs(g, t):
-        if not hasattr(bc, "get_gamma"):
-            continue
-        ids = bc.tri_ids
-        v = t.nodes[:, t.tris[:, ids]]                                  # (3, 3 verts, n)
-        if bc._include_force:
-            loc = np.einsum("ij,jvn->ivn", bc.get_inv_basis(), v - bc.cs.origin[:, None, None])
-            x, y = loc[0].T, loc[1].T
-            S = O.tri_surface_matrix(x, y)
-            xq, yq = x @ DP[1:4], y @ DP[1:4]
-            U = bc.get_Uinc(xq.T.ravel(), yq.T.ravel(), k0).reshape(3, 6, len(ids))
-            bl = O.tri_forcing(x, y, U[:2])
-            bv = np.zeros(N, dtype=complex)
-            np.add.at(bv, t.tri_to_field[:, ids].T, bl)
-            bvecs[bc.port_number] = bv
-        else:
-            x, y = O.abc_local_frame(v.transpose(2, 1, 0))
-            S = O.tri_surface_matrix(x, y, t.edge_lengths[t.tri_to_edge[:, ids]].T)
-        K = K + O.gen_csr_tri(N, t.tri_to_field, ids, bc.get_gamma(k0) * S)
-    return K, bvecs
+    return oracle_system(g, t, k0, E, Bm)
 
 
 @pytest.mark.parametrize("name", ["wg_tiny", "wg_materials", "abc_lumped", "modal_microstrip", "lossy_slabs"])

@@ -65,3 +65,34 @@ def db_deg_close(S, Sref, db_tol=1e-3, deg_tol=0.1, floor=1e-4):
         ok &= abs(20 * np.log10(abs(a) / abs(b))) < db_tol
         ok &= abs(np.angle(a / b, deg=True)) < deg_tol
     return bool(ok)
+
+
+def oracle_system(g, t, k0, E, Bm):
+    """K(f) = E - k0^2 B + sum gamma_p S_p and the port right-hand sides from the numpy oracle (TEST INFRASTRUCTURE),
+    following Assembler.assemble_freq_matrix (fem/physics/edm/assembler.py:312-388)."""
+    from oracle import ned2_oracle as O
+    from emerge_b200.sweep import dunavant4
+    N = t.n_field
+    K = E - Bm * k0 ** 2
+    DP = dunavant4()
+    bvecs = {}
+    for bc in golden_bcs(g, t):
+        if not hasattr(bc, "get_gamma"):
+            continue
+        ids = bc.tri_ids
+        v = t.nodes[:, t.tris[:, ids]]                                  # (3, 3 verts, n)
+        if bc._include_force:
+            loc = np.einsum("ij,jvn->ivn", bc.get_inv_basis(), v - bc.cs.origin[:, None, None])
+            x, y = loc[0].T, loc[1].T
+            S = O.tri_surface_matrix(x, y)
+            xq, yq = x @ DP[1:4], y @ DP[1:4]
+            U = bc.get_Uinc(xq.T.ravel(), yq.T.ravel(), k0).reshape(3, 6, len(ids))
+            bl = O.tri_forcing(x, y, U[:2])
+            bv = np.zeros(N, dtype=complex)
+            np.add.at(bv, t.tri_to_field[:, ids].T, bl)
+            bvecs[bc.port_number] = bv
+        else:
+            x, y = O.abc_local_frame(v.transpose(2, 1, 0))
+            S = O.tri_surface_matrix(x, y, t.edge_lengths[t.tri_to_edge[:, ids]].T)
+        K = K + O.gen_csr_tri(N, t.tri_to_field, ids, bc.get_gamma(k0) * S)
+    return K, bvecs
