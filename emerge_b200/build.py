@@ -9,7 +9,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 REPO = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["capi.cu", "assembly.cu", "operators.cu", "solver.cu"]
+SOURCES = ["capi.cu", "assembly.cu", "operators.cu", "solver.cu", "topology.cu"]
 LIB = os.path.join(HERE, "libemerge_b200.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-I" + os.path.join(REPO, "include")]
@@ -32,7 +32,7 @@ def _stale(target: str, deps: list[str]) -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     objdir = os.path.join(REPO, "build")
     os.makedirs(objdir, exist_ok=True)
-    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h", ".hpp"))]
     headers.append(os.path.join(REPO, "include", "emerge_b200.h"))
     nvcc = _nvcc()
     jobs = []

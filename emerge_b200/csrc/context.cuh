@@ -209,6 +209,8 @@ struct emb_ctx {
     int64_t graph_launches = 0;
 };
 
+void topology_release(emb_ctx* c);      // topology.cu: device tables of emb_topology_build not yet fetched
+
 template <typename T>
 static int dev_alloc(emb_ctx* c, DevBuf<T>& b, size_t n) {
     if (b.n == n && b.p) return EMB_OK;

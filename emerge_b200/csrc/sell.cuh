@@ -6,9 +6,10 @@
 // the block-rows are grouped in slices of 8 with the blocks of a slice interleaved (slot = sptr[s] + 8 q + r for block q
 // of slice-row r), so the same warp-wide load reads 8 consecutive 32-byte blocks (two full lines) and 8 consecutive
 // column indices (one sector); what is left for the load/store unit are the x gathers.  Slices are padded to their
-// longest block-row; block-rows are sorted by length inside windows of SIGMA rows first (padding < 1 % on the waveguide
-// meshes instead of ~25 % - edge rows alternate between 25 and 37 blocks), which only permutes which rows a warp owns:
-// the numbering of x and y is untouched.
+// longest block-row; block-rows are sorted by length inside windows of sigma rows first (waveguide mesh: padding 11 %
+// unsorted, 1.7 % with sigma = 64, 0.2 % with 1024 - but a large window scatters the rows of a slice and with them the
+// x entries a warp gathers, so sigma stays small), which only permutes which rows a warp owns: the numbering of x and y
+// is untouched.
 // Block storage is column-major, [h][r]: the two values a lane needs (rows 2j, 2j+1 of column 2c+h) are one 16-byte load.
 // The reference has no counterpart (it factorises, fem/solver.py:243-309).
 #pragma once
@@ -16,16 +17,16 @@
 #include <cub/cub.cuh>
 
 constexpr int SELL_C = 8;
-constexpr int SELL_SIGMA = 1024;
+constexpr int SELL_SIGMA_DEFAULT = 64;      // sorting window in block-rows (EMB_SELL_SIGMA overrides; measured, profiles/)
 constexpr int SELL_LENBITS = 12;
 
-__global__ void k_sell_keys(int nbr, const int64_t* __restrict__ rowptr_s, unsigned* __restrict__ key, int* __restrict__ val,
-                            int* __restrict__ flag) {
+__global__ void k_sell_keys(int nbr, int sigma, const int64_t* __restrict__ rowptr_s, unsigned* __restrict__ key,
+                            int* __restrict__ val, int* __restrict__ flag) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= nbr) return;
     const int64_t len = (rowptr_s[2 * j + 1] - rowptr_s[2 * j]) >> 1;
     if (len >= (1 << SELL_LENBITS)) atomicExch(flag, 1);
-    key[j] = ((unsigned)(j / SELL_SIGMA) << SELL_LENBITS) | (unsigned)(len & ((1 << SELL_LENBITS) - 1));
+    key[j] = ((unsigned)(j / sigma) << SELL_LENBITS) | (unsigned)(len & ((1 << SELL_LENBITS) - 1));
     val[j] = j;
 }
 // rows[R] = block-row of slice-row R (or -1), pos[j] = R, slen[s] = 8 * (longest block-row of slice s)
@@ -80,10 +81,13 @@ static int sell_build(emb_ctx* c) {
     EMB_TRY(dev_alloc(c, sorted, (size_t)nbr));
     EMB_TRY(dev_alloc(c, flag, 2));
     EMB_CUDA(c, cudaMemsetAsync(flag.p, 0, 2 * sizeof(int), c->stream));
-    k_sell_keys<<<blocks_for(nbr, 256), 256, 0, c->stream>>>(nbr, c->rowptr_s.p, key.p, val.p, flag.p);
+    int sigma = getenv("EMB_SELL_SIGMA") ? atoi(getenv("EMB_SELL_SIGMA")) : SELL_SIGMA_DEFAULT;
+    if (sigma < SELL_C) sigma = SELL_C;
+    k_sell_keys<<<blocks_for(nbr, 256), 256, 0, c->stream>>>(nbr, sigma, c->rowptr_s.p, key.p, val.p, flag.p);
     EMB_LAUNCH_CHECK(c);
     int wbits = 1;
-    while (((int64_t)1 << wbits) < (nbr + SELL_SIGMA - 1) / SELL_SIGMA + 1) ++wbits;
+    while (((int64_t)1 << wbits) < (nbr + sigma - 1) / sigma + 1) ++wbits;
+    if (SELL_LENBITS + wbits > 32) { c->err = "sell_build: sorting window too small for this many rows"; return EMB_ERR_LIMIT; }
     size_t tb = 0;
     EMB_CUDA(c, cub::DeviceRadixSort::SortPairs(nullptr, tb, key.p, key2.p, val.p, sorted.p, nbr, 0, SELL_LENBITS + wbits, c->stream));
     EMB_TRY(dev_alloc(c, tmp, tb));
@@ -339,7 +343,7 @@ __global__ void __launch_bounds__(STG_WARPS * 32, 1) k_bsell_tma(int nslices, co
 template <int NV>
 static int bsell_launch(emb_ctx* c, const cf* val, const cx* x, cx* y) {
     static const int mode = getenv("EMB_SPMV_TMA") ? atoi(getenv("EMB_SPMV_TMA")) : 1;
-    if constexpr (NV >= 2) {
+    if constexpr (NV == 2) {               // NV = 4 in two passes over the staged chunk was measured slower than k_bsell
         if (mode && !c->sell_has_empty) {      // (a slice without any block is never visited by the staged kernel)
             int nsm = 0;
             EMB_CUDA(c, cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->device));

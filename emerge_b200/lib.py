@@ -40,6 +40,9 @@ _SIGS = {
     "emb_profiler": (C.c_int, [C.c_void_p, C.c_int]),
     "emb_upload_mesh": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64] + [C.c_void_p] * 5),
     "emb_upload_materials": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "emb_topology_build": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
+                                     C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "emb_topology_get": (C.c_int, [C.c_void_p] + [C.c_void_p] * 10),
     "emb_symbolic": (C.c_int, [C.c_void_p]),
     "emb_assemble_KM": (C.c_int, [C.c_void_p]),
     "emb_assemble_config": (C.c_int, [C.c_void_p, C.c_int64, C.c_int]),
@@ -205,6 +208,31 @@ class Context:
         self._check(self.lib.emb_upload_mesh(self.h, nodes_n3.shape[0], tets_n4.shape[0], int(n_edges), tris_n3.shape[0],
                                              _p(nodes_n3), _p(tets_n4), _p(tris_n3), _p(ttf), _p(t2f)))
         self.n_tets = tets_n4.shape[0]
+
+    def mesh_tables(self, nodes_xyz, tets_n4, edges=None, tris=None):
+        """Device counterpart of Mesh3D.update() + Nedelec2.__init__ (fem/mesh3d.py:224-355, fem/elements/nedelec2.py:32-62):
+        -> emerge_b200.synthmesh.MeshTables.  edges (2,nE) / tris (3,nTri): the caller's numbering (the reference's), kept
+        verbatim; None: lexicographic numbering (what synthmesh.mesh_tables produces on the host)."""
+        from .synthmesh import MeshTables
+        nodes = np.ascontiguousarray(nodes_xyz, dtype=np.float64)
+        tets = np.ascontiguousarray(tets_n4, dtype=np.int64)
+        nN, nT = nodes.shape[0], tets.shape[0]
+        ge = np.ascontiguousarray(edges, dtype=np.int64) if edges is not None else None
+        gt = np.ascontiguousarray(tris, dtype=np.int64) if tris is not None else None
+        nE, nTri = C.c_int64(), C.c_int64()
+        self._check(self.lib.emb_topology_build(self.h, nN, nT, _p(nodes), _p(tets), ge.shape[1] if ge is not None else 0, _p(ge),
+                                                gt.shape[1] if gt is not None else 0, _p(gt), C.byref(nE), C.byref(nTri)))
+        nE, nTri = nE.value, nTri.value
+        i8 = np.int64
+        out = dict(edges=np.empty((2, nE), i8), tris=np.empty((3, nTri), i8), tet_to_edge=np.empty((6, nT), i8),
+                   tet_to_tri=np.empty((4, nT), i8), tri_to_edge=np.empty((3, nTri), i8), tri_to_tet=np.empty((2, nTri), i8),
+                   edge_lengths=np.empty(nE, np.float64), tet_to_field=np.empty((20, nT), i8),
+                   tri_to_field=np.empty((8, nTri), i8), edge_to_field=np.empty((2, nE), i8))
+        self._check(self.lib.emb_topology_get(self.h, *[_p(out[k]) for k in (
+            "edges", "tris", "tet_to_edge", "tet_to_tri", "tri_to_edge", "tri_to_tet", "edge_lengths", "tet_to_field",
+            "tri_to_field", "edge_to_field")]))
+        return MeshTables(nodes.T, tets.T, out["edges"], out["tris"], out["tet_to_edge"], out["tet_to_tri"], out["tri_to_edge"],
+                          out["tri_to_tet"], out["edge_lengths"], out["tet_to_field"], out["tri_to_field"], out["edge_to_field"])
 
     def upload_materials(self, er, ur):
         er = _c(er, np.complex128)

@@ -42,6 +42,20 @@ int emb_timer_stop(emb_ctx* ctx, double* ms);
 /* cudaProfilerStart (on=1) / cudaProfilerStop (on=0) after a stream sync: window for `ncu --profile-from-start off` */
 int emb_profiler(emb_ctx* ctx, int on);
 
+/* ---- mesh topology tables ---------------------------------------------------------------------- */
+/* Builds on the device what Mesh3D.update() (fem/mesh3d.py:224-355) and Nedelec2.__init__ (fem/elements/
+ * nedelec2.py:32-62) build with Python sets and per-tetrahedron loops: edges, tris, tet_to_edge, tet_to_tri, tri_to_edge,
+ * tri_to_tet, edge_lengths, tet_to_field, tri_to_field, edge_to_field, all int64 in the reference's layouts.
+ * given_edges (2,nE) / given_tris (3,nTri) int64 C-order: the caller's numbering (e.g. the reference's CPython-set order,
+ * mesh3d.py:252-271) is kept verbatim and verified against the mesh; NULL: lexicographic numbering of the sorted
+ * vertex tuples.  emb_topology_get copies the tables out (any pointer may be NULL) and frees the device copies. */
+int emb_topology_build(emb_ctx* ctx, int64_t nN, int64_t nT, const double* nodes_n3, const int64_t* tets_n4,
+                       int64_t nE_given, const int64_t* given_edges, int64_t nTri_given, const int64_t* given_tris,
+                       int64_t* nE_out, int64_t* nTri_out);
+int emb_topology_get(emb_ctx* ctx, int64_t* edges_2xnE, int64_t* tris_3xnTri, int64_t* tet_to_edge_6xnT,
+                     int64_t* tet_to_tri_4xnT, int64_t* tri_to_edge_3xnTri, int64_t* tri_to_tet_2xnTri, double* edge_lengths,
+                     int64_t* tet_to_field_20xnT, int64_t* tri_to_field_8xnTri, int64_t* edge_to_field_2xnE);
+
 /* ---- mesh + DOF tables (input contract of Nedelec2 / Mesh3D; consumed, never renumbered) ---- */
 /* replaces the array gathering at fem/physics/edm/optimized_assembly.py:47-57 */
 int emb_upload_mesh(emb_ctx* ctx, int64_t nN, int64_t nT, int64_t nE, int64_t nTri,

@@ -16,9 +16,11 @@ sw.setup()
 ctx = sw.ctx
 sw.assemble_frequency(10e9)
 nnz, Ns = int(ctx.lib.emb_csr_nnz(ctx.h, 2)), ctx.n_solve
-for nv in (1, 2, 4):
-    for fp32 in (False, True):
+only = os.environ.get("SPMV_TUNE_ONLY")          # e.g. "2,1": nv = 2, complex64 only
+cases = [(int(only.split(",")[0]), bool(int(only.split(",")[1])))] if only else [(nv, f) for nv in (1, 2, 4) for f in (False, True)]
+for nv, fp32 in cases:
+    if True:
         ms = ctx.spmv_bench(20, nv=nv, fp32=fp32)
         b = (8 if fp32 else 16) * nnz + nnz + (4 + 32 * nv) * Ns
-        print(f"KPR={os.environ.get('EMB_SPMV_KPR')} SELL={os.environ.get('EMB_SPMV_SELL', '1')} paired={ctx.paired} nv={nv} fp32={fp32}: "
+        print(f"KPR={os.environ.get('EMB_SPMV_KPR')} SELL={os.environ.get('EMB_SPMV_SELL', '1')} TMA={os.environ.get('EMB_SPMV_TMA', '1')} sigma={os.environ.get('EMB_SELL_SIGMA', 'default')} paired={ctx.paired} nv={nv} fp32={fp32}: "
               f"{ms:.3f} ms  {b / ms / 1e6:.0f} GB/s", flush=True)
