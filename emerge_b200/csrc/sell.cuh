@@ -7,9 +7,9 @@
 // of slice-row r), so the same warp-wide load reads 8 consecutive 32-byte blocks (two full lines) and 8 consecutive
 // column indices (one sector); what is left for the load/store unit are the x gathers.  Slices are padded to their
 // longest block-row; block-rows are sorted by length inside windows of sigma rows first (waveguide mesh: padding 11 %
-// unsorted, 1.7 % with sigma = 64, 0.2 % with 1024 - but a large window scatters the rows of a slice and with them the
-// x entries a warp gathers, so sigma stays small), which only permutes which rows a warp owns: the numbering of x and y
-// is untouched.
+// unsorted, 1.7 % with sigma = 64, 0.5 % with 256, 0.2 % with 1024; measured 0.818 / 0.853 / 0.804 / 0.816 ms for sigma =
+// 8 / 64 / 256 / 1024 with the staged kernel at 1M tets, profiles/r2_spmv_sell_tuning.txt), which only permutes which rows
+// a warp owns: the numbering of x and y is untouched.
 // Block storage is column-major, [h][r]: the two values a lane needs (rows 2j, 2j+1 of column 2c+h) are one 16-byte load.
 // The reference has no counterpart (it factorises, fem/solver.py:243-309).
 #pragma once
@@ -17,7 +17,7 @@
 #include <cub/cub.cuh>
 
 constexpr int SELL_C = 8;
-constexpr int SELL_SIGMA_DEFAULT = 64;      // sorting window in block-rows (EMB_SELL_SIGMA overrides; measured, profiles/)
+constexpr int SELL_SIGMA_DEFAULT = 256;     // sorting window in block-rows (EMB_SELL_SIGMA overrides; profiles/r2_spmv_sell_tuning.txt)
 constexpr int SELL_LENBITS = 12;
 
 __global__ void k_sell_keys(int nbr, int sigma, const int64_t* __restrict__ rowptr_s, unsigned* __restrict__ key,

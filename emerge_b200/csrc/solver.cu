@@ -39,8 +39,11 @@ static int apply_inner(emb_ctx* c, const VT* As, const VX* x, VX* y) {
 }
 // complex64 storage of the inner operator in the layout of this pattern: SELL-8-sigma on a pair-ordered solve space
 // (EMB_SPMV_SELL=0: block layout), with the padding slots zeroed once per buffer
-static int alloc_As32(emb_ctx* c, cf** out) {
-    static const bool want_sell = !(getenv("EMB_SPMV_SELL") && atoi(getenv("EMB_SPMV_SELL")) == 0);
+static int alloc_As32(emb_ctx* c, cf** out, int nv) {
+    // SELL for one or two right-hand sides; four interleaved columns gather 128 contiguous bytes per block already and
+    // were measured faster in the block layout (1.44 vs 1.59 ms at 1M tets)
+    static const bool sell_env = !(getenv("EMB_SPMV_SELL") && atoi(getenv("EMB_SPMV_SELL")) == 0);
+    const bool want_sell = sell_env && nv <= 2;
     if (want_sell && c->paired && !c->sell_tried) {
         c->sell_tried = true;
         EMB_TRY(sell_build(c));
@@ -524,7 +527,7 @@ static int solve_device(emb_ctx* c, const emb_solve_opts* o, const cx* bs, cx* x
                 EMB_TRY(rc_coarse_update(c));          // experimental: coefficient map of the coarse space for this A(f)
             if (fp32) {
                 cf* As = nullptr;
-                EMB_TRY(alloc_As32(c, &As));
+                EMB_TRY(alloc_As32(c, &As, NV));
                 EMB_TRY(ensure_operator<cf>(c, o->precond, As));
                 rc = cocr<NV, cf, cx>(c, o->precond, blk ? 1 : 0, As, rr, dd, stop, o->maxit - its, &iit, &spmvs, irn);
             } else {
@@ -744,7 +747,7 @@ extern "C" int emb_spmv_bench_ex(emb_ctx* c, int reps, int nv, int fp32, double*
     EMB_CUDA(c, cudaMemsetAsync(dy.p, 0, (size_t)c->Ns * nv * sizeof(cx), c->stream));
     cf* A32 = nullptr;
     if (fp32) {
-        EMB_TRY(alloc_As32(c, &A32));
+        EMB_TRY(alloc_As32(c, &A32, nv));
         EMB_TRY(fill_As<cf>(c, A32));
         c->have_As = false;
     }

@@ -227,6 +227,31 @@ def _sim_error(physics):
     return getattr(importlib.import_module(type(physics).__module__), "SimulationError", RuntimeError)
 
 
+def install_postproc(physics, asm: GpuAssembler):
+    """Routes EMDataSet.interpolate (emdata.py:181-199) through the device: replaces `basis.interpolate` and
+    `basis.interpolate_curl` (fem/elements/nedelec2.py:72-86) of the physics' basis by versions that locate the points and
+    evaluate E / curl E with emb_interp_fields.  Calls that restrict the candidate tets (`tetids=...`, the S-parameter
+    path of the reference's own sweep loop) keep the reference implementation."""
+    basis = physics.basis
+    if basis is None or getattr(basis, "_emb_postproc", False):
+        return
+    ref_interp, ref_curl = basis.interpolate, basis.interpolate_curl
+
+    def interpolate(field, xs, ys, zs, tetids=None):
+        if tetids is not None or asm.sweep is None:
+            return ref_interp(field, xs, ys, zs, tetids) if tetids is not None else ref_interp(field, xs, ys, zs)
+        E, _ = asm.ctx.interp_fields(field, np.array([xs, ys, zs], dtype=float))
+        return E[0], E[1], E[2]
+
+    def interpolate_curl(field, xs, ys, zs, c, tetids=None):
+        if tetids is not None or asm.sweep is None:
+            return ref_curl(field, xs, ys, zs, c, tetids) if tetids is not None else ref_curl(field, xs, ys, zs, c)
+        _, H = asm.ctx.interp_fields(field, np.array([xs, ys, zs], dtype=float), curl_const=c)
+        return H[0], H[1], H[2]
+    basis.interpolate, basis.interpolate_curl = interpolate, interpolate_curl
+    basis._emb_postproc = True
+
+
 def _gpu_frequency_domain(physics, asm: GpuAssembler, dist=None, keep_fields: bool = True):
     """Fast driver behind physics.frequency_domain() / frequency_domain_par(): same preamble, same EMSimData filling as
     emfreq3d.py:607-732 (and :545-601 for the parallel variant), but the per-frequency loop is FrequencySweep's - all ports
@@ -247,6 +272,7 @@ def _gpu_frequency_domain(physics, asm: GpuAssembler, dist=None, keep_fields: bo
     bcs = physics.boundary_conditions
     freqs = list(physics.frequencies)
     asm._bind(physics.basis, er, ur, bcs, float(np.median(freqs)))
+    install_postproc(physics, asm)
     sw = asm.sweep
     all_ports = [bc for bc in bcs if isinstance(bc, mod.PortBC)]
     port_numbers = [p.port_number for p in all_ports]
@@ -297,7 +323,8 @@ def install(physics, fast: bool = False, keep_fields: bool = True, **kw) -> GpuA
     fast=True additionally replaces the two sweep drivers themselves:
       physics.frequency_domain()          -> EMSimData   (emfreq3d.py:607-732)
       physics.frequency_domain_par(njobs) -> EMSimData   (emfreq3d.py:469-605)
-    by FrequencySweep-backed versions that fill the same EMSimData (Sp, _fields[port], er/ur[0,0,:], port properties).
+    by FrequencySweep-backed versions that fill the same EMSimData (Sp, _fields[port], er/ur[0,0,:], port properties);
+    the result object's .interpolate(xs, ys, zs) (emdata.py:181-199) then evaluates E and H on the device (install_postproc).
     frequency_domain_par shards the frequency points over the ranks of the initialised torch.distributed process group
     (one process per GPU, launched with torchrun - the counterpart of the reference's multiprocessing.Pool(njobs)); njobs
     is accepted for signature compatibility, the parallel width is the world size.  Without a process group it runs on

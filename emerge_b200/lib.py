@@ -40,6 +40,8 @@ _SIGS = {
     "emb_profiler": (C.c_int, [C.c_void_p, C.c_int]),
     "emb_upload_mesh": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64] + [C.c_void_p] * 5),
     "emb_upload_materials": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "emb_locate_points": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "emb_interp_fields": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "emb_topology_build": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
                                      C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "emb_topology_get": (C.c_int, [C.c_void_p] + [C.c_void_p] * 10),
@@ -233,6 +235,26 @@ class Context:
             "tri_to_field", "edge_to_field")]))
         return MeshTables(nodes.T, tets.T, out["edges"], out["tris"], out["tet_to_edge"], out["tet_to_tri"], out["tri_to_edge"],
                           out["tri_to_tet"], out["edge_lengths"], out["tet_to_field"], out["tri_to_field"], out["edge_to_field"])
+
+    def locate(self, pts):
+        """tetrahedron of every point (3,n) as the reference's interpolation picks it (last containing tet), -1 outside"""
+        pts = np.ascontiguousarray(pts, dtype=np.float64)
+        out = np.empty(pts.shape[1], dtype=np.int64)
+        self._check(self.lib.emb_locate_points(self.h, pts.shape[1], _p(pts), _p(out)))
+        return out
+
+    def interp_fields(self, x_full, pts, tet_ids=None, curl_const=None):
+        """-> (E (3,n), H (3,n) or None): EMDataSet.interpolate on the device (emdata.py:181-199).  x_full None: the
+        device-resident solution of the last solve; curl_const (nT,) complex: H = curl(E) * curl_const[tet]."""
+        pts = np.ascontiguousarray(pts, dtype=np.float64)
+        n = pts.shape[1]
+        x = None if x_full is None else np.ascontiguousarray(x_full, dtype=np.complex128)
+        tid = None if tet_ids is None else np.ascontiguousarray(tet_ids, dtype=np.int64)
+        cc = None if curl_const is None else np.ascontiguousarray(curl_const, dtype=np.complex128)
+        E = np.empty((3, n), dtype=np.complex128)
+        H = np.empty((3, n), dtype=np.complex128) if cc is not None else None
+        self._check(self.lib.emb_interp_fields(self.h, _p(x), n, _p(pts), _p(tid), _p(cc), _p(E), _p(H)))
+        return E, H
 
     def upload_materials(self, er, ur):
         er = _c(er, np.complex128)

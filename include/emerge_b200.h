@@ -242,6 +242,18 @@ int emb_interp(emb_ctx* ctx, const emb_c128* x_full, int64_t npts, const int64_t
 int emb_interp_last(emb_ctx* ctx, int64_t npts, const int64_t* tet_ids, const double* xyz_3xnpts,
                     emb_c128* E_3xnpts);
 
+
+/* ---- field post-processing ------------------------------------------------------------------------ */
+/* Tetrahedron of each point as the reference's interpolation picks it: the LAST tet whose local-coordinate test passes
+ * (fem/mth/tet.py:393-497, test at :425); -1 for points outside the mesh.  xyz is (3,npts) C-order. */
+int emb_locate_points(emb_ctx* ctx, int64_t npts, const double* xyz_3xnpts, int64_t* tet_ids);
+/* E (3,npts) and optionally H = curl(E) * curl_const[tet] (3,npts) of solution x_full (n_field entries; NULL: the
+ * device-resident solution of the last solve) at arbitrary points: EMDataSet.interpolate (fem/physics/edm/emdata.py:181-
+ * 199) = ned2_tet_interp + ned2_tet_interp_curl (fem/mth/tet.py:371-626).  tet_ids NULL: located on the device.
+ * curl_const (nT complex; the reference passes 1/(-j w mu0 mu_r[0,0,tet]), emdata.py:193) and H may be NULL. */
+int emb_interp_fields(emb_ctx* ctx, const emb_c128* x_full, int64_t npts, const double* xyz_3xnpts, const int64_t* tet_ids,
+                      const emb_c128* curl_const_nT, emb_c128* E_3xnpts, emb_c128* H_3xnpts);
+
 #ifdef __cplusplus
 }
 #endif

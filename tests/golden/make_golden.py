@@ -297,8 +297,34 @@ def case_lossy_slabs():
     return out
 
 
+def case_interp_wg_tiny():
+    """Field post-processing pins: EMDataSet.interpolate (emdata.py:181-199) -> ned2_tet_interp /
+    ned2_tet_interp_curl (mth/tet.py:371-626) on the wg_tiny mesh at random points (some outside the mesh): E and H of the
+    port-1 solution.  Stores the field vector too, so the test needs no solve."""
+    box = box_mesh(3, 2, 4, *WR90, 20e-3, jitter=0.1, seed=0)
+    fem, phys, mesh = H.build_physics(box)
+    H.rect_waveguide_ports(fem, phys, box)
+    phys.frequencies = [9e9]
+    data = phys.frequency_domain()
+    ds = data.item(0)
+    rng = np.random.default_rng(42)
+    a, b, L = box.dims
+    n = 160
+    pts = np.stack([(rng.random(n) - 0.5) * a * 1.15, (rng.random(n) - 0.5) * b * 1.15, (rng.random(n) * 1.15 - 0.075) * L])
+    # a few points exactly on vertices / faces of the mesh: the "last containing tetrahedron wins" rule decides
+    pts[:, :6] = mesh.nodes[:, [5, 17, 23, 31, 40, 47]]
+    pts[:, 6:10] = mesh.nodes[:, mesh.tris[:, [3, 30, 60, 90]]].mean(axis=1)
+    ds.interpolate(pts[0], pts[1], pts[2])
+    out = dict(_mesh_dict(mesh))
+    out.update(kind="rectwg", dims=np.array(box.dims), face_tris=box.face_tris.astype(np.int32), face_tag=box.face_tag,
+               freq=np.float64(9e9), x=np.asarray(ds._field), ur00=np.asarray(ds.ur), pts=pts,
+               E=np.array([ds.Ex, ds.Ey, ds.Ez]), H=np.array([ds.Hx, ds.Hy, ds.Hz]))
+    return out
+
+
 CASES = dict(wg_tiny=case_wg_tiny, wg_materials=case_wg_materials, wg_medium=case_wg_medium,
-             abc_lumped=case_abc_lumped, modal_microstrip=case_modal_microstrip, lossy_slabs=case_lossy_slabs)
+             abc_lumped=case_abc_lumped, modal_microstrip=case_modal_microstrip, lossy_slabs=case_lossy_slabs,
+             interp_wg_tiny=case_interp_wg_tiny)
 
 if __name__ == "__main__":
     if not os.path.isdir("/root/reference/fem"):
@@ -308,4 +334,4 @@ if __name__ == "__main__":
         out = CASES[n]()
         path = os.path.join(HERE, n + ".npz")
         np.savez_compressed(path, **out)
-        print(n, "->", path, f"{os.path.getsize(path) / 1e6:.2f} MB", "S[0]=", out["S"][0].ravel()[:4])
+        print(n, "->", path, f"{os.path.getsize(path) / 1e6:.2f} MB", "S[0]=", out["S"][0].ravel()[:4] if "S" in out else "-")

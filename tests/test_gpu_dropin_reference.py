@@ -47,6 +47,17 @@ def _builders():
     return dict(rectwg=rectwg, abc_lumped=abc_lumped, modal=modal)
 
 
+def _interp(data, i, seed=0):
+    """EMDataSet.interpolate at 200 random points around the mesh (emdata.py:181-199): (E (3,n), H (3,n))"""
+    ds = data.item(i)
+    nodes = ds._basis.mesh.nodes
+    lo, hi = nodes.min(axis=1), nodes.max(axis=1)
+    rng = np.random.default_rng(seed)
+    pts = lo[:, None] + (hi - lo)[:, None] * (rng.random((3, 200)) * 1.1 - 0.05)
+    ds.interpolate(pts[0], pts[1], pts[2])
+    return np.array([ds.Ex, ds.Ey, ds.Ez]), np.array([ds.Hx, ds.Hy, ds.Hz])
+
+
 def _collect(data, nf):
     S = np.array([data.item(i).Sp.arry.copy() for i in range(nf)])
     fields = [{k: np.array(v) for k, v in data.item(i)._fields.items()} for i in range(nf)]
@@ -75,6 +86,7 @@ def test_reference_frequency_domain_on_top_of_install(case, tmp_path):
     phys.frequencies = list(freqs)
     data = phys.frequency_domain()                                   # 1. the reference, untouched
     S_ref, F_ref = _collect(data, nf)
+    E_ref, H_ref = _interp(data, 0)                                  # reference post-processing (numba, all tets x all points)
     stock_solve = type(phys.solveroutine).solve
 
     asm = install(phys, rtol=1e-10)                                  # 2. the two seams
@@ -90,6 +102,10 @@ def test_reference_frequency_domain_on_top_of_install(case, tmp_path):
     assert asm.solver_opts["rtol"] == 1e-8
     data = phys.frequency_domain()
     _check(data, nf, S_ref, F_ref, "fast driver")
+    assert getattr(phys.basis, "_emb_postproc", False)
+    E, Hf = _interp(data, 0)                                         # same call, now located + evaluated on the device
+    assert np.array_equal(np.abs(E).sum(axis=0) == 0, np.abs(E_ref).sum(axis=0) == 0)       # same points outside the mesh
+    assert np.abs(E - E_ref).max() <= 1e-6 * np.abs(E_ref).max() and np.abs(Hf - H_ref).max() <= 1e-6 * np.abs(H_ref).max()
     data = phys.frequency_domain_par(njobs=2)
     _check(data, nf, S_ref, F_ref, "fast parallel driver (one rank)")
     # result API of the reference on the GPU-filled object: axis access and Touchstone export (emdata.py:284-331)
