@@ -49,16 +49,37 @@ A_WG, B_WG = 22.86e-3, 10.16e-3
 FREQS = np.linspace(8e9, 12e9, 201)
 
 
-def make_waveguide(nx, ny, nz):
+SLABS = False          # --workload slabs: BASELINE config 5 (ceramic slabs eps_r = 9.8 (1 - 1e-4 j), periodic in z)
+
+
+def make_waveguide(nx, ny, nz, device=None, slabs=None):
+    """device: build the topology tables on that GPU (csrc/topology.cu) instead of numpy on the host (same tables)"""
     from emerge_b200.synthmesh import box_mesh, mesh_tables, tri_ids_of
     from emerge_b200 import bc as B
     L = nz * A_WG / nx
-    box = box_mesh(nx, ny, nz, A_WG, B_WG, L)
-    t = mesh_tables(box.nodes_xyz, box.tets)
+    slabs = SLABS if slabs is None else slabs
+    vol = None
+    if slabs:
+        period = 12 * L / nz             # two of every twelve cell layers are ceramic
+
+        def vol(x, y, z):
+            return np.where((z % period) >= period * 10.0 / 12.0, 2, 1)
+    box = box_mesh(nx, ny, nz, A_WG, B_WG, L, vol_fn=vol)
+    if device is None:
+        t = mesh_tables(box.nodes_xyz, box.tets)
+    else:
+        from emerge_b200.lib import Context
+        tc = Context(device)
+        t = tc.mesh_tables(box.nodes_xyz, box.tets)
+        tc.close()
     nT = t.tets.shape[1]
     er = np.zeros((3, 3, nT), complex)
     er[0, 0] = er[1, 1] = er[2, 2] = 1
     ur = er.copy()
+    if slabs:
+        cer = box.tet_vol == 2
+        for k in range(3):
+            er[k, k, cer] = 9.8 * (1 - 1e-4j)
     tag = lambda k: tri_ids_of(t, box.face_tris[box.face_tag == k])
     bcs = [B.PEC(np.concatenate([tag(k) for k in (1, 2, 3, 4)])),
            B.RectangularWaveguide(tag(5), 1, B.CoordSys(origin=(0, 0, 0)), (A_WG, B_WG)),
@@ -209,8 +230,10 @@ def reference_config(args, t):
 
 def workload_config(args):
     nx, ny, nz = args.cells
-    return {"workload": f"synthetic WR-90 rectangular waveguide, {nx}x{ny}x{nz} cells x 6 Kuhn tets = {6*nx*ny*nz} tets, "
-                        f"2 RectangularWaveguide ports + PEC walls, 201-point sweep 8-12 GHz (BASELINE config 4); "
+    what = ("dielectric-loaded WR-90 waveguide (ceramic slabs eps_r = 9.8 (1 - 1e-4 j), two of every twelve cell layers; BASELINE "
+            "config 5)" if SLABS else "WR-90 rectangular waveguide (BASELINE config 4)")
+    return {"workload": f"synthetic {what}, {nx}x{ny}x{nz} cells x 6 Kuhn tets = {6*nx*ny*nz} tets, "
+                        f"2 RectangularWaveguide ports + PEC walls, {len(FREQS)}-point sweep 8-12 GHz; "
                         f"step = one frequency point (A(f) + 2 port solves + S-parameters), K/M assembly once per job",
             "cells": [nx, ny, nz], "rtol": args.rtol,
             "solver": "reduced-basis recycling across points (affine A(f)) + block COCR over the ports (one Krylov space) on the "
@@ -311,7 +334,7 @@ def run_gpu(args):
     from emerge_b200.sweep import FrequencySweep
     nx, ny, nz = args.cells
     t0 = time.perf_counter()
-    box, t, er, ur, bcs, L = make_waveguide(nx, ny, nz)
+    box, t, er, ur, bcs, L = make_waveguide(nx, ny, nz, device=None if args.host_tables else local)
     host_mesh_s = time.perf_counter() - t0
     dev = f"cuda:{local}"
 
@@ -375,6 +398,8 @@ def run_gpu(args):
         sw.solve_point(FREQS[i], raise_on_fail=False)
     main = resident_pass(args, sw, dist, rank, world, local, K, barrier)
     full = resident_pass(args, sw, dist, rank, world, local, None, barrier, clock=False) if (partial and do_full) else main
+    free_b, total_b = torch.cuda.mem_get_info(local)
+    hbm = allgather_obj({"rank": rank, "used_GB": (total_b - free_b) / 1e9, "total_GB": total_b / 1e9})
     # BASELINE's third metric: the single right-hand side complex128 operator application A(f) x, timed alone
     sw.assemble_frequency(float(FREQS[nf // 2]))
     spmv128_ms = ctx.spmv_bench(20, nv=1, fp32=False)
@@ -470,7 +495,7 @@ def run_gpu(args):
                 "sizes": {"tets": nT, "n_field": N, "n_solve": Ns, "nnz_full": nnz_full, "nnz_solve": nnz_s},
                 "setup": {"host_mesh_tables_s": host_mesh_s, "gpu_setup_s": setup_s, **{k: v for k, v in sw.timings.items()}},
                 "e2e_setup": (e2e_k or e2e_full)["setup"] if (e2e_k or e2e_full) else {},
-                "clocks": main["clocks"]}
+                "hbm_after_sweep": hbm, "clocks": main["clocks"]}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args)
             line["same_size_as_cpu_sample"] = gpu_same_size(args, local, line["cpu_baseline"])
@@ -479,7 +504,7 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
-CPU_SAMPLE_POINTS = (0, 50)      # indices into FREQS of the points the CPU baseline solves
+CPU_SAMPLE_FREQS = (8.0e9, 9.0e9)      # the points the CPU baseline solves (indices 0 and 50 of the 201-point sweep)
 
 
 def gpu_same_size(args, device, cpu):
@@ -494,10 +519,10 @@ def gpu_same_size(args, device, cpu):
     sw.setup()
     for p in sw.ports:
         p.active = False
-    for f in FREQS[100:102]:
+    for f in FREQS[len(FREQS) // 2:len(FREQS) // 2 + 2]:
         sw.solve_point(f)
     sw.ctx.recycle_config(args.recycle, args.snap)
-    pts = [float(FREQS[i]) for i in CPU_SAMPLE_POINTS]
+    pts = [float(f) for f in CPU_SAMPLE_FREQS]
     sw.ctx.timer_start()                       # K/M already assembled, as in the CPU sample
     sw.run(pts, order=list(range(len(pts))))
     ms_pts = sw.ctx.timer_stop()
@@ -524,9 +549,9 @@ def cpu_baseline(args):
     assemble()
     asm_s = time.perf_counter() - t0
     t0 = time.perf_counter()
-    for i in CPU_SAMPLE_POINTS:
-        point(FREQS[i])
-    n = len(CPU_SAMPLE_POINTS)
+    for f in CPU_SAMPLE_FREQS:
+        point(f)
+    n = len(CPU_SAMPLE_FREQS)
     dt = time.perf_counter() - t0
     return {"value": n / dt, "unit": UNIT, "cores": 1, "host_cores": os.cpu_count(), "kind": "port",
             "cells": [nx, ny, nz], "tets": int(t.tets.shape[1]),
@@ -567,7 +592,15 @@ def main():
     ap.add_argument("--no-coarse-basis", action="store_true",
                     help="switch off the reduced basis as an extra coarse space of the preconditioner (default on)")
     ap.add_argument("--no-full-sweep", action="store_true", help="skip the whole-job pass when --steps is smaller than the job")
+    ap.add_argument("--workload", default="waveguide", choices=["waveguide", "slabs"],
+                    help="waveguide: BASELINE config 4 (default); slabs: config 5 (use with --cells 76,34,323 --points 401)")
+    ap.add_argument("--points", type=int, default=201, help="frequency points of the sweep, 8-12 GHz")
+    ap.add_argument("--host-tables", action="store_true", help="build the mesh topology tables with numpy on the host")
+    ap.add_argument("--mem", action="store_true", help="report the HBM footprint (cudaMemGetInfo) in the line")
     args = ap.parse_args()
+    global FREQS, SLABS
+    FREQS = np.linspace(8e9, 12e9, args.points)
+    SLABS = args.workload == "slabs"
     if args.ref_cells is None:
         args.ref_cells = pick_ref_cells(max(args.steps, 1) + args.warmup) if args.impl == "reference" else pick_ref_cells(3, 60.0)
     if args.impl == "reference":
