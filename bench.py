@@ -64,7 +64,7 @@ def make_waveguide(nx, ny, nz, device=None, slabs=None):
 
         def vol(x, y, z):
             return np.where((z % period) >= period * 10.0 / 12.0, 2, 1)
-    box = box_mesh(nx, ny, nz, A_WG, B_WG, L, vol_fn=vol)
+    box = box_mesh(nx, ny, nz, A_WG, B_WG, L, vol_fn=vol, node_order=os.environ.get("EMB_MESH_ORDER", "lex"))
     if device is None:
         t = mesh_tables(box.nodes_xyz, box.tets)
     else:

@@ -194,3 +194,157 @@ extern "C" int emb_interp_fields(emb_ctx* c, const emb_c128* x_full, int64_t npt
     dx.release(); dcc.release(); dE.release(); dH.release(); dp.release(); dt.release();
     return EMB_OK;
 }
+
+// ---- Stratton-Chu far field ---------------------------------------------------------------------------
+// Replaces stratton_chu_ff (reference fem/physics/edm/sc.py:27-142): E_far(r) = Q r x SUM_j [ (n x E_j - Z0 r x (n x H_j))
+// exp(j k0 r . v_j) ],  Q = -j k0 / 4 pi,  H_far = r x E_far / Z0,  r = (cos th cos ph, cos th sin ph, sin th) (the
+// reference's convention, sc.py:78-80), over the surface samples j (edge midpoints v_j with area-weighted normals n_j)
+// whose |E_j| exceeds LR = 1e-3 of the largest one (sc.py:57-74).  The reference works in complex64 / float32 with
+// fastmath; here the inputs are rounded to float32 exactly as its .astype() calls do (sc.py:172-178) and the sums run in
+// FP64, so results agree to float32 round-off.  Mapping: a CTA per (direction, source chunk): every thread forms the three
+// tangential-current components of its sources times the phase factor, fixed-order tree reduction in shared memory, the
+// chunk partials are summed in ascending order by k_sc_finish (bitwise reproducible).
+constexpr int SC_THREADS = 256;
+constexpr int SC_CHUNK = 8192;            // sources per CTA
+
+__global__ void k_sc_prepare(int64_t n, const cx* __restrict__ E, const cx* __restrict__ H, const double* __restrict__ vis,
+                             const double* __restrict__ wns, float* __restrict__ src, float* __restrict__ emag) {
+    const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    float e[6], h[6], nv[3];
+    for (int a = 0; a < 3; ++a) {
+        e[2 * a] = (float)E[a * n + j].re; e[2 * a + 1] = (float)E[a * n + j].im;
+        h[2 * a] = (float)H[a * n + j].re; h[2 * a + 1] = (float)H[a * n + j].im;
+        nv[a] = (float)wns[a * n + j];
+    }
+    float* s = src + j * 18;            // one record per sample: E, H (re, im pairs), weighted normal, position
+    for (int a = 0; a < 6; ++a) { s[a] = e[a]; s[6 + a] = h[a]; }
+    s[12] = nv[0]; s[13] = nv[1]; s[14] = nv[2];
+    s[15] = (float)vis[j]; s[16] = (float)vis[n + j]; s[17] = (float)vis[2 * n + j];
+    const double m = sqrt((double)e[0] * e[0] + (double)e[1] * e[1] + (double)e[2] * e[2] + (double)e[3] * e[3] +
+                          (double)e[4] * e[4] + (double)e[5] * e[5]);
+    emag[j] = (float)m;
+}
+__global__ void k_sc_max(int64_t n, const float* __restrict__ emag, unsigned* __restrict__ mx) {
+    __shared__ float sh[SC_THREADS];
+    float m = 0.f;
+    for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) m = fmaxf(m, emag[j]);
+    sh[threadIdx.x] = m;
+    __syncthreads();
+    for (int s = SC_THREADS / 2; s > 0; s >>= 1) {
+        if (threadIdx.x < s) sh[threadIdx.x] = fmaxf(sh[threadIdx.x], sh[threadIdx.x + s]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) atomicMax(mx, __float_as_uint(sh[0]));        // non-negative floats order like their bit patterns
+}
+__global__ void __launch_bounds__(SC_THREADS) k_sc_partial(int64_t n, int64_t nout, const float* __restrict__ src,
+                                                           const float* __restrict__ emag, const unsigned* __restrict__ mx,
+                                                           const double* __restrict__ theta, const double* __restrict__ phi,
+                                                           double k0, double* __restrict__ part) {
+    __shared__ double sh[6][SC_THREADS];
+    const int64_t d = blockIdx.x;
+    const int chunk = blockIdx.y;
+    const float th = (float)theta[d], ph = (float)phi[d];
+    const float kf = (float)k0;
+    const double rx = (double)(cosf(th) * cosf(ph)), ry = (double)(cosf(th) * sinf(ph)), rz = (double)sinf(th);
+    const double kx = (double)kf * rx, ky = (double)kf * ry, kz = (double)kf * rz;
+    const double Z0 = (double)376.73031366857f;
+    const float level = __uint_as_float(*mx) * 0.001f;
+    double acc[6] = {0, 0, 0, 0, 0, 0};
+    const int64_t j1 = min(n, (int64_t)(chunk + 1) * SC_CHUNK);
+    for (int64_t j = (int64_t)chunk * SC_CHUNK + threadIdx.x; j < j1; j += SC_THREADS) {
+        if (!(emag[j] > level)) continue;
+        const float* s = src + j * 18;
+        const double nx = s[12], ny = s[13], nz = s[14];
+        double sn, cs;
+        sincos(kx * (double)s[15] + ky * (double)s[16] + kz * (double)s[17], &sn, &cs);
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {            // real and imaginary parts of the (linear) current terms
+            const double Ex = s[0 + p], Ey = s[2 + p], Ez = s[4 + p], Hx = s[6 + p], Hy = s[8 + p], Hz = s[10 + p];
+            const double nHx = ny * Hz - nz * Hy, nHy = nz * Hx - nx * Hz, nHz = nx * Hy - ny * Hx;
+            const double nEx = ny * Ez - nz * Ey, nEy = nz * Ex - nx * Ez, nEz = nx * Ey - ny * Ex;
+            const double tx = nEx - Z0 * (ry * nHz - rz * nHy);
+            const double ty = nEy - Z0 * (rz * nHx - rx * nHz);
+            const double tz = nEz - Z0 * (rx * nHy - ry * nHx);
+            // (t_re + j t_im)(cs + j sn): p = 0 adds t_re * (cs, sn), p = 1 adds t_im * (-sn, cs)
+            const double a = p == 0 ? cs : -sn, b = p == 0 ? sn : cs;
+            acc[0] += tx * a; acc[1] += tx * b;
+            acc[2] += ty * a; acc[3] += ty * b;
+            acc[4] += tz * a; acc[5] += tz * b;
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 6; ++q) sh[q][threadIdx.x] = acc[q];
+    __syncthreads();
+    for (int s2 = SC_THREADS / 2; s2 > 0; s2 >>= 1) {
+        if (threadIdx.x < s2)
+#pragma unroll
+            for (int q = 0; q < 6; ++q) sh[q][threadIdx.x] += sh[q][threadIdx.x + s2];
+        __syncthreads();
+    }
+    if (threadIdx.x < 6) part[((int64_t)chunk * nout + d) * 6 + threadIdx.x] = sh[threadIdx.x][0];
+}
+__global__ void k_sc_finish(int64_t nout, int nchunk, const double* __restrict__ part, const double* __restrict__ theta,
+                            const double* __restrict__ phi, double k0, cx* __restrict__ Eout, cx* __restrict__ Hout) {
+    const int64_t d = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (d >= nout) return;
+    double s[6] = {0, 0, 0, 0, 0, 0};
+    for (int c = 0; c < nchunk; ++c)
+        for (int q = 0; q < 6; ++q) s[q] += part[((int64_t)c * nout + d) * 6 + q];
+    const float th = (float)theta[d], ph = (float)phi[d];
+    const double rx = (double)(cosf(th) * cosf(ph)), ry = (double)(cosf(th) * sinf(ph)), rz = (double)sinf(th);
+    const double Z0 = (double)376.73031366857f;
+    const double q = -(double)(float)k0 / (double)(4.0f * 3.14159265358979323846f);   // Q = j q
+    const cx ix{s[0], s[1]}, iy{s[2], s[3]}, iz{s[4], s[5]};
+    auto jmul = [q](double re, double im) { return cx{-q * im, q * re}; };             // (j q)(re + j im)
+    const cx ex = jmul(ry * iz.re - rz * iy.re, ry * iz.im - rz * iy.im);
+    const cx ey = jmul(rz * ix.re - rx * iz.re, rz * ix.im - rx * iz.im);
+    const cx ez = jmul(rx * iy.re - ry * ix.re, rx * iy.im - ry * ix.im);
+    Eout[d] = ex; Eout[nout + d] = ey; Eout[2 * nout + d] = ez;
+    Hout[d] = cx{(ry * ez.re - rz * ey.re) / Z0, (ry * ez.im - rz * ey.im) / Z0};
+    Hout[nout + d] = cx{(rz * ex.re - rx * ez.re) / Z0, (rz * ex.im - rx * ez.im) / Z0};
+    Hout[2 * nout + d] = cx{(rx * ey.re - ry * ex.re) / Z0, (rx * ey.im - ry * ex.im) / Z0};
+}
+
+extern "C" int emb_stratton_chu(emb_ctx* c, int64_t nsrc, const emb_c128* E_3xn, const emb_c128* H_3xn, const double* pos_3xn,
+                                const double* wnormal_3xn, int64_t nout, const double* theta, const double* phi, double k0,
+                                emb_c128* Eout_3xnout, emb_c128* Hout_3xnout) {
+    if (!c || nsrc <= 0 || nout <= 0 || !E_3xn || !H_3xn || !pos_3xn || !wnormal_3xn || !theta || !phi || !Eout_3xnout ||
+        !Hout_3xnout)
+        return EMB_ERR_ARG;
+    PhaseTimer pt(c, "stratton_chu");
+    DevBuf<cx> dE, dH, dEo, dHo;
+    DevBuf<double> dv, dn, dth, dph, part;
+    DevBuf<float> src, emag;
+    DevBuf<unsigned> mx;
+    EMB_TRY(h2d(c, dE, reinterpret_cast<const cx*>(E_3xn), (size_t)nsrc * 3));
+    EMB_TRY(h2d(c, dH, reinterpret_cast<const cx*>(H_3xn), (size_t)nsrc * 3));
+    EMB_TRY(h2d(c, dv, pos_3xn, (size_t)nsrc * 3));
+    EMB_TRY(h2d(c, dn, wnormal_3xn, (size_t)nsrc * 3));
+    EMB_TRY(h2d(c, dth, theta, (size_t)nout));
+    EMB_TRY(h2d(c, dph, phi, (size_t)nout));
+    const int nchunk = (int)((nsrc + SC_CHUNK - 1) / SC_CHUNK);
+    if (nchunk > 65535) { c->err = "emb_stratton_chu: more than 65535 x 8192 surface samples"; return EMB_ERR_LIMIT; }
+    EMB_TRY(dev_alloc(c, src, (size_t)nsrc * 18));
+    EMB_TRY(dev_alloc(c, emag, (size_t)nsrc));
+    EMB_TRY(dev_alloc(c, mx, 1));
+    EMB_TRY(dev_alloc(c, part, (size_t)nchunk * nout * 6));
+    EMB_TRY(dev_alloc(c, dEo, (size_t)nout * 3));
+    EMB_TRY(dev_alloc(c, dHo, (size_t)nout * 3));
+    EMB_CUDA(c, cudaMemsetAsync(mx.p, 0, sizeof(unsigned), c->stream));
+    k_sc_prepare<<<blocks_for(nsrc, 256), 256, 0, c->stream>>>(nsrc, dE.p, dH.p, dv.p, dn.p, src.p, emag.p);
+    EMB_LAUNCH_CHECK(c);
+    k_sc_max<<<(unsigned)std::min<int64_t>(blocks_for(nsrc, SC_THREADS), 1024), SC_THREADS, 0, c->stream>>>(nsrc, emag.p, mx.p);
+    EMB_LAUNCH_CHECK(c);
+    k_sc_partial<<<dim3((unsigned)nout, (unsigned)nchunk), SC_THREADS, 0, c->stream>>>(nsrc, nout, src.p, emag.p, mx.p, dth.p, dph.p,
+                                                                                       k0, part.p);
+    EMB_LAUNCH_CHECK(c);
+    k_sc_finish<<<blocks_for(nout, 128), 128, 0, c->stream>>>(nout, nchunk, part.p, dth.p, dph.p, k0, dEo.p, dHo.p);
+    EMB_LAUNCH_CHECK(c);
+    EMB_CUDA(c, cudaMemcpyAsync(Eout_3xnout, dEo.p, (size_t)nout * 3 * sizeof(cx), cudaMemcpyDeviceToHost, c->stream));
+    EMB_CUDA(c, cudaMemcpyAsync(Hout_3xnout, dHo.p, (size_t)nout * 3 * sizeof(cx), cudaMemcpyDeviceToHost, c->stream));
+    EMB_CUDA(c, cudaStreamSynchronize(c->stream));
+    dE.release(); dH.release(); dv.release(); dn.release(); dth.release(); dph.release(); part.release(); src.release();
+    emag.release(); mx.release(); dEo.release(); dHo.release();
+    return EMB_OK;
+}

@@ -242,7 +242,7 @@ template <int NV>
 __global__ void __launch_bounds__(STG_WARPS * 32, 1) k_bsell_tma(int nslices, const int* __restrict__ rows,
                                                                  const int64_t* __restrict__ sptr, const int* __restrict__ bcol,
                                                                  const float4* __restrict__ val, const cx* __restrict__ x,
-                                                                 cx* __restrict__ y) {
+                                                                 cx* __restrict__ y, int blocked) {
     constexpr int LPB = 2 * NV;                 // lanes per block-row
     constexpr int RPW = 32 / LPB;               // rows a warp covers per pass (8 or 4)
     constexpr int NPASS = SELL_C / RPW;         // 1 (NV = 2) or 2 (NV = 4)
@@ -253,7 +253,27 @@ __global__ void __launch_bounds__(STG_WARPS * 32, 1) k_bsell_tma(int nslices, co
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncwarp();
     const int u = lane % LPB, h = u / NV, rl = lane / LPB;
-    const int gw = blockIdx.x * STG_WARPS + warp, G = gridDim.x * STG_WARPS;
+    // Slices of a warp.  blocked: the CTA owns a CONTIGUOUS run of slices holding 1/gridDim of all blocks (its 16 warps walk
+    // it side by side), so the x entries a slice gathers are still in this SM's L1 when the neighbouring slices need them;
+    // otherwise warp g of the grid takes slices g, g + G, ...
+    int gw = blockIdx.x * STG_WARPS + warp, G = gridDim.x * STG_WARPS;
+    if (blocked) {
+        const int64_t total = __ldg(sptr + nslices);
+        int lim[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int64_t target = total / gridDim.x * (blockIdx.x + e);
+            int lo = 0, hi = nslices;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (__ldg(sptr + mid) < target) lo = mid + 1; else hi = mid;
+            }
+            lim[e] = (blockIdx.x + e == (int)gridDim.x) ? nslices : lo;
+        }
+        gw = lim[0] + warp;
+        G = STG_WARPS;
+        nslices = lim[1];
+    }
     // chunk iterator over this warp's slices: (slice s, first block column q0); issue() starts the copies of a chunk
     int s_i = gw, q_i = 0;                       // next chunk to ISSUE
     int64_t base_i = 0;
@@ -343,6 +363,7 @@ __global__ void __launch_bounds__(STG_WARPS * 32, 1) k_bsell_tma(int nslices, co
 template <int NV>
 static int bsell_launch(emb_ctx* c, const cf* val, const cx* x, cx* y) {
     static const int mode = getenv("EMB_SPMV_TMA") ? atoi(getenv("EMB_SPMV_TMA")) : 1;
+    static const int blocked = getenv("EMB_SELL_BLOCKED") ? atoi(getenv("EMB_SELL_BLOCKED")) : 1;
     if constexpr (NV == 2) {               // NV = 4 in two passes over the staged chunk was measured slower than k_bsell
         if (mode && !c->sell_has_empty) {      // (a slice without any block is never visited by the staged kernel)
             int nsm = 0;
@@ -351,7 +372,7 @@ static int bsell_launch(emb_ctx* c, const cf* val, const cx* x, cx* y) {
             auto kern = k_bsell_tma<NV>;
             EMB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             kern<<<nsm, STG_WARPS * 32, smem, c->stream>>>((int)c->sell_nslices, c->sell_rows.p, c->sell_sptr.p, c->sell_bcol.p,
-                                                          reinterpret_cast<const float4*>(val), x, y);
+                                                          reinterpret_cast<const float4*>(val), x, y, blocked);
             EMB_LAUNCH_CHECK(c);
             return EMB_OK;
         }

@@ -324,7 +324,8 @@ def install(physics, fast: bool = False, keep_fields: bool = True, **kw) -> GpuA
       physics.frequency_domain()          -> EMSimData   (emfreq3d.py:607-732)
       physics.frequency_domain_par(njobs) -> EMSimData   (emfreq3d.py:469-605)
     by FrequencySweep-backed versions that fill the same EMSimData (Sp, _fields[port], er/ur[0,0,:], port properties);
-    the result object's .interpolate(xs, ys, zs) (emdata.py:181-199) then evaluates E and H on the device (install_postproc).
+    the result object's .interpolate(xs, ys, zs) (emdata.py:181-199) then evaluates E and H on the device (install_postproc)
+    and `fem.physics.edm.stratton_chu` (sc.py:144-180) runs on the device (farfield.install_farfield).
     frequency_domain_par shards the frequency points over the ranks of the initialised torch.distributed process group
     (one process per GPU, launched with torchrun - the counterpart of the reference's multiprocessing.Pool(njobs)); njobs
     is accepted for signature compatibility, the parallel width is the world size.  Without a process group it runs on
@@ -351,4 +352,12 @@ def install(physics, fast: bool = False, keep_fields: bool = True, **kw) -> GpuA
             return _gpu_frequency_domain(self, asm, dist, keep_fields)
         physics.frequency_domain = types.MethodType(frequency_domain, physics)
         physics.frequency_domain_par = types.MethodType(frequency_domain_par, physics)
+        # far field: fem.physics.edm.stratton_chu (sc.py:144-180) -> emb_stratton_chu on the assembler's context
+        import importlib
+        pkg = type(physics).__module__.rsplit(".", 1)[0]            # "...physics.edm"
+        try:
+            from .farfield import install_farfield
+            install_farfield(importlib.import_module(pkg), lambda: asm.ctx)
+        except ImportError:
+            pass
     return asm

@@ -42,6 +42,8 @@ _SIGS = {
     "emb_upload_materials": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "emb_locate_points": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "emb_interp_fields": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "emb_stratton_chu": (C.c_int, [C.c_void_p, C.c_int64] + [C.c_void_p] * 4 + [C.c_int64, C.c_void_p, C.c_void_p, C.c_double,
+                                   C.c_void_p, C.c_void_p]),
     "emb_topology_build": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
                                      C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "emb_topology_get": (C.c_int, [C.c_void_p] + [C.c_void_p] * 10),
@@ -255,6 +257,19 @@ class Context:
         H = np.empty((3, n), dtype=np.complex128) if cc is not None else None
         self._check(self.lib.emb_interp_fields(self.h, _p(x), n, _p(pts), _p(tid), _p(cc), _p(E), _p(H)))
         return E, H
+
+    def stratton_chu(self, E, H, pos, wnormal, theta, phi, k0):
+        """far field (E (3,nout), H (3,nout)) of surface samples: stratton_chu_ff (fem/physics/edm/sc.py:27-142)"""
+        E, H = _c(E, np.complex128), _c(H, np.complex128)
+        pos, wn = _c(pos, np.float64), _c(wnormal, np.float64)
+        th, ph = _c(np.atleast_1d(theta), np.float64), _c(np.atleast_1d(phi), np.float64)
+        n, nout = E.shape[1], th.shape[0]
+        if H.shape != E.shape or pos.shape != (3, n) or wn.shape != (3, n) or ph.shape[0] != nout:
+            raise ValueError("stratton_chu: E, H, pos, wnormal must be (3,n); theta, phi of equal length")
+        Eo = np.empty((3, nout), dtype=np.complex128)
+        Ho = np.empty((3, nout), dtype=np.complex128)
+        self._check(self.lib.emb_stratton_chu(self.h, n, _p(E), _p(H), _p(pos), _p(wn), nout, _p(th), _p(ph), float(k0), _p(Eo), _p(Ho)))
+        return Eo, Ho
 
     def upload_materials(self, er, ur):
         er = _c(er, np.complex128)

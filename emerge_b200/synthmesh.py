@@ -43,9 +43,21 @@ def _perm_sign(p):
     return s
 
 
+def _morton3(i, j, k):
+    def spread(v):
+        v = v.astype(np.uint64) & np.uint64(0x1FFFFF)
+        v = (v | (v << np.uint64(32))) & np.uint64(0x1F00000000FFFF)
+        v = (v | (v << np.uint64(16))) & np.uint64(0x1F0000FF0000FF)
+        v = (v | (v << np.uint64(8))) & np.uint64(0x100F00F00F00F00F)
+        v = (v | (v << np.uint64(4))) & np.uint64(0x10C30C30C30C30C3)
+        v = (v | (v << np.uint64(2))) & np.uint64(0x1249249249249249)
+        return v
+    return spread(i) | (spread(j) << np.uint64(1)) | (spread(k) << np.uint64(2))
+
+
 def box_mesh(nx: int, ny: int, nz: int, a: float, b: float, L: float,
              jitter: float = 0.0, seed: int = 0, vol_fn=None,
-             internal_faces=None) -> BoxMesh:
+             internal_faces=None, node_order: str = "lex") -> BoxMesh:
     """Structured box [−a/2,a/2]×[−b/2,b/2]×[0,L] → Kuhn tets.
 
     Face tags: 1:x=-a/2  2:x=+a/2  3:y=-b/2  4:y=+b/2  5:z=0  6:z=L.
@@ -120,6 +132,16 @@ def box_mesh(nx: int, ny: int, nz: int, a: float, b: float, L: float,
     face_tris = np.concatenate(face_tris)
     face_tag = np.concatenate(face_tag)
 
+    if node_order == "morton":       # renumber the nodes along a Z-order curve (a mesher's numbering has no such guarantee)
+        I, J, K = np.meshgrid(np.arange(nx + 1), np.arange(ny + 1), np.arange(nz + 1), indexing="ij")
+        perm = np.argsort(_morton3(I.ravel(), J.ravel(), K.ravel()), kind="stable")
+        inv = np.empty_like(perm)
+        inv[perm] = np.arange(len(perm))
+        nodes = nodes[perm]
+        tets = inv[tets]
+        face_tris = inv[face_tris]
+    elif node_order != "lex":
+        raise ValueError(node_order)
     cen = nodes[tets].mean(axis=1)
     tet_vol = np.ones(len(tets), dtype=np.int64) if vol_fn is None else \
         np.asarray(vol_fn(cen[:, 0], cen[:, 1], cen[:, 2]), dtype=np.int64)

@@ -253,6 +253,14 @@ int emb_locate_points(emb_ctx* ctx, int64_t npts, const double* xyz_3xnpts, int6
  * curl_const (nT complex; the reference passes 1/(-j w mu0 mu_r[0,0,tet]), emdata.py:193) and H may be NULL. */
 int emb_interp_fields(emb_ctx* ctx, const emb_c128* x_full, int64_t npts, const double* xyz_3xnpts, const int64_t* tet_ids,
                       const emb_c128* curl_const_nT, emb_c128* E_3xnpts, emb_c128* H_3xnpts);
+/* Stratton-Chu far field of surface samples: stratton_chu_ff (fem/physics/edm/sc.py:27-142).  E, H (3,nsrc) tangential-field
+ * samples at pos (3,nsrc) with area-weighted outward normals wnormal (3,nsrc) (built by stratton_chu, sc.py:144-166, from
+ * a SurfaceMesh); directions theta, phi (nout each; r = (cos th cos ph, cos th sin ph, sin th), sc.py:78-80); outputs
+ * (3,nout).  Inputs are rounded to float32 as the reference does (sc.py:172-178), samples below 1e-3 of the largest |E|
+ * are skipped (sc.py:57-74), the sums run in FP64. */
+int emb_stratton_chu(emb_ctx* ctx, int64_t nsrc, const emb_c128* E_3xn, const emb_c128* H_3xn, const double* pos_3xn,
+                     const double* wnormal_3xn, int64_t nout, const double* theta, const double* phi, double k0,
+                     emb_c128* Eout_3xnout, emb_c128* Hout_3xnout);
 
 #ifdef __cplusplus
 }

@@ -322,9 +322,28 @@ def case_interp_wg_tiny():
     return out
 
 
+def case_farfield_patch():
+    """Far-field pin: the demo3 flow (demo3_patch_antenna.py:94-100) on the abc_lumped look-alike -
+    SurfaceMesh of the absorbing boundary, E/H at its edge midpoints, fem.physics.edm.stratton_chu over a theta cut and a
+    phi cut.  Stores the SurfaceMesh arrays the function reads, so the test needs neither mesh nor solve."""
+    fem, phys, mesh, box, port, hx, hz = abc_lumped_physics()
+    phys.frequencies = [2.4e9]
+    data = phys.frequency_domain()
+    surf = mesh.boundary_surface([1, 2, 3, 4, 6], (0, 0, box.dims[2] / 2))
+    ds = data.item(0)
+    Ein, Hin = ds.interpolate(*surf.exyz).EH
+    theta = np.concatenate([np.linspace(-np.pi, np.pi, 61), np.full(24, 0.3)])
+    phi = np.concatenate([np.zeros(61), np.linspace(0, 2 * np.pi, 24)])
+    from fem.physics.edm import stratton_chu
+    E, Hf = stratton_chu(Ein, Hin, surf, theta, phi, ds.k0)
+    return dict(kind="farfield", Ein=np.asarray(Ein), Hin=np.asarray(Hin), areas=np.asarray(surf.areas),
+                normals=np.asarray(surf.normals), tri_to_edge=np.asarray(surf.tri_to_edge).astype(np.int32),
+                edge_centers=np.asarray(surf.edge_centers), theta=theta, phi=phi, k0=np.float64(ds.k0), E=E, H=Hf)
+
+
 CASES = dict(wg_tiny=case_wg_tiny, wg_materials=case_wg_materials, wg_medium=case_wg_medium,
              abc_lumped=case_abc_lumped, modal_microstrip=case_modal_microstrip, lossy_slabs=case_lossy_slabs,
-             interp_wg_tiny=case_interp_wg_tiny)
+             interp_wg_tiny=case_interp_wg_tiny, farfield_patch=case_farfield_patch)
 
 if __name__ == "__main__":
     if not os.path.isdir("/root/reference/fem"):

@@ -58,6 +58,16 @@ def _interp(data, i, seed=0):
     return np.array([ds.Ex, ds.Ey, ds.Ez]), np.array([ds.Hx, ds.Hy, ds.Hz])
 
 
+def _far_field(phys, data):
+    """demo3_patch_antenna.py:94-100: far field of the absorbing boundary's surface mesh over a theta cut"""
+    import fem.physics.edm as edm
+    surf = phys.mesh.boundary_surface([1, 2, 3, 4, 6], (0.0, 0.0, 6e-3))
+    ds = data.item(0)
+    Ein, Hin = ds.interpolate(*surf.exyz).EH
+    theta = np.linspace(-np.pi, np.pi, 73)
+    return edm.stratton_chu(Ein, Hin, surf, theta, 0 * theta + 0.2, ds.k0)
+
+
 def _collect(data, nf):
     S = np.array([data.item(i).Sp.arry.copy() for i in range(nf)])
     fields = [{k: np.array(v) for k, v in data.item(i)._fields.items()} for i in range(nf)]
@@ -88,6 +98,7 @@ def test_reference_frequency_domain_on_top_of_install(case, tmp_path):
     S_ref, F_ref = _collect(data, nf)
     E_ref, H_ref = _interp(data, 0)                                  # reference post-processing (numba, all tets x all points)
     stock_solve = type(phys.solveroutine).solve
+    ff_ref = _far_field(phys, data) if case == "abc_lumped" else None      # reference Stratton-Chu (sc.py), demo3 flow
 
     asm = install(phys, rtol=1e-10)                                  # 2. the two seams
     assert isinstance(phys.assembler, GpuAssembler)
@@ -106,6 +117,12 @@ def test_reference_frequency_domain_on_top_of_install(case, tmp_path):
     E, Hf = _interp(data, 0)                                         # same call, now located + evaluated on the device
     assert np.array_equal(np.abs(E).sum(axis=0) == 0, np.abs(E_ref).sum(axis=0) == 0)       # same points outside the mesh
     assert np.abs(E - E_ref).max() <= 1e-6 * np.abs(E_ref).max() and np.abs(Hf - H_ref).max() <= 1e-6 * np.abs(H_ref).max()
+    if ff_ref is not None:                                           # fem.physics.edm.stratton_chu now runs emb_stratton_chu
+        import fem.physics.edm as edm
+        assert edm.stratton_chu.__module__ == "emerge_b200.farfield"
+        ff = _far_field(phys, data)
+        for a, b in zip(ff, ff_ref):
+            assert np.abs(a - b).max() <= 2e-5 * np.abs(b).max()
     data = phys.frequency_domain_par(njobs=2)
     _check(data, nf, S_ref, F_ref, "fast parallel driver (one rank)")
     # result API of the reference on the GPU-filled object: axis access and Touchstone export (emdata.py:284-331)

@@ -63,3 +63,27 @@ def test_one_million_tets_20k_points(gpu_ctx):
     Bm = np.stack([v[:, k] - v[:, 0] for k in (1, 2, 3)], axis=1).transpose(2, 0, 1)      # (n, 3, 3) columns
     loc = np.linalg.solve(Bm, (pts - v[:, 0]).T[:, :, None])[:, :, 0]
     assert (loc >= -1e-6).all() and (loc.sum(axis=1) <= 1.00000001).all()
+
+
+def test_far_field_matches_reference_and_oracle(gpu_ctx):
+    """emb_stratton_chu against fem.physics.edm.stratton_chu (tests/golden/farfield_patch.npz) and, on a larger random
+    surface sample set with a field-strength cut-off that actually drops samples, against the oracle."""
+    from tests.test_oracle_farfield_cpu import _g, surface_of, FF_TOL
+    from emerge_b200.farfield import stratton_chu
+    g = _g()
+    E, H = stratton_chu(g["Ein"], g["Hin"], surface_of(g), g["theta"], g["phi"], float(g["k0"]), ctx=gpu_ctx)
+    assert np.abs(E - g["E"]).max() <= FF_TOL * np.abs(g["E"]).max()
+    assert np.abs(H - g["H"]).max() <= FF_TOL * np.abs(g["H"]).max()
+    rng = np.random.default_rng(11)
+    n, nout = 20011, 333                                   # three source chunks
+    Ein = (rng.standard_normal((3, n)) + 1j * rng.standard_normal((3, n))) * rng.random(n) ** 6     # many weak samples
+    Hin = (rng.standard_normal((3, n)) + 1j * rng.standard_normal((3, n))) / 377.0
+    pos = rng.standard_normal((3, n)) * 0.05
+    wns = rng.standard_normal((3, n)) * 1e-5
+    th, ph = rng.uniform(-np.pi, np.pi, nout), rng.uniform(0, 2 * np.pi, nout)
+    E, H = gpu_ctx.stratton_chu(Ein, Hin, pos, wns, th, ph, 52.3)
+    Er, Hr = O.stratton_chu_ff(Ein, Hin, pos, wns, th, ph, 52.3)
+    assert np.abs(E - Er).max() <= 1e-6 * np.abs(Er).max()          # both sum in FP64 on the same float32-rounded inputs
+    assert np.abs(H - Hr).max() <= 1e-6 * np.abs(Hr).max()
+    E2, H2 = gpu_ctx.stratton_chu(Ein, Hin, pos, wns, th, ph, 52.3)
+    assert np.array_equal(E, E2) and np.array_equal(H, H2)          # fixed-order reduction: reproducible
