@@ -33,6 +33,11 @@ extern "C" void emb_destroy(emb_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+    for (int k = 0; k < 4; ++k) {
+        c->xstage[k].release();
+        if (c->ev_stage_ready[k]) { cudaEventDestroy(c->ev_stage_ready[k]); cudaEventDestroy(c->ev_stage_done[k]); }
+    }
     topology_release(c);
     c->nodes.release(); c->tris.release(); c->tri2f.release(); c->tetc.release(); c->tetord.release(); c->gid.release();
     c->er.release(); c->ur.release(); c->adjptr.release(); c->adj.release(); c->rowptr.release(); c->col.release();

@@ -149,6 +149,12 @@ struct emb_ctx {
     DevBuf<cx> xs;            // last solution (solve space)
     DevBuf<cx> bs;            // right-hand side of the current solve (solve space)
     DevBuf<cx> xfull;         // last solution (full space)
+    // asynchronous field output (emb_fields_async): per-column staging copies of the full-space solutions, moved to the
+    // caller's (pinned) buffers by a copy stream while the next point is being solved
+    bool fields_async = false;
+    cudaStream_t copy_stream = nullptr;
+    DevBuf<cx> xstage[4];
+    cudaEvent_t ev_stage_ready[4] = {}, ev_stage_done[4] = {};
     std::vector<DevBuf<cx>> work;
     DevBuf<cx> dinv;          // Jacobi / block-Jacobi inverse blocks
     DevBuf<int> pairmate;     // solve-space index of the paired dof (block-Jacobi) or -1

@@ -592,8 +592,35 @@ static int solve_dispatch(emb_ctx* c, int nv, const emb_solve_opts* o, const cx*
     return EMB_ERR_ARG;
 }
 
+// Asynchronous variant of the host copy: column k is scattered into its own staging vector on the compute stream; the
+// copy stream moves it to the caller's buffer.  The staging vector is not rewritten before its previous copy has finished
+// (the compute stream waits on that copy's event - no host synchronisation anywhere); emb_fields_sync() is the host's wait.
+static int finish_solution_async(emb_ctx* c, int k, emb_c128* x_full) {
+    DevBuf<cx>& st = c->xstage[k];
+    EMB_TRY(dev_alloc(c, st, (size_t)c->N));
+    if (!c->ev_stage_ready[k]) {
+        EMB_CUDA(c, cudaEventCreateWithFlags(&c->ev_stage_ready[k], cudaEventDisableTiming));
+        EMB_CUDA(c, cudaEventCreateWithFlags(&c->ev_stage_done[k], cudaEventDisableTiming));
+    } else {
+        EMB_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_stage_done[k], 0));
+    }
+    EMB_CUDA(c, cudaMemsetAsync(st.p, 0, (size_t)c->N * sizeof(cx), c->stream));
+    k_scatter_col<<<blocks_for(c->Ns, 256), 256, 0, c->stream>>>(c->Ns, c->solve_ids.p, c->xs.p, c->nsol, k, st.p);
+    EMB_LAUNCH_CHECK(c);
+    EMB_CUDA(c, cudaEventRecord(c->ev_stage_ready[k], c->stream));
+    EMB_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_stage_ready[k], 0));
+    EMB_CUDA(c, cudaMemcpyAsync(x_full, st.p, (size_t)c->N * sizeof(cx), cudaMemcpyDeviceToHost, c->copy_stream));
+    EMB_CUDA(c, cudaEventRecord(c->ev_stage_done[k], c->copy_stream));
+    return EMB_OK;
+}
+
 // full-space copy of column k of the last solve (zeros at eliminated dofs), optionally to the host
 static int finish_solution(emb_ctx* c, int k, emb_c128* x_full) {
+    if (x_full && c->fields_async && c->copy_stream && k < 4) {
+        EMB_TRY(finish_solution_async(c, k, x_full));
+        if (k != 0) return EMB_OK;
+        x_full = nullptr;                 // column 0 also becomes the device-resident "last solution" below
+    }
     EMB_TRY(dev_alloc(c, c->xfull, (size_t)c->N));
     EMB_CUDA(c, cudaMemsetAsync(c->xfull.p, 0, (size_t)c->N * sizeof(cx), c->stream));
     k_scatter_col<<<blocks_for(c->Ns, 256), 256, 0, c->stream>>>(c->Ns, c->solve_ids.p, c->xs.p, c->nsol, k, c->xfull.p);
@@ -649,6 +676,22 @@ extern "C" int emb_solve_multi(emb_ctx* c, int nrhs, const int* sids, const emb_
 extern "C" int emb_solve(emb_ctx* c, int sid, const emb_solve_opts* opts, emb_c128* x_full, emb_solve_info* info) {
     emb_c128* xs[1] = {x_full};
     return emb_solve_multi(c, 1, &sid, opts, xs, info);
+}
+
+// Field output mode.  on = 1: the host copies of emb_solve_multi's solutions are issued on a copy stream and overlap the
+// following work; the buffers (pinned memory, or the copy degenerates to a synchronous one) are valid after
+// emb_fields_sync().  Counterpart of `data._fields[port] = solution` (emfreq3d.py:699), which the reference does on the host.
+extern "C" int emb_fields_async(emb_ctx* c, int on) {
+    if (!c) return EMB_ERR_ARG;
+    if (on && !c->copy_stream) EMB_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    if (!on && c->copy_stream) EMB_CUDA(c, cudaStreamSynchronize(c->copy_stream));
+    c->fields_async = on != 0;
+    return EMB_OK;
+}
+extern "C" int emb_fields_sync(emb_ctx* c) {
+    if (!c) return EMB_ERR_ARG;
+    if (c->copy_stream) EMB_CUDA(c, cudaStreamSynchronize(c->copy_stream));
+    return EMB_OK;
 }
 
 // makes column k of the last emb_solve_multi the device-resident solution read by emb_interp_last

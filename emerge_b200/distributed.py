@@ -51,6 +51,10 @@ class GpuEngine:
     def solve_point(self, f, **kw):
         return self.sweep.solve_point(f, **kw)
 
+    def fields_async(self, on):
+        """the D2H copies of the solved fields overlap the next point (emb_fields_async); off = wait for the last one"""
+        self.sweep.ctx.fields_async(on)
+
     def accepted(self):
         """monotonic count of directions this rank's basis has accepted (emb_recycle_accepted)"""
         return self.sweep.ctx.recycle_accepted()
@@ -170,6 +174,9 @@ class ShardedSweep:
                 for k, v in fl.items():
                     fields_out[(i, k)] = v
 
+        overlap = out_bufs is not None and fields_out is None and hasattr(eng, "fields_async")
+        if overlap:                          # the caller reads the buffers after run(): copies overlap the next point
+            eng.fields_async(True)
         t0 = time.perf_counter()
         t_ex = 0.0
         self.rounds = 0
@@ -190,6 +197,8 @@ class ShardedSweep:
             if len(stats) >= budget:
                 break
             solve(i)
+        if overlap:
+            eng.fields_async(False)          # waits for the last copy
         self.timings = dict(seed_s=t_seed - t_ex, exchange_s=t_ex, fill_s=time.perf_counter() - t0,
                             seed_rounds=self.rounds, imported_directions=self.exchanged)
         res = SweepResult(self.freqs, [], S)

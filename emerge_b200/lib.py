@@ -79,6 +79,8 @@ _SIGS = {
     "emb_solve": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(SolveOpts), C.c_void_p, C.POINTER(SolveInfo)]),
     "emb_solve_multi": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(SolveOpts), C.c_void_p, C.c_void_p]),
     "emb_select_solution": (C.c_int, [C.c_void_p, C.c_int]),
+    "emb_fields_async": (C.c_int, [C.c_void_p, C.c_int]),
+    "emb_fields_sync": (C.c_int, [C.c_void_p]),
     "emb_precond_sampled": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "emb_spmv_bench_ex": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "emb_solver_config": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
@@ -523,6 +525,13 @@ class Context:
             for d in out:
                 d["converged"] = True
         return xs, out
+
+    def fields_async(self, on: bool = True):
+        """host copies of the solved fields (solve_multi(outs=...)) overlap the following work; valid after fields_sync()"""
+        self._check(self.lib.emb_fields_async(self.h, 1 if on else 0))
+
+    def fields_sync(self):
+        self._check(self.lib.emb_fields_sync(self.h))
 
     def select_solution(self, k: int):
         """column k of the last solve_multi becomes the device-resident solution used by interp(None, ...)"""

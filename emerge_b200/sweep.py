@@ -385,13 +385,20 @@ class FrequencySweep:
         if order is None:
             order = hierarchical_order(len(freqs)) if self.recycle else list(range(len(freqs)))
         stats = {}
-        for i in order:
-            S[i], st, fl = self.solve_point(freqs[i], keep_fields, raise_on_fail, out_bufs=out_bufs)
-            stats[i] = st
-            if on_point is not None:
-                on_point(i, S[i], st)
-            for k, v in fl.items():
-                res.fields[(i, k)] = v
+        overlap = out_bufs is not None and on_point is None and not keep_fields
+        if overlap:                 # nobody reads the buffers before run() returns: their D2H copies overlap the next point
+            self.ctx.fields_async(True)
+        try:
+            for i in order:
+                S[i], st, fl = self.solve_point(freqs[i], keep_fields, raise_on_fail, out_bufs=out_bufs)
+                stats[i] = st
+                if on_point is not None:
+                    on_point(i, S[i], st)
+                for k, v in fl.items():
+                    res.fields[(i, k)] = v
+        finally:
+            if overlap:
+                self.ctx.fields_async(False)        # waits for the last copy
         for i in range(len(freqs)):
             res.stats.extend(stats.get(i, []))
         res.timings = dict(self.timings)

@@ -203,6 +203,11 @@ int emb_solve(emb_ctx* ctx, int sid, const emb_solve_opts* opts, emb_c128* x_ful
 int emb_solve_multi(emb_ctx* ctx, int nrhs, const int* sids, const emb_solve_opts* opts, emb_c128* const* x_full,
                     emb_solve_info* infos);
 int emb_select_solution(emb_ctx* ctx, int k);
+/* Field output mode (emfreq3d.py:699 `data._fields[port] = solution`).  on = 1: the host copies of emb_solve_multi's
+ * solutions are issued on a copy stream from per-column staging vectors and overlap the next point's work; the caller's
+ * buffers (pinned memory) are valid after emb_fields_sync().  on = 0 (default): the copy has finished on return. */
+int emb_fields_async(emb_ctx* ctx, int on);
+int emb_fields_sync(emb_ctx* ctx);
 /* same with an explicit host RHS of length n_field (the b + port_vectors[p] of emfreq3d.py:691) */
 int emb_solve_rhs(emb_ctx* ctx, const emb_c128* b_full, const emb_solve_opts* opts, emb_c128* x_full,
                   emb_solve_info* info);
