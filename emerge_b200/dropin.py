@@ -28,7 +28,7 @@ import numpy as np
 import scipy.sparse as sp
 
 from .lib import Context, EmergeB200Error
-from .sweep import FrequencySweep
+from .sweep import FrequencySweep, _is
 
 
 class _RefTables:
@@ -204,6 +204,54 @@ class GpuAssembler:
         return DeviceCSR.lazy(n, self, frequency), _ZeroRHS(n), self.solve_ids.copy(), port_vectors
 
     # ---- solver seam ---------------------------------------------------------------------------------------------
+    def assemble_bma_matrices(self, field, er, ur, k0, port, bcs):
+        """Assembler.assemble_bma_matrices (assembler.py:246-308): matrices of the port's boundary-mode eigenproblem.
+        Same arguments and return value (E, B, solve_ids, NedelecLegrange2 field).  The element loop - the numba prange
+        kernel generalized_matrix_GQ, nedeleclegrange2.py:223-417 - runs on the device (emb_bma_element_matrices); the
+        port's SurfaceMesh / NedelecLegrange2 objects and the PEC bookkeeping are the reference's own, because
+        modal_analysis keeps using them afterwards (emfreq3d.py:330-362)."""
+        import importlib
+        pkg = type(field).__module__.rsplit(".", 1)[0]                       # "...fem.elements"
+        NedelecLegrange2 = importlib.import_module(pkg + ".nedleg2").NedelecLegrange2
+        mesh = field.mesh
+        tri_ids = mesh.get_triangles(port.tags)
+        origin = tuple([c - n for c, n in zip(port.cs.origin, port.cs.gzhat)])
+        surf = mesh.boundary_surface(port.tags, origin)
+        nlf = NedelecLegrange2(surf, port.cs)
+        xy = (np.linalg.pinv(port.cs._basis) @ surf.nodes)[:2]               # nedeleclegrange2.py:43
+        eA, eB = self.ctx.bma_element_matrices(xy, surf.tris, surf.edges, nlf.tri_to_field[:3, :], er[:, :, tri_ids],
+                                               ur[:, :, tri_ids], k0)
+        ttf = np.asarray(nlf.tri_to_field, dtype=np.int64)
+        rows = np.repeat(ttf.T[:, :, None], 14, axis=2).ravel()
+        cols = np.repeat(ttf.T[:, None, :], 14, axis=1).ravel()
+        n = nlf.n_field
+        E = sp.coo_matrix((eA.ravel(), (rows, cols)), shape=(n, n)).tocsr()
+        B = sp.coo_matrix((eB.ravel(), (rows, cols)), shape=(n, n)).tocsr()
+        pec_ids, pec_edges, pec_vertices = [], [], []
+        for bc in bcs:                                                       # assembler.py:268-296
+            if not _is(bc, "PEC"):
+                continue
+            tids = mesh.get_triangles(bc.tags)
+            for ii in list(mesh.tri_to_edge[:, tids].flatten()):
+                i2 = surf.from_source_edge(ii)
+                if i2 is None:
+                    continue
+                eids = nlf.edge_to_field[:, i2]
+                pec_ids.extend(list(eids))
+                pec_edges.append(eids[0])
+                pec_vertices.append(eids[3] - nlf.n_xy)
+                pec_vertices.append(eids[4] - nlf.n_xy)
+            for ii in tids:
+                i2 = surf.from_source_tri(ii)
+                if i2 is None:
+                    continue
+                pec_ids.extend(list(nlf.tri_to_field[:, i2]))
+        port._field, port._pece, port._pecv = nlf, pec_edges, pec_vertices
+        gone = np.zeros(n, dtype=bool)
+        if pec_ids:
+            gone[np.asarray(pec_ids, dtype=np.int64)] = True
+        return E, B, np.nonzero(~gone)[0], nlf
+
     def solve(self, A, b, solve_ids, reuse=False):
         """SolveRoutine.solve(A, b, solve_ids, reuse) -> x (length N, zeros at eliminated dofs), solver.py:405-469.
         A must be the DeviceCSR of the last assemble_freq_matrix call (the device holds exactly that A(f))."""

@@ -44,6 +44,8 @@ _SIGS = {
     "emb_interp_fields": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "emb_stratton_chu": (C.c_int, [C.c_void_p, C.c_int64] + [C.c_void_p] * 4 + [C.c_int64, C.c_void_p, C.c_void_p, C.c_double,
                                    C.c_void_p, C.c_void_p]),
+    "emb_bma_element_matrices": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64] + [C.c_void_p] * 6 + [C.c_double, C.c_void_p,
+                                           C.c_void_p]),
     "emb_topology_build": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
                                      C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "emb_topology_get": (C.c_int, [C.c_void_p] + [C.c_void_p] * 10),
@@ -272,6 +274,21 @@ class Context:
         Ho = np.empty((3, nout), dtype=np.complex128)
         self._check(self.lib.emb_stratton_chu(self.h, n, _p(E), _p(H), _p(pos), _p(wn), nout, _p(th), _p(ph), float(k0), _p(Eo), _p(Ho)))
         return Eo, Ho
+
+    def bma_element_matrices(self, xy, tris, edges, tri_to_edge, er, ur, k0):
+        """(A, B) (nt,14,14) element matrices of the port eigenproblem (nedeleclegrange2.py:223-417) on the device"""
+        xy = _c(xy, np.float64)
+        tris, edges, t2e = _c(tris, np.int64), _c(edges, np.int64), _c(tri_to_edge, np.int64)
+        er, ur = _c(er, np.complex128), _c(ur, np.complex128)
+        nt = tris.shape[1]
+        if xy.shape[0] != 2 or tris.shape[0] != 3 or edges.shape[0] != 2 or t2e.shape != (3, nt) or er.shape != (3, 3, nt) \
+                or ur.shape != (3, 3, nt):
+            raise ValueError("bma_element_matrices: xy (2,n), tris (3,nt), edges (2,ne), tri_to_edge (3,nt), er/ur (3,3,nt)")
+        A = np.empty((nt, 14, 14), dtype=np.complex128)
+        B = np.empty((nt, 14, 14), dtype=np.complex128)
+        self._check(self.lib.emb_bma_element_matrices(self.h, nt, xy.shape[1], edges.shape[1], _p(xy), _p(tris), _p(edges), _p(t2e),
+                                                      _p(er), _p(ur), float(k0), _p(A), _p(B)))
+        return A, B
 
     def upload_materials(self, er, ur):
         er = _c(er, np.complex128)

@@ -267,6 +267,18 @@ int emb_stratton_chu(emb_ctx* ctx, int64_t nsrc, const emb_c128* E_3xn, const em
                      const double* wnormal_3xn, int64_t nout, const double* theta, const double* phi, double k0,
                      emb_c128* Eout_3xnout, emb_c128* Hout_3xnout);
 
+/* ---- port boundary-mode analysis ------------------------------------------------------------------- */
+/* The 14 x 14 element matrices (A, B) of the generalised eigenproblem A e = -beta^2 B e on the port triangles:
+ * generalized_matrix_GQ / _matrix_builder (fem/physics/edm/nedeleclegrange2.py:223-417).  xy (2,n_nodes): port-local node
+ * coordinates (rows 0, 1 of pinv(basis) @ nodes, :43); tris (3,nt), edges (2,ne), tri_to_edge (3,nt): the SurfaceMesh
+ * tables (fem/mesh3d.py:458-575); er, ur (3,3,nt) as assemble_bma_matrices slices them (assembler.py:262-263).  Outputs
+ * (nt,14,14) row-major in the local order of NedelecLegrange2.tri_to_field (fem/elements/nedleg2.py:57-65): 3 edge-a, face-a,
+ * 3 edge-b, face-b, 3 vertices, 3 edges. */
+int emb_bma_element_matrices(emb_ctx* ctx, int64_t n_tris, int64_t n_nodes, int64_t n_edges, const double* xy_2xn,
+                             const int64_t* tris_3xnt, const int64_t* edges_2xne, const int64_t* tri_to_edge_3xnt,
+                             const emb_c128* er_3x3xnt, const emb_c128* ur_3x3xnt, double k0, emb_c128* A_ntx14x14,
+                             emb_c128* B_ntx14x14);
+
 #ifdef __cplusplus
 }
 #endif

@@ -322,6 +322,51 @@ def case_interp_wg_tiny():
     return out
 
 
+def case_bma_microstrip():
+    """Boundary-mode analysis pins: the reference's Assembler.assemble_bma_matrices (assembler.py:246-308)
+    on port 1 of the microstrip look-alike - inputs (SurfaceMesh tables, port-local coordinates, er/ur per port triangle),
+    the assembled E, B (CSR), solve_ids - plus element matrices straight from generalized_matrix_GQ for a few triangles
+    with FULL non-symmetric complex tensors, and the eigenpair modal_analysis(direct=True, TEM=True) selects."""
+    from fem.physics.edm.nedeleclegrange2 import generalized_matrix_GQ, local_tri_to_edgeid
+    from fem.mth.optimized import matinv
+    box = microstrip_box()
+    fem, phys, mesh, ports = modal_physics(box)
+    freq = 1e9
+    phys.frequencies = [freq]
+    port = ports[0]
+    phys.modal_analysis(port, 1, direct=True, TEM=True, freq=freq)
+    k0 = 2 * np.pi * freq / 299792458
+    er, ur = port._er, port._ur                                   # (3,3,n_tris of the whole mesh), emfreq3d.py:322-323
+    E, B, solve_ids, nlf = phys.assembler.assemble_bma_matrices(phys.basis, er, ur, k0, port, phys.boundary_conditions)
+    sm = nlf.mesh
+    tri_ids = mesh.get_triangles(port.tags)
+    xy = (np.linalg.pinv(port.cs._basis) @ sm.nodes)[:2]
+    out = dict(kind="bma", k0=np.float64(k0), xy=xy, s_tris=sm.tris.astype(np.int64), s_edges=sm.edges.astype(np.int64),
+               s_tri_to_edge=sm.tri_to_edge.astype(np.int64), er=er[:, :, tri_ids], ur=ur[:, :, tri_ids],
+               n_nodes=np.int64(sm.n_nodes), tri_to_field=nlf.tri_to_field.astype(np.int64), n_field=np.int64(nlf.n_field),
+               solve_ids=np.asarray(solve_ids, dtype=np.int64))
+    out.update(_csr_dict("E", E))
+    out.update(_csr_dict("B", B))
+    mode = port.get_mode()
+    out["beta"] = np.float64(mode.beta)
+    out["mode_field"] = np.asarray(mode.modefield, dtype=np.complex128) if hasattr(mode, "modefield") else np.zeros(0)
+    # element level, full tensors
+    rng = np.random.default_rng(7)
+    sel = np.array([0, 3, 11, 20])
+    fer = rng.standard_normal((4, 3, 3)) + 1j * rng.standard_normal((4, 3, 3)) + 3 * np.eye(3)
+    fur = rng.standard_normal((4, 3, 3)) * 0.3 + 0.2j * rng.standard_normal((4, 3, 3)) + 2 * np.eye(3)
+    eA, eB = [], []
+    tri_to_edge = nlf.tri_to_field[:3, :].astype(np.int64)
+    for k, it in enumerate(sel):
+        lm = local_tri_to_edgeid(int(it), sm.tris.astype(np.int64), sm.edges.astype(np.int64), tri_to_edge)
+        a_, b_ = generalized_matrix_GQ(np.ascontiguousarray(xy[:, sm.tris[:, it]]).astype(np.float64), lm,
+                                       matinv(np.ascontiguousarray(fur[k])), np.ascontiguousarray(fer[k]), float(k0))
+        eA.append(a_)
+        eB.append(b_)
+    out.update(full_sel=sel, full_er=fer, full_ur=fur, full_A=np.array(eA), full_B=np.array(eB))
+    return out
+
+
 def case_farfield_patch():
     """Far-field pin: the demo3 flow (demo3_patch_antenna.py:94-100) on the abc_lumped look-alike -
     SurfaceMesh of the absorbing boundary, E/H at its edge midpoints, fem.physics.edm.stratton_chu over a theta cut and a
@@ -343,7 +388,7 @@ def case_farfield_patch():
 
 CASES = dict(wg_tiny=case_wg_tiny, wg_materials=case_wg_materials, wg_medium=case_wg_medium,
              abc_lumped=case_abc_lumped, modal_microstrip=case_modal_microstrip, lossy_slabs=case_lossy_slabs,
-             interp_wg_tiny=case_interp_wg_tiny, farfield_patch=case_farfield_patch)
+             interp_wg_tiny=case_interp_wg_tiny, farfield_patch=case_farfield_patch, bma_microstrip=case_bma_microstrip)
 
 if __name__ == "__main__":
     if not os.path.isdir("/root/reference/fem"):

@@ -68,6 +68,32 @@ def _far_field(phys, data):
     return edm.stratton_chu(Ein, Hin, surf, theta, 0 * theta + 0.2, ds.k0)
 
 
+def _check_modal_analysis(phys, asm):
+    """Electrodynamics3D.modal_analysis (emfreq3d.py:201-364) with GpuAssembler.assemble_bma_matrices underneath: the
+    matrices equal the stock assembler's to round-off and the re-computed mode has the same propagation constant,
+    impedance and (sampled) field as the mode the stock path found."""
+    import fem.physics.edm.assembler as ref_asm
+    from fem.bc import ModalPort
+    ports = [b for b in phys.boundary_conditions if isinstance(b, ModalPort)]
+    port = ports[0]
+    old = port.get_mode()
+    k0 = 2 * np.pi * 1e9 / 299792458
+    E0, B0, ids0, _ = ref_asm.Assembler().assemble_bma_matrices(phys.basis, port._er, port._ur, k0, port, phys.boundary_conditions)
+    E1, B1, ids1, nlf = asm.assemble_bma_matrices(phys.basis, port._er, port._ur, k0, port, phys.boundary_conditions)
+    assert np.array_equal(ids0, ids1)
+    assert abs(E1 - E0).max() <= 1e-12 * abs(E0).max() and abs(B1 - B0).max() <= 1e-12 * abs(B0).max()
+    tri = phys.mesh.get_triangles(port.tags)
+    c = phys.mesh.nodes[:, phys.mesh.tris[:, tri]].mean(axis=1)
+    F_old = np.asarray(port.port_mode_3d_global(c[0], c[1], c[2], 1.0))
+    port.modes = []
+    phys.modal_analysis(port, 1, direct=True, TEM=True, freq=1e9)           # the reference driver on the device element loop
+    new = port.get_mode()
+    assert abs(new.beta - old.beta) <= 1e-9 * abs(old.beta)
+    assert abs(complex(new.Z0) - complex(old.Z0)) <= 1e-7 * abs(complex(old.Z0))
+    F_new = np.asarray(port.port_mode_3d_global(c[0], c[1], c[2], 1.0))
+    assert np.abs(np.abs(F_new) - np.abs(F_old)).max() <= 1e-7 * np.abs(F_old).max()
+
+
 def _collect(data, nf):
     S = np.array([data.item(i).Sp.arry.copy() for i in range(nf)])
     fields = [{k: np.array(v) for k, v in data.item(i)._fields.items()} for i in range(nf)]
@@ -102,6 +128,8 @@ def test_reference_frequency_domain_on_top_of_install(case, tmp_path):
 
     asm = install(phys, rtol=1e-10)                                  # 2. the two seams
     assert isinstance(phys.assembler, GpuAssembler)
+    if case == "modal":                                              # boundary-mode analysis on top of the device element loop
+        _check_modal_analysis(phys, asm)
     data = phys.frequency_domain()
     _check(data, nf, S_ref, F_ref, "seams")
     data = phys.frequency_domain()                                   # same problem again: the device state is reused
