@@ -39,6 +39,7 @@ extern "C" void emb_destroy(emb_ctx* c) {
         if (c->ev_stage_ready[k]) { cudaEventDestroy(c->ev_stage_ready[k]); cudaEventDestroy(c->ev_stage_done[k]); }
     }
     topology_release(c);
+    emb_shift_invert_free(c);
     c->nodes.release(); c->tris.release(); c->tri2f.release(); c->tetc.release(); c->tetord.release(); c->gid.release();
     c->er.release(); c->ur.release(); c->adjptr.release(); c->adj.release(); c->rowptr.release(); c->col.release();
     c->K.release(); c->M.release(); c->asm_items.release(); c->asm_ent.release(); c->sell_rows.release(); c->sell_pos.release(); c->sell_bcol.release(); c->sell_sptr.release(); c->sperm.release(); c->blkcol.release(); c->newid.release(); c->solve_ids.release(); c->rowptr_s.release();

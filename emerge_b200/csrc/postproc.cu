@@ -348,81 +348,3 @@ extern "C" int emb_stratton_chu(emb_ctx* c, int64_t nsrc, const emb_c128* E_3xn,
     emag.release(); mx.release(); dEo.release(); dHo.release();
     return EMB_OK;
 }
-
-// ---- port boundary-mode analysis: element matrices ----------------------------------------------------
-// Replaces the numba prange loop _matrix_builder / generalized_matrix_GQ (reference fem/physics/edm/nedeleclegrange2.py:
-// 223-417).  16 lanes per port triangle, lane = matrix row (14 live): each lane sets the triangle up (a few hundred flops)
-// and integrates its row of both 14 x 14 matrices with the 6-point rule, 224-byte contiguous row stores.
-#include "bma.cuh"
-
-__global__ void __launch_bounds__(128) k_bma_elements(int64_t nT, const double* __restrict__ xy, int64_t nN,
-                                                      const int64_t* __restrict__ tris, const int64_t* __restrict__ edges,
-                                                      int64_t nE, const int64_t* __restrict__ t2e, const cx* __restrict__ er,
-                                                      const cx* __restrict__ ur, double k0, cx* __restrict__ A,
-                                                      cx* __restrict__ B, int* __restrict__ bad) {
-    const int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    const int64_t t = g >> 4;
-    const int r = (int)(g & 15);
-    if (t >= nT || r >= 14) return;
-    double p[3][2];
-    int64_t v[3];
-    for (int k = 0; k < 3; ++k) {
-        v[k] = tris[k * nT + t];
-        p[k][0] = xy[v[k]];
-        p[k][1] = xy[nN + v[k]];
-    }
-    int lmap[3][2];
-    for (int e = 0; e < 3; ++e) {
-        const int64_t eid = t2e[e * nT + t];
-        const int64_t g0 = edges[eid], g1 = edges[nE + eid];
-        lmap[e][0] = g0 == v[0] ? 0 : (g0 == v[1] ? 1 : (g0 == v[2] ? 2 : -1));
-        lmap[e][1] = g1 == v[0] ? 0 : (g1 == v[1] ? 1 : (g1 == v[2] ? 2 : -1));
-        if (lmap[e][0] < 0 || lmap[e][1] < 0) { atomicExch(bad, 1); return; }
-    }
-    cx mu[3][3], ep[3][3];
-    for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 3; ++j) { mu[i][j] = ur[(i * 3 + j) * nT + t]; ep[i][j] = er[(i * 3 + j) * nT + t]; }
-    bma::TriData d;
-    bma::tri_setup(p, lmap, mu, ep, d);
-    bma::element_row(d, k0, r, A + (t * 14 + r) * 14, B + (t * 14 + r) * 14);
-}
-
-extern "C" int emb_bma_element_matrices(emb_ctx* c, int64_t n_tris, int64_t n_nodes, int64_t n_edges, const double* xy_2xn,
-                                        const int64_t* tris_3xnt, const int64_t* edges_2xne, const int64_t* tri_to_edge_3xnt,
-                                        const emb_c128* er_3x3xnt, const emb_c128* ur_3x3xnt, double k0, emb_c128* A_ntx14x14,
-                                        emb_c128* B_ntx14x14) {
-    if (!c || n_tris <= 0 || n_nodes <= 0 || n_edges <= 0 || !xy_2xn || !tris_3xnt || !edges_2xne || !tri_to_edge_3xnt ||
-        !er_3x3xnt || !ur_3x3xnt || !A_ntx14x14 || !B_ntx14x14)
-        return EMB_ERR_ARG;
-    for (int64_t i = 0; i < 3 * n_tris; ++i)
-        if (tris_3xnt[i] < 0 || tris_3xnt[i] >= n_nodes || tri_to_edge_3xnt[i] < 0 || tri_to_edge_3xnt[i] >= n_edges) {
-            c->err = "emb_bma_element_matrices: vertex or edge index out of range";
-            return EMB_ERR_ARG;
-        }
-    PhaseTimer pt(c, "bma_elements");
-    DevBuf<double> dxy;
-    DevBuf<int64_t> dt, de, dte;
-    DevBuf<cx> der, dur, dA, dB;
-    DevBuf<int> bad;
-    EMB_TRY(h2d(c, dxy, xy_2xn, (size_t)n_nodes * 2));
-    EMB_TRY(h2d(c, dt, tris_3xnt, (size_t)n_tris * 3));
-    EMB_TRY(h2d(c, de, edges_2xne, (size_t)n_edges * 2));
-    EMB_TRY(h2d(c, dte, tri_to_edge_3xnt, (size_t)n_tris * 3));
-    EMB_TRY(h2d(c, der, reinterpret_cast<const cx*>(er_3x3xnt), (size_t)n_tris * 9));
-    EMB_TRY(h2d(c, dur, reinterpret_cast<const cx*>(ur_3x3xnt), (size_t)n_tris * 9));
-    EMB_TRY(dev_alloc(c, dA, (size_t)n_tris * 196));
-    EMB_TRY(dev_alloc(c, dB, (size_t)n_tris * 196));
-    EMB_TRY(dev_alloc(c, bad, 1));
-    EMB_CUDA(c, cudaMemsetAsync(bad.p, 0, sizeof(int), c->stream));
-    k_bma_elements<<<blocks_for(n_tris * 16, 128), 128, 0, c->stream>>>(n_tris, dxy.p, n_nodes, dt.p, de.p, n_edges, dte.p, der.p,
-                                                                       dur.p, k0, dA.p, dB.p, bad.p);
-    EMB_LAUNCH_CHECK(c);
-    int hbad = 0;
-    EMB_CUDA(c, cudaMemcpyAsync(&hbad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    EMB_CUDA(c, cudaMemcpyAsync(A_ntx14x14, dA.p, (size_t)n_tris * 196 * sizeof(cx), cudaMemcpyDeviceToHost, c->stream));
-    EMB_CUDA(c, cudaMemcpyAsync(B_ntx14x14, dB.p, (size_t)n_tris * 196 * sizeof(cx), cudaMemcpyDeviceToHost, c->stream));
-    EMB_CUDA(c, cudaStreamSynchronize(c->stream));
-    dxy.release(); dt.release(); de.release(); dte.release(); der.release(); dur.release(); dA.release(); dB.release(); bad.release();
-    if (hbad) { c->err = "emb_bma_element_matrices: an edge of tri_to_edge is not an edge of its triangle"; return EMB_ERR_ARG; }
-    return EMB_OK;
-}

@@ -365,8 +365,9 @@ def install(physics, fast: bool = False, keep_fields: bool = True, **kw) -> GpuA
     """Wires the CUDA path into a reference Electrodynamics3D.
 
     Always: replaces `physics.assembler` (emfreq3d.py:94) and the `solve` method of `physics.solveroutine`
-    (emfreq3d.py:98), so the reference's own frequency_domain() loop runs unchanged on top of the CUDA path;
-    `solveroutine.eig` (modal analysis) is left untouched.
+    (emfreq3d.py:98), so the reference's own frequency_domain() loop runs unchanged on top of the CUDA path; and
+    `solveroutine.eig` (solver.py:471-505), so that modal_analysis (emfreq3d.py:201-364) runs its element loop
+    (GpuAssembler.assemble_bma_matrices) and the spectral transformation of its eigen-solve (modal.gpu_eig) on the device.
 
     fast=True additionally replaces the two sweep drivers themselves:
       physics.frequency_domain()          -> EMSimData   (emfreq3d.py:607-732)
@@ -385,6 +386,9 @@ def install(physics, fast: bool = False, keep_fields: bool = True, **kw) -> GpuA
     def solve(self, A, b, solve_ids, reuse=False):
         return asm.solve(A, b, solve_ids, reuse)
     routine.solve = types.MethodType(solve, routine)
+    if hasattr(routine, "eig"):          # modal_analysis: element loop via asm.assemble_bma_matrices, eigen-solve operator on the device
+        from .modal import install_modal
+        install_modal(physics, asm)
     if fast:
         def frequency_domain(self):
             return _gpu_frequency_domain(self, asm, None, keep_fields)

@@ -46,6 +46,9 @@ _SIGS = {
                                    C.c_void_p, C.c_void_p]),
     "emb_bma_element_matrices": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64] + [C.c_void_p] * 6 + [C.c_double, C.c_void_p,
                                            C.c_void_p]),
+    "emb_shift_invert_setup": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_double, C.c_double]),
+    "emb_shift_invert_apply": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "emb_shift_invert_free": (C.c_int, [C.c_void_p]),
     "emb_topology_build": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
                                      C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "emb_topology_get": (C.c_int, [C.c_void_p] + [C.c_void_p] * 10),
@@ -289,6 +292,25 @@ class Context:
         self._check(self.lib.emb_bma_element_matrices(self.h, nt, xy.shape[1], edges.shape[1], _p(xy), _p(tris), _p(edges), _p(t2e),
                                                       _p(er), _p(ur), float(k0), _p(A), _p(B)))
         return A, B
+
+    def shift_invert_setup(self, A, B, sigma):
+        """device-resident operator v -> (A - sigma B)^-1 B v for dense (n,n) A, B (fem/solver.py:311-357)"""
+        A, B = _c(A, np.complex128), _c(B, np.complex128)
+        n = A.shape[0]
+        if A.shape != (n, n) or B.shape != (n, n):
+            raise ValueError("shift_invert_setup: A and B must be square and of equal size")
+        sigma = complex(sigma)
+        self._check(self.lib.emb_shift_invert_setup(self.h, n, _p(A), _p(B), sigma.real, sigma.imag))
+        return n
+
+    def shift_invert_apply(self, x):
+        x = _c(x, np.complex128).ravel()
+        y = np.empty_like(x)
+        self._check(self.lib.emb_shift_invert_apply(self.h, _p(x), _p(y)))
+        return y
+
+    def shift_invert_free(self):
+        self._check(self.lib.emb_shift_invert_free(self.h))
 
     def upload_materials(self, er, ur):
         er = _c(er, np.complex128)

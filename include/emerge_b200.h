@@ -278,6 +278,13 @@ int emb_bma_element_matrices(emb_ctx* ctx, int64_t n_tris, int64_t n_nodes, int6
                              const int64_t* tris_3xnt, const int64_t* edges_2xne, const int64_t* tri_to_edge_3xnt,
                              const emb_c128* er_3x3xnt, const emb_c128* ur_3x3xnt, double k0, emb_c128* A_ntx14x14,
                              emb_c128* B_ntx14x14);
+/* Shift-invert operator of that eigenproblem, v -> (A - sigma B)^-1 B v, for dense n x n row-major A, B restricted to
+ * the solve ids: the device-side replacement of the factorisations inside SolverLAPACK.eig / SolverARPACK.eig
+ * (fem/solver.py:311-357; the reference's shift is sigma = -target_kz^2, :355).  setup inverts A - sigma B on the device
+ * (Gauss-Jordan, partial pivoting), apply is two dense matrix-vector products; one operator per context. */
+int emb_shift_invert_setup(emb_ctx* ctx, int64_t n, const emb_c128* A_nxn, const emb_c128* B_nxn, double sigma_re, double sigma_im);
+int emb_shift_invert_apply(emb_ctx* ctx, const emb_c128* x_n, emb_c128* y_n);
+int emb_shift_invert_free(emb_ctx* ctx);
 
 #ifdef __cplusplus
 }

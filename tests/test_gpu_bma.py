@@ -59,3 +59,27 @@ def test_larger_port_mesh_against_oracle(gpu_ctx):
         bad = t2e.copy()
         bad[0, 0] = (bad[0, 0] + 7) % edges.shape[1]              # an edge that does not belong to its triangle
         gpu_ctx.bma_element_matrices(xy, tris, edges, bad, er, ur, 83.7)
+
+
+def test_shift_invert_operator_and_eigen_solve(gpu_ctx):
+    """emb_shift_invert_*: the device operator equals (A - sigma B)^-1 B of numpy on a random complex pair (pivoting
+    exercised by a zero diagonal), and modal.gpu_eig on the reference port matrices returns the reference's mode."""
+    from emerge_b200 import modal
+    from tests.test_host_bma import reference_target
+    rng = np.random.default_rng(2)
+    n = 333
+    A = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+    A[np.arange(n), np.arange(n)] = 0.0
+    B = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+    sigma = 0.3 - 0.2j
+    gpu_ctx.shift_invert_setup(A, B, sigma)
+    x = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    y = gpu_ctx.shift_invert_apply(x)
+    ref = np.linalg.solve(A - sigma * B, B @ x)
+    assert np.linalg.norm(y - ref) <= 1e-9 * np.linalg.norm(ref)
+    gpu_ctx.shift_invert_free()
+    with pytest.raises(Exception):
+        gpu_ctx.shift_invert_apply(x)
+    g = load_bma()
+    lam, V = modal.gpu_eig(gpu_ctx, ref_csr(g, "E"), ref_csr(g, "B"), g["solve_ids"], 1, True, reference_target(g))
+    assert abs(np.sqrt(-lam[0]).real - float(g["beta"])) <= 1e-9 * float(g["beta"])

@@ -99,3 +99,36 @@ def test_oracle_restatement_matches_reference():
     eA, eB = O.bma_element_matrices(g["xy"], g["s_tris"][:, sel], g["s_edges"], g["s_tri_to_edge"][:, sel], fer, fur, float(g["k0"]))
     assert np.abs(eA - g["full_A"]).max() <= 1e-12 * np.abs(g["full_A"]).max()
     assert np.abs(eB - g["full_B"]).max() <= 1e-12 * np.abs(g["full_B"]).max()
+
+
+class _HostShiftInvert:
+    """numpy stand-in for the device operator (emb_shift_invert_*), so the eigen-solve logic can be pinned without a GPU"""
+
+    def shift_invert_setup(self, A, B, sigma):
+        self.M, self.B = np.linalg.inv(A - sigma * B), B
+
+    def shift_invert_apply(self, x):
+        return self.M @ (self.B @ x)
+
+    def shift_invert_free(self):
+        pass
+
+
+def reference_target(g):
+    """target_kz of modal_analysis(TEM=True) (emfreq3d.py:270-272): mean(er) * mean(ur) * 1.1 * k0"""
+    er, ur = g["er"], g["ur"]
+    return np.mean(er[er > 0]) * np.mean(ur[ur > 0]) * 1.1 * float(g["k0"])
+
+
+def test_eigen_solve_logic_finds_the_reference_mode():
+    """modal.gpu_eig (shift-invert Arnoldi + filter_real_modes) returns the propagation constant the reference's dense
+    LAPACK path selected for this port (mode.beta of the fixture)."""
+    from emerge_b200 import modal
+    g = load_bma()
+    lam, V = modal.gpu_eig(_HostShiftInvert(), ref_csr(g, "E"), ref_csr(g, "B"), g["solve_ids"], 1, True, reference_target(g))
+    assert len(lam) >= 1 and V.shape == (len(g["solve_ids"]), len(lam))
+    assert abs(np.sqrt(-lam[0]).real - float(g["beta"])) <= 1e-9 * float(g["beta"])
+    ids = g["solve_ids"]
+    ix = np.ix_(ids, ids)
+    r = ref_csr(g, "E")[ix] @ V[:, 0] - lam[0] * (ref_csr(g, "B")[ix] @ V[:, 0])
+    assert np.linalg.norm(r) <= 1e-8 * np.linalg.norm(ref_csr(g, "E")[ix] @ V[:, 0])
