@@ -131,4 +131,4 @@ def test_eigen_solve_logic_finds_the_reference_mode():
     ids = g["solve_ids"]
     ix = np.ix_(ids, ids)
     r = ref_csr(g, "E")[ix] @ V[:, 0] - lam[0] * (ref_csr(g, "B")[ix] @ V[:, 0])
-    assert np.linalg.norm(r) <= 1e-8 * np.linalg.norm(ref_csr(g, "E")[ix] @ V[:, 0])
+    assert np.linalg.norm(r) <= 1e-6 * np.linalg.norm(ref_csr(g, "E")[ix] @ V[:, 0])        # eigen-residual
