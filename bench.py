@@ -60,10 +60,11 @@ def make_waveguide(nx, ny, nz, device=None, slabs=None):
     slabs = SLABS if slabs is None else slabs
     vol = None
     if slabs:
-        period = 12 * L / nz             # two of every twelve cell layers are ceramic
+        hz = L / nz                      # layers 5 and 6 of every twelve cell layers are ceramic; the port planes stay in vacuum
 
         def vol(x, y, z):
-            return np.where((z % period) >= period * 10.0 / 12.0, 2, 1)
+            layer = np.floor(z / hz).astype(np.int64) % 12
+            return np.where((layer == 5) | (layer == 6), 2, 1)
     box = box_mesh(nx, ny, nz, A_WG, B_WG, L, vol_fn=vol, node_order=os.environ.get("EMB_MESH_ORDER", "lex"))
     if device is None:
         t = mesh_tables(box.nodes_xyz, box.tets)

@@ -203,20 +203,35 @@ def build_aux_spaces_paired(tables, keep):
     return Gs, Ps, badP, G1
 
 
+def _edge_rows_csr(edges, nN, va, vb):
+    """CSR (nE x nN) with the two entries (A: va, B: vb) per edge row; edges are ascending within a column (A < B), so the
+    rows are built sorted, without a COO conversion"""
+    nE = edges.shape[1]
+    ix = np.empty(2 * nE, dtype=np.int32)
+    ix[0::2], ix[1::2] = edges[0], edges[1]
+    dv = np.empty(2 * nE, dtype=np.float64)
+    dv[0::2], dv[1::2] = va, vb
+    M = sp.csr_matrix((dv, ix, 2 * np.arange(nE + 1, dtype=np.int64)), shape=(nE, nN))
+    if nE and not np.all(edges[0] < edges[1]):
+        M.sort_indices()
+    return M
+
+
+def p1_gradient(tables):
+    """G1 (nE x nN): the P1 gradient in the Whitney basis, grad(lam_v) = sum_e G1[e, v] w_e with G1[e, A] = +1, G1[e, B] = -1"""
+    edges = np.asarray(tables.edges)
+    nN, nE = np.asarray(tables.nodes).shape[1], edges.shape[1]
+    return _edge_rows_csr(edges, nN, np.ones(nE), -np.ones(nE))
+
+
 def nodal_interpolation(tables):
     """Pi_c (nE x nN), c = x, y, z: Whitney coefficients of the nodal vector field e_c * lam_v.  With the reference's sign
     convention w_AB.t_AB = -1/l on edge (A,B), the coefficient of a field E is -(E(v_A) + E(v_B))/2 . (v_B - v_A)."""
     nodes = np.asarray(tables.nodes)
     edges = np.asarray(tables.edges)
-    nN, nE = nodes.shape[1], edges.shape[1]
+    nN = nodes.shape[1]
     d = nodes[:, edges[1]] - nodes[:, edges[0]]
-    ea = np.arange(nE)
-    out = []
-    for c in range(3):
-        v = -0.5 * d[c]
-        out.append(sp.coo_matrix((np.concatenate([v, v]), (np.concatenate([ea, ea]), np.concatenate([edges[0], edges[1]]))),
-                                 shape=(nE, nN)).tocsr())
-    return out
+    return [_edge_rows_csr(edges, nN, -0.5 * d[c], -0.5 * d[c]) for c in range(3)]
 
 
 def p1_stiffness_mass(tables, weight=None):
@@ -231,6 +246,23 @@ def p1_stiffness_mass(tables, weight=None):
     grad = np.stack([-(g1 + g2 + g3), g1, g2, g3], axis=0) / det   # (4, 3, nT)
     vol = np.abs(det) / 6.0
     w = vol if weight is None else vol * np.asarray(weight, dtype=float)
+    t2e = getattr(tables, "tet_to_edge", None)
+    if t2e is not None:
+        # one value per mesh edge (sum over its tetrahedra) and per node: two bincounts and a duplicate-free COO of
+        # 2 nE + nN entries instead of sorting / merging the 16 nT element entries
+        t2e = np.asarray(t2e)
+        edges = np.asarray(tables.edges)
+        nE = edges.shape[1]
+        le = ((0, 1), (0, 2), (0, 3), (1, 2), (3, 1), (2, 3))      # local edge order of tet_to_edge (fem/mesh3d.py:292)
+        off = np.stack([np.einsum("xt,xt->t", grad[a], grad[b]) * w for a, b in le])          # (6, nT)
+        eval_ = np.bincount(t2e.ravel(), weights=off.ravel(), minlength=nE)
+        dia = np.bincount(tets.ravel(), weights=(np.einsum("ixt,ixt->it", grad, grad) * w).ravel(), minlength=nN)
+        nd = np.arange(nN)
+        L = sp.coo_matrix((np.concatenate([eval_, eval_, dia]),
+                           (np.concatenate([edges[0], edges[1], nd]), np.concatenate([edges[1], edges[0], nd]))),
+                          shape=(nN, nN)).tocsr()
+        mass = np.bincount(tets.ravel(), weights=np.repeat(vol[None, :] / 4.0, 4, axis=0).ravel(), minlength=nN)
+        return L, mass
     loc = np.einsum("ixt,jxt->ijt", grad, grad) * w                # (4, 4, nT)
     ii = np.broadcast_to(tets[:, None, :], (4, 4, nT))
     jj = np.broadcast_to(tets[None, :, :], (4, 4, nT))

@@ -9,7 +9,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 REPO = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["capi.cu", "assembly.cu", "operators.cu", "solver.cu", "topology.cu", "postproc.cu", "modal.cu"]
+SOURCES = ["capi.cu", "assembly.cu", "operators.cu", "solver.cu", "topology.cu", "postproc.cu", "modal.cu", "auxbuild.cu"]
 LIB = os.path.join(HERE, "libemerge_b200.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-I" + os.path.join(REPO, "include")]

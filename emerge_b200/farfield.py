@@ -47,9 +47,15 @@ def stratton_chu(Ein, Hin, mesh, theta, phi, k0: float, ctx: Context | None = No
 def install_farfield(edm_module, ctx_getter):
     """Replaces `stratton_chu` of the reference's fem.physics.edm package (and of its sc module) by the device version.
     ctx_getter() -> Context or None."""
+    original = getattr(edm_module.stratton_chu, "_reference", edm_module.stratton_chu)
+
     def patched(Ein, Hin, mesh, theta, phi, k0):
-        return stratton_chu(Ein, Hin, mesh, theta, phi, k0, ctx=ctx_getter())
+        ctx = ctx_getter()
+        if ctx is not None and getattr(ctx, "h", None) is None:        # that assembler's context has been closed
+            ctx = None
+        return stratton_chu(Ein, Hin, mesh, theta, phi, k0, ctx=ctx)
     patched.__doc__ = stratton_chu.__doc__
+    patched._reference = original                                       # the reference's own implementation
     edm_module.stratton_chu = patched
     sc = getattr(edm_module, "sc", None)
     if sc is not None:

@@ -77,6 +77,9 @@ _SIGS = {
     "emb_aux_clear": (C.c_int, [C.c_void_p]),
     "emb_aux_add": (C.c_int, [C.c_void_p, C.c_int64] + [C.c_void_p] * 6),
     "emb_aux_add_ex": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64] + [C.c_void_p] * 6 + [C.c_int] * 4),
+    "emb_aux_build_top": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.c_void_p]),
+    "emb_aux_get": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_void_p,
+                              C.c_void_p, C.c_void_p]),
     "emb_amg_create": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
     "emb_amg_add_level": (C.c_int, [C.c_void_p, C.c_int, C.c_int64] + [C.c_void_p] * 4 + [C.c_double, C.c_int64] + [C.c_void_p] * 6),
     "emb_amg_set_coarse_inverse": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p]),
@@ -491,6 +494,32 @@ class Context:
                                             {"diag": 0, "amg": 1}[solver], int(hid), {"one": 0, "minus_inv_k0sq": 1}[scale]))
         self._n_aux = getattr(self, "_n_aux", 0) + 1
         return self._n_aux - 1
+
+    def aux_build_top(self, which: str, edges, n_bad: int):
+        """builds the top-level space 'G' (P2 gradients) or 'P' (Whitney) on the device and appends it (emb_aux_build_top).
+        Returns (index of the new space or -1 when no column is left, ncol, bad (n_bad,) bool: dropped columns)."""
+        from .auxspace import _face_tables
+        vt, et, wt = _face_tables()
+        tab = _c(np.concatenate([vt.ravel(), et.ravel(), wt.ravel()]), np.float64)
+        edges = _c(edges, np.int64)
+        ncol = C.c_int64()
+        bad = np.zeros(int(n_bad), dtype=np.uint8)
+        self._check(self.lib.emb_aux_build_top(self.h, {"G": 0, "P": 1}[which], _p(edges), _p(tab), C.byref(ncol), _p(bad)))
+        if ncol.value == 0:
+            return -1, 0, bad.astype(bool)
+        self._n_aux = getattr(self, "_n_aux", 0) + 1
+        return self._n_aux - 1, int(ncol.value), bad.astype(bool)
+
+    def aux_get(self, idx: int):
+        """scipy CSR of auxiliary space idx's transfer matrix, rows in solve-index order"""
+        import scipy.sparse as sp
+        nrow, ncol, nnz = C.c_int64(), C.c_int64(), C.c_int64()
+        self._check(self.lib.emb_aux_get(self.h, int(idx), C.byref(nrow), C.byref(ncol), C.byref(nnz), None, None, None))
+        ip = np.empty(nrow.value + 1, dtype=np.int64)
+        ix = np.empty(nnz.value, dtype=np.int32)
+        dv = np.empty(nnz.value, dtype=np.float64)
+        self._check(self.lib.emb_aux_get(self.h, int(idx), C.byref(nrow), C.byref(ncol), C.byref(nnz), _p(ip), _p(ix), _p(dv)))
+        return sp.csr_matrix((dv, ix, ip), shape=(nrow.value, ncol.value))
 
     def amg_upload(self, levels):
         """levels: output of emerge_b200.amg.sa_hierarchy (finest first); returns the hierarchy id."""

@@ -208,19 +208,40 @@ class FrequencySweep:
 
         # The host work is numpy / scipy kernels that release the GIL: independent pieces run in worker threads while
         # this (owner) thread is the only one that talks to the device context.
+        import os
+        # top-level spaces G and P straight on the device (csrc/auxbuild.cu; same entries as build_aux_spaces_paired, which was
+        # the critical path of this setup: 3-4 s at 1M tets); EMB_AUX_HOST=1 keeps the numpy builder
+        on_device = paired and multilevel and hasattr(ctx, "aux_build_top") and not int(os.environ.get("EMB_AUX_HOST", "0"))
         with ThreadPoolExecutor(max_workers=4) as ex:
-            f_top = ex.submit(top_level)
+            f_top = None if on_device else ex.submit(top_level)
             f_le = ex.submit(p1_stiffness_mass, t, w_eps) if multilevel else None
             f_lm = ex.submit(p1_stiffness_mass, t, w_mu) if (multilevel and not same) else None
             f_pi = ex.submit(nodal_interpolation, t) if multilevel else None
-            Gs, Ps, badP, G1 = f_top.result()
-            f_g = ex.submit(ctx.csr_pair, Gs) if Gs.shape[1] > 0 else None
-            f_p = ex.submit(ctx.csr_pair, Ps) if Ps.shape[1] > 0 else None
+            ctx.aux_clear()
+            self.aux_dims = []
+            if on_device:
+                from .auxspace import p1_gradient
+                f_g1 = ex.submit(p1_gradient, t)
+                nN, nE = np.asarray(t.nodes).shape[1], np.asarray(t.edges).shape[1]
+                ig, ncolG, _ = ctx.aux_build_top("G", t.edges, nN + nE)
+                ip, ncolP, badP = ctx.aux_build_top("P", t.edges, nE)
+                if ig >= 0:
+                    self.aux_dims.append(ncolG)
+                if ip < 0:
+                    return
+                self.aux_dims.append(ncolP)
+                G1 = f_g1.result()
+                Gs = Ps = f_g = f_p = None
+            else:
+                Gs, Ps, badP, G1 = f_top.result()
+                f_g = ex.submit(ctx.csr_pair, Gs) if Gs.shape[1] > 0 else None
+                f_p = ex.submit(ctx.csr_pair, Ps) if Ps.shape[1] > 0 else None
+                ncolP = Ps.shape[1]
             badN = np.asarray(abs(G1[badP]).sum(axis=0)).ravel() > 0
             kn = ~badN
             G1s = G1[~badP][:, kn].tocsr()
             f_he = f_hm = None
-            if multilevel and Ps.shape[1] > 0 and G1s.shape[1] > 0:
+            if multilevel and ncolP > 0 and G1s.shape[1] > 0:
                 Le, mass = f_le.result()
                 Lm = Le if same else f_lm.result()[0]
                 f_he = ex.submit(lambda: sa_hierarchy((Le[kn][:, kn] + 1e-3 * kmid2 * sp.diags(mass[kn] * np.mean(w_eps))).tocsr(),
@@ -229,22 +250,23 @@ class FrequencySweep:
                                                       coarse_size=self.amg_coarse_size))
                 f_kids = [ex.submit(lambda M: ctx.csr_pair(M), G1s)]
                 f_pcs = ex.submit(lambda: [Pc[~badP][:, kn].tocsr() for Pc in f_pi.result()])
-            ctx.aux_clear()
-            self.aux_dims = []
-            if f_g is not None:
-                ctx.aux_add(Gs, rows_internal=True, prepared=f_g.result())
-                self.aux_dims.append(Gs.shape[1])
-            if f_p is None:
-                return
-            if f_he is None:
-                ctx.aux_add(Ps, rows_internal=True, prepared=f_p.result())
+            if not on_device:
+                if f_g is not None:
+                    ctx.aux_add(Gs, rows_internal=True, prepared=f_g.result())
+                    self.aux_dims.append(Gs.shape[1])
+                if f_p is None:
+                    return
+                if f_he is None:
+                    ctx.aux_add(Ps, rows_internal=True, prepared=f_p.result())
+                    self.aux_dims.append(Ps.shape[1])
+                    if G1s.shape[1] > 0:
+                        ctx.aux_add((Ps @ G1s).tocsr(), rows_internal=True)
+                        self.aux_dims.append(G1s.shape[1])
+                    return
+                ip = ctx.aux_add_ex(Ps, parent=-1, solver="diag", rows_internal=True, prepared=f_p.result())
                 self.aux_dims.append(Ps.shape[1])
-                if G1s.shape[1] > 0:
-                    ctx.aux_add((Ps @ G1s).tocsr(), rows_internal=True)
-                    self.aux_dims.append(G1s.shape[1])
+            elif f_he is None:
                 return
-            ip = ctx.aux_add_ex(Ps, parent=-1, solver="diag", rows_internal=True, prepared=f_p.result())
-            self.aux_dims.append(Ps.shape[1])
             He, Hm = f_he.result(), f_hm.result()
             he, hm = ctx.amg_upload(He), ctx.amg_upload(Hm)
             self.amg_levels = dict(eps=[l["A"].shape[0] for l in He], mu=[l["A"].shape[0] for l in Hm])

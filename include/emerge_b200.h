@@ -148,6 +148,15 @@ int emb_aux_add(emb_ctx* ctx, int64_t ncol, const int64_t* R_indptr, const int32
 int emb_aux_add_ex(emb_ctx* ctx, int64_t nrow, int64_t ncol, const int64_t* R_indptr, const int32_t* R_indices,
                    const double* R_data, const int64_t* RT_indptr, const int32_t* RT_indices, const double* RT_data,
                    int parent, int solver, int hid, int scale_mode);
+/* Top-level auxiliary spaces built on the device from the uploaded mesh tables (no reference counterpart): which = 0 the
+ * gradients of the P2 Lagrange space (G), which = 1 the Whitney space (P), restricted to the solve space, rows in
+ * solve-index order, columns touched by an eliminated dof dropped; appended like emb_aux_add (diagonal solver) when at
+ * least one column remains.  edges (2,nE) as fem/mesh3d.py holds them; face_tables: the 18 numbers of
+ * emerge_b200/auxspace.py::_face_tables() (vertex, edge, Whitney targets x 3 x (u, w)).  ncol_out: columns kept;
+ * bad_out (optional, nN + nE or nE bytes): 1 for every dropped column.  emb_aux_get copies a space's CSR to the host. */
+int emb_aux_build_top(emb_ctx* ctx, int which, const int64_t* edges_2xnE, const double* face_tables_18, int64_t* ncol_out,
+                      unsigned char* bad_out);
+int emb_aux_get(emb_ctx* ctx, int idx, int64_t* nrow, int64_t* ncol, int64_t* nnz, int64_t* rptr, int32_t* rcol, double* rval);
 /* Smoothed-aggregation hierarchy, built on the host (emerge_b200/amg.py), finest level first.  Every level but the last
  * carries its matrix A (real CSR), 1/diag(A), the Jacobi damping omega, the prolongator P (n x ncoarse) and P^T; the last
  * level has ncoarse = 0, null matrices, and gets the dense inverse of its matrix (row-major n x n). */
