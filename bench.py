@@ -496,6 +496,8 @@ def run_gpu(args):
                 "sizes": {"tets": nT, "n_field": N, "n_solve": Ns, "nnz_full": nnz_full, "nnz_solve": nnz_s},
                 "setup": {"host_mesh_tables_s": host_mesh_s, "gpu_setup_s": setup_s, **{k: v for k, v in sw.timings.items()}},
                 "e2e_setup": (e2e_k or e2e_full)["setup"] if (e2e_k or e2e_full) else {},
+                "e2e_split": {"steps_leg": e2e_k["split"] if e2e_k else None, "full_leg": e2e_full["split"] if e2e_full else None,
+                              "steps_leg_ms": e2e_k["ms"] if e2e_k else None, "full_leg_ms": e2e_full["ms"] if e2e_full else None},
                 "hbm_after_sweep": hbm, "clocks": main["clocks"]}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args)

@@ -104,12 +104,16 @@ __device__ __forceinline__ cx block_sum1(cx v) {
 template <int NV, bool CONJ = true>
 __global__ void __launch_bounds__(VBLOCK) k_rc_dots(int64_t n, const cx* __restrict__ Q, const cx* __restrict__ r,
                                                     cx* __restrict__ part) {
-    const cx* q = Q + (int64_t)blockIdx.y * n;
+    // blocks are scheduled x-fastest: remap so that consecutive blocks share the ROW RANGE p and differ in the column j -
+    // the range of r is then fetched from HBM once and served from L2 to the other columns (launched as (RC_NP, ncols))
+    const int lin = blockIdx.y * gridDim.x + blockIdx.x;
+    const int bj = lin % (int)gridDim.y, bp = lin / (int)gridDim.y;
+    const cx* q = Q + (int64_t)bj * n;
     cx acc[NV];
 #pragma unroll
     for (int v = 0; v < NV; ++v) acc[v] = mk(0.0);
     const int64_t per = (n + RC_NP - 1) / RC_NP;
-    const int64_t i0 = blockIdx.x * per, i1 = (i0 + per < n) ? i0 + per : n;
+    const int64_t i0 = bp * per, i1 = (i0 + per < n) ? i0 + per : n;
     for (int64_t i = i0 + threadIdx.x; i < i1; i += VBLOCK) {
         const cx u = q[i];
 #pragma unroll
@@ -126,7 +130,7 @@ __global__ void __launch_bounds__(VBLOCK) k_rc_dots(int64_t n, const cx* __restr
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
         const cx t = block_sum1(acc[v]);
-        if (threadIdx.x == 0) part[((int64_t)blockIdx.y * RC_NP + blockIdx.x) * NV + v] = t;
+        if (threadIdx.x == 0) part[((int64_t)bj * RC_NP + bp) * NV + v] = t;
     }
 }
 // coef[j * NV + v] = sum of the RC_NP partials in fixed order (one block per column j, RC_NP == VBLOCK threads)

@@ -200,21 +200,21 @@ __global__ void __launch_bounds__(256) k_bsell(int64_t nR, const int* __restrict
 
 // ---- the same product with the slice streams staged by the TMA engine -------------------------------------------------
 // The column indices and values of a slice are two CONTIGUOUS byte ranges.  One elected lane per warp copies them chunk by
-// chunk (STG_Q block columns = 2.25 KB) into the warp's own shared-memory ring with cp.async.bulk (UBLKCP) completing on an
-// mbarrier, STG_N - 1 chunks ahead of the arithmetic; the lanes read indices and values from shared memory, so the
-// load/store unit only sees the x gathers.  Those are software-pipelined as well: the STG_Q gathers of chunk k + 1 are
-// issued (into a second register set) BEFORE the arithmetic of chunk k, so a warp always has a chunk of gathers and
-// STG_N - 1 bulk copies in flight.  (The first staged version waited for its gathers right after issuing them: ncu showed
-// 42 % of the samples on the long scoreboard with every unit below 50 % - profiles/r2_bsell_tma_v1_ncu.csv - and neither a
-// Z-order numbering of the mesh nor a blocked slice distribution changed the time, so latency, not locality, bound it.)
-// Persistent warps: warp g of the grid owns slices g, g + G, ...
-constexpr int STG_Q = 8;                                    // block columns per chunk
-constexpr int STG_N = 4;                                    // ring depth (chunks)
+// chunk (STG_Q block columns = 4.5 KB) into the warp's own shared-memory ring with cp.async.bulk (UBLKCP) completing on an
+// mbarrier, one chunk ahead of the arithmetic; the lanes then read indices and values from shared memory and have all
+// STG_Q x gathers of a chunk in flight at once - the load/store unit only sees the gathers, which is what the kernel is
+// bound by (the dependent index -> x chain left k_bspmv / k_bsell at 50 % of the HBM roofline with 4 gathers in flight).
+// Persistent warps: warp g of the grid owns slices g, g + G, ...   NV = 4: a warp covers the 8 rows in two passes.
+// Measured and rejected (profiles/r2_spmv_sell_tuning.txt): a deeper ring with the gathers of the next chunk issued before
+// the arithmetic of the current one and the slice metadata prefetched a slice ahead (1.00 ms instead of 0.80 - the stall
+// samples stay on the first use of the gathered x), a Z-order numbering of the mesh, a blocked slice distribution.
+// XT = cf: the gathers read a complex64 COPY of x (half the gather bytes; the copy of two right-hand sides fits the L2).
+constexpr int STG_Q = 16;                                   // block columns per chunk
 constexpr int STG_WARPS = 16;                               // warps per CTA (one CTA per SM)
 struct __align__(128) SellStage {
-    float4 val[STG_N][STG_Q * SELL_C * 2];                  // 4 x 2 KB
-    int col[STG_N][STG_Q * SELL_C];                         // 4 x 256 B
-    unsigned long long bar[STG_N];
+    float4 val[2][STG_Q * SELL_C * 2];                      // 2 x 4 KB
+    int col[2][STG_Q * SELL_C];                             // 2 x 512 B
+    unsigned long long bar[2];
 };
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
@@ -242,173 +242,147 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
         : "memory");
 }
 
-// Walks the chunks of a warp's slices: (slice s, first block column q, count()).  The slice offsets (and, for the compute
-// cursor, the row ids) of the NEXT slice are loaded when the current one is entered, so the dependent loads at a slice
-// boundary were issued a whole slice earlier (they showed up as exposed long-scoreboard stalls in the first versions).
-struct SellCursor {
-    int s, q, nb, step, lim;
-    int64_t base;
-    int64_t pb, pe;             // sptr[s + step], sptr[s + step + 1] (prefetched)
-    int j, jn;                  // block-row of this lane in slice s / s + step (compute cursor only)
-    const int* rows;
-    int r;
-    __device__ __forceinline__ void prefetch(const int64_t* __restrict__ sptr) {
-        const int sn = s + step;
-        if (sn < lim) {
-            pb = __ldg(sptr + sn);
-            pe = __ldg(sptr + sn + 1);
-            if (rows) jn = __ldg(rows + (int64_t)sn * SELL_C + r);
-        }
-    }
-    __device__ __forceinline__ void enter(const int64_t* __restrict__ sptr) {      // s was just set to the prefetched slice
-        base = pb;
-        nb = (int)((pe - pb) / SELL_C);
-        j = jn;
-        prefetch(sptr);
-    }
-    __device__ __forceinline__ void skip(const int64_t* __restrict__ sptr) {
-        while (s < lim && q >= nb) {
-            s += step;
-            q = 0;
-            if (s < lim) enter(sptr);
-        }
-    }
-    __device__ __forceinline__ void init(int s0, int step_, int lim_, const int64_t* __restrict__ sptr, const int* rows_, int r_) {
-        s = s0; step = step_; lim = lim_; q = 0; nb = 0; base = 0; pb = pe = 0; j = jn = -1; rows = rows_; r = r_;
-        if (s < lim) {
-            pb = __ldg(sptr + s);
-            pe = __ldg(sptr + s + 1);
-            if (rows) jn = __ldg(rows + (int64_t)s * SELL_C + r);
-            enter(sptr);
-        }
-        skip(sptr);
-    }
-    __device__ __forceinline__ bool valid() const { return s < lim; }
-    __device__ __forceinline__ int count() const { return min(STG_Q, nb - q); }
-    __device__ __forceinline__ void advance(const int64_t* __restrict__ sptr) { q += count(); skip(sptr); }
-};
+__device__ __forceinline__ cx ldraw(const cx* __restrict__ p) { return ldx(p); }
+__device__ __forceinline__ cf ldraw(const cf* __restrict__ p) {
+    const float2 a = __ldg(reinterpret_cast<const float2*>(p));
+    return cf{a.x, a.y};
+}
+__device__ __forceinline__ cx widen(cx v) { return v; }
+__device__ __forceinline__ cx widen(cf v) { return cx{(double)v.re, (double)v.im}; }
 
-template <int NV>
+template <int NV, typename XT>
 __global__ void __launch_bounds__(STG_WARPS * 32, 1) k_bsell_tma(int nslices, const int* __restrict__ rows,
                                                                  const int64_t* __restrict__ sptr, const int* __restrict__ bcol,
-                                                                 const float4* __restrict__ val, const cx* __restrict__ x,
-                                                                 cx* __restrict__ y, int blocked) {
-    static_assert(NV == 2, "a warp is exactly one slice (8 block-rows x 4 lanes)");
+                                                                 const float4* __restrict__ val, const XT* __restrict__ x,
+                                                                 cx* __restrict__ y) {
     constexpr int LPB = 2 * NV;                 // lanes per block-row
+    constexpr int RPW = 32 / LPB;               // rows a warp covers per pass (8 or 4)
+    constexpr int NPASS = SELL_C / RPW;         // 1 (NV = 2) or 2 (NV = 4)
     extern __shared__ __align__(128) unsigned char stage_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     SellStage& st = reinterpret_cast<SellStage*>(stage_raw)[warp];
-    if (lane == 0)
-        for (int b = 0; b < STG_N; ++b) mbar_init(&st.bar[b], 1);
+    if (lane == 0) { mbar_init(&st.bar[0], 1); mbar_init(&st.bar[1], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncwarp();
-    const int u = lane % LPB, h = u / NV, r = lane / LPB;
-    // Slices of a warp.  blocked: the CTA owns a CONTIGUOUS run of slices holding 1/gridDim of all blocks (its 16 warps walk
-    // it side by side); otherwise warp g of the grid takes slices g, g + G, ...  (measured: blocked is slower)
-    int gw = blockIdx.x * STG_WARPS + warp, G = gridDim.x * STG_WARPS;
-    if (blocked) {
-        const int64_t total = __ldg(sptr + nslices);
-        int lim[2];
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            const int64_t target = total / gridDim.x * (blockIdx.x + e);
-            int lo = 0, hi = nslices;
-            while (lo < hi) {
-                const int mid = (lo + hi) >> 1;
-                if (__ldg(sptr + mid) < target) lo = mid + 1; else hi = mid;
-            }
-            lim[e] = (blockIdx.x + e == (int)gridDim.x) ? nslices : lo;
+    const int u = lane % LPB, h = u / NV, rl = lane / LPB;
+    const int gw = blockIdx.x * STG_WARPS + warp, G = gridDim.x * STG_WARPS;
+    // chunk iterator over this warp's slices: (slice s, first block column q0); issue() starts the copies of a chunk
+    int s_i = gw, q_i = 0;                       // next chunk to ISSUE
+    int64_t base_i = 0;
+    int nb_i = 0;
+    if (s_i < nslices) { base_i = __ldg(sptr + s_i); nb_i = (int)((__ldg(sptr + s_i + 1) - base_i) / SELL_C); }
+    auto skip_empty = [&]() {                    // advance the issue cursor past exhausted / empty slices
+        while (s_i < nslices && q_i >= nb_i) {
+            s_i += G;
+            q_i = 0;
+            if (s_i < nslices) { base_i = __ldg(sptr + s_i); nb_i = (int)((__ldg(sptr + s_i + 1) - base_i) / SELL_C); }
         }
-        gw = lim[0] + warp;
-        G = STG_WARPS;
-        nslices = lim[1];
-    }
-    SellCursor ci, cg, cc;                       // issue (bulk copies), gather (x), compute
-    ci.init(gw, G, nslices, sptr, nullptr, r);
-    cg = ci;
-    cc.init(gw, G, nslices, sptr, rows, r);
-    int ki = 0, kg = 0, kc = 0;                  // chunk counters: stage = k % STG_N, mbarrier parity = (k / STG_N) & 1
-    auto issue = [&]() {                         // all lanes call; lane 0 talks to the TMA engine
-        if (!ci.valid()) return;
+    };
+    auto issue = [&](int b) {                    // all lanes call; lane 0 talks to the TMA engine
+        const int nq = min(STG_Q, nb_i - q_i);
         if (lane == 0) {
-            const int b = ki % STG_N;
-            const int64_t blk0 = ci.base + (int64_t)ci.q * SELL_C;
-            const unsigned nblk = (unsigned)(ci.count() * SELL_C);
+            const int64_t blk0 = base_i + (int64_t)q_i * SELL_C;
+            const unsigned nblk = (unsigned)(nq * SELL_C);
             mbar_expect_tx(&st.bar[b], nblk * 36u);
             bulk_g2s(st.val[b], val + blk0 * 2, nblk * 32u, &st.bar[b]);
             bulk_g2s(st.col[b], bcol + blk0, nblk * 4u, &st.bar[b]);
         }
-        ci.advance(sptr);
-        ++ki;
+        q_i += nq;
     };
-    auto gather = [&](cx (&w)[STG_Q]) {          // waits for the chunk's indices, starts its x loads
-        if (!cg.valid()) return;
-        const int b = kg % STG_N;
-        mbar_wait(&st.bar[b], (unsigned)((kg / STG_N) & 1));
-        const int nq = cg.count();
-#pragma unroll
-        for (int q = 0; q < STG_Q; ++q)
-            if (q < nq) w[q] = ldx(x + (int64_t)st.col[b][q * SELL_C + r] * LPB + u);
-        cg.advance(sptr);
-        ++kg;
-    };
-    double acc[4] = {0.0, 0.0, 0.0, 0.0};
-    auto compute = [&](const cx (&w)[STG_Q]) {   // the chunk's arithmetic; writes the slice's rows after its last chunk
-        const int b = kc % STG_N;
-        const int nq = cc.count();
-#pragma unroll
-        for (int q = 0; q < STG_Q; ++q)
-            if (q < nq) {
-                const float4 e = st.val[b][(q * SELL_C + r) * 2 + h];
-                acc[0] += (double)e.x * w[q].re - (double)e.y * w[q].im;
-                acc[1] += (double)e.x * w[q].im + (double)e.y * w[q].re;
-                acc[2] += (double)e.z * w[q].re - (double)e.w * w[q].im;
-                acc[3] += (double)e.z * w[q].im + (double)e.w * w[q].re;
-            }
-        const bool last = cc.q + nq >= cc.nb;
-        const int j = cc.j;
-        cc.advance(sptr);
-        ++kc;
-        if (last) {                              // slice finished: reduce over the column halves, write the two rows
-#pragma unroll
-            for (int k = 0; k < 4; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], NV);
-            if (j >= 0 && h == 0) {
-                stv(y, (int64_t)(2 * j) * NV + u, cx{acc[0], acc[1]});
-                stv(y, (int64_t)(2 * j + 1) * NV + u, cx{acc[2], acc[3]});
-            }
-            acc[0] = acc[1] = acc[2] = acc[3] = 0.0;
-        }
-    };
-#pragma unroll
-    for (int k = 0; k < STG_N - 1; ++k) issue();
-    cx wa[STG_Q], wb[STG_Q];
-    gather(wa);
-    while (cc.valid()) {
-        issue();                                 // refills the stage whose chunk was computed in the previous step
-        gather(wb);
-        compute(wa);
-        __syncwarp();                            // every lane is done with the chunk's stage before it is refilled
-        if (!cc.valid()) break;
-        issue();
-        gather(wa);
-        compute(wb);
-        __syncwarp();
+    skip_empty();
+    int buf = 0;
+    unsigned phase[2] = {0u, 0u};
+    if (s_i < nslices) issue(0);
+    // consume cursor
+    int s_c = gw, q_c = 0, nb_c = 0;
+    if (s_c < nslices) nb_c = (int)((__ldg(sptr + s_c + 1) - __ldg(sptr + s_c)) / SELL_C);
+    while (s_c < nslices && nb_c == 0) {         // same skipping rule as the issue cursor
+        s_c += G;
+        if (s_c < nslices) nb_c = (int)((__ldg(sptr + s_c + 1) - __ldg(sptr + s_c)) / SELL_C);
     }
+    double acc[NPASS][4];
+#pragma unroll
+    for (int p = 0; p < NPASS; ++p) acc[p][0] = acc[p][1] = acc[p][2] = acc[p][3] = 0.0;
+    while (s_c < nslices) {
+        // start the next chunk's copies, then wait for this one
+        skip_empty();
+        if (s_i < nslices) issue(buf ^ 1);
+        mbar_wait(&st.bar[buf], phase[buf]);
+        phase[buf] ^= 1u;
+        const int nq = min(STG_Q, nb_c - q_c);
+#pragma unroll
+        for (int p = 0; p < NPASS; ++p) {
+            const int r = p * RPW + rl;
+            XT wr[STG_Q];                        // raw storage type: a complex64 copy of x keeps 16 gathers in 32 registers
+#pragma unroll
+            for (int q = 0; q < STG_Q; ++q)
+                if (q < nq) wr[q] = ldraw(x + (int64_t)st.col[buf][q * SELL_C + r] * LPB + u);
+#pragma unroll
+            for (int q = 0; q < STG_Q; ++q)
+                if (q < nq) {
+                    const float4 e = st.val[buf][(q * SELL_C + r) * 2 + h];
+                    const cx w = widen(wr[q]);
+                    acc[p][0] += (double)e.x * w.re - (double)e.y * w.im;
+                    acc[p][1] += (double)e.x * w.im + (double)e.y * w.re;
+                    acc[p][2] += (double)e.z * w.re - (double)e.w * w.im;
+                    acc[p][3] += (double)e.z * w.im + (double)e.w * w.re;
+                }
+        }
+        __syncwarp();                            // every lane is done with this buffer before it is refilled
+        q_c += nq;
+        buf ^= 1;
+        if (q_c >= nb_c) {                       // slice finished: reduce over the column halves, write the two rows
+#pragma unroll
+            for (int p = 0; p < NPASS; ++p) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) acc[p][k] += __shfl_xor_sync(0xffffffffu, acc[p][k], NV);
+                const int j = __ldg(rows + (int64_t)s_c * SELL_C + p * RPW + rl);
+                if (j >= 0 && h == 0) {
+                    stv(y, (int64_t)(2 * j) * NV + u, cx{acc[p][0], acc[p][1]});
+                    stv(y, (int64_t)(2 * j + 1) * NV + u, cx{acc[p][2], acc[p][3]});
+                }
+                acc[p][0] = acc[p][1] = acc[p][2] = acc[p][3] = 0.0;
+            }
+            q_c = 0;
+            nb_c = 0;
+            while (s_c < nslices && nb_c == 0) {
+                s_c += G;
+                if (s_c < nslices) nb_c = (int)((__ldg(sptr + s_c + 1) - __ldg(sptr + s_c)) / SELL_C);
+            }
+        }
+    }
+}
+
+__global__ void k_x_to_c64(int64_t n, const cx* __restrict__ x, cf* __restrict__ x32) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) stv(x32, i, ldx(x + i));
 }
 
 template <int NV>
 static int bsell_launch(emb_ctx* c, const cf* val, const cx* x, cx* y) {
     static const int mode = getenv("EMB_SPMV_TMA") ? atoi(getenv("EMB_SPMV_TMA")) : 1;
-    static const int blocked = getenv("EMB_SELL_BLOCKED") ? atoi(getenv("EMB_SELL_BLOCKED")) : 1;
+    static const int x32 = getenv("EMB_SELL_X32") ? atoi(getenv("EMB_SELL_X32")) : 0;
     if constexpr (NV == 2) {               // NV = 4 in two passes over the staged chunk was measured slower than k_bsell
         if (mode && !c->sell_has_empty) {      // (a slice without any block is never visited by the staged kernel)
             int nsm = 0;
             EMB_CUDA(c, cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->device));
             const size_t smem = (size_t)STG_WARPS * sizeof(SellStage);
-            auto kern = k_bsell_tma<NV>;
+            if (x32) {
+                EMB_TRY(dev_alloc(c, c->sell_x32, (size_t)c->Ns * NV * 2));
+                cf* xs = reinterpret_cast<cf*>(c->sell_x32.p);
+                k_x_to_c64<<<blocks_for(c->Ns * NV, 256), 256, 0, c->stream>>>(c->Ns * NV, x, xs);
+                EMB_LAUNCH_CHECK(c);
+                auto kern = k_bsell_tma<NV, cf>;
+                EMB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                kern<<<nsm, STG_WARPS * 32, smem, c->stream>>>((int)c->sell_nslices, c->sell_rows.p, c->sell_sptr.p, c->sell_bcol.p,
+                                                              reinterpret_cast<const float4*>(val), xs, y);
+                EMB_LAUNCH_CHECK(c);
+                return EMB_OK;
+            }
+            auto kern = k_bsell_tma<NV, cx>;
             EMB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             kern<<<nsm, STG_WARPS * 32, smem, c->stream>>>((int)c->sell_nslices, c->sell_rows.p, c->sell_sptr.p, c->sell_bcol.p,
-                                                          reinterpret_cast<const float4*>(val), x, y, blocked);
+                                                          reinterpret_cast<const float4*>(val), x, y);
             EMB_LAUNCH_CHECK(c);
             return EMB_OK;
         }
