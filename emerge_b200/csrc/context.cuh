@@ -139,7 +139,6 @@ struct emb_ctx {
     int64_t sell_nslices = 0, sell_blocks = 0;
     DevBuf<int> sell_rows, sell_pos, sell_bcol;
     DevBuf<int64_t> sell_sptr;
-    DevBuf<float> sell_x32;   // complex64 copy of the operator's input vectors (EMB_SELL_X32)
     DevBuf<cx> A;             // [nnz_s]
     bool have_dirichlet = false, have_A = false;
     double k0 = 0;

@@ -208,7 +208,8 @@ __global__ void __launch_bounds__(256) k_bsell(int64_t nR, const int* __restrict
 // Measured and rejected (profiles/r2_spmv_sell_tuning.txt): a deeper ring with the gathers of the next chunk issued before
 // the arithmetic of the current one and the slice metadata prefetched a slice ahead (1.00 ms instead of 0.80 - the stall
 // samples stay on the first use of the gathered x), a Z-order numbering of the mesh, a blocked slice distribution.
-// XT = cf: the gathers read a complex64 COPY of x (half the gather bytes; the copy of two right-hand sides fits the L2).
+// Also rejected: gathering from a complex64 COPY of x (XT = cf; half the gather bytes, the copy fits the L2): 0.86 ms with the
+// conversion pass, and the rounded operator input costs iterations (3,420 -> 3,940 on the sweep; one lossy fixture stalls).
 constexpr int STG_Q = 16;                                   // block columns per chunk
 constexpr int STG_WARPS = 16;                               // warps per CTA (one CTA per SM)
 struct __align__(128) SellStage {
@@ -353,32 +354,14 @@ __global__ void __launch_bounds__(STG_WARPS * 32, 1) k_bsell_tma(int nslices, co
     }
 }
 
-__global__ void k_x_to_c64(int64_t n, const cx* __restrict__ x, cf* __restrict__ x32) {
-    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i < n) stv(x32, i, ldx(x + i));
-}
-
 template <int NV>
 static int bsell_launch(emb_ctx* c, const cf* val, const cx* x, cx* y) {
     static const int mode = getenv("EMB_SPMV_TMA") ? atoi(getenv("EMB_SPMV_TMA")) : 1;
-    static const int x32 = getenv("EMB_SELL_X32") ? atoi(getenv("EMB_SELL_X32")) : 0;
     if constexpr (NV == 2) {               // NV = 4 in two passes over the staged chunk was measured slower than k_bsell
         if (mode && !c->sell_has_empty) {      // (a slice without any block is never visited by the staged kernel)
             int nsm = 0;
             EMB_CUDA(c, cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->device));
             const size_t smem = (size_t)STG_WARPS * sizeof(SellStage);
-            if (x32) {
-                EMB_TRY(dev_alloc(c, c->sell_x32, (size_t)c->Ns * NV * 2));
-                cf* xs = reinterpret_cast<cf*>(c->sell_x32.p);
-                k_x_to_c64<<<blocks_for(c->Ns * NV, 256), 256, 0, c->stream>>>(c->Ns * NV, x, xs);
-                EMB_LAUNCH_CHECK(c);
-                auto kern = k_bsell_tma<NV, cf>;
-                EMB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                kern<<<nsm, STG_WARPS * 32, smem, c->stream>>>((int)c->sell_nslices, c->sell_rows.p, c->sell_sptr.p, c->sell_bcol.p,
-                                                              reinterpret_cast<const float4*>(val), xs, y);
-                EMB_LAUNCH_CHECK(c);
-                return EMB_OK;
-            }
             auto kern = k_bsell_tma<NV, cx>;
             EMB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             kern<<<nsm, STG_WARPS * 32, smem, c->stream>>>((int)c->sell_nslices, c->sell_rows.p, c->sell_sptr.p, c->sell_bcol.p,
