@@ -185,6 +185,7 @@ extern "C" int emb_aux_build_top(emb_ctx* c, int which, const int64_t* edges_2xn
     EMB_CUDA(c, cudaMemcpyAsync(&nnz, a.rptr.p + Ns, sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
     EMB_CUDA(c, cudaStreamSynchronize(c->stream));
     a.nnz = nnz;
+    if (nnz >= ((int64_t)1 << 31)) { c->aux.pop_back(); c->err = "emb_aux_build_top: more than 2^31 entries"; return EMB_ERR_LIMIT; }
     DevBuf<unsigned long long> tkey, skey;
     DevBuf<int> tcnt;
     EMB_TRY(dev_alloc(c, a.rcol, (size_t)nnz));
