@@ -297,6 +297,38 @@ def case_lossy_slabs():
     return out
 
 
+def case_lossy_slabs_50k():
+    """Config-5 look-alike at the largest size the reference's direct solver handles in minutes here (49,680 tets, 320k
+    dofs): ceramic slabs eps_r = 9.8 (1 - 1e-4j) in two of every twelve cell layers (port planes in vacuum), three
+    frequencies.  Slim fixture: mesh in the reference's numbering, the slab flag per tet, S-parameters and the reference's
+    own residuals - the pin for the iterative solver on a lossy, strongly resonant operator beyond toy size."""
+    a, b = WR90
+    nx, ny, nz = 20, 9, 46
+    L = nz * a / nx
+    hz = L / nz
+
+    def vol(x, y, z):
+        layer = np.floor(z / hz).astype(np.int64) % 12
+        return np.where((layer == 5) | (layer == 6), 2, 1)
+
+    box = box_mesh(nx, ny, nz, a, b, L, jitter=0.05, seed=11, vol_fn=vol)
+    H.setup_paths()
+    import fem
+    cer = fem.Material(_fer=_mat_fn([9.8 * (1 - 1e-4j)] * 3))
+    fem, phys, mesh = H.build_physics(box, {1: fem.VACUUM, 2: cer})
+    H.rect_waveguide_ports(fem, phys, box)
+    freqs = [8.5e9, 10e9, 11.5e9]
+    full = {}
+    _sweep(fem, phys, mesh, freqs, False, full)
+    out = dict(kind="rectwg", dims=np.array(box.dims), face_tris=box.face_tris.astype(np.int32), face_tag=box.face_tag)
+    out.update(_mesh_dict(mesh))
+    ceramic = np.abs(full["er"][0, 0] - 1.0) > 1e-12
+    out.update(ceramic=ceramic, eps_ceramic=np.complex128(9.8 * (1 - 1e-4j)), freqs=full["freqs"], S=full["S"],
+               port_numbers=full["port_numbers"], solve_ids_len=np.int64(len(full["solve_ids"])),
+               xres=np.array([[full[f"xres_{i}_p{p}"] for p in full["port_numbers"]] for i in range(len(freqs))]))
+    return out
+
+
 def case_interp_wg_tiny():
     """Field post-processing pins: EMDataSet.interpolate (emdata.py:181-199) -> ned2_tet_interp /
     ned2_tet_interp_curl (mth/tet.py:371-626) on the wg_tiny mesh at random points (some outside the mesh): E and H of the
@@ -388,7 +420,7 @@ def case_farfield_patch():
 
 CASES = dict(wg_tiny=case_wg_tiny, wg_materials=case_wg_materials, wg_medium=case_wg_medium,
              abc_lumped=case_abc_lumped, modal_microstrip=case_modal_microstrip, lossy_slabs=case_lossy_slabs,
-             interp_wg_tiny=case_interp_wg_tiny, farfield_patch=case_farfield_patch, bma_microstrip=case_bma_microstrip)
+             interp_wg_tiny=case_interp_wg_tiny, farfield_patch=case_farfield_patch, bma_microstrip=case_bma_microstrip, lossy_slabs_50k=case_lossy_slabs_50k)
 
 if __name__ == "__main__":
     if not os.path.isdir("/root/reference/fem"):
