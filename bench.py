@@ -428,9 +428,9 @@ def run_gpu(args):
         peak, peak_src = peaks()
         nv = min(4, len(sw.ports)) if sw.lockstep > 1 else 1
         nv = 4 if nv == 3 else nv
-        # dominant kernel: the operator application of the block COCR iteration, k_bspmv<NV, complex64 values> (2x2
-        # block-CSR): per nonzero 8 B value + 1 B (one 4 B column per 2x2 block), per row 4 B rowptr (8 B per block-row) +
-        # NV x (16 B x + 16 B y)   
+        # dominant kernel: the operator application of the block COCR iteration on complex64 2x2 blocks - k_bsell_tma<2> (SELL
+        # layout, bulk-async staged) for two right-hand sides, k_bspmv (block-CSR) otherwise: per nonzero 8 B value + 1 B (one
+        # 4 B column per 2x2 block), per row 4 B rowptr (8 B per block-row) + NV x (16 B x + 16 B y)   
         spmv_bytes = 9 * nnz_s + (4 + 32 * nv) * Ns + 8
         spmv_ms = main["spmv_ms"]
         achieved = spmv_bytes / (spmv_ms * 1e-3) / 1e9 if spmv_ms > 0 else None
@@ -467,8 +467,11 @@ def run_gpu(args):
                                        "points / slowest rank's time; this is the strong-scaling number",
                                "per_rank": splits},
                 "gpu_launches": int(launches_total),
-                "roofline": {"kernel": f"k_bspmv<NV={nv}, complex64 values> (2x2 block-CSR operator application of the "
-                                       f"block COCR iteration on {nv} interleaved right-hand sides)",
+                "roofline": {"kernel": (f"k_bsell_tma<NV={nv}> (operator application of the block COCR iteration: complex64 2x2 "
+                                        f"blocks in a SELL-8 layout staged with cp.async.bulk, {nv} interleaved right-hand sides)"
+                                        if nv == 2 else
+                                        f"k_bspmv<NV={nv}, complex64 values> (2x2 block-CSR operator application of the block "
+                                        f"COCR iteration on {nv} interleaved right-hand sides)"),
                              "bound": "hbm", "achieved": achieved,
                              "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                              "frac": (achieved / peak) if achieved else None, "traffic": traffic,
