@@ -33,6 +33,11 @@ from __future__ import annotations
 import argparse
 import json
 import os
+
+# Load every kernel of the process when the CUDA context is created instead of at its first launch: lazy loading cost the
+# first sweep of a process ~6 s at 1M tets (first launches inside the solves and CUDA-graph captures: tools/e2e_probe.py,
+# 18.9 s -> 12.3 s for the first 12 points).  Must be set before the CUDA driver initialises; a user's own setting wins.
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
 import subprocess
 import sys
 import threading
