@@ -44,6 +44,7 @@ extern "C" void emb_destroy(emb_ctx* c) {
     c->er.release(); c->ur.release(); c->adjptr.release(); c->adj.release(); c->rowptr.release(); c->col.release();
     c->K.release(); c->M.release(); c->asm_items.release(); c->asm_ent.release(); c->sell_rows.release(); c->sell_pos.release(); c->sell_bcol.release(); c->sell_sptr.release(); c->sperm.release(); c->blkcol.release(); c->newid.release(); c->solve_ids.release(); c->rowptr_s.release();
     c->col_s.release(); c->src.release(); c->A.release(); c->xs.release(); c->xfull.release();
+    c->itp_tet.release(); c->itp_xyz.release(); c->itp_E.release();
     for (auto& w : c->work) w.release();
     c->dinv.release(); c->pairmate.release(); c->red.release(); c->As.release(); c->rc_x0.release();
     c->rcU.release(); c->rcQ.release(); c->rc_part.release(); c->rc_tmp.release(); c->bs.release(); c->As32.release();

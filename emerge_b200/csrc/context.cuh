@@ -149,6 +149,12 @@ struct emb_ctx {
     DevBuf<cx> xs;            // last solution (solve space)
     DevBuf<cx> bs;            // right-hand side of the current solve (solve space)
     DevBuf<cx> xfull;         // last solution (full space)
+    // scratch of the point evaluations (emb_interp*): grown on demand and kept, six calls per frequency point otherwise
+    // paid three cudaMalloc / cudaFree each
+    DevBuf<int> itp_tet;
+    DevBuf<double> itp_xyz;
+    DevBuf<cx> itp_E;
+    std::vector<int> itp_host;
     void* shift_invert = nullptr;     // dense shift-invert operator of the port eigenproblem (modal.cu)
     // asynchronous field output (emb_fields_async): per-column staging copies of the full-space solutions, moved to the
     // caller's (pinned) buffers by a copy stream while the next point is being solved

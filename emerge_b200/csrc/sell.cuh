@@ -198,25 +198,6 @@ __global__ void __launch_bounds__(256) k_bsell(int64_t nR, const int* __restrict
     }
 }
 
-// ---- the same product with the slice streams staged by the TMA engine -------------------------------------------------
-// The column indices and values of a slice are two CONTIGUOUS byte ranges.  One elected lane per warp copies them chunk by
-// chunk (STG_Q block columns = 4.5 KB) into the warp's own shared-memory ring with cp.async.bulk (UBLKCP) completing on an
-// mbarrier, one chunk ahead of the arithmetic; the lanes then read indices and values from shared memory and have all
-// STG_Q x gathers of a chunk in flight at once - the load/store unit only sees the gathers, which is what the kernel is
-// bound by (the dependent index -> x chain left k_bspmv / k_bsell at 50 % of the HBM roofline with 4 gathers in flight).
-// Persistent warps: warp g of the grid owns slices g, g + G, ...   NV = 4: a warp covers the 8 rows in two passes.
-// Measured and rejected (profiles/r2_spmv_sell_tuning.txt): a deeper ring with the gathers of the next chunk issued before
-// the arithmetic of the current one and the slice metadata prefetched a slice ahead (1.00 ms instead of 0.80 - the stall
-// samples stay on the first use of the gathered x), a Z-order numbering of the mesh, a blocked slice distribution.
-// Also rejected: gathering from a complex64 COPY of x (XT = cf; half the gather bytes, the copy fits the L2): 0.86 ms with the
-// conversion pass, and the rounded operator input costs iterations (3,420 -> 3,940 on the sweep; one lossy fixture stalls).
-constexpr int STG_Q = 16;                                   // block columns per chunk
-constexpr int STG_WARPS = 16;                               // warps per CTA (one CTA per SM)
-struct __align__(128) SellStage {
-    float4 val[2][STG_Q * SELL_C * 2];                      // 2 x 4 KB
-    int col[2][STG_Q * SELL_C];                             // 2 x 512 B
-    unsigned long long bar[2];
-};
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -243,115 +224,188 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
         : "memory");
 }
 
-__device__ __forceinline__ cx ldraw(const cx* __restrict__ p) { return ldx(p); }
-__device__ __forceinline__ cf ldraw(const cf* __restrict__ p) {
-    const float2 a = __ldg(reinterpret_cast<const float2*>(p));
-    return cf{a.x, a.y};
+// ---- the same product with the slice streams staged by the TMA engine -------------------------------------------------
+// The column indices and values of a slice are two CONTIGUOUS byte ranges.  One elected lane per warp copies them chunk by
+// chunk (Q block columns) into the warp's own shared-memory ring with cp.async.bulk (SASS UBLKCP) completing on an
+// mbarrier, DEPTH - 1 chunks ahead of the arithmetic; the lanes then read indices and values from shared memory and have
+// the Q x gathers of a chunk in flight at once - the load/store unit only sees the gathers.  Persistent warps: warp g of
+// the grid owns slices g, g + G, ...  (NV = 2: a warp = the 8 block-rows of a slice x 4 lanes = column half x right-hand side.)
+//   Q      block columns per chunk (gathers a lane keeps in flight), WARPS warps per CTA (one CTA per SM)
+//   DEPTH  chunk buffers per warp
+//   HINT   bit 0: the value / index streams are copied with an L2 evict-first policy (they are read exactly once; x, which
+//          is re-read by neighbouring rows, keeps the L2), bit 1: the x gathers carry an evict-last policy, bit 2: y is
+//          written with streaming stores
+// No dependent global load is left on a slice boundary: the [begin, end) offsets of the warp's next 32 slices are fetched
+// by ONE load per lane and handed out by shuffles, the block-column count of every slice the copy cursor enters is parked
+// in a 4-entry shared-memory ring for the arithmetic cursor, and the row ids of a slice are loaded when the slice starts
+// (used when it ends).
+// Measured at 1M tets (profiles/r2_spmv_sell_tuning.txt): first generation (Q = 16, 16 warps, offsets and row ids loaded
+// on the boundary, no cache policy) 0.826 ms; boundary loads removed 0.72; + evict-first streams 0.70; Q = 8 with 24
+// warps (80 registers) 0.596 ms = 4.7 TB/s; deeper rings, 28 / 32 warps, evict-last gathers, streaming stores: no gain.
+// Rejected: accumulating the block Gram matrix x^T y (rho = Z^T A Z of block COCR) in the epilogue - the rows of x re-read
+// at every slice end cost 0.18 ms, the separate k_gram pass it would replace 0.08 ms; gathers of the next chunk issued
+// before the arithmetic of the current one (register-held, 1.0 ms); a Z-order numbering of the mesh; a blocked slice
+// distribution; gathering from a complex64 copy of x (costs iterations).
+constexpr int STG_Q = 8, STG_WARPS = 24, STG_DEPTH = 2, STG_HINT = 1;      // shipped configuration
+template <int Q, int DEPTH>
+struct __align__(128) SellStageQ {
+    float4 val[DEPTH][Q * SELL_C * 2];
+    int col[DEPTH][Q * SELL_C];
+    unsigned long long bar[DEPTH];
+    int nbq[4];
+};
+__device__ __forceinline__ void bulk_g2s_hint(void* dst, const void* src, unsigned bytes, unsigned long long* bar,
+                                              unsigned long long pol) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+                 : "memory");
 }
-__device__ __forceinline__ cx widen(cx v) { return v; }
-__device__ __forceinline__ cx widen(cf v) { return cx{(double)v.re, (double)v.im}; }
+__device__ __forceinline__ cx ldx_hint(const cx* __restrict__ p, unsigned long long pol) {
+    double a, b;
+    asm volatile("ld.global.nc.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(a), "=d"(b) : "l"(p), "l"(pol));
+    return cx{a, b};
+}
+__device__ __forceinline__ void st_stream(cx* p, cx v) {
+    asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.re), "d"(v.im) : "memory");
+}
 
-template <int NV, typename XT>
-__global__ void __launch_bounds__(STG_WARPS * 32, 1) k_bsell_tma(int nslices, const int* __restrict__ rows,
-                                                                 const int64_t* __restrict__ sptr, const int* __restrict__ bcol,
-                                                                 const float4* __restrict__ val, const XT* __restrict__ x,
-                                                                 cx* __restrict__ y) {
-    constexpr int LPB = 2 * NV;                 // lanes per block-row
-    constexpr int RPW = 32 / LPB;               // rows a warp covers per pass (8 or 4)
-    constexpr int NPASS = SELL_C / RPW;         // 1 (NV = 2) or 2 (NV = 4)
+template <int Q, int WARPS, int DEPTH, int HINT>
+__global__ void __launch_bounds__(WARPS * 32, 1) k_bsell_tma(int nslices, const int* __restrict__ rows,
+                                                             const int64_t* __restrict__ sptr, const int* __restrict__ bcol,
+                                                             const float4* __restrict__ val, const cx* __restrict__ x,
+                                                             cx* __restrict__ y) {
+    constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(128) unsigned char stage_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    SellStage& st = reinterpret_cast<SellStage*>(stage_raw)[warp];
-    if (lane == 0) { mbar_init(&st.bar[0], 1); mbar_init(&st.bar[1], 1); }
+    SellStageQ<Q, DEPTH>& st = reinterpret_cast<SellStageQ<Q, DEPTH>*>(stage_raw)[warp];
+    if (lane == 0)
+        for (int b = 0; b < DEPTH; ++b) mbar_init(&st.bar[b], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncwarp();
-    const int u = lane % LPB, h = u / NV, rl = lane / LPB;
-    const int gw = blockIdx.x * STG_WARPS + warp, G = gridDim.x * STG_WARPS;
-    // chunk iterator over this warp's slices: (slice s, first block column q0); issue() starts the copies of a chunk
-    int s_i = gw, q_i = 0;                       // next chunk to ISSUE
+    const int u = lane & 3, h = u >> 1, rl = lane >> 2;
+    const int gw = blockIdx.x * WARPS + warp, G = gridDim.x * WARPS;
+    const int n_my = gw < nslices ? (nslices - gw + G - 1) / G : 0;        // this warp owns slices gw, gw + G, ...
+    unsigned long long pol = 0, polx = 0;
+    if constexpr ((HINT & 1) != 0) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    if constexpr ((HINT & 2) != 0) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(polx));
+    long long mb = 0, me = 0;                    // offsets of the warp's slice number (batch * 32 + lane)
+    int q_i = 0, nb_i = 0, i_i = -1, b_i = 0;    // copy cursor: slice number, next block column, block columns, next buffer
     int64_t base_i = 0;
-    int nb_i = 0;
-    if (s_i < nslices) { base_i = __ldg(sptr + s_i); nb_i = (int)((__ldg(sptr + s_i + 1) - base_i) / SELL_C); }
-    auto skip_empty = [&]() {                    // advance the issue cursor past exhausted / empty slices
-        while (s_i < nslices && q_i >= nb_i) {
-            s_i += G;
+    auto issue_next = [&]() {                    // all lanes call; lane 0 talks to the TMA engine
+        if (i_i >= n_my) return;
+        if (q_i >= nb_i) {                       // enter the warp's next slice
+            ++i_i;
+            if (i_i >= n_my) return;
+            if ((i_i & 31) == 0) {
+                const int k = i_i + lane;
+                if (k < n_my) {
+                    const int64_t s = gw + (int64_t)k * G;
+                    mb = __ldg(sptr + s);
+                    me = __ldg(sptr + s + 1);
+                }
+            }
+            base_i = __shfl_sync(FULL, mb, i_i & 31);
+            nb_i = (int)((__shfl_sync(FULL, me, i_i & 31) - base_i) / SELL_C);
             q_i = 0;
-            if (s_i < nslices) { base_i = __ldg(sptr + s_i); nb_i = (int)((__ldg(sptr + s_i + 1) - base_i) / SELL_C); }
+            if (lane == 0) st.nbq[i_i & 3] = nb_i;
         }
-    };
-    auto issue = [&](int b) {                    // all lanes call; lane 0 talks to the TMA engine
-        const int nq = min(STG_Q, nb_i - q_i);
+        const int nq = min(Q, nb_i - q_i);
         if (lane == 0) {
             const int64_t blk0 = base_i + (int64_t)q_i * SELL_C;
             const unsigned nblk = (unsigned)(nq * SELL_C);
-            mbar_expect_tx(&st.bar[b], nblk * 36u);
-            bulk_g2s(st.val[b], val + blk0 * 2, nblk * 32u, &st.bar[b]);
-            bulk_g2s(st.col[b], bcol + blk0, nblk * 4u, &st.bar[b]);
+            mbar_expect_tx(&st.bar[b_i], nblk * 36u);
+            if constexpr ((HINT & 1) != 0) {
+                bulk_g2s_hint(st.val[b_i], val + blk0 * 2, nblk * 32u, &st.bar[b_i], pol);
+                bulk_g2s_hint(st.col[b_i], bcol + blk0, nblk * 4u, &st.bar[b_i], pol);
+            } else {
+                bulk_g2s(st.val[b_i], val + blk0 * 2, nblk * 32u, &st.bar[b_i]);
+                bulk_g2s(st.col[b_i], bcol + blk0, nblk * 4u, &st.bar[b_i]);
+            }
         }
         q_i += nq;
+        b_i = (b_i + 1 == DEPTH) ? 0 : b_i + 1;
     };
-    skip_empty();
+#pragma unroll
+    for (int d = 0; d < DEPTH - 1; ++d) issue_next();
+    __syncwarp();
+    int i_c = 0, q_c = 0, nb_c = n_my > 0 ? st.nbq[0] : 0;      // arithmetic cursor
+    int j = n_my > 0 ? __ldg(rows + (int64_t)gw * SELL_C + rl) : -1;
     int buf = 0;
-    unsigned phase[2] = {0u, 0u};
-    if (s_i < nslices) issue(0);
-    // consume cursor
-    int s_c = gw, q_c = 0, nb_c = 0;
-    if (s_c < nslices) nb_c = (int)((__ldg(sptr + s_c + 1) - __ldg(sptr + s_c)) / SELL_C);
-    while (s_c < nslices && nb_c == 0) {         // same skipping rule as the issue cursor
-        s_c += G;
-        if (s_c < nslices) nb_c = (int)((__ldg(sptr + s_c + 1) - __ldg(sptr + s_c)) / SELL_C);
-    }
-    double acc[NPASS][4];
+    unsigned phases = 0u;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    while (i_c < n_my) {
+        issue_next();                            // refills the buffer the previous iteration released
+        mbar_wait(&st.bar[buf], (phases >> buf) & 1u);
+        phases ^= 1u << buf;
+        const int nq = min(Q, nb_c - q_c);
+        cx wr[Q];
 #pragma unroll
-    for (int p = 0; p < NPASS; ++p) acc[p][0] = acc[p][1] = acc[p][2] = acc[p][3] = 0.0;
-    while (s_c < nslices) {
-        // start the next chunk's copies, then wait for this one
-        skip_empty();
-        if (s_i < nslices) issue(buf ^ 1);
-        mbar_wait(&st.bar[buf], phase[buf]);
-        phase[buf] ^= 1u;
-        const int nq = min(STG_Q, nb_c - q_c);
+        for (int q = 0; q < Q; ++q)
+            if (q < nq) {
+                const cx* px = x + (int64_t)st.col[buf][q * SELL_C + rl] * 4 + u;
+                if constexpr ((HINT & 2) != 0) wr[q] = ldx_hint(px, polx);
+                else wr[q] = ldx(px);
+            }
 #pragma unroll
-        for (int p = 0; p < NPASS; ++p) {
-            const int r = p * RPW + rl;
-            XT wr[STG_Q];                        // raw storage type: a complex64 copy of x keeps 16 gathers in 32 registers
-#pragma unroll
-            for (int q = 0; q < STG_Q; ++q)
-                if (q < nq) wr[q] = ldraw(x + (int64_t)st.col[buf][q * SELL_C + r] * LPB + u);
-#pragma unroll
-            for (int q = 0; q < STG_Q; ++q)
-                if (q < nq) {
-                    const float4 e = st.val[buf][(q * SELL_C + r) * 2 + h];
-                    const cx w = widen(wr[q]);
-                    acc[p][0] += (double)e.x * w.re - (double)e.y * w.im;
-                    acc[p][1] += (double)e.x * w.im + (double)e.y * w.re;
-                    acc[p][2] += (double)e.z * w.re - (double)e.w * w.im;
-                    acc[p][3] += (double)e.z * w.im + (double)e.w * w.re;
-                }
-        }
+        for (int q = 0; q < Q; ++q)
+            if (q < nq) {
+                const float4 e = st.val[buf][(q * SELL_C + rl) * 2 + h];
+                const cx w = wr[q];
+                a0 += (double)e.x * w.re - (double)e.y * w.im;
+                a1 += (double)e.x * w.im + (double)e.y * w.re;
+                a2 += (double)e.z * w.re - (double)e.w * w.im;
+                a3 += (double)e.z * w.im + (double)e.w * w.re;
+            }
         __syncwarp();                            // every lane is done with this buffer before it is refilled
         q_c += nq;
-        buf ^= 1;
+        buf = (buf + 1 == DEPTH) ? 0 : buf + 1;
         if (q_c >= nb_c) {                       // slice finished: reduce over the column halves, write the two rows
-#pragma unroll
-            for (int p = 0; p < NPASS; ++p) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) acc[p][k] += __shfl_xor_sync(0xffffffffu, acc[p][k], NV);
-                const int j = __ldg(rows + (int64_t)s_c * SELL_C + p * RPW + rl);
-                if (j >= 0 && h == 0) {
-                    stv(y, (int64_t)(2 * j) * NV + u, cx{acc[p][0], acc[p][1]});
-                    stv(y, (int64_t)(2 * j + 1) * NV + u, cx{acc[p][2], acc[p][3]});
+            a0 += __shfl_xor_sync(FULL, a0, 2);
+            a1 += __shfl_xor_sync(FULL, a1, 2);
+            a2 += __shfl_xor_sync(FULL, a2, 2);
+            a3 += __shfl_xor_sync(FULL, a3, 2);
+            if (j >= 0 && h == 0) {
+                if constexpr ((HINT & 4) != 0) {
+                    st_stream(y + (int64_t)(2 * j) * 2 + u, cx{a0, a1});
+                    st_stream(y + (int64_t)(2 * j + 1) * 2 + u, cx{a2, a3});
+                } else {
+                    stv(y, (int64_t)(2 * j) * 2 + u, cx{a0, a1});
+                    stv(y, (int64_t)(2 * j + 1) * 2 + u, cx{a2, a3});
                 }
-                acc[p][0] = acc[p][1] = acc[p][2] = acc[p][3] = 0.0;
             }
+            a0 = a1 = a2 = a3 = 0.0;
+            ++i_c;
             q_c = 0;
-            nb_c = 0;
-            while (s_c < nslices && nb_c == 0) {
-                s_c += G;
-                if (s_c < nslices) nb_c = (int)((__ldg(sptr + s_c + 1) - __ldg(sptr + s_c)) / SELL_C);
+            if (i_c < n_my) {                    // the copy cursor is at least one chunk ahead: it has entered this slice
+                nb_c = st.nbq[i_c & 3];
+                j = __ldg(rows + ((int64_t)gw + (int64_t)i_c * G) * SELL_C + rl);
             }
         }
     }
+}
+
+template <int Q, int WARPS, int DEPTH, int HINT>
+static int bsell_tma_launch(emb_ctx* c, const cf* val, const cx* x, cx* y, int nsm) {
+    const size_t smem = (size_t)WARPS * sizeof(SellStageQ<Q, DEPTH>);
+    auto kern = k_bsell_tma<Q, WARPS, DEPTH, HINT>;
+    EMB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<nsm, WARPS * 32, smem, c->stream>>>((int)c->sell_nslices, c->sell_rows.p, c->sell_sptr.p, c->sell_bcol.p,
+                                               reinterpret_cast<const float4*>(val), x, y);
+    EMB_LAUNCH_CHECK(c);
+    return EMB_OK;
+}
+// EMB_SELL_VARIANT = "Q:WARPS:DEPTH:HINT": the alternatives kept for tools/sell_variants.py (tuning probe; read per launch)
+static int bsell_tma_dispatch(emb_ctx* c, const char* v, const cf* val, const cx* x, cx* y, int nsm) {
+    int Q = 0, W = 0, D = 0, H = 0;
+    if (sscanf(v, "%d:%d:%d:%d", &Q, &W, &D, &H) == 4) {
+#define EMB_V(q, w, d, hh) if (Q == q && W == w && D == d && H == hh) return bsell_tma_launch<q, w, d, hh>(c, val, x, y, nsm)
+        EMB_V(8, 24, 2, 1); EMB_V(8, 24, 2, 0); EMB_V(8, 24, 3, 1); EMB_V(8, 24, 2, 5); EMB_V(8, 24, 2, 3);
+        EMB_V(6, 28, 2, 1); EMB_V(5, 32, 2, 1); EMB_V(10, 20, 2, 1); EMB_V(16, 16, 2, 1); EMB_V(16, 16, 2, 0);
+#undef EMB_V
+    }
+    c->err = std::string("EMB_SELL_VARIANT: no such instantiation: ") + v;
+    return EMB_ERR_ARG;
 }
 
 template <int NV>
@@ -361,13 +415,8 @@ static int bsell_launch(emb_ctx* c, const cf* val, const cx* x, cx* y) {
         if (mode && !c->sell_has_empty) {      // (a slice without any block is never visited by the staged kernel)
             int nsm = 0;
             EMB_CUDA(c, cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->device));
-            const size_t smem = (size_t)STG_WARPS * sizeof(SellStage);
-            auto kern = k_bsell_tma<NV, cx>;
-            EMB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            kern<<<nsm, STG_WARPS * 32, smem, c->stream>>>((int)c->sell_nslices, c->sell_rows.p, c->sell_sptr.p, c->sell_bcol.p,
-                                                          reinterpret_cast<const float4*>(val), x, y);
-            EMB_LAUNCH_CHECK(c);
-            return EMB_OK;
+            if (const char* v = getenv("EMB_SELL_VARIANT")) return bsell_tma_dispatch(c, v, val, x, y, nsm);
+            return bsell_tma_launch<STG_Q, STG_WARPS, STG_DEPTH, STG_HINT>(c, val, x, y, nsm);
         }
     }
     const int64_t nR = (int64_t)c->sell_nslices * SELL_C;

@@ -817,6 +817,37 @@ extern "C" int emb_spmv_bench_ex(emb_ctx* c, int reps, int nv, int fp32, double*
     }
     *ms_per_spmv = c->ms["spmv"] / reps;
     c->ms["spmv"] = *ms_per_spmv;
+    if (getenv("EMB_SPMV_CHECK")) {      // tuning probe: weighted checksum of y = Op x for a fixed pseudo-random x (emb_last_ms "spmv_check_*")
+        const size_t n = (size_t)c->Ns * nv;
+        std::vector<cx> hx(n), hy(n);
+        uint64_t st = 0x9e3779b97f4a7c15ull;
+        auto rnd = [&]() { st = st * 6364136223846793005ull + 1442695040888963407ull; return (double)(st >> 11) / 9007199254740992.0 - 0.5; };
+        for (size_t i = 0; i < n; ++i) hx[i] = cx{rnd(), rnd()};
+        EMB_CUDA(c, cudaMemcpyAsync(dx.p, hx.data(), n * sizeof(cx), cudaMemcpyHostToDevice, c->stream));
+        EMB_TRY(one(dx.p, dy.p));
+        EMB_CUDA(c, cudaMemcpyAsync(hy.data(), dy.p, n * sizeof(cx), cudaMemcpyDeviceToHost, c->stream));
+        EMB_CUDA(c, cudaStreamSynchronize(c->stream));
+        double sr = 0, si = 0, sa = 0;
+        for (size_t i = 0; i < n; ++i) {
+            const double w = 0.5 + (double)((i * 2654435761ull) & 1023u) / 1024.0;
+            sr += w * hy[i].re; si += w * hy[i].im; sa += hy[i].re * hy[i].re + hy[i].im * hy[i].im;
+        }
+        c->ms["spmv_check_re"] = sr; c->ms["spmv_check_im"] = si; c->ms["spmv_check_abs2"] = sa;
+        // against the complex128 operator A(f) on the same x (As is its symmetric part rounded to complex64: ~1e-4 apart)
+        {
+            std::vector<cx> hz(n);
+            int rc2 = nv == 1 ? spmv<1, cx>(c, c->A.p, dx.p, dy.p) : nv == 2 ? spmv<2, cx>(c, c->A.p, dx.p, dy.p) : spmv<4, cx>(c, c->A.p, dx.p, dy.p);
+            if (rc2 < 0) return rc2;
+            EMB_CUDA(c, cudaMemcpyAsync(hz.data(), dy.p, n * sizeof(cx), cudaMemcpyDeviceToHost, c->stream));
+            EMB_CUDA(c, cudaStreamSynchronize(c->stream));
+            double num = 0, den = 0;
+            for (size_t i = 0; i < n; ++i) {
+                num += (hy[i].re - hz[i].re) * (hy[i].re - hz[i].re) + (hy[i].im - hz[i].im) * (hy[i].im - hz[i].im);
+                den += hz[i].re * hz[i].re + hz[i].im * hz[i].im;
+            }
+            c->ms["spmv_check_vs_A"] = den > 0 ? sqrt(num / den) : -1.0;
+        }
+    }
     dx.release(); dy.release();
     return EMB_OK;
 }
@@ -879,22 +910,24 @@ __global__ void k_interp(int64_t npts, const int* __restrict__ tet, const double
 }
 
 static int interp_impl(emb_ctx* c, const cx* dxfull, int64_t npts, const int64_t* tet_ids, const double* xyz, emb_c128* E) {
-    std::vector<int> ht((size_t)npts);
+    std::vector<int>& ht = c->itp_host;
+    ht.resize((size_t)npts);
     for (int64_t i = 0; i < npts; ++i) {
         if (tet_ids[i] < 0 || tet_ids[i] >= c->nT) { c->err = "emb_interp: tet id out of range"; return EMB_ERR_ARG; }
         ht[i] = (int)tet_ids[i];
     }
-    DevBuf<int> dt;
-    DevBuf<double> dp;
-    DevBuf<cx> dE;
-    EMB_TRY(h2d(c, dt, ht.data(), (size_t)npts));
-    EMB_TRY(h2d(c, dp, xyz, (size_t)npts * 3));
-    EMB_TRY(dev_alloc(c, dE, (size_t)npts * 3));
-    k_interp<<<blocks_for(npts, 128), 128, 0, c->stream>>>(npts, dt.p, dp.p, c->tetc.p, c->gid.p, c->nodes.p, dxfull, dE.p);
+    if (c->itp_tet.n < (size_t)npts) {
+        EMB_TRY(dev_alloc(c, c->itp_tet, (size_t)npts));
+        EMB_TRY(dev_alloc(c, c->itp_xyz, (size_t)npts * 3));
+        EMB_TRY(dev_alloc(c, c->itp_E, (size_t)npts * 3));
+    }
+    EMB_CUDA(c, cudaMemcpyAsync(c->itp_tet.p, ht.data(), (size_t)npts * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    EMB_CUDA(c, cudaMemcpyAsync(c->itp_xyz.p, xyz, (size_t)npts * 3 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    k_interp<<<blocks_for(npts, 128), 128, 0, c->stream>>>(npts, c->itp_tet.p, c->itp_xyz.p, c->tetc.p, c->gid.p, c->nodes.p,
+                                                           dxfull, c->itp_E.p);
     EMB_LAUNCH_CHECK(c);
-    EMB_CUDA(c, cudaMemcpyAsync(E, dE.p, (size_t)npts * 3 * sizeof(cx), cudaMemcpyDeviceToHost, c->stream));
+    EMB_CUDA(c, cudaMemcpyAsync(E, c->itp_E.p, (size_t)npts * 3 * sizeof(cx), cudaMemcpyDeviceToHost, c->stream));
     EMB_CUDA(c, cudaStreamSynchronize(c->stream));
-    dt.release(); dp.release(); dE.release();
     return EMB_OK;
 }
 

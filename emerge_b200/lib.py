@@ -133,8 +133,40 @@ def load_library():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
+    if os.environ.get("EMB_API_TRACE"):
+        lib = _TracedLib(lib)
     _lib = lib
     return lib
+
+
+API_TRACE = {}      # symbol -> [calls, host wall seconds], filled when EMB_API_TRACE is set (diagnostic of the end-to-end legs)
+
+
+class _TracedLib:
+    """Proxy of the loaded library that accumulates the host wall time spent inside every entry point."""
+
+    def __init__(self, lib):
+        import time
+        for name in _SIGS:
+            fn = getattr(lib, name)
+
+            def timed(*a, _fn=fn, _name=name, _clock=time.perf_counter):
+                t0 = _clock()
+                try:
+                    return _fn(*a)
+                finally:
+                    rec = API_TRACE.setdefault(_name, [0, 0.0])
+                    rec[0] += 1
+                    rec[1] += _clock() - t0
+            setattr(self, name, timed)
+
+
+def api_trace_report(reset=True, top=14):
+    rows = sorted(API_TRACE.items(), key=lambda kv: -kv[1][1])[:top]
+    out = ", ".join(f"{k}:{v[0]}x{v[1]:.3f}s" for k, v in rows)
+    if reset:
+        API_TRACE.clear()
+    return out
 
 
 def _p(a):
