@@ -154,6 +154,57 @@ __global__ void __launch_bounds__(256) k_rc_sub(int64_t n, int m, const cx* __re
     for (int k = 0; k < m; ++k) fma_c(a, -s_h[k], Q[(int64_t)k * n + i]);
     w[i] = a;
 }
+// The same two kernels for NB CONTIGUOUS columns w_v = W + v n at once (the T products of a new direction): Q is read
+// once for all of them.   part[(j * RC_NP + p) * NB + v] = partial of <q_j, w_v>;   w_v -= sum_{j<m} coef[j * NB + v] q_j
+template <int NB, bool CONJ = true>
+__global__ void __launch_bounds__(VBLOCK) k_rc_dots_cols(int64_t n, const cx* __restrict__ Q, const cx* __restrict__ W,
+                                                         cx* __restrict__ part) {
+    const int lin = blockIdx.y * gridDim.x + blockIdx.x;
+    const int bj = lin % (int)gridDim.y, bp = lin / (int)gridDim.y;       // consecutive blocks share the row range (see k_rc_dots)
+    const cx* q = Q + (int64_t)bj * n;
+    cx acc[NB];
+#pragma unroll
+    for (int v = 0; v < NB; ++v) acc[v] = mk(0.0);
+    const int64_t per = (n + RC_NP - 1) / RC_NP;
+    const int64_t i0 = bp * per, i1 = (i0 + per < n) ? i0 + per : n;
+    for (int64_t i = i0 + threadIdx.x; i < i1; i += VBLOCK) {
+        const cx u = q[i];
+#pragma unroll
+        for (int v = 0; v < NB; ++v) {
+            const cx w = W[(int64_t)v * n + i];
+            if (CONJ) {
+                acc[v].re += u.re * w.re + u.im * w.im;
+                acc[v].im += u.re * w.im - u.im * w.re;
+            } else {
+                fma_c(acc[v], u, w);
+            }
+        }
+    }
+#pragma unroll
+    for (int v = 0; v < NB; ++v) {
+        const cx t = block_sum1(acc[v]);
+        if (threadIdx.x == 0) part[((int64_t)bj * RC_NP + bp) * NB + v] = t;
+    }
+}
+template <int NB>
+__global__ void __launch_bounds__(256) k_rc_sub_cols(int64_t n, int m, const cx* __restrict__ coef, const cx* __restrict__ Q,
+                                                     cx* __restrict__ W) {
+    extern __shared__ cx s_h[];
+    for (int k = threadIdx.x; k < m * NB; k += blockDim.x) s_h[k] = coef[k];
+    __syncthreads();
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    cx a[NB];
+#pragma unroll
+    for (int v = 0; v < NB; ++v) a[v] = W[(int64_t)v * n + i];
+    for (int k = 0; k < m; ++k) {
+        const cx q = Q[(int64_t)k * n + i];
+#pragma unroll
+        for (int v = 0; v < NB; ++v) fma_c(a[v], -s_h[k * NB + v], q);
+    }
+#pragma unroll
+    for (int v = 0; v < NB; ++v) W[(int64_t)v * n + i] = a[v];
+}
 // x[i][v] += sum_{j<m} y[j * NV + v] u_j[i]
 template <int NV>
 __global__ void __launch_bounds__(256) k_rc_combine(int64_t n, int m, const cx* __restrict__ y, const cx* __restrict__ U,
@@ -277,39 +328,119 @@ static int rc_insert(emb_ctx* c, int slot, bool accept_test, bool* accepted) {
     const int T = rc_T(c);
     const unsigned vb = blocks_for(n, 256);
     cx* part = c->rc_part.p;
-    cx* coef = rc_coef_area(c);                 // h1 [qcap], h2 [qcap], norms [2]
     const int qc = c->rc_qcap;
-    std::vector<cx> host((size_t)2 * qc + 2);
-    const int nq_before = c->rc_nq;
+    // coefficient area (12 qc + .. entries): block coefficients [qc * 4], in-block coefficients of the two passes [2][qc] and
+    // a squared norm, squared norms of the raw products [T]
+    cx* coef = rc_coef_area(c);
+    cx* hB = coef;
+    cx* hC = coef + (size_t)8 * qc;
+    cx* nrm = coef + (size_t)10 * qc;
+    const int nq0 = c->rc_nq;                    // columns of Q before this direction
+    if (nq0 + T > qc) { c->err = "recycling: orthonormal basis is full"; return EMB_ERR_LIMIT; }
+    // A: the T products W_t u, side by side behind the basis
     for (int t = 0; t < T; ++t) {
-        const int nq = c->rc_nq;
-        if (nq >= qc) { c->err = "recycling: orthonormal basis is full"; return EMB_ERR_LIMIT; }
-        cx* w = rc_Q(c, nq);
+        cx* w = rc_Q(c, nq0 + t);
         EMB_TRY(rc_term_mv(c, t, rc_U(c, slot), w));
-        cx* pn = part;                          // NPART partials fit: qcap * RC_NP * NVMAX >= NPART (qcap >= 2, RC_NP = 256, NVMAX = 4)
-        k_dot<1, true><<<NPART, VBLOCK, 0, c->stream>>>(n, w, w, pn); EMB_LAUNCH_CHECK(c);
-        k_finish<1><<<1, VBLOCK, 0, c->stream>>>(pn, coef + 2 * qc); EMB_LAUNCH_CHECK(c);
-        for (int pass = 0; pass < 2 && nq > 0; ++pass) {
-            cx* h = coef + (size_t)pass * qc;
-            k_rc_dots<1><<<dim3(RC_NP, nq), VBLOCK, 0, c->stream>>>(n, c->rcQ.p, w, part); EMB_LAUNCH_CHECK(c);
-            k_rc_coef<1><<<nq, VBLOCK, 0, c->stream>>>(part, h); EMB_LAUNCH_CHECK(c);
-            k_rc_sub<<<vb, 256, nq * sizeof(cx), c->stream>>>(n, nq, h, c->rcQ.p, w); EMB_LAUNCH_CHECK(c);
+        k_dot<1, true><<<NPART, VBLOCK, 0, c->stream>>>(n, w, w, part); EMB_LAUNCH_CHECK(c);
+        k_finish<1><<<1, VBLOCK, 0, c->stream>>>(part, nrm + t); EMB_LAUNCH_CHECK(c);
+    }
+    // Block classical Gram-Schmidt with re-orthogonalisation (BCGS2) of the T products against the basis:
+    //   W = Qold H1 + W1,  W1 = Q1 R1 (in-block CGS2; a product inside the span of the others is dropped),
+    //   Q1 = Qold H2 + Q1', Q1' = Qnew R2 (in-block CGS2)   =>   W = Qold (H1 + H2 R1) + Qnew (R2 R1).
+    // Qold is read once per pass for up to four columns instead of twice per product.  (One block pass followed by the
+    // in-block step only is NOT enough: K u and M u are nearly parallel, the in-block cancellation amplifies the rounding
+    // left along Qold and the basis loses orthogonality within a few directions - measured, tools/rc_ab.py.)
+    auto proj_old = [&](int first, int ncols, std::vector<zc>& H) -> int {      // H[v * nq0 + i] += <q_i, col(first + v)>
+        for (int g0 = 0; g0 < ncols && nq0 > 0; g0 += 4) {
+            const int gs = ncols - g0 < 4 ? ncols - g0 : 4;
+            cx* W = rc_Q(c, first + g0);
+            const dim3 grid(RC_NP, nq0);
+            const size_t sh = (size_t)nq0 * gs * sizeof(cx);
+            switch (gs) {
+                case 1: k_rc_dots_cols<1><<<grid, VBLOCK, 0, c->stream>>>(n, c->rcQ.p, W, part); EMB_LAUNCH_CHECK(c);
+                        k_rc_coef<1><<<nq0, VBLOCK, 0, c->stream>>>(part, hB); EMB_LAUNCH_CHECK(c);
+                        k_rc_sub_cols<1><<<vb, 256, sh, c->stream>>>(n, nq0, hB, c->rcQ.p, W); EMB_LAUNCH_CHECK(c); break;
+                case 2: k_rc_dots_cols<2><<<grid, VBLOCK, 0, c->stream>>>(n, c->rcQ.p, W, part); EMB_LAUNCH_CHECK(c);
+                        k_rc_coef<2><<<nq0, VBLOCK, 0, c->stream>>>(part, hB); EMB_LAUNCH_CHECK(c);
+                        k_rc_sub_cols<2><<<vb, 256, sh, c->stream>>>(n, nq0, hB, c->rcQ.p, W); EMB_LAUNCH_CHECK(c); break;
+                case 3: k_rc_dots_cols<3><<<grid, VBLOCK, 0, c->stream>>>(n, c->rcQ.p, W, part); EMB_LAUNCH_CHECK(c);
+                        k_rc_coef<3><<<nq0, VBLOCK, 0, c->stream>>>(part, hB); EMB_LAUNCH_CHECK(c);
+                        k_rc_sub_cols<3><<<vb, 256, sh, c->stream>>>(n, nq0, hB, c->rcQ.p, W); EMB_LAUNCH_CHECK(c); break;
+                default: k_rc_dots_cols<4><<<grid, VBLOCK, 0, c->stream>>>(n, c->rcQ.p, W, part); EMB_LAUNCH_CHECK(c);
+                        k_rc_coef<4><<<nq0, VBLOCK, 0, c->stream>>>(part, hB); EMB_LAUNCH_CHECK(c);
+                        k_rc_sub_cols<4><<<vb, 256, sh, c->stream>>>(n, nq0, hB, c->rcQ.p, W); EMB_LAUNCH_CHECK(c); break;
+            }
+            std::vector<cx> hh((size_t)nq0 * gs);
+            EMB_CUDA(c, cudaMemcpyAsync(hh.data(), hB, hh.size() * sizeof(cx), cudaMemcpyDeviceToHost, c->stream));
+            EMB_CUDA(c, cudaStreamSynchronize(c->stream));
+            for (int v = 0; v < gs; ++v)
+                for (int i = 0; i < nq0; ++i)
+                    H[(size_t)(g0 + v) * nq0 + i] += zc(hh[(size_t)i * gs + v].re, hh[(size_t)i * gs + v].im);
         }
-        k_dot<1, true><<<NPART, VBLOCK, 0, c->stream>>>(n, w, w, pn); EMB_LAUNCH_CHECK(c);
-        k_finish<1><<<1, VBLOCK, 0, c->stream>>>(pn, coef + 2 * qc + 1); EMB_LAUNCH_CHECK(c);
-        EMB_CUDA(c, cudaMemcpyAsync(host.data(), coef, host.size() * sizeof(cx), cudaMemcpyDeviceToHost, c->stream));
-        EMB_CUDA(c, cudaStreamSynchronize(c->stream));
-        const double n0 = std::sqrt(std::fabs(host[(size_t)2 * qc].re)), n1 = std::sqrt(std::fabs(host[(size_t)2 * qc + 1].re));
+        return EMB_OK;
+    };
+    // in-block CGS2 of `ncols` columns (column v of the input sits at slot nq0 + v); accepted columns end up dense at
+    // nq0, nq0 + 1, ...; R[v * T + k] = coefficient of input column v on accepted column k; n0 (may be null): norms the
+    // drop test refers to.  Returns the number of accepted columns in *na.
+    auto in_block = [&](int ncols, const double* n0, std::vector<zc>& R, int* na) -> int {
+        int acc = 0;
+        std::vector<cx> host((size_t)2 * qc + 1);
+        for (int v = 0; v < ncols; ++v) {
+            cx* w = rc_Q(c, nq0 + acc);
+            if (acc != v)            // an earlier column was dropped: keep the columns dense
+                EMB_CUDA(c, cudaMemcpyAsync(w, rc_Q(c, nq0 + v), (size_t)n * sizeof(cx), cudaMemcpyDeviceToDevice, c->stream));
+            for (int pass = 0; pass < 2 && acc > 0; ++pass) {
+                cx* h = hC + (size_t)pass * qc;
+                k_rc_dots<1><<<dim3(RC_NP, acc), VBLOCK, 0, c->stream>>>(n, rc_Q(c, nq0), w, part); EMB_LAUNCH_CHECK(c);
+                k_rc_coef<1><<<acc, VBLOCK, 0, c->stream>>>(part, h); EMB_LAUNCH_CHECK(c);
+                k_rc_sub<<<vb, 256, acc * sizeof(cx), c->stream>>>(n, acc, h, rc_Q(c, nq0), w); EMB_LAUNCH_CHECK(c);
+            }
+            k_dot<1, true><<<NPART, VBLOCK, 0, c->stream>>>(n, w, w, part); EMB_LAUNCH_CHECK(c);
+            k_finish<1><<<1, VBLOCK, 0, c->stream>>>(part, hC + (size_t)2 * qc); EMB_LAUNCH_CHECK(c);
+            EMB_CUDA(c, cudaMemcpyAsync(host.data(), hC, host.size() * sizeof(cx), cudaMemcpyDeviceToHost, c->stream));
+            EMB_CUDA(c, cudaStreamSynchronize(c->stream));
+            const double n1 = std::sqrt(std::fabs(host[(size_t)2 * qc].re));
+            for (int k = 0; k < acc; ++k)
+                R[(size_t)v * T + k] = zc(host[(size_t)k].re + host[(size_t)qc + k].re, host[(size_t)k].im + host[(size_t)qc + k].im);
+            const double ref = n0 ? n0[v] : 1.0;
+            if (ref > 0 && n1 > 1e-11 * ref && n1 == n1) {
+                k_scale_real<<<vb, 256, 0, c->stream>>>(n, 1.0 / n1, w); EMB_LAUNCH_CHECK(c);
+                R[(size_t)v * T + acc] = zc(n1, 0.0);
+                ++acc;
+            }
+        }
+        *na = acc;
+        return EMB_OK;
+    };
+    std::vector<cx> hn((size_t)T);
+    EMB_CUDA(c, cudaMemcpyAsync(hn.data(), nrm, (size_t)T * sizeof(cx), cudaMemcpyDeviceToHost, c->stream));
+    EMB_CUDA(c, cudaStreamSynchronize(c->stream));
+    std::vector<double> n0((size_t)T);
+    for (int t = 0; t < T; ++t) n0[(size_t)t] = std::sqrt(std::fabs(hn[(size_t)t].re));
+    std::vector<zc> H1((size_t)T * nq0, zc(0.0, 0.0)), H2((size_t)T * nq0, zc(0.0, 0.0));
+    std::vector<zc> R1((size_t)T * T, zc(0.0, 0.0)), R2((size_t)T * T, zc(0.0, 0.0));
+    int a1 = 0, a2 = 0;
+    EMB_TRY(proj_old(nq0, T, H1));
+    EMB_TRY(in_block(T, n0.data(), R1, &a1));
+    EMB_TRY(proj_old(nq0, a1, H2));
+    EMB_TRY(in_block(a1, nullptr, R2, &a2));
+    if (a2 != a1) { c->err = "recycling: re-orthogonalisation dropped a column"; return EMB_ERR_CUDA; }
+    for (int t = 0; t < T; ++t) {
         std::vector<zc>& R = c->rc_R[(size_t)t];
         for (int i = 0; i < qc; ++i) R[(size_t)slot * qc + i] = zc(0.0, 0.0);
-        for (int i = 0; i < nq; ++i)
-            R[(size_t)slot * qc + i] = zc(host[(size_t)i].re + host[(size_t)qc + i].re, host[(size_t)i].im + host[(size_t)qc + i].im);
-        if (n0 > 0 && n1 > 1e-11 * n0 && n1 == n1) {
-            k_scale_real<<<vb, 256, 0, c->stream>>>(n, 1.0 / n1, w); EMB_LAUNCH_CHECK(c);
-            R[(size_t)slot * qc + nq] = zc(n1, 0.0);
-            c->rc_nq = nq + 1;
+        for (int i = 0; i < nq0; ++i) {
+            zc v = H1[(size_t)t * nq0 + i];
+            for (int k = 0; k < a1; ++k) v += H2[(size_t)k * nq0 + i] * R1[(size_t)t * T + k];
+            R[(size_t)slot * qc + i] = v;
+        }
+        for (int j = 0; j < a1; ++j) {          // (R2 R1)[j, t]: R2[k * T + j] = coefficient of pass-1 column k on final column j
+            zc v(0.0, 0.0);
+            for (int k = 0; k < a1; ++k) v += R2[(size_t)k * T + j] * R1[(size_t)t * T + k];
+            R[(size_t)slot * qc + nq0 + j] = v;
         }
     }
+    c->rc_nq = nq0 + a1;
+    const int nq_before = nq0;
     // scale so that A(f) u has unit norm at its birth frequency; acceptance against the existing directions
     const int nq = c->rc_nq;
     std::vector<zc> cn((size_t)nq, zc(0.0, 0.0));
@@ -352,11 +483,23 @@ static int rc_insert(emb_ctx* c, int slot, bool accept_test, bool* accepted) {
         EMB_TRY(fetch(nq1, hb));
         for (int i = 0; i < qc; ++i) c->rc_UtQ[(size_t)slot * qc + i] = i < nq1 ? zc(hb[(size_t)i].re, hb[(size_t)i].im) : zc(0.0, 0.0);
         if (slot > 0)
-            for (int i = nq_before; i < nq1; ++i) {
-                k_rc_dots<1, false><<<dim3(RC_NP, slot), VBLOCK, 0, c->stream>>>(n, c->rcU.p, rc_Q(c, i), part); EMB_LAUNCH_CHECK(c);
-                k_rc_coef<1><<<slot, VBLOCK, 0, c->stream>>>(part, coef); EMB_LAUNCH_CHECK(c);
-                EMB_TRY(fetch(slot, hb));
-                for (int j = 0; j < slot; ++j) c->rc_UtQ[(size_t)j * qc + i] = zc(hb[(size_t)j].re, hb[(size_t)j].im);
+            for (int i0 = nq_before; i0 < nq1; i0 += 4) {      // up to four new basis columns per pass over U
+                const int gs = nq1 - i0 < 4 ? nq1 - i0 : 4;
+                const dim3 grid(RC_NP, slot);
+                switch (gs) {
+                    case 1: k_rc_dots_cols<1, false><<<grid, VBLOCK, 0, c->stream>>>(n, c->rcU.p, rc_Q(c, i0), part); EMB_LAUNCH_CHECK(c);
+                            k_rc_coef<1><<<slot, VBLOCK, 0, c->stream>>>(part, coef); EMB_LAUNCH_CHECK(c); break;
+                    case 2: k_rc_dots_cols<2, false><<<grid, VBLOCK, 0, c->stream>>>(n, c->rcU.p, rc_Q(c, i0), part); EMB_LAUNCH_CHECK(c);
+                            k_rc_coef<2><<<slot, VBLOCK, 0, c->stream>>>(part, coef); EMB_LAUNCH_CHECK(c); break;
+                    case 3: k_rc_dots_cols<3, false><<<grid, VBLOCK, 0, c->stream>>>(n, c->rcU.p, rc_Q(c, i0), part); EMB_LAUNCH_CHECK(c);
+                            k_rc_coef<3><<<slot, VBLOCK, 0, c->stream>>>(part, coef); EMB_LAUNCH_CHECK(c); break;
+                    default: k_rc_dots_cols<4, false><<<grid, VBLOCK, 0, c->stream>>>(n, c->rcU.p, rc_Q(c, i0), part); EMB_LAUNCH_CHECK(c);
+                            k_rc_coef<4><<<slot, VBLOCK, 0, c->stream>>>(part, coef); EMB_LAUNCH_CHECK(c); break;
+                }
+                EMB_TRY(fetch(slot * gs, hb));
+                for (int j = 0; j < slot; ++j)
+                    for (int v = 0; v < gs; ++v)
+                        c->rc_UtQ[(size_t)j * qc + i0 + v] = zc(hb[(size_t)j * gs + v].re, hb[(size_t)j * gs + v].im);
             }
         k_rc_dots<1, true><<<dim3(RC_NP, slot + 1), VBLOCK, 0, c->stream>>>(n, c->rcU.p, rc_U(c, slot), part); EMB_LAUNCH_CHECK(c);
         k_rc_coef<1><<<slot + 1, VBLOCK, 0, c->stream>>>(part, coef); EMB_LAUNCH_CHECK(c);
@@ -365,6 +508,50 @@ static int rc_insert(emb_ctx* c, int slot, bool accept_test, bool* accepted) {
         for (int j = 0; j <= slot; ++j) {                 // hb[j] = u_j^H u_slot
             c->rc_UhU[(size_t)j * cap + slot] = zc(hb[(size_t)j].re, hb[(size_t)j].im);
             c->rc_UhU[(size_t)slot * cap + j] = zc(hb[(size_t)j].re, -hb[(size_t)j].im);
+        }
+    }
+    if (ok && getenv("EMB_RC_DEBUG")) {
+        // W_t (s u) - Q R_t[:, slot] relative to W_t (s u), and the orthonormality of the new columns against the basis
+        const int nq1 = c->rc_nq;
+        for (int t = 0; t < T; ++t) {
+            EMB_TRY(rc_term_mv(c, t, rc_U(c, slot), c->rc_tmp.p));
+            c->rc_spmvs--;
+            std::vector<cx> hc((size_t)nq1);
+            const double sc = c->rc_uscale[(size_t)slot];
+            for (int i = 0; i < nq1; ++i) {
+                const zc r = c->rc_R[(size_t)t][(size_t)slot * qc + i] / sc;
+                hc[(size_t)i] = cx{r.real(), r.imag()};
+            }
+            double nn[2] = {0, 0};
+            for (int k = 0; k < 2; ++k) {
+                k_dot<1, true><<<NPART, VBLOCK, 0, c->stream>>>(n, c->rc_tmp.p, c->rc_tmp.p, part); EMB_LAUNCH_CHECK(c);
+                k_finish<1><<<1, VBLOCK, 0, c->stream>>>(part, nrm); EMB_LAUNCH_CHECK(c);
+                cx hv;
+                EMB_CUDA(c, cudaMemcpyAsync(&hv, nrm, sizeof(cx), cudaMemcpyDeviceToHost, c->stream));
+                EMB_CUDA(c, cudaStreamSynchronize(c->stream));
+                nn[k] = std::sqrt(std::fabs(hv.re));
+                if (k == 0) {
+                    EMB_CUDA(c, cudaMemcpyAsync(hC, hc.data(), (size_t)nq1 * sizeof(cx), cudaMemcpyHostToDevice, c->stream));
+                    k_rc_sub<<<vb, 256, nq1 * sizeof(cx), c->stream>>>(n, nq1, hC, c->rcQ.p, c->rc_tmp.p); EMB_LAUNCH_CHECK(c);
+                }
+            }
+            if (t == 0) {       // orthonormality of the new columns against the whole basis
+                double worst = 0;
+                for (int i = nq_before; i < nq1; ++i) {
+                    k_rc_dots<1><<<dim3(RC_NP, nq1), VBLOCK, 0, c->stream>>>(n, c->rcQ.p, rc_Q(c, i), part); EMB_LAUNCH_CHECK(c);
+                    k_rc_coef<1><<<nq1, VBLOCK, 0, c->stream>>>(part, hB); EMB_LAUNCH_CHECK(c);
+                    std::vector<cx> hq((size_t)nq1);
+                    EMB_CUDA(c, cudaMemcpyAsync(hq.data(), hB, (size_t)nq1 * sizeof(cx), cudaMemcpyDeviceToHost, c->stream));
+                    EMB_CUDA(c, cudaStreamSynchronize(c->stream));
+                    for (int j = 0; j < nq1; ++j) {
+                        const double d = std::hypot(hq[(size_t)j].re - (j == i ? 1.0 : 0.0), hq[(size_t)j].im);
+                        if (d > worst) worst = d;
+                    }
+                }
+                fprintf(stderr, "[rc debug] slot %d: max |Q^H q_new - e| %.3e\n", slot, worst);
+            }
+            fprintf(stderr, "[rc debug] slot %d term %d: |W u| %.3e  |W u - Q R| / |W u| %.3e  (nq %d -> %d)\n", slot, t, nn[0],
+                    nn[0] > 0 ? nn[1] / nn[0] : 0.0, nq_before, nq1);
         }
     }
     if (ok) c->rc_version++;
