@@ -472,8 +472,9 @@ def run_gpu(args):
                                        "points / slowest rank's time; this is the strong-scaling number",
                                "per_rank": splits},
                 "gpu_launches": int(launches_total),
-                "roofline": {"kernel": (f"k_bsell_tma<NV={nv}> (operator application of the block COCR iteration: complex64 2x2 "
-                                        f"blocks in a SELL-8 layout staged with cp.async.bulk, {nv} interleaved right-hand sides)"
+                "roofline": {"kernel": (f"k_bsell_tma<8,24,2,1> (operator application of the block COCR iteration: complex64 2x2 "
+                                        f"blocks in a SELL-8 layout, slice streams staged with cp.async.bulk + mbarrier under an L2 "
+                                        f"evict-first policy, {nv} interleaved right-hand sides)"
                                         if nv == 2 else
                                         f"k_bspmv<NV={nv}, complex64 values> (2x2 block-CSR operator application of the block "
                                         f"COCR iteration on {nv} interleaved right-hand sides)"),

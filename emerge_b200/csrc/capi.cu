@@ -34,6 +34,7 @@ extern "C" void emb_destroy(emb_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+    if (c->coarse_stream) { cudaStreamDestroy(c->coarse_stream); cudaEventDestroy(c->ev_coarse_fork); cudaEventDestroy(c->ev_coarse_done); }
     for (int k = 0; k < 4; ++k) {
         c->xstage[k].release();
         if (c->ev_stage_ready[k]) { cudaEventDestroy(c->ev_stage_ready[k]); cudaEventDestroy(c->ev_stage_done[k]); }
@@ -47,7 +48,7 @@ extern "C" void emb_destroy(emb_ctx* c) {
     c->itp_tet.release(); c->itp_xyz.release(); c->itp_E.release();
     for (auto& w : c->work) w.release();
     c->dinv.release(); c->pairmate.release(); c->red.release(); c->As.release(); c->rc_x0.release();
-    c->rcU.release(); c->rcQ.release(); c->rc_part.release(); c->rc_tmp.release(); c->bs.release(); c->As32.release();
+    c->rcU.release(); c->rcU32.release(); c->rcQ.release(); c->rc_part.release(); c->rc_tmp.release(); c->bs.release(); c->As32.release();
     for (auto e : c->ev_restr) cudaEventDestroy(e);
     for (auto e : c->ev_done) cudaEventDestroy(e);
     if (c->evp0) { cudaEventDestroy(c->evp0); cudaEventDestroy(c->evp1); }

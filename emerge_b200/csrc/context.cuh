@@ -210,6 +210,9 @@ struct emb_ctx {
     std::vector<std::complex<double>> rc_UtQ;      // [rc_cap][rc_qcap]  u_j^T q_i (unconjugated)
     std::vector<std::complex<double>> rc_UhU;      // [rc_cap][rc_cap]   u_i^H u_j
     DevBuf<cx> rc_ceff, rc_ct;                     // [rc_cap][rc_cap] coefficient map; [2][rc_cap][NVMAX] small vectors
+    cudaStream_t coarse_stream = nullptr;          // the projection U^T r of the coarse-space correction overlaps the multilevel cycle
+    cudaEvent_t ev_coarse_fork = nullptr, ev_coarse_done = nullptr;
+    DevBuf<float> rcU32;                           // [rc_cap][Ns][2] complex64 copy of U: what the coarse-space correction streams
     int coarse_m = 0;                              // directions in the coarse space of the current operator (0 = none)
     int rc_version = 0, coarse_version = -1;       // basis change counter / the one the coefficient map was built for
     double coarse_k0 = -1;

@@ -543,7 +543,7 @@ extern "C" int emb_set_dirichlet(emb_ctx* c, int64_t npec, const int64_t* pec_id
     c->have_A = false;
     c->rc_n = 0; c->rc_nq = 0;
     if (c->rc_cap > 0) {   // vectors are sized by the solve space
-        c->rcU.release(); c->rcQ.release(); c->rc_part.release(); c->rc_tmp.release(); c->rc_x0.release();
+        c->rcU.release(); c->rcU32.release(); c->rcQ.release(); c->rc_part.release(); c->rc_tmp.release(); c->rc_x0.release();
         c->rc_cap = 0;
     }
     // every solve-space buffer is sized by Ns

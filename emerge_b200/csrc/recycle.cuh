@@ -101,21 +101,21 @@ __device__ __forceinline__ cx block_sum1(cx v) {
 // part[(j * RC_NP + blockIdx.x) * NV + v] = partial of <q_j, r_v> over this block's rows;  j = blockIdx.y;
 // Q: contiguous columns of length n, r: NV interleaved columns
 // CONJ = false: unconjugated products q_j^T r_v
-template <int NV, bool CONJ = true>
-__global__ void __launch_bounds__(VBLOCK) k_rc_dots(int64_t n, const cx* __restrict__ Q, const cx* __restrict__ r,
+template <int NV, bool CONJ = true, typename QT = cx>
+__global__ void __launch_bounds__(VBLOCK) k_rc_dots(int64_t n, const QT* __restrict__ Q, const cx* __restrict__ r,
                                                     cx* __restrict__ part) {
     // blocks are scheduled x-fastest: remap so that consecutive blocks share the ROW RANGE p and differ in the column j -
     // the range of r is then fetched from HBM once and served from L2 to the other columns (launched as (RC_NP, ncols))
     const int lin = blockIdx.y * gridDim.x + blockIdx.x;
     const int bj = lin % (int)gridDim.y, bp = lin / (int)gridDim.y;
-    const cx* q = Q + (int64_t)bj * n;
+    const QT* q = Q + (int64_t)bj * n;
     cx acc[NV];
 #pragma unroll
     for (int v = 0; v < NV; ++v) acc[v] = mk(0.0);
     const int64_t per = (n + RC_NP - 1) / RC_NP;
     const int64_t i0 = bp * per, i1 = (i0 + per < n) ? i0 + per : n;
     for (int64_t i = i0 + threadIdx.x; i < i1; i += VBLOCK) {
-        const cx u = q[i];
+        const cx u = ldv(q, i);
 #pragma unroll
         for (int v = 0; v < NV; ++v) {
             const cx w = r[i * NV + v];
@@ -206,8 +206,8 @@ __global__ void __launch_bounds__(256) k_rc_sub_cols(int64_t n, int m, const cx*
     for (int v = 0; v < NB; ++v) W[(int64_t)v * n + i] = a[v];
 }
 // x[i][v] += sum_{j<m} y[j * NV + v] u_j[i]
-template <int NV>
-__global__ void __launch_bounds__(256) k_rc_combine(int64_t n, int m, const cx* __restrict__ y, const cx* __restrict__ U,
+template <int NV, typename UT = cx>
+__global__ void __launch_bounds__(256) k_rc_combine(int64_t n, int m, const cx* __restrict__ y, const UT* __restrict__ U,
                                                     cx* __restrict__ x) {
     extern __shared__ cx s_h[];
     for (int k = threadIdx.x; k < m * NV; k += blockDim.x) s_h[k] = y[k];
@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(256) k_rc_combine(int64_t n, int m, const cx* 
 #pragma unroll
     for (int v = 0; v < NV; ++v) a[v] = x[i * NV + v];
     for (int k = 0; k < m; ++k) {
-        const cx u = U[(int64_t)k * n + i];
+        const cx u = ldv(U, (int64_t)k * n + i);
 #pragma unroll
         for (int v = 0; v < NV; ++v) fma_c(a[v], s_h[k * NV + v], u);
     }
@@ -252,10 +252,10 @@ static int rc_prepare(emb_ctx* c) {
     const int T = rc_T(c);
     // the basis costs (1 + T) vectors per direction: never take more than half of the free HBM (5M tets: ~10 directions
     // fewer than asked for rather than an allocation failure in the middle of a sweep)
-    c->rcU.release(); c->rcQ.release();
+    c->rcU.release(); c->rcU32.release(); c->rcQ.release();
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
-        const double per_dir = (double)(1 + T) * (double)c->Ns * sizeof(cx);
+        const double per_dir = ((double)(1 + T) + (c->coarse_basis ? 0.5 : 0.0)) * (double)c->Ns * sizeof(cx);
         const int fit = (int)(0.5 * (double)free_b / per_dir);
         if (fit < c->rc_cap) c->rc_cap = fit > 0 ? fit : 0;
     }
@@ -274,6 +274,7 @@ static int rc_prepare(emb_ctx* c) {
         c->rc_UtQ.assign((size_t)c->rc_cap * c->rc_qcap, zc(0.0, 0.0));
         c->rc_UhU.assign((size_t)c->rc_cap * c->rc_cap, zc(0.0, 0.0));
         EMB_TRY(dev_alloc(c, c->rc_ceff, (size_t)c->rc_cap * c->rc_cap));
+        EMB_TRY(dev_alloc(c, c->rcU32, (size_t)c->rc_cap * c->Ns * 2));
         EMB_TRY(dev_alloc(c, c->rc_ct, (size_t)2 * c->rc_cap * NVMAX));
     }
     rc_clear(c);
@@ -466,6 +467,10 @@ static int rc_insert(emb_ctx* c, int slot, bool accept_test, bool* accepted) {
     } else {
         for (int t = 0; t < T; ++t)
             for (int i = 0; i < qc; ++i) c->rc_R[(size_t)t][(size_t)slot * qc + i] = zc(0.0, 0.0);
+    }
+    if (ok && c->coarse_basis && c->rcU32.p) {       // the complex64 copy the coarse-space correction streams (a preconditioner)
+        k_convert<cx, cf><<<vb, 256, 0, c->stream>>>(n, rc_U(c, slot), reinterpret_cast<cf*>(c->rcU32.p) + (int64_t)slot * n);
+        EMB_LAUNCH_CHECK(c);
     }
     if (ok && c->coarse_basis && !c->rc_UtQ.empty()) {
         // bookkeeping of the experimental coarse space: u^T q for the new direction against every basis column, for the
@@ -711,17 +716,53 @@ static int rc_coarse_update(emb_ctx* c) {
     return EMB_OK;
 }
 
-// z += U Ceff (U^T r) for NV interleaved columns (three launches on the context stream; capturable)
+// z += U Ceff (U^T r) for NV interleaved columns, in two halves so that the first one (the projection: a bandwidth-bound
+// pass over U and the small product) runs on its own stream next to the latency-bound multilevel cycle of the same
+// residual; the second half (z += U y) follows the kernel that writes z.  Capturable (fork / join by events).
+// Both passes stream the complex64 copy of U (half the bytes; U32 Ceff U32^T is still complex symmetric, and the 6e-8
+// rounding of a coarse space is irrelevant for a preconditioner); EMB_COARSE_U64=1 streams U itself.
+static inline bool rc_coarse_u64() {
+    static const bool u64 = getenv("EMB_COARSE_U64") && atoi(getenv("EMB_COARSE_U64")) != 0;
+    return u64;
+}
 template <int NV>
-static int rc_coarse_apply(emb_ctx* c, const cx* r, cx* z) {
+static int rc_coarse_begin(emb_ctx* c, const cx* r) {
     const int m = c->coarse_m;
     if (m <= 0) return EMB_OK;
     const int64_t n = c->Ns;
+    cudaStream_t s = c->stream;
+    if (c->use_side_streams) {
+        if (!c->coarse_stream) {
+            int least = 0, greatest = 0;
+            cudaDeviceGetStreamPriorityRange(&least, &greatest);
+            EMB_CUDA(c, cudaStreamCreateWithPriority(&c->coarse_stream, cudaStreamNonBlocking, least));
+            EMB_CUDA(c, cudaEventCreateWithFlags(&c->ev_coarse_fork, cudaEventDisableTiming));
+            EMB_CUDA(c, cudaEventCreateWithFlags(&c->ev_coarse_done, cudaEventDisableTiming));
+        }
+        s = c->coarse_stream;
+        EMB_CUDA(c, cudaEventRecord(c->ev_coarse_fork, c->stream));      // r is complete here
+        EMB_CUDA(c, cudaStreamWaitEvent(s, c->ev_coarse_fork, 0));
+    }
     cx* t = c->rc_ct.p;
     cx* cc = c->rc_ct.p + (size_t)c->rc_cap * NVMAX;
-    k_rc_dots<NV, false><<<dim3(RC_NP, m), VBLOCK, 0, c->stream>>>(n, c->rcU.p, r, c->rc_part.p); EMB_LAUNCH_CHECK(c);
-    k_rc_coef<NV><<<m, VBLOCK, 0, c->stream>>>(c->rc_part.p, t); EMB_LAUNCH_CHECK(c);
-    k_small_mm<<<1, 256, 0, c->stream>>>(m, NV, c->rc_ceff.p, t, cc); EMB_LAUNCH_CHECK(c);
-    k_rc_combine<NV><<<blocks_for(n, 256), 256, (size_t)m * NV * sizeof(cx), c->stream>>>(n, m, cc, c->rcU.p, z); EMB_LAUNCH_CHECK(c);
+    const cf* U32 = reinterpret_cast<const cf*>(c->rcU32.p);
+    if (rc_coarse_u64() || !U32) { k_rc_dots<NV, false><<<dim3(RC_NP, m), VBLOCK, 0, s>>>(n, c->rcU.p, r, c->rc_part.p); EMB_LAUNCH_CHECK(c); }
+    else { k_rc_dots<NV, false, cf><<<dim3(RC_NP, m), VBLOCK, 0, s>>>(n, U32, r, c->rc_part.p); EMB_LAUNCH_CHECK(c); }
+    k_rc_coef<NV><<<m, VBLOCK, 0, s>>>(c->rc_part.p, t); EMB_LAUNCH_CHECK(c);
+    k_small_mm<<<1, 256, 0, s>>>(m, NV, c->rc_ceff.p, t, cc); EMB_LAUNCH_CHECK(c);
+    if (s != c->stream) EMB_CUDA(c, cudaEventRecord(c->ev_coarse_done, s));
+    return EMB_OK;
+}
+template <int NV>
+static int rc_coarse_finish(emb_ctx* c, cx* z) {
+    const int m = c->coarse_m;
+    if (m <= 0) return EMB_OK;
+    const int64_t n = c->Ns;
+    if (c->use_side_streams && c->coarse_stream) EMB_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_coarse_done, 0));
+    const cx* cc = c->rc_ct.p + (size_t)c->rc_cap * NVMAX;
+    const cf* U32 = reinterpret_cast<const cf*>(c->rcU32.p);
+    const size_t sh = (size_t)m * NV * sizeof(cx);
+    if (rc_coarse_u64() || !U32) { k_rc_combine<NV><<<blocks_for(n, 256), 256, sh, c->stream>>>(n, m, cc, c->rcU.p, z); EMB_LAUNCH_CHECK(c); }
+    else { k_rc_combine<NV, cf><<<blocks_for(n, 256), 256, sh, c->stream>>>(n, m, cc, U32, z); EMB_LAUNCH_CHECK(c); }
     return EMB_OK;
 }

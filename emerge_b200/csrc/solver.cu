@@ -133,9 +133,14 @@ static int norms2_host(emb_ctx* c, const cx* a, double* out) {
 // coarse space
 template <int NV, typename VX>
 static int precond_inner(emb_ctx* c, int pmode, const VX* r, VX* z) {
+    bool coarse = false;
+    if constexpr (std::is_same<VX, cx>::value) {
+        coarse = c->coarse_basis && c->coarse_m > 0;
+        if (coarse) EMB_TRY(rc_coarse_begin<NV>(c, r));        // U^T r on its own stream, next to the multilevel cycle
+    }
     EMB_TRY((precond_apply<NV, VX>(c, pmode, r, z)));
     if constexpr (std::is_same<VX, cx>::value)
-        if (c->coarse_basis && c->coarse_m > 0) EMB_TRY(rc_coarse_apply<NV>(c, r, z));
+        if (coarse) EMB_TRY(rc_coarse_finish<NV>(c, z));
     return EMB_OK;
 }
 
@@ -736,7 +741,7 @@ extern "C" int emb_recycle_config(emb_ctx* c, int max_vectors, double snapshot_r
     if (!c || max_vectors < 0 || max_vectors > 256) return EMB_ERR_ARG;
     if (max_vectors > 0 && !c->have_dirichlet) { c->err = "emb_recycle_config: needs emb_set_dirichlet first"; return EMB_ERR_STATE; }
     if (max_vectors != c->rc_cap) {       // vectors are allocated when the first direction arrives (recycle.cuh::rc_prepare)
-        c->rcU.release(); c->rcQ.release(); c->rc_part.release();
+        c->rcU.release(); c->rcU32.release(); c->rcQ.release(); c->rc_part.release();
         c->rc_terms.clear();
         c->rc_terms.push_back(-1);        // never equal to a real term list => rc_prepare reallocates
     }

@@ -108,6 +108,7 @@ class ShardedSweep:
         self.global_order = hierarchical_order(len(self.freqs))
         self.rounds = 0
         self.exchanged = 0
+        self.import_s = 0.0
         self.timings = {}
         self._bufs = None
 
@@ -146,12 +147,15 @@ class ShardedSweep:
             parts = list(allb.view(W, P, -1).unbind(0))
             dist.all_gather(parts, mine)
             eng.sync()
+            import time
+            t0 = time.perf_counter()
             for r in range(W):
                 if r == self.rank:
                     continue
                 for j in range(counts[r]):
                     eng.import_direction(parts[r][j])
                     self.exchanged += 1
+            self.import_s += time.perf_counter() - t0     # the rest of exchange_s is waiting for the slowest rank + NCCL
         return int(sum(counts))
 
     # ------------------------------------------------------------------ the sweep
@@ -200,7 +204,7 @@ class ShardedSweep:
         if overlap:
             eng.fields_async(False)          # waits for the last copy
         self.timings = dict(seed_s=t_seed - t_ex, exchange_s=t_ex, fill_s=time.perf_counter() - t0,
-                            seed_rounds=self.rounds, imported_directions=self.exchanged)
+                            seed_rounds=self.rounds, imported_directions=self.exchanged, import_s=self.import_s)
         res = SweepResult(self.freqs, [], S)
         for i in sorted(stats):
             res.stats.extend(stats[i])

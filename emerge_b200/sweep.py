@@ -106,6 +106,9 @@ class FrequencySweep:
         t, ctx = self.t, self.ctx
         n_edges = t.edges.shape[1]
         t0 = time.perf_counter()
+        # the host pieces of the multilevel setup that only need the mesh tables start now, in worker threads (numpy /
+        # scipy release the GIL), and overlap the upload, the symbolic phase and the assembly on the device
+        self._early = self._start_early_aux() if self.solver_opts.get("precond") == "multilevel" else None
         ctx.upload_mesh(t.nodes, t.tets, t.tris, t.tet_to_field, t.tri_to_field, n_edges)
         ctx.upload_materials(self.er, self.ur)
         self.timings["upload_s"] = time.perf_counter() - t0
@@ -160,6 +163,21 @@ class FrequencySweep:
                 self._setup_vline(b, ids)
         self._setup_done = True
 
+    def _start_early_aux(self):
+        from concurrent.futures import ThreadPoolExecutor
+        from .auxspace import nodal_interpolation, p1_gradient, p1_stiffness_mass
+        if not self.multilevel:
+            return None
+        t = self.t
+        tr = lambda T: np.real(T[0, 0] + T[1, 1] + T[2, 2]) / 3.0
+        w_eps, w_mu = tr(self.er), 1.0 / tr(self.ur)
+        same = bool(np.allclose(w_eps, w_mu))
+        ex = ThreadPoolExecutor(max_workers=4)
+        return dict(pool=ex, w_eps=w_eps, w_mu=w_mu, same=same,
+                    f_le=ex.submit(p1_stiffness_mass, t, w_eps),
+                    f_lm=None if same else ex.submit(p1_stiffness_mass, t, w_mu),
+                    f_pi=ex.submit(nodal_interpolation, t), f_g1=ex.submit(p1_gradient, t))
+
     def _setup_aux_spaces(self):
         """Auxiliary spaces of the additive multilevel preconditioner, restricted to the solve space; columns whose
         support touches an eliminated dof are dropped (their potential / Whitney / nodal dof is fixed by the PEC condition).
@@ -181,9 +199,14 @@ class FrequencySweep:
         keep = np.ones(N, dtype=bool)
         keep[self.pec_ids] = False
         multilevel = self.multilevel
-        tr = lambda T: np.real(T[0, 0] + T[1, 1] + T[2, 2]) / 3.0
-        w_eps, w_mu = tr(self.er), 1.0 / tr(self.ur)
-        same = np.allclose(w_eps, w_mu)
+        early = getattr(self, "_early", None)
+        self._early = None
+        if early is not None:
+            w_eps, w_mu, same = early["w_eps"], early["w_mu"], early["same"]
+        else:
+            tr = lambda T: np.real(T[0, 0] + T[1, 1] + T[2, 2]) / 3.0
+            w_eps, w_mu = tr(self.er), 1.0 / tr(self.ur)
+            same = np.allclose(w_eps, w_mu)
         kmid2 = (2 * np.pi * self.f_ref / C0) ** 2
 
         paired = ctx.paired                           # device queries from the owner thread only
@@ -212,16 +235,19 @@ class FrequencySweep:
         # top-level spaces G and P straight on the device (csrc/auxbuild.cu; same entries as build_aux_spaces_paired, which was
         # the critical path of this setup: 3-4 s at 1M tets); EMB_AUX_HOST=1 keeps the numpy builder
         on_device = paired and multilevel and hasattr(ctx, "aux_build_top") and not int(os.environ.get("EMB_AUX_HOST", "0"))
-        with ThreadPoolExecutor(max_workers=4) as ex:
+        with (early["pool"] if early is not None else ThreadPoolExecutor(max_workers=4)) as ex:
             f_top = None if on_device else ex.submit(top_level)
-            f_le = ex.submit(p1_stiffness_mass, t, w_eps) if multilevel else None
-            f_lm = ex.submit(p1_stiffness_mass, t, w_mu) if (multilevel and not same) else None
-            f_pi = ex.submit(nodal_interpolation, t) if multilevel else None
+            if early is not None:
+                f_le, f_lm, f_pi = early["f_le"], early["f_lm"], early["f_pi"]
+            else:
+                f_le = ex.submit(p1_stiffness_mass, t, w_eps) if multilevel else None
+                f_lm = ex.submit(p1_stiffness_mass, t, w_mu) if (multilevel and not same) else None
+                f_pi = ex.submit(nodal_interpolation, t) if multilevel else None
             ctx.aux_clear()
             self.aux_dims = []
             if on_device:
                 from .auxspace import p1_gradient
-                f_g1 = ex.submit(p1_gradient, t)
+                f_g1 = early["f_g1"] if early is not None else ex.submit(p1_gradient, t)
                 nN, nE = np.asarray(t.nodes).shape[1], np.asarray(t.edges).shape[1]
                 ig, ncolG, _ = ctx.aux_build_top("G", t.edges, nN + nE)
                 ip, ncolP, badP = ctx.aux_build_top("P", t.edges, nE)
