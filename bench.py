@@ -279,7 +279,8 @@ def e2e_pass(args, torch, dist, rank, world, local, t, er, ur, bcs, max_points, 
                   + np.asarray(t.tet_to_field).nbytes + np.asarray(t.tri_to_field).nbytes)
     per_step_h2d = sum(18 * 16 * sw2.ntri[id(p)] for p in sw2.ports)
     h2d = (er_p.nbytes + ur_p.nbytes + mesh_bytes) / npts + per_step_h2d
-    d2h = sum(o.nbytes for o in outs.values()) + sum(2 * 3 * 16 * sw2._sp[id(p)]["pts"].shape[1] * len(sw2.ports) for p in sw2.ports)
+    # fields of every port + per solved port one read-back of E (3 complex128) at the S-parameter sample points of all ports
+    d2h = sum(o.nbytes for o in outs.values()) + sum(3 * 16 * sw2._sp[id(p)]["pts"].shape[1] * len(sw2.ports) for p in sw2.ports)
     out = dict(ms=ms, points=len(res.solved), h2d=h2d, d2h=d2h, setup=dict(sw2.timings), split=dict(sh2.timings),
                not_converged=res.not_converged, max_relres=res.max_relres)
     sw2.ctx.close()

@@ -148,6 +148,7 @@ class FrequencySweep:
         nodes = np.asarray(t.nodes)
         tris = np.asarray(t.tris)
         self._sp = {}
+        self._sp_all = None
         for b in self.ports:
             ids = _tri_ids(b, self.get_triangles)
             tv = tris[:, ids]                                           # (3, ntri)
@@ -340,8 +341,32 @@ class FrequencySweep:
             return 1 / (tr_u / 3)
         return 1 / (tr_e / 3)
 
-    def _s_data(self, b, k0, x_full):
-        """(pfield, pmode) of _compute_s_data (emfreq3d.py:734-779)."""
+    def _interp_all(self, x_full):
+        """E at the S-parameter sample points of EVERY port with one device call (one kernel, one read-back instead of
+        one per port pair) -> {id(port): E (3, n_port_points)}; x_full None: the device-resident solution."""
+        lay = getattr(self, "_sp_all", None)
+        if lay is None:
+            tets, pts, sl, o = [], [], {}, 0
+            for b in self.ports:
+                sp = self._sp[id(b)]
+                if getattr(b, "v_integration", False):
+                    ok = sp["vline"]["tet"] >= 0
+                    tt, pp = sp["vline"]["tet"][ok], sp["vline"]["mid"][:, ok]
+                else:
+                    tt, pp = sp["tet"], sp["pts"]
+                tets.append(np.asarray(tt, dtype=np.int64))
+                pts.append(np.asarray(pp, dtype=np.float64))
+                sl[id(b)] = (o, o + len(tt))
+                o += len(tt)
+            lay = self._sp_all = (np.concatenate(tets), np.ascontiguousarray(np.concatenate(pts, axis=1)), sl)
+        tets, pts, sl = lay
+        E = self.ctx.interp(x_full, tets, pts) if len(tets) else np.zeros((3, 0), dtype=np.complex128)
+        return {k: E[:, a:b] for k, (a, b) in sl.items()}
+
+    def _s_data(self, b, k0, x_full, E_all=None, modes=None):
+        """(pfield, pmode) of _compute_s_data (emfreq3d.py:734-779).  E_all: the output of _interp_all for this solution;
+        modes: a dict shared by the calls of one frequency point (mode field, impedance and material constants of a port
+        do not depend on which port is excited)."""
         sp = self._sp[id(b)]
         ctx = self.ctx
         if getattr(b, "v_integration", False):
@@ -349,15 +374,20 @@ class FrequencySweep:
             ok = vl["tet"] >= 0
             E = np.zeros((3, len(ok)), dtype=np.complex128)
             if ok.any():
-                E[:, ok] = ctx.interp(x_full, vl["tet"][ok], vl["mid"][:, ok])
+                E[:, ok] = E_all[id(b)] if E_all is not None else ctx.interp(x_full, vl["tet"][ok], vl["mid"][:, ok])
             V = np.sum(E[0] * vl["d"][:, 0] + E[1] * vl["d"][:, 1] + E[2] * vl["d"][:, 2])
             a, bb = (b.voltage, V - b.voltage) if b.active else (0, V)
             return np.sqrt(bb ** 2 / (2 * b.Z0)), np.sqrt(a ** 2 / (2 * b.Z0))
-        const = np.squeeze(self._port_constants(b, sp)).astype(np.complex128)
-        E = ctx.interp(x_full, sp["tet"], sp["pts"])
-        mode = np.asarray(b.port_mode_3d_global(sp["pts"][0], sp["pts"][1], sp["pts"][2], k0))
+        got = modes.get(id(b)) if modes is not None else None
+        if got is None:
+            const = np.squeeze(self._port_constants(b, sp)).astype(np.complex128)
+            mode = np.asarray(b.port_mode_3d_global(sp["pts"][0], sp["pts"][1], sp["pts"][2], k0))
+            got = (const, mode, b.Zmode(k0))
+            if modes is not None:
+                modes[id(b)] = got
+        const, mode, Z = got
+        E = E_all[id(b)] if E_all is not None else ctx.interp(x_full, sp["tet"], sp["pts"])
         Q = 1 if b.active else 0
-        Z = b.Zmode(k0)
         DP = dunavant4()
         f1 = (((E - Q * mode) * np.conj(mode)).sum(axis=0) / (2 * Z)).reshape(6, sp["ntri"])
         f2 = ((mode * np.conj(mode)).sum(axis=0) / (2 * Z)).reshape(6, sp["ntri"])
@@ -390,6 +420,7 @@ class FrequencySweep:
         k0 = self.assemble_frequency(freq)
         want = keep_fields or (out_bufs is not None)
         lock = self.lockstep if self.solver_opts.get("method", "cocr") == "cocr" else 1
+        modes = {}
         ja0 = 0
         while ja0 < len(ports):
             group = ports[ja0:ja0 + max(1, min(4, lock))]       # lockstep groups of up to 4 ports
@@ -407,10 +438,11 @@ class FrequencySweep:
                 if keep_fields:
                     fields[pa.port_number] = xs[k]
                 self.ctx.select_solution(k)
+                E_all = self._interp_all(None)       # one device call per solution for the sample points of all ports
                 pa.active = True
-                _, pout = self._s_data(pa, k0, None)
+                _, pout = self._s_data(pa, k0, None, E_all, modes)
                 for ib, pb in enumerate(ports):
-                    pf, _ = self._s_data(pb, k0, None)
+                    pf, _ = self._s_data(pb, k0, None, E_all, modes)
                     S[ib, ja] = pf / pout
                 pa.active = False
             ja0 += len(group)
