@@ -40,3 +40,19 @@ def test_paired_construction_matches_generic_path():
         B.eliminate_zeros()
         assert np.array_equal(A.indptr, B.indptr) and np.array_equal(A.indices, B.indices)
         assert np.array_equal(A.data, B.data)
+
+
+def test_p1_stiffness_edge_path_matches_element_path():
+    """The edge-wise P1 stiffness (two bincounts over the mesh edges, products of the unscaled gradients scaled once) equals
+    the element-wise COO assembly, with a per-tet weight, on a jittered mesh; the lumped mass sums to the volume."""
+    from types import SimpleNamespace
+    a, b, L = 22.86e-3, 10.16e-3, 30e-3
+    box = box_mesh(5, 3, 7, a, b, L, jitter=0.15, seed=3)
+    t = mesh_tables(box.nodes_xyz, box.tets)
+    w = np.random.default_rng(0).uniform(0.5, 2.0, t.tets.shape[1])
+    L1, m1 = auxspace.p1_stiffness_mass(t, w)
+    L2, m2 = auxspace.p1_stiffness_mass(SimpleNamespace(nodes=t.nodes, tets=t.tets), w)      # no tet_to_edge: element path
+    assert abs(L1 - L2).max() <= 1e-13 * abs(L2).max()
+    assert np.allclose(m1, m2, rtol=1e-14, atol=0)
+    assert abs(m1.sum() - a * b * L) <= 1e-12 * a * b * L
+    assert abs(np.asarray(L1.sum(axis=1)).ravel()).max() <= 1e-10 * abs(L1).max()           # constants are in the kernel
