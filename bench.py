@@ -461,6 +461,11 @@ def run_gpu(args):
                 "steps": args.steps if partial else jm["points"], "warmup": args.warmup,
                 "ms_per_step": jm["ms"] / (args.steps if partial else max(1, -(-jm["points"] // world))), "higher_is_better": True,
                 "scaling": "weak" if partial else "strong", "vs_baseline": None,
+                # with --steps K below a rank's share, `value` times the first K points of EVERY rank: cold seed points at
+                # N = 1, mostly points filled from the shared basis at large N - different work, so value(N) / value(1) is
+                # not a scaling efficiency; the whole-job numbers of `full_sweep` are
+                "value_comparable_across_n": not partial,
+                "strong_scaling_value": jf["value"], "strong_scaling_e2e": jf.get("e2e_value"),
                 "dtype": "f64", "data": "synthetic", "config": workload_config(args),
                 "e2e": {"value": jm.get("e2e_value"), "unit": UNIT,
                         "h2d_bytes_per_step": int((e2e_k or e2e_full)["h2d"]) if (e2e_k or e2e_full) else None,
