@@ -143,7 +143,12 @@ class FrequencySweep:
             t1 = time.perf_counter()
             self._setup_aux_spaces()
             self.timings["aux_setup_s"] = time.perf_counter() - t1
-        # S-parameter sample points per port
+        self._setup_sample_points()
+        self._setup_done = True
+
+    def _setup_sample_points(self):
+        """S-parameter sample points per port (host only: generate_int_points_tri / calc_area of the port triangles)"""
+        t = self.t
         DP = dunavant4()
         nodes = np.asarray(t.nodes)
         tris = np.asarray(t.tris)
@@ -162,7 +167,6 @@ class FrequencySweep:
                                    tet0=tet0, ntri=len(ids))
             if getattr(b, "v_integration", False):
                 self._setup_vline(b, ids)
-        self._setup_done = True
 
     def _start_early_aux(self):
         from concurrent.futures import ThreadPoolExecutor
